@@ -1,0 +1,78 @@
+"""ctypes binding of the CPU oracle (oracle/traversal_oracle.c).
+
+TEST INFRASTRUCTURE: importable only from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference leg.  The product package rodent_b200
+never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_DIR = Path(__file__).resolve().parent
+_LIB = None
+
+
+class OracleStats(ctypes.Structure):
+    _fields_ = [("nodes", ctypes.c_uint64), ("tri4", ctypes.c_uint64), ("max_stack", ctypes.c_uint64)]
+
+
+def build(force: bool = False) -> Path:
+    so = _DIR / "liboracle.so"
+    src = _DIR / "traversal_oracle.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"] + (["-s"] if force else []), check=True)
+    return so
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(str(build()))
+        _LIB.oracle_traverse.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int,
+                                         ctypes.POINTER(OracleStats)]
+        _LIB.oracle_traverse.restype = None
+        _LIB.oracle_brute_force.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+        _LIB.oracle_brute_force.restype = None
+        _LIB.oracle_network.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB.oracle_network.restype = ctypes.c_int
+    return _LIB
+
+
+def _ptr(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def traverse(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit: bool = False,
+             threads: int | None = None, want_stats: bool = False):
+    """Run the oracle; returns hits (and OracleStats when want_stats)."""
+    from rodent_b200.formats import HIT1
+    arity = nodes.dtype["child"].shape[0]
+    hits = np.zeros(len(rays), HIT1)
+    if any_hit:
+        hits["tri_id"] = -2   # make "written" visible; t/u/v stay 0 (untouched by occluded)
+    stats = OracleStats()
+    if threads is None:
+        threads = os.cpu_count() or 1
+    lib().oracle_traverse(arity, int(any_hit), _ptr(nodes), _ptr(tris), _ptr(rays), _ptr(hits), len(rays),
+                          threads, ctypes.byref(stats) if want_stats else None)
+    return (hits, stats) if want_stats else hits
+
+
+def brute_force(tris: np.ndarray, rays: np.ndarray) -> np.ndarray:
+    from rodent_b200.formats import HIT1
+    hits = np.zeros(len(rays), HIT1)
+    lib().oracle_brute_force(_ptr(tris), len(tris), _ptr(rays), _ptr(hits), len(rays))
+    return hits
+
+
+def network(arity: int, n: int):
+    a = np.zeros(32, np.int8); b = np.zeros(32, np.int8)
+    k = lib().oracle_network(arity, n, _ptr(a), _ptr(b))
+    return [(int(a[i]), int(b[i])) for i in range(k)]

@@ -1,0 +1,394 @@
+/*
+ * traversal_oracle.c -- CPU restatement of the reference's single-ray BVH
+ * traversal.  TEST INFRASTRUCTURE ONLY: nothing under rodent_b200/ may link or
+ * call this; it exists to check the CUDA path (tests/, __graft_entry__.smoke())
+ * and to be timed as the CPU baseline (bench.py cpu_baseline / --impl reference).
+ *
+ * Parity status: PINNED for hit distance t by the reference's golden images
+ * testing/ref-primary.png and testing/ref-random.png (tests/test_oracle_golden.py);
+ * tri_id/u/v have no golden vector in the reference, for those this file *is* the
+ * definition (see DESIGN.md "Parity contract").
+ *
+ * Arithmetic contract: IEEE-754 binary32, round-to-nearest, no FMA contraction
+ * (build with -ffp-contract=off, no -ffast-math), operations in the source order
+ * of the reference, integer compares of float bits where the reference uses them
+ * (enable_cpu_int_min_max = true, tools/bench_traversal/bench_traversal.impala:11).
+ * The reference binary itself is built -ffast-math (CMakeLists.txt:12), so its own
+ * last bits are not reproducible; this contract is what "bit-exact" means here.
+ *
+ * Each function cites the reference lines it restates (paths relative to the
+ * reference tree).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+#include "../include/rodent_b200.h"
+
+#define FLT_MAX_ 3.4028234664e+38f  /* src/core/common.impala:4 */
+#define STACK_SIZE 64               /* src/traversal/stack.impala:53-54 */
+
+typedef struct { int32_t node; float tmin; } NodeRef;
+
+/* Work counters, for the roofline's algorithmic bytes. */
+typedef struct OracleStats {
+    uint64_t nodes;   /* inner nodes popped and box-tested  */
+    uint64_t tri4;    /* Tri4 packets fetched in leaves     */
+    uint64_t max_stack;
+} OracleStats;
+
+static inline int32_t f2i(float x) { int32_t i; memcpy(&i, &x, 4); return i; }
+static inline float   i2f(int32_t i) { float x; memcpy(&x, &i, 4); return x; }
+
+/* src/core/common.impala:78-80 */
+static inline float prodsign(float x, float y) {
+    return i2f(f2i(x) ^ (f2i(y) & (int32_t)0x80000000u));
+}
+/* src/core/common.impala:82-85 */
+static inline float safe_rcp(float x) {
+    const float min_rcp = 1e-8f;
+    float ax = x > 0.0f ? x : -x;
+    return ax < min_rcp ? prodsign(FLT_MAX_, x) : 1.0f / x;
+}
+/* src/traversal/mapping_cpu.impala:123-133 : min/max on the float bits as signed ints */
+static inline float imin(float a, float b) { int32_t x = f2i(a), y = f2i(b); return i2f(x < y ? x : y); }
+static inline float imax(float a, float b) { int32_t x = f2i(a), y = f2i(b); return i2f(x > y ? x : y); }
+
+/* ---- sorting networks, src/core/sort.impala:3-66 ------------------------- */
+typedef struct { int n; int8_t a[32], b[32]; } Network;
+static Network g_batcher[9];      /* arity 8: batcher_sort(n), n = 3..8      */
+static Network g_bose_nelson[5];  /* arity <= 4: bose_nelson_sort(n), n = 3,4 */
+static pthread_once_t g_net_once = PTHREAD_ONCE_INIT;
+
+static void net_add(Network* w, int i, int j) { w->a[w->n] = (int8_t)i; w->b[w->n] = (int8_t)j; w->n++; }
+
+/* src/core/common.impala:107-116 : smallest p with i <= 2^p */
+static int ilog2_(int i) { int p = 0; while (i > (1 << p)) p++; return p; }
+
+/* src/core/sort.impala:35-52 */
+static void batcher_merge(Network* w, int n, int i, int len, int r) {
+    int step = r * 2;
+    if (step < len) {
+        batcher_merge(w, n, i, len, step);
+        batcher_merge(w, n, i + r, len, step);
+        for (int j = i + r; j < i + len - r; j += step)
+            if (j < n && j + r < n) net_add(w, j, j + r);
+    } else {
+        if (i < n && i + r < n) net_add(w, i, i + r);
+    }
+}
+/* src/core/sort.impala:54-61 */
+static void batcher_sort_rec(Network* w, int n, int i, int len) {
+    if (len > 1) {
+        int m = len / 2;
+        batcher_sort_rec(w, n, i, m);
+        batcher_sort_rec(w, n, i + m, m);
+        batcher_merge(w, n, i, len, 1);
+    }
+}
+/* src/core/sort.impala:13-29 */
+static void bn_bracket(Network* w, int i1, int len1, int i2, int len2) {
+    if (len1 == 1 && len2 == 1) {
+        net_add(w, i1, i2);
+    } else if (len1 == 1 && len2 == 2) {
+        net_add(w, i1, i2 + 1);
+        net_add(w, i1, i2);
+    } else if (len1 == 2 && len2 == 1) {
+        net_add(w, i1, i2);
+        net_add(w, i1 + 1, i2);
+    } else {
+        int a = len1 / 2;
+        int b = (len1 % 2 != 0) ? len2 / 2 : (len2 + 1) / 2;
+        bn_bracket(w, i1, a, i2, b);
+        bn_bracket(w, i1 + a, len1 - a, i2 + b, len2 - b);
+        bn_bracket(w, i1 + a, len1 - a, i2, b);
+    }
+}
+/* src/core/sort.impala:4-11 */
+static void bn_star(Network* w, int i, int len) {
+    if (len > 1) {
+        int m = len / 2;
+        bn_star(w, i, m);
+        bn_star(w, i + m, len - m);
+        bn_bracket(w, i, m, i + m, len - m);
+    }
+}
+static void init_networks(void) {
+    for (int n = 3; n <= 8; n++) {
+        g_batcher[n].n = 0;
+        batcher_sort_rec(&g_batcher[n], n, 0, 1 << ilog2_(n));   /* sort.impala:63-65 */
+    }
+    for (int n = 3; n <= 4; n++) {
+        g_bose_nelson[n].n = 0;
+        bn_star(&g_bose_nelson[n], 0, n);
+    }
+}
+
+/* Exposed so the tests can pin the comparator sequences. */
+int oracle_network(int arity, int n, int8_t* a, int8_t* b) {
+    pthread_once(&g_net_once, init_networks);
+    const Network* w = arity == 8 ? &g_batcher[n] : &g_bose_nelson[n];
+    memcpy(a, w->a, (size_t)w->n); memcpy(b, w->b, (size_t)w->n);
+    return w->n;
+}
+
+/* ---- ray/triangle, src/traversal/intersection.impala:164-192 -------------
+ * One lane of a Tri4 (src/traversal/mapping_cpu.impala:24-42).  Returns 1 on hit. */
+static inline int intersect_ray_tri_lane(const Tri4* tp, int i,
+                                         const float org[3], const float dir[3],
+                                         float tmin, float tmax,
+                                         float* out_t, float* out_u, float* out_v) {
+    const float v0x = tp->v0[0][i], v0y = tp->v0[1][i], v0z = tp->v0[2][i];
+    const float e1x = tp->e1[0][i], e1y = tp->e1[1][i], e1z = tp->e1[2][i];
+    const float e2x = tp->e2[0][i], e2y = tp->e2[1][i], e2z = tp->e2[2][i];
+    const float nx  = tp->n[0][i],  ny  = tp->n[1][i],  nz  = tp->n[2][i];
+    /* c = v0 - org ; r = dir x c ; det = n . dir   (vector.impala:60-67) */
+    const float cx = v0x - org[0], cy = v0y - org[1], cz = v0z - org[2];
+    const float rx = dir[1] * cz - dir[2] * cy;
+    const float ry = dir[2] * cx - dir[0] * cz;
+    const float rz = dir[0] * cy - dir[1] * cx;
+    const float det = nx * dir[0] + ny * dir[1] + nz * dir[2];
+    const float abs_det = i2f(f2i(det) & 0x7FFFFFFF);
+
+    const float u = prodsign(rx * e2x + ry * e2y + rz * e2z, det);
+    int mask = u >= 0.0f;
+    const float v = prodsign(rx * e1x + ry * e1y + rz * e1z, det);
+    mask &= v >= 0.0f;
+    mask &= (u + v) <= abs_det;
+    if (!mask) return 0;
+
+    const float t = prodsign(cx * nx + cy * ny + cz * nz, det);
+    mask &= abs_det != 0.0f;                 /* no backface culling, mapping_cpu.impala:33 */
+    mask &= t >= abs_det * tmin;
+    mask &= t <= abs_det * tmax;
+    if (!mask) return 0;
+
+    const float inv_det = 1.0f / abs_det;
+    *out_t = t * inv_det; *out_u = u * inv_det; *out_v = v * inv_det;
+    return 1;
+}
+
+/* ---- the traversal kernel, src/traversal/mapping_cpu.impala:138-256 ------
+ * N = arity (4 or 8); `nodes` is Node4* or Node8* (same field order, bounds[6][N],
+ * child[N], pad[N]).  Stack discipline of src/traversal/stack.impala:52-123: the
+ * top entry lives in (top_node, top_t); `st` is the memory part. */
+static inline __attribute__((always_inline))
+void traverse_single(const int N, const int any_hit,
+                     const void* nodes_v, const Tri4* tris, const Ray1* rp, Hit1* hp,
+                     OracleStats* stats) {
+    const size_t node_stride = (size_t)N * 32;       /* 6N floats + N + N ints */
+    const char* nodes = (const char*)nodes_v;
+    const Network* nets = N == 8 ? g_batcher : g_bose_nelson;
+
+    /* make_cpu_ray1 + make_ray, bench_traversal.impala:85-95, intersection.impala:88-99 */
+    const float org[3] = { rp->org[0], rp->org[1], rp->org[2] };
+    const float dir[3] = { rp->dir[0], rp->dir[1], rp->dir[2] };
+    const float tmin = rp->tmin;
+    float tmax = rp->tmax;
+    const float idx = safe_rcp(dir[0]), idy = safe_rcp(dir[1]), idz = safe_rcp(dir[2]);
+    const float iox = -(org[0] * idx), ioy = -(org[1] * idy), ioz = -(org[2] * idz);
+    /* ray_octant, intersection.impala:128-132 ; ordered_bbox, mapping_cpu.impala:88-106 */
+    const int ox = dir[0] > 0.0f ? N : 0, oy = dir[1] > 0.0f ? N : 0, oz = dir[2] > 0.0f ? N : 0;
+    const int near_x = N - ox, far_x = ox;
+    const int near_y = 3 * N - oy, far_y = 2 * N + oy;
+    const int near_z = 5 * N - oz, far_z = 4 * N + oz;
+
+    /* empty_hit, intersection.impala:134-136 (u, v undefined there; 0 here) */
+    int32_t hit_prim = -1; float hit_t = tmax, hit_u = 0.0f, hit_v = 0.0f;
+
+    NodeRef st[STACK_SIZE + 8];
+    int ptr = -1;
+    int32_t top_node = 0; float top_t = FLT_MAX_;
+#define PUSH(n_, t_)       do { ++ptr; st[ptr].node = top_node; st[ptr].tmin = top_t; top_node = (n_); top_t = (t_); } while (0)
+#define PUSH_AFTER(n_, t_) do { ++ptr; st[ptr].node = (n_); st[ptr].tmin = (t_); } while (0)
+#define POP()              do { top_node = st[ptr].node; top_t = st[ptr].tmin; --ptr; } while (0)
+    PUSH(1 /*root*/, tmin);                                              /* :153 */
+
+    uint64_t n_nodes = 0, n_tri4 = 0; int max_ptr = 0;
+
+    for (;;) {
+        if (top_node == 0) break;                                        /* :168 */
+        if (!any_hit && top_t > tmax) { POP(); continue; }               /* :170-174 */
+
+        int restart = 0;
+        while (top_node > 0) {                                           /* :177 */
+            const float* nb = (const float*)(nodes + (size_t)(top_node - 1) * node_stride);
+            const int32_t* child = (const int32_t*)(nb + 6 * N);
+            POP();
+            n_nodes++;
+
+            /* intersect_ray_box ordered, intersection.impala:194-208, integer min/max */
+            float tentry[8]; int mask = 0;
+            for (int i = 0; i < N; i++) {
+                const float t0x = idx * nb[near_x + i] + iox;
+                const float t0y = idy * nb[near_y + i] + ioy;
+                const float t0z = idz * nb[near_z + i] + ioz;
+                const float t1x = idx * nb[far_x + i] + iox;
+                const float t1y = idy * nb[far_y + i] + ioy;
+                const float t1z = idz * nb[far_z + i] + ioz;
+                const float te = imax(imax(t0x, t0y), imax(t0z, tmin));
+                const float tx = imin(imin(t1x, t1y), imin(t1z, tmax));
+                tentry[i] = te;
+                mask |= (f2i(tx) < f2i(te) ? 0 : 1) << i;                /* :184 */
+            }
+            if (mask == 0) {                                             /* :189-191 */
+                if (any_hit) continue;
+                restart = 1; break;
+            }
+
+            int num_intrs = 0;                                           /* :195-208 */
+            for (int m = mask; m != 0; m &= m - 1) {
+                const int lane = __builtin_ctz((unsigned)m);
+                const int32_t child_id = child[lane];
+                const float t = tentry[lane];
+                num_intrs++;
+                if (any_hit || t < top_t) PUSH(child_id, t);
+                else                      PUSH_AFTER(child_id, t);
+            }
+            if (ptr > max_ptr) max_ptr = ptr;
+
+            if (!any_hit && num_intrs >= 3) {                            /* :210-218, stack.impala:79-111 */
+                NodeRef* e = &st[ptr - num_intrs + 1];
+                const Network* w = &nets[num_intrs];
+                for (int c = 0; c < w->n; c++) {
+                    const int i = w->a[c], j = w->b[c];
+                    if (e[i].tmin < e[j].tmin) { NodeRef tmp = e[i]; e[i] = e[j]; e[j] = tmp; }
+                }
+            }
+        }
+        if (restart) continue;
+
+        if (top_node == 0) break;   /* :221 for any_hit; for closest-hit the reference would read
+                                       prim -1 here (only reachable with a non-finite/FLT_MAX entry key) */
+
+        int32_t prim_id = ~top_node;                                     /* :224 */
+        POP();
+        int terminated = 0;
+        for (;;) {
+            const Tri4* tp = &tris[prim_id++];
+            n_tri4++;
+            float lt[4], lu[4], lv[4]; int hm = 0;
+            for (int j = 0; j < 4; j++) {
+                lt[j] = FLT_MAX_; lu[j] = 0.0f; lv[j] = 0.0f;
+                if (tp->prim_id[j] == -1) continue;                      /* is_valid, mapping_cpu.impala:39 */
+                if (intersect_ray_tri_lane(tp, j, org, dir, tmin, tmax, &lt[j], &lu[j], &lv[j]))
+                    hm |= 1 << j;
+                else
+                    lt[j] = FLT_MAX_;
+            }
+            if (hm) {
+                int lane;
+                if (any_hit) {
+                    lane = __builtin_ctz((unsigned)hm);                  /* :234-237 */
+                    terminated = 1;
+                } else {
+                    /* cpu_reduce with the integer min + cpu_index_of, cpu_common.impala:37-56, :239-243 */
+                    const float mn = imin(imin(lt[0], lt[2]), imin(lt[1], lt[3]));
+                    lane = 0;
+                    while (!(lt[lane] == mn)) lane++;
+                }
+                hit_prim = tp->prim_id[lane] & 0x7FFFFFFF;               /* mapping_cpu.impala:34 */
+                hit_t = lt[lane]; hit_u = lu[lane]; hit_v = lv[lane];
+                if (!any_hit) tmax = hit_t;                              /* :243 */
+            }
+            if (tp->prim_id[3] < 0) break;                               /* is_last, mapping_cpu.impala:40 */
+        }
+        if (any_hit && terminated) break;                                /* :252 */
+    }
+#undef PUSH
+#undef PUSH_AFTER
+#undef POP
+
+    /* make_cpu_hit1, bench_traversal.impala:121-131 */
+    hp->tri_id = hit_prim;
+    if (!any_hit) { hp->t = hit_t; hp->u = hit_u; hp->v = hit_v; }
+    if (stats) {
+        stats->nodes += n_nodes; stats->tri4 += n_tri4;
+        if ((uint64_t)max_ptr > stats->max_stack) stats->max_stack = (uint64_t)max_ptr;
+    }
+}
+
+/* ---- cpu_traverse_single, src/traversal/mapping_cpu.impala:404-418 -------- */
+typedef struct {
+    int arity, any_hit;
+    const void* nodes; const Tri4* tris; const Ray1* rays; Hit1* hits;
+    int32_t begin, end;
+    OracleStats stats; int want_stats;
+} Job;
+
+static void run_range(Job* j) {
+    OracleStats* s = j->want_stats ? &j->stats : NULL;
+    if (j->arity == 8) {
+        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+    } else {
+        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+    }
+}
+static void* run_range_thread(void* p) { run_range((Job*)p); return NULL; }
+
+/* Contiguous ray ranges over `threads` host threads (the reference loop is
+ * serial; threads > 1 is this repo's "all host cores" baseline). */
+void oracle_traverse(int arity, int any_hit, const void* nodes, const Tri4* tris,
+                     const Ray1* rays, Hit1* hits, int32_t num_rays, int threads,
+                     OracleStats* stats) {
+    pthread_once(&g_net_once, init_networks);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    Job jobs[256]; pthread_t th[256];
+    for (int k = 0; k < threads; k++) {
+        Job* j = &jobs[k];
+        j->arity = arity; j->any_hit = any_hit; j->nodes = nodes; j->tris = tris; j->rays = rays; j->hits = hits;
+        j->begin = (int32_t)((int64_t)num_rays * k / threads);
+        j->end   = (int32_t)((int64_t)num_rays * (k + 1) / threads);
+        memset(&j->stats, 0, sizeof j->stats); j->want_stats = stats != NULL;
+    }
+    if (threads == 1) run_range(&jobs[0]);
+    else {
+        for (int k = 0; k < threads; k++) pthread_create(&th[k], NULL, run_range_thread, &jobs[k]);
+        for (int k = 0; k < threads; k++) pthread_join(th[k], NULL);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int k = 0; k < threads; k++) {
+            stats->nodes += jobs[k].stats.nodes; stats->tri4 += jobs[k].stats.tri4;
+            if (jobs[k].stats.max_stack > stats->max_stack) stats->max_stack = jobs[k].stats.max_stack;
+        }
+    }
+}
+
+/* The reference's exported names, tools/bench_traversal/bench_traversal.impala:279-305,429-455 */
+void cpu_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    oracle_traverse(8, 0, nodes, tris, rays, hits, num_packets, 1, NULL);
+}
+void cpu_occluded_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    oracle_traverse(8, 1, nodes, tris, rays, hits, num_packets, 1, NULL);
+}
+void cpu_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    oracle_traverse(4, 0, nodes, tris, rays, hits, num_packets, 1, NULL);
+}
+void cpu_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    oracle_traverse(4, 1, nodes, tris, rays, hits, num_packets, 1, NULL);
+}
+
+/* Brute force over every Tri4 lane in array order: closest hit with the same
+ * acceptance rule; a self-check for the traversal above. */
+void oracle_brute_force(const Tri4* tris, int32_t num_tri4, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    for (int32_t r = 0; r < num_rays; r++) {
+        const Ray1* rp = &rays[r];
+        const float org[3] = { rp->org[0], rp->org[1], rp->org[2] };
+        const float dir[3] = { rp->dir[0], rp->dir[1], rp->dir[2] };
+        float tmax = rp->tmax; Hit1 h = { -1, tmax, 0.0f, 0.0f };
+        for (int32_t k = 0; k < num_tri4; k++)
+            for (int j = 0; j < 4; j++) {
+                float t, u, v;
+                if (tris[k].prim_id[j] == -1) continue;
+                if (intersect_ray_tri_lane(&tris[k], j, org, dir, rp->tmin, tmax, &t, &u, &v) && t < h.t) {
+                    h.tri_id = tris[k].prim_id[j] & 0x7FFFFFFF; h.t = t; h.u = u; h.v = v; tmax = t;
+                }
+            }
+        hits[r] = h;
+    }
+}

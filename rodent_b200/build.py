@@ -1,0 +1,77 @@
+"""Build recipes: the sm_100a shared library (C ABI of include/rodent_b200.h) and the
+C++ command-line tools.  Everything is built in-tree so the binaries travel with a
+snapshot of the repo; nothing is JIT-compiled at run time.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "rodent_b200"
+CSRC = PKG / "csrc"
+LIB = PKG / "librodent_b200.so"
+TOOLS = ROOT / "tools"
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",            # parity contract: no FMA contraction anywhere
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def cuda_sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    srcs = cuda_sources()
+    deps = srcs + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "rodent_b200.h"]
+    if not force and _newer(LIB, deps):
+        return LIB
+    cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+    print("+", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_tools(force: bool = False) -> None:
+    """ray_gen, bench_traversal (linked against librodent_b200.so), fbuf2png."""
+    (TOOLS / "bin").mkdir(exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    common = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall"]
+    jobs = [("ray_gen", ["ray_gen.cpp"], [])]
+    if (TOOLS / "bench_traversal.cpp").exists():
+        jobs.append(("bench_traversal", ["bench_traversal.cpp"],
+                     [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
+    if (TOOLS / "fbuf2png.cpp").exists():
+        jobs.append(("fbuf2png", ["fbuf2png.cpp"], ["-lz"]))
+    for name, srcs, extra in jobs:
+        out = TOOLS / "bin" / name
+        deps = [TOOLS / s for s in srcs] + [TOOLS / "formats.h", ROOT / "include" / "rodent_b200.h"]
+        if not force and _newer(out, deps):
+            continue
+        cmd = [*common, "-o", str(out), *[str(TOOLS / s) for s in srcs], *extra]
+        print("+", " ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force, verbose)
+    build_tools(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,319 @@
+// bench_traversal entry points: persistent-threads BVH8/Tri4 traversal kernels for
+// sm_100a and the C ABI around them (include/rodent_b200.h).
+//
+// Kernel organisation (replaces gpu_traverse_single, src/traversal/mapping_gpu.impala:182-203,
+// and competes with the Aila-Laine kernel tools/bench_aila/kepler_dynamic_fetch.cu:70-371):
+//   * persistent CTAs, one resident set per SM (grid = SMs x occupancy);
+//   * each warp pulls rays from a global counter; lanes whose ray finished wait
+//     until the number of busy lanes in the warp drops below a threshold, then the
+//     idle lanes are refilled together with one atomicAdd (ballot + popc ranks);
+//   * while-while traversal of the reference's own order (traverse.cuh).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "traverse.cuh"
+
+namespace rb200 {
+
+constexpr int kBlock = 128;          // 4 warps per CTA
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+struct Tuning {
+    int persistent = 1;      // 0: one thread per ray, plain grid
+    int refill_below = 24;   // refill a warp when fewer than this many lanes are busy
+    int blocks_per_sm = 0;   // 0: occupancy API
+};
+static Tuning g_tuning;
+
+template <bool ANY>
+__device__ __forceinline__ void store_hit(Hit1* __restrict__ hits, int i, const HitRecord& h) {
+    // make_cpu_hit1, tools/bench_traversal/bench_traversal.impala:121-131
+    if (ANY) hits[i].tri_id = h.prim;
+    else *reinterpret_cast<float4*>(hits + i) = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock)
+traverse_bvh8_grid(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= num_rays) return;
+    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+    Traversal<ANY> tr;
+    tr.begin(ldg4(rp), ldg4(rp + 1));
+    tr.template run<false>(nodes, tris, [] { return false; });
+    store_hit<ANY>(hits, i, tr.hit);
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock)
+traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                         const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                         int* __restrict__ work_counter, int refill_below) {
+    __shared__ int busy_lanes[kWarpsPerBlock];
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    volatile int* busy = &busy_lanes[warp];
+    if (lane == 0) *busy = 0;
+    __syncwarp();
+
+    Traversal<ANY> tr;
+    int ray_idx = -1;            // -1: this lane holds no ray
+    bool drained = false;        // the global queue is empty
+
+    for (;;) {
+        // ---- refill idle lanes: one atomicAdd per warp, ranks from ballot/popc ----
+        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
+        if (idle != 0 && !drained) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ray_idx < 0) {
+                const int i = base + __popc(idle & lanemask_lt());
+                if (i < num_rays) {
+                    ray_idx = i;
+                    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+                    tr.begin(ldg4(rp), ldg4(rp + 1));
+                }
+            }
+            if (base + __popc(idle) >= num_rays) drained = true;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, ray_idx >= 0);
+        if (active == 0) break;
+        if (lane == 0) *busy = __popc(active);
+        __syncwarp();
+
+        if (ray_idx >= 0) {
+            const bool done = tr.template run<false>(nodes, tris, [&] { return !drained && *busy < refill_below; });
+            if (done) {
+                store_hit<ANY>(hits, ray_idx, tr.hit);
+                ray_idx = -1;
+                atomicSub(const_cast<int*>(busy), 1);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- per-device state ---------------------------------------------------------
+struct DeviceState {
+    bool init = false;
+    int sm_count = 0;
+    int* counter = nullptr;    // 64 ints: slot 0 for the synchronous entry points, 8/16/24 for the host-path streams
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
+    // host-pointer path
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
+    std::map<std::pair<const void*, const void*>, std::pair<Node8*, Tri4*>> bvh_cache;
+};
+static DeviceState g_dev[64];
+static std::mutex g_mutex;
+static std::atomic<int64_t> g_launches{0};
+static int g_host_dev = 0;
+
+static DeviceState& device_state(int dev) {
+    if (dev < 0 || dev >= 64) { std::fprintf(stderr, "rodent_b200: bad device %d\n", dev); std::abort(); }
+    DeviceState& s = g_dev[dev];
+    RB_CUDA_CHECK(cudaSetDevice(dev));
+    if (!s.init) {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if (!s.init) {
+            cudaDeviceProp prop;
+            RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+            if (prop.major != 10) {
+                std::fprintf(stderr, "rodent_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", dev, prop.major, prop.minor);
+                std::abort();
+            }
+            s.sm_count = prop.multiProcessorCount;
+            RB_CUDA_CHECK(cudaMalloc(&s.counter, 256));
+            RB_CUDA_CHECK(cudaEventCreate(&s.ev0));
+            RB_CUDA_CHECK(cudaEventCreate(&s.ev1));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[0], traverse_bvh8_persistent<false>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[1], traverse_bvh8_persistent<true>, kBlock, 0));
+            s.init = true;
+        }
+    }
+    return s;
+}
+
+template <bool ANY>
+static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
+                   int num_rays, cudaStream_t stream, int* counter) {
+    if (num_rays <= 0) return;
+    if (g_tuning.persistent) {
+        if (!counter) counter = s.counter;
+        RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ[ANY ? 1 : 0];
+        const int needed = (num_rays + kBlock - 1) / kBlock;
+        const int grid = std::min(needed, s.sm_count * per_sm);     // a multiple of the SM count when saturated
+        traverse_bvh8_persistent<ANY><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_below);
+    } else {
+        traverse_bvh8_grid<ANY><<<(num_rays + kBlock - 1) / kBlock, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays);
+    }
+    RB_CUDA_CHECK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <bool ANY>
+static void run_sync(int dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+    DeviceState& s = device_state(dev);
+    RB_CUDA_CHECK(cudaEventRecord(s.ev0, 0));
+    launch<ANY>(s, nodes, tris, rays, hits, num_rays, 0, nullptr);
+    RB_CUDA_CHECK(cudaEventRecord(s.ev1, 0));
+    RB_CUDA_CHECK(cudaEventSynchronize(s.ev1));
+    float ms = 0.0f;
+    RB_CUDA_CHECK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    s.last_ms = ms;
+}
+
+// ---- host-pointer path ----------------------------------------------------------
+// Extent of a BVH8 given only its arrays: walk from the root (node 1).
+static void bvh8_extent(const Node8* nodes, const Tri4* tris, size_t& num_nodes, size_t& num_tri4) {
+    std::vector<int> todo{1};
+    num_nodes = 0; num_tri4 = 0;
+    while (!todo.empty()) {
+        const int id = todo.back(); todo.pop_back();
+        num_nodes = std::max(num_nodes, size_t(id));
+        const Node8& n = nodes[id - 1];
+        for (int i = 0; i < 8; i++) {
+            const int c = n.child[i];
+            if (c > 0) todo.push_back(c);
+            else if (c < 0) {
+                size_t k = size_t(~c);
+                while (tris[k].prim_id[3] >= 0) k++;     // is_last sentinel, mapping_cpu.impala:40
+                num_tri4 = std::max(num_tri4, k + 1);
+            }
+        }
+    }
+}
+
+static std::pair<Node8*, Tri4*> cached_bvh(DeviceState& s, const Node8* nodes, const Tri4* tris) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto key = std::make_pair((const void*)nodes, (const void*)tris);
+    auto it = s.bvh_cache.find(key);
+    if (it != s.bvh_cache.end()) return it->second;
+    size_t nn, nt;
+    bvh8_extent(nodes, tris, nn, nt);
+    Node8* dn; Tri4* dt;
+    RB_CUDA_CHECK(cudaMalloc(&dn, nn * sizeof(Node8)));
+    RB_CUDA_CHECK(cudaMalloc(&dt, std::max<size_t>(nt, 1) * sizeof(Tri4)));
+    RB_CUDA_CHECK(cudaMemcpy(dn, nodes, nn * sizeof(Node8), cudaMemcpyHostToDevice));
+    RB_CUDA_CHECK(cudaMemcpy(dt, tris, nt * sizeof(Tri4), cudaMemcpyHostToDevice));
+    return s.bvh_cache[key] = std::make_pair(dn, dt);
+}
+
+// Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
+// transfers of one chunk overlap the traversal of another.
+template <bool ANY>
+static void run_host(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+    if (num_rays <= 0) return;
+    DeviceState& s = device_state(g_host_dev);
+    auto bvh = cached_bvh(s, nodes, tris);
+    if (!s.streams[0]) {
+        for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
+    if (s.ray_capacity < size_t(num_rays)) {
+        if (s.d_rays) { RB_CUDA_CHECK(cudaFree(s.d_rays)); RB_CUDA_CHECK(cudaFree(s.d_hits)); }
+        RB_CUDA_CHECK(cudaMalloc(&s.d_rays, size_t(num_rays) * sizeof(Ray1)));
+        RB_CUDA_CHECK(cudaMalloc(&s.d_hits, size_t(num_rays) * sizeof(Hit1)));
+        s.ray_capacity = size_t(num_rays);
+    }
+    if (ANY)   // occluded leaves t/u/v untouched: round-trip the caller's records
+        RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, s.streams[0]));
+    if (ANY) RB_CUDA_CHECK(cudaStreamSynchronize(s.streams[0]));
+    const int chunk = std::max(1 << 16, (num_rays + 7) / 8);
+    int k = 0;
+    for (int first = 0; first < num_rays; first += chunk, k++) {
+        const int n = std::min(chunk, num_rays - first);
+        cudaStream_t st = s.streams[k % 3];
+        RB_CUDA_CHECK(cudaMemcpyAsync(s.d_rays + first, rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
+        launch<ANY>(s, bvh.first, bvh.second, s.d_rays + first, s.d_hits + first, n, st, s.counter + 8 * (1 + k % 3));
+        RB_CUDA_CHECK(cudaMemcpyAsync(hits + first, s.d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+    }
+    for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+void cuda_intersect_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<false>(dev, nodes, tris, rays, hits, num_rays);
+}
+void cuda_occluded_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<true>(dev, nodes, tris, rays, hits, num_rays);
+}
+void cuda_intersect_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
+                                                int32_t num_rays, void* stream, int32_t* work_counter) {
+    launch<false>(device_state(dev), nodes, tris, rays, hits, num_rays, (cudaStream_t)stream, work_counter);
+}
+void cuda_occluded_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
+                                               int32_t num_rays, void* stream, int32_t* work_counter) {
+    launch<true>(device_state(dev), nodes, tris, rays, hits, num_rays, (cudaStream_t)stream, work_counter);
+}
+
+void b200_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    run_host<false>(nodes, tris, rays, hits, num_packets);
+}
+void b200_occluded_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    run_host<true>(nodes, tris, rays, hits, num_packets);
+}
+void rodent_b200_forget_bvh(const Node8* nodes, const Tri4* tris) {
+    DeviceState& s = device_state(g_host_dev);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = s.bvh_cache.find(std::make_pair((const void*)nodes, (const void*)tris));
+    if (it == s.bvh_cache.end()) return;
+    RB_CUDA_CHECK(cudaFree(it->second.first));
+    RB_CUDA_CHECK(cudaFree(it->second.second));
+    s.bvh_cache.erase(it);
+}
+
+int32_t rodent_b200_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+void rodent_b200_set_device(int32_t dev) { device_state(dev); g_host_dev = dev; }
+void* rodent_b200_alloc_device(int32_t dev, size_t bytes) {
+    device_state(dev);
+    void* p = nullptr;
+    RB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    return p;
+}
+void rodent_b200_free_device(int32_t dev, void* ptr) { device_state(dev); RB_CUDA_CHECK(cudaFree(ptr)); }
+void* rodent_b200_alloc_host(size_t bytes) {
+    void* p = nullptr;
+    RB_CUDA_CHECK(cudaMallocHost(&p, std::max<size_t>(bytes, 16)));
+    return p;
+}
+void rodent_b200_free_host(void* ptr) { RB_CUDA_CHECK(cudaFreeHost(ptr)); }
+void rodent_b200_copy_to_device(int32_t dev, void* dst, const void* src, size_t bytes) {
+    device_state(dev);
+    RB_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+}
+void rodent_b200_copy_to_host(int32_t dev, void* dst, const void* src, size_t bytes) {
+    device_state(dev);
+    RB_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+}
+void rodent_b200_sync(int32_t dev) { device_state(dev); RB_CUDA_CHECK(cudaDeviceSynchronize()); }
+double rodent_b200_last_kernel_ms(int32_t dev) { return device_state(dev).last_ms; }
+int64_t rodent_b200_launch_count(void) { return g_launches.load(); }
+const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }
+
+// Tuning knobs for experiments (not part of the drop-in surface).
+void rodent_b200_tune(const char* key, int32_t value) {
+    if (!std::strcmp(key, "persistent")) g_tuning.persistent = value;
+    else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = value;
+    else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
+    else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+"""The C-ABI library loads and exports every symbol include/rodent_b200.h declares
+(no compute: this runs without a GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "rodent_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:cuda|b200|rodent_b200|rodent|render|get_spp)\w*)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rodent_b200 import build, lib
+    build.build_cuda()
+    L = lib.load()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(L, name), f"{name} declared in include/rodent_b200.h but not exported"
+    assert set(names) == set(lib.SIGNATURES), "python binding and header disagree"
+    assert L.rodent_b200_version().decode().startswith("rodent_b200")
+
+
+def test_struct_sizes_match_header():
+    from rodent_b200 import formats
+    text = (ROOT / "include" / "rodent_b200.h").read_text()
+    for name, dt in (("Node8", formats.NODE8), ("Node4", formats.NODE4), ("Tri4", formats.TRI4),
+                     ("Ray1", formats.RAY1), ("Hit1", formats.HIT1)):
+        assert f"typedef struct {name}" in text
+    assert formats.NODE8.itemsize == 256 and formats.TRI4.itemsize == 224
+    assert formats.RAY1.itemsize == 32 and formats.HIT1.itemsize == 16
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import pytest
+    from rodent_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lib.load()

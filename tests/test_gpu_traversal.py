@@ -1,0 +1,162 @@
+"""Parity of the CUDA traversal (through the C ABI) with the oracle: bit-exact hit
+records on both full Sponza ray sets, the golden PNGs, edge cases, and
+size-independent properties.  Runs on the B200 box (`-m gpu`)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from rodent_b200 import formats
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gpu(sponza):
+    from rodent_b200 import lib, traversal
+    L = lib.load()
+    assert L.rodent_b200_device_count() >= 1, "no CUDA device"
+    nodes, tris = sponza
+    return traversal.Bvh8(0, nodes, tris)
+
+
+def run_gpu(bvh, rays, any_hit=False, prefill=None):
+    from rodent_b200 import traversal
+    d_rays = traversal.DeviceArray.from_host(0, rays)
+    init = np.zeros(len(rays), formats.HIT1) if prefill is None else prefill
+    d_hits = traversal.DeviceArray.from_host(0, init)
+    traversal.intersect(bvh, d_rays, d_hits, any_hit=any_hit)
+    return d_hits.to_host()
+
+
+def assert_records_equal(got, want):
+    """Bit-exact on every field (t/u/v compared as bit patterns)."""
+    assert got.dtype == want.dtype and len(got) == len(want)
+    if got.tobytes() != want.tobytes():
+        bad = np.nonzero((got["tri_id"] != want["tri_id"]) | (got["t"].view("i4") != want["t"].view("i4")) |
+                         (got["u"].view("i4") != want["u"].view("i4")) | (got["v"].view("i4") != want["v"].view("i4")))[0]
+        raise AssertionError(f"{len(bad)} of {len(got)} records differ, first: ray {bad[0]} got {got[bad[0]]} want {want[bad[0]]}")
+
+
+@pytest.mark.parametrize("persistent", [1, 0])
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_closest_hit_bit_exact(name, persistent, gpu, ray_sets, oracle_hits):
+    from rodent_b200 import lib
+    lib.tune("persistent", persistent)
+    try:
+        got = run_gpu(gpu, ray_sets[name])
+    finally:
+        lib.tune("persistent", 1)
+    assert_records_equal(got, oracle_hits[name])
+
+
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_golden_png(name, gpu, ray_sets):
+    """cmake/test/run_traversal.cmake: bench_traversal -o x.fbuf ; fbuf2png -n ; compare."""
+    got = run_gpu(gpu, ray_sets[name])
+    ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
+    assert int((ref != formats.fbuf_to_gray(got["t"]).reshape(1024, 1024)).sum()) <= 2
+
+
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_any_hit(name, gpu, sponza, ray_sets, oracle_hits):
+    from oracle import oracle
+    nodes, tris = sponza
+    want = oracle.traverse(nodes, tris, ray_sets[name], any_hit=True)
+    prefill = np.zeros(len(want), formats.HIT1)
+    prefill["tri_id"] = -2
+    prefill["t"] = 7.0
+    got = run_gpu(gpu, ray_sets[name], any_hit=True, prefill=prefill)
+    assert np.array_equal(got["tri_id"], want["tri_id"])          # same first-found triangle, same order
+    assert (got["t"] == 7.0).all() and (got["u"] == 0).all()      # occluded writes tri_id only
+    assert ((got["tri_id"] >= 0) == (oracle_hits[name]["tri_id"] >= 0)).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, 1000, 4097])
+def test_ragged_sizes(n, gpu, ray_sets, oracle_hits):
+    rays = np.ascontiguousarray(ray_sets["random"][:n])
+    sentinel = np.zeros(n + 8, formats.HIT1)
+    sentinel["tri_id"] = -77
+    from rodent_b200 import traversal
+    d_rays = traversal.DeviceArray.from_host(0, rays)
+    d_hits = traversal.DeviceArray.from_host(0, sentinel)
+    traversal.intersect(gpu, d_rays, d_hits, count=n)
+    out = d_hits.to_host()
+    assert_records_equal(out[:n], oracle_hits["random"][:n])
+    assert (out[n:]["tri_id"] == -77).all(), "wrote past the end"
+
+
+def test_frozen_known_answers(gpu):
+    z = np.load(GOLDEN / "sponza_hits_sample.npz")
+    for name in ("primary", "random"):
+        assert_records_equal(run_gpu(gpu, z[f"{name}_rays"]), z[f"{name}_hits"])
+        occl = run_gpu(gpu, z[f"{name}_rays"], any_hit=True, prefill=np.full(len(z[f"{name}_rays"]), -2, "i4").astype(formats.HIT1))
+        assert ((occl["tri_id"] >= 0) == z[f"{name}_any"]).all()
+
+
+def test_degenerate_rays(gpu, sponza):
+    """Axis-parallel / zero direction components (safe_rcp), tmin > 0, tmax < tmin, far origin."""
+    from oracle import oracle
+    nodes, tris = sponza
+    rng = np.random.default_rng(7)
+    n = 20_000
+    od = np.empty((n, 6), np.float32)
+    od[:, :3] = rng.uniform([-1900, -100, -1100], [1800, 1400, 1100], (n, 3))
+    od[:, 3:] = rng.normal(size=(n, 3)) * 300
+    od[::7, 3] = 0.0
+    od[::11, 4] = 0.0
+    od[::13, 5] = -0.0
+    od[::77, 3:] = 0.0                      # null direction
+    od[::5, 3:] *= 1e-12                    # |d| below the safe_rcp threshold
+    od[::101, :3] += 1e6                    # origin far outside
+    rays = formats.make_rays(od, 0.0, 10.0)
+    rays["tmin"][::3] = 0.25
+    rays["tmax"][::17] = 0.1                # tmax < tmin on some
+    want = oracle.traverse(nodes, tris, rays)
+    assert_records_equal(run_gpu(gpu, rays), want)
+    occl = run_gpu(gpu, rays, any_hit=True)
+    assert ((occl["tri_id"] >= 0) == (oracle.traverse(nodes, tris, rays, any_hit=True)["tri_id"] >= 0)).all()
+
+
+def test_host_pointer_entry_points(sponza, ray_sets, oracle_hits):
+    """b200_* : the drop-in for the cpu_* call sites, host buffers in and out."""
+    from rodent_b200 import traversal
+    nodes, tris = sponza
+    for name in ("primary", "random"):
+        got = traversal.intersect_host(nodes, tris, ray_sets[name])
+        assert_records_equal(got, oracle_hits[name])
+    pre = np.zeros(5000, formats.HIT1)
+    pre["t"] = 3.0
+    occl = traversal.intersect_host(nodes, tris, np.ascontiguousarray(ray_sets["random"][:5000]), hits=pre, any_hit=True)
+    assert ((occl["tri_id"] >= 0) == (oracle_hits["random"][:5000]["tri_id"] >= 0)).all()
+    assert (occl["t"] == 3.0).all()
+
+
+def test_properties_full_size(gpu, ray_sets):
+    """Size-independent properties on the full 1 Mi sets: order independence (a
+    permutation of the rays permutes the records), idempotence, tmax clipping
+    (re-tracing with tmax = found t finds the same triangle or a tie at that t)."""
+    rays = ray_sets["random"]
+    base = run_gpu(gpu, rays)
+    perm = np.random.default_rng(3).permutation(len(rays))
+    shuffled = run_gpu(gpu, np.ascontiguousarray(rays[perm]))
+    assert_records_equal(shuffled, base[perm])
+    assert_records_equal(run_gpu(gpu, rays), base)
+    clipped = rays.copy()
+    clipped["tmax"] = base["t"]
+    again = run_gpu(gpu, clipped)
+    hit = base["tri_id"] >= 0
+    assert (again["tri_id"][hit] >= 0).all()
+    assert (again["t"][hit] <= base["t"][hit]).all()
+    assert (again["tri_id"][~hit] == -1).all()
+
+
+def test_kernel_launches_are_counted(gpu, ray_sets):
+    from rodent_b200 import lib
+    L = lib.load()
+    before = L.rodent_b200_launch_count()
+    run_gpu(gpu, np.ascontiguousarray(ray_sets["primary"][:1024]))
+    assert L.rodent_b200_launch_count() == before + 1
+    assert L.rodent_b200_last_kernel_ms(0) > 0
