@@ -16,15 +16,19 @@
 #include <vector>
 
 #include "traverse.cuh"
+#include "traverse_quad.cuh"
 
 namespace rb200 {
 
 constexpr int kBlock = 128;          // 4 warps per CTA
 constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kSmemStackDepth = 16;  // stack levels kept in shared memory by the persistent thread-per-ray kernel
 
 struct Tuning {
-    int persistent = 1;      // 0: one thread per ray, plain grid
-    int refill_below = 24;   // refill a warp when fewer than this many lanes are busy
+    int mapping = 1;         // lanes per ray: 4 = quad kernel (traverse_quad.cuh), 1 = thread per ray (traverse.cuh)
+    int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
+    int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
+    int refill_below = 8;    // refill a warp when fewer than this many lanes are busy
     int blocks_per_sm = 0;   // 0: occupancy API
 };
 static Tuning g_tuning;
@@ -50,7 +54,7 @@ traverse_bvh8_grid(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
 }
 
 template <bool ANY>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 6)
 traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                          const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
                          int* __restrict__ work_counter, int refill_below) {
@@ -61,7 +65,9 @@ traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict
     if (lane == 0) *busy = 0;
     __syncwarp();
 
-    Traversal<ANY> tr;
+    __shared__ StackEntry smem_stack[kSmemStackDepth][kBlock];
+    Traversal<ANY, kSmemStackDepth, kBlock> tr;
+    tr.st.smem = &smem_stack[0][threadIdx.x];
     int ray_idx = -1;            // -1: this lane holds no ray
     bool drained = false;        // the global queue is empty
 
@@ -100,6 +106,65 @@ traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict
     }
 }
 
+
+// Quad-per-ray persistent kernel: eight rays per warp (traverse_quad.cuh).  Idle quads are
+// refilled together: one atomicAdd per warp, ray index = base + rank of the quad among the
+// idle ones (ballot + popc).
+template <bool ANY>
+__global__ void __launch_bounds__(kQuadBlock)
+traverse_bvh8_quad(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                   int* __restrict__ work_counter, int refill_below) {
+    __shared__ Entry stacks[kQuadBlock / 32][kStackSize][kQuadsPerWarp];
+    __shared__ int busy_quads[kQuadBlock / 32];
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int q = lane >> 2;
+    volatile int* busy = &busy_quads[warp];
+
+    QuadTraversal<ANY> tr;
+    tr.s = lane & 3;
+    tr.qmask = 0xFu << (q * 4);
+    tr.sp = &stacks[warp][0][q];
+    int ray_idx = -1;
+    bool drained = false;
+
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0) & 0x11111111u;   // one bit per idle quad
+        if (idle != 0 && !drained) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ray_idx < 0) {
+                const int i = base + __popc(idle & ((1u << (q * 4)) - 1u));
+                if (i < num_rays) {
+                    ray_idx = i;
+                    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+                    tr.begin(ldg4(rp), ldg4(rp + 1));
+                }
+            }
+            if (base + __popc(idle) >= num_rays) drained = true;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, ray_idx >= 0) & 0x11111111u;
+        if (active == 0) break;
+        if (lane == 0) *busy = __popc(active);
+        __syncwarp();
+
+        if (ray_idx >= 0) {
+            const bool done = tr.template run<false>(nodes, tris, [&] { return !drained && *busy < refill_below; });
+            if (done) {
+                if (tr.s == 0) {
+                    store_hit<ANY>(hits, ray_idx, tr.hit);
+                    atomicSub(const_cast<int*>(busy), 1);
+                }
+                ray_idx = -1;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- per-device state ---------------------------------------------------------
 struct DeviceState {
     bool init = false;
@@ -108,6 +173,7 @@ struct DeviceState {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
+    int occ_quad[2] = {0, 0};
     // host-pointer path
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
@@ -137,6 +203,8 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaEventCreate(&s.ev1));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[0], traverse_bvh8_persistent<false>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[1], traverse_bvh8_persistent<true>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[0], traverse_bvh8_quad<false>, kQuadBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[1], traverse_bvh8_quad<true>, kQuadBlock, 0));
             s.init = true;
         }
     }
@@ -147,7 +215,15 @@ template <bool ANY>
 static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
                    int num_rays, cudaStream_t stream, int* counter) {
     if (num_rays <= 0) return;
-    if (g_tuning.persistent) {
+    if (g_tuning.mapping == 4) {
+        if (!counter) counter = s.counter;
+        RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_quad[ANY ? 1 : 0];
+        const int rays_per_block = kQuadBlock / 4;
+        const int needed = (num_rays + rays_per_block - 1) / rays_per_block;
+        const int grid = std::min(needed, s.sm_count * per_sm);
+        traverse_bvh8_quad<ANY><<<grid, kQuadBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.quad_refill_below);
+    } else if (g_tuning.persistent) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ[ANY ? 1 : 0];
@@ -311,6 +387,8 @@ const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }
 // Tuning knobs for experiments (not part of the drop-in surface).
 void rodent_b200_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "persistent")) g_tuning.persistent = value;
+    else if (!std::strcmp(key, "mapping")) g_tuning.mapping = value;
+    else if (!std::strcmp(key, "quad_refill_below")) g_tuning.quad_refill_below = value;
     else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = value;
     else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }

