@@ -138,6 +138,120 @@ int64_t rodent_b200_launch_count(void);
 /* Library/version string, e.g. "rodent_b200 0.1 sm_100a". */
 const char* rodent_b200_version(void);
 
+
+/* ======================================================================== *
+ * Scene description and wavefront path tracer (the `rodent` driver surface)
+ * ======================================================================== */
+
+/* src/dummy_main.impala:3-13, src/driver/converter.cpp:617-626 */
+typedef struct Vec3 { float x, y, z; } Vec3;
+typedef struct Settings {
+    Vec3  eye, dir, up, right;
+    float width, height;       /* half extents of the image plane: w = tan(fov/2), h = w / ratio (driver.cpp:36-37) */
+} Settings;
+
+/* The reference compiles one shader per material into the renderer
+ * (src/driver/converter.cpp:857-919).  Here the same rules produce a table that the
+ * shade kernel interprets; `bsdf` selects the constructor of src/render/material.impala. */
+enum RodentBsdf {
+    RODENT_BSDF_BLACK   = 0,   /* make_black_bsdf,   material.impala:65-72   */
+    RODENT_BSDF_DIFFUSE = 1,   /* make_diffuse_bsdf, material.impala:75-91   */
+    RODENT_BSDF_PHONG   = 2,   /* make_phong_bsdf,   material.impala:94-116  */
+    RODENT_BSDF_MIX     = 3,   /* make_mix_bsdf(diffuse, phong, k), material.impala:167-192, k from converter.cpp:897-902 */
+    RODENT_BSDF_MIRROR  = 4,   /* make_mirror_bsdf,  material.impala:119-128 */
+    RODENT_BSDF_GLASS   = 5    /* make_glass_bsdf(1.0, ni, ks, tf), material.impala:131-164 */
+};
+typedef struct RodentMaterial {
+    int32_t bsdf;              /* enum RodentBsdf */
+    int32_t is_emissive;       /* make_emissive_material with lights(light_ids[prim]) (converter.cpp:915) */
+    float   ns, ni;
+    float   kd[3], mix_k;
+    float   ks[3], pad0;
+    float   tf[3], pad1;
+    float   ke[3], pad2;       /* emitted radiance of an emissive material (MTL Ke) */
+} RodentMaterial;
+
+/* make_precomputed_triangle_light inputs (src/render/light.impala:147-154,
+ * data/light_{verts,norms,areas,colors}.bin of converter.cpp:807-818) */
+typedef struct RodentLight {
+    float v0[3], inv_area;
+    float v1[3], pad0;
+    float v2[3], pad1;
+    float n[3],  pad2;
+    float color[3], pad3;
+} RodentLight;
+
+/* Host-side view of a loaded scene: the buffers the reference's converter writes to
+ * its data directory (vertices.bin, normals.bin, ...: converter.cpp:403-409, 832) with the 16-byte padding it uses for GPU
+ * targets, plus the BVH8/Tri4 arrays and the material / light tables. */
+typedef struct RodentSceneView {
+    int32_t num_tris, num_vertices, num_materials, num_lights, num_nodes, num_tri4;
+    const float*          vertices;      /* num_vertices x float4 (xyz, 0)            */
+    const float*          normals;       /* num_vertices x float4                     */
+    const float*          face_normals;  /* num_tris x float4                         */
+    const float*          texcoords;     /* num_vertices x float4 (uv, 0, 0)          */
+    const int32_t*        indices;       /* num_tris x int4: i0, i1, i2, material id  */
+    const int32_t*        light_ids;     /* num_tris: light of an emissive triangle   */
+    const RodentMaterial* materials;
+    const RodentLight*    lights;
+    const Node8*          nodes;
+    const Tri4*           tris;
+} RodentSceneView;
+
+typedef struct RodentScene RodentScene;
+
+/* Runtime replacement of the reference's scene compiler (src/driver/converter.cpp:
+ * convert_obj): OBJ/MTL parsing, material clean-up and de-duplication (:440-557),
+ * triangle mesh (src/driver/obj.cpp:412-509), light extraction (:778-818), material
+ * rules (:857-913) and a BVH8/Tri4 build.  Returns NULL and prints the reason on error. */
+RodentScene* rodent_b200_scene_load_obj(const char* obj_file);
+/* A scene whose geometry is an existing BVH8/Tri4 (e.g. the Sponza block of
+ * testing/sponza.bvh, which carries no materials): triangles are recovered as
+ * v1 = v0 - e1, v2 = v0 + e2 (src/traversal/intersection.impala:110-119), flat normals;
+ * `material_of_prim[p]` indexes `materials`; emissive materials make their triangles lights. */
+RodentScene* rodent_b200_scene_from_bvh8(const Node8* nodes, int32_t num_nodes, const Tri4* tris, int32_t num_tri4,
+                                         const RodentMaterial* materials, int32_t num_materials,
+                                         const int32_t* material_of_prim, int32_t num_prims);
+void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out);
+void rodent_b200_scene_free(RodentScene* scene);
+
+typedef struct RodentRenderer RodentRenderer;
+
+/* A wavefront path tracer bound to one scene and one device (the role of the generated
+ * `render` + make_nvvm_device(dev, streaming) of src/render/mapping_gpu.impala:537-593).
+ * `spp` and `max_path_len` are the reference's CMake cache variables SPP / MAX_PATH_LEN
+ * (src/CMakeLists.txt:6-8).  Multi-GPU: the renderer owns the rows y with
+ * (y / band) % num_parts == part; pass part 0 of 1 for the whole film. */
+RodentRenderer* rodent_b200_renderer_create(const RodentScene* scene, int32_t dev, int32_t width, int32_t height,
+                                            int32_t spp, int32_t max_path_len, int32_t part, int32_t num_parts, int32_t band);
+void  rodent_b200_renderer_free(RodentRenderer* r);
+/* render(settings, iter) of the generated main (converter.cpp:628-967): adds
+ * (sum over spp samples) / spp of iteration `iter` to the device film and copies the
+ * film to the host (device.present -> rodent_present, interface.cpp:494-496). */
+void  rodent_b200_render(RodentRenderer* r, const Settings* settings, int32_t iter);
+/* Same without the device->host film copy (for timing the device work alone). */
+void  rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int32_t iter);
+void  rodent_b200_present(RodentRenderer* r);
+float* rodent_b200_film(RodentRenderer* r);            /* host film, width*height*3 floats (get_pixels, interface.cpp:520-522) */
+void*  rodent_b200_film_device(RodentRenderer* r);     /* device film, same layout                                          */
+void  rodent_b200_clear(RodentRenderer* r);            /* clear_pixels, interface.cpp:524-526                               */
+/* Work counters of the last render call: [0] camera samples, [1] closest-hit rays,
+ * [2] shadow rays, [3] wavefronts, [4] kernels launched. */
+void  rodent_b200_render_stats(const RodentRenderer* r, int64_t out[5]);
+double rodent_b200_render_last_ms(const RodentRenderer* r);   /* CUDA-event time of the last render call */
+
+/* The reference driver's own entry points (src/driver/driver.cpp:55-58,266-296 calls
+ * them; interface.cpp:512-526 and the generated main define them).  They act on the
+ * renderer made current by rodent_b200_bind(), which stands for what the reference
+ * bakes in at build time (SCENE_FILE, SPP, MAX_PATH_LEN, TARGET_DEVICE). */
+void   rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len);
+void   setup_interface(size_t width, size_t height);
+void   cleanup_interface(void);
+float* get_pixels(void);
+void   clear_pixels(void);
+int32_t get_spp(void);
+void   render(const Settings* settings, int32_t iter);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,8 +23,8 @@ class OracleStats(ctypes.Structure):
 
 def build(force: bool = False) -> Path:
     so = _DIR / "liboracle.so"
-    src = _DIR / "traversal_oracle.c"
-    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+    newest = max((_DIR / f).stat().st_mtime for f in ("traversal_oracle.c", "render_oracle.c", "Makefile"))
+    if force or not so.exists() or so.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"] + (["-s"] if force else []), check=True)
     return so
 
@@ -76,3 +76,22 @@ def network(arity: int, n: int):
     a = np.zeros(32, np.int8); b = np.zeros(32, np.int8)
     k = lib().oracle_network(arity, n, _ptr(a), _ptr(b))
     return [(int(a[i]), int(b[i])) for i in range(k)]
+
+
+class OracleRenderStats(ctypes.Structure):
+    _fields_ = [("samples", ctypes.c_uint64), ("primary_rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64), ("trav", OracleStats)]
+
+
+def render(scene_view, settings, width: int, height: int, spp: int, max_path_len: int, iteration: int,
+           film: np.ndarray | None = None, threads: int | None = None):
+    """One render(settings, iter) call of the CPU path tracer; returns (film, stats).  `scene_view` is a
+    rodent_b200.render.SceneView (host arrays of a loaded scene), `settings` a rodent_b200.render.Settings."""
+    L = lib()
+    L.oracle_render.restype = None
+    L.oracle_render.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    if film is None:
+        film = np.zeros((height, width, 3), np.float32)
+    stats = OracleRenderStats()
+    L.oracle_render(ctypes.byref(scene_view), ctypes.byref(settings), width, height, spp, max_path_len, iteration,
+                    film.ctypes.data, threads or (os.cpu_count() or 1), ctypes.byref(stats))
+    return film, stats

@@ -176,7 +176,7 @@ static inline int intersect_ray_tri_lane(const Tri4* tp, int i,
 static inline __attribute__((always_inline))
 void traverse_single(const int N, const int any_hit,
                      const void* nodes_v, const Tri4* tris, const Ray1* rp, Hit1* hp,
-                     OracleStats* stats) {
+                     OracleStats* stats, int32_t* geom_out) {
     const size_t node_stride = (size_t)N * 32;       /* 6N floats + N + N ints */
     const char* nodes = (const char*)nodes_v;
     const Network* nets = N == 8 ? g_batcher : g_bose_nelson;
@@ -195,7 +195,7 @@ void traverse_single(const int N, const int any_hit,
     const int near_z = 5 * N - oz, far_z = 4 * N + oz;
 
     /* empty_hit, intersection.impala:134-136 (u, v undefined there; 0 here) */
-    int32_t hit_prim = -1; float hit_t = tmax, hit_u = 0.0f, hit_v = 0.0f;
+    int32_t hit_prim = -1, hit_geom = -1; float hit_t = tmax, hit_u = 0.0f, hit_v = 0.0f;
 
     NodeRef st[STACK_SIZE + 8];
     int ptr = -1;
@@ -289,6 +289,7 @@ void traverse_single(const int N, const int any_hit,
                     while (!(lt[lane] == mn)) lane++;
                 }
                 hit_prim = tp->prim_id[lane] & 0x7FFFFFFF;               /* mapping_cpu.impala:34 */
+                hit_geom = tp->geom_id[lane];
                 hit_t = lt[lane]; hit_u = lu[lane]; hit_v = lv[lane];
                 if (!any_hit) tmax = hit_t;                              /* :243 */
             }
@@ -302,6 +303,7 @@ void traverse_single(const int N, const int any_hit,
 
     /* make_cpu_hit1, bench_traversal.impala:121-131 */
     hp->tri_id = hit_prim;
+    if (geom_out) *geom_out = hit_geom;
     if (!any_hit) { hp->t = hit_t; hp->u = hit_u; hp->v = hit_v; }
     if (stats) {
         stats->nodes += n_nodes; stats->tri4 += n_tri4;
@@ -320,11 +322,11 @@ typedef struct {
 static void run_range(Job* j) {
     OracleStats* s = j->want_stats ? &j->stats : NULL;
     if (j->arity == 8) {
-        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
-        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s, NULL);
+        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(8, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s, NULL);
     } else {
-        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
-        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s);
+        if (j->any_hit) for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 1, j->nodes, j->tris, &j->rays[i], &j->hits[i], s, NULL);
+        else            for (int32_t i = j->begin; i < j->end; i++) traverse_single(4, 0, j->nodes, j->tris, &j->rays[i], &j->hits[i], s, NULL);
     }
 }
 static void* run_range_thread(void* p) { run_range((Job*)p); return NULL; }

@@ -33,12 +33,12 @@ def _newer(target: Path, sources) -> bool:
 
 
 def cuda_sources():
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = cuda_sources()
-    deps = srcs + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "rodent_b200.h"]
+    deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "rodent_b200.h"]
     if not force and _newer(LIB, deps):
         return LIB
     cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]

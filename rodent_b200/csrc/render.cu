@@ -1,0 +1,492 @@
+// Wavefront path tracer for sm_100a: the B200 counterpart of gpu_streaming_trace
+// (src/render/mapping_gpu.impala:308-369) behind render() / the rodent_b200_render* C ABI.
+//
+// One wavefront = up to 1 Mi rays (the reference's stream capacity, :319) and six launches,
+// all fed from device-side counters; the host reads back two integers per wavefront (the
+// reference blocks on four copies, :201,208,279,298):
+//
+//   generate          refill the free tail of the primary stream with camera rays      (:223-265)
+//   traverse_primary  persistent closest-hit traversal; writes the hit record and
+//                     counts rays per material in shared memory                       (:18-30 + count pass of :191-199)
+//   scan              exclusive scan of the per-material counts on the device          (host scan of :201-208)
+//   scatter           counting-sort scatter of the hit rays by material                (:210-220); misses are dropped here
+//   shade             surface element + emission + next-event estimation + bounce,
+//                     material looked up in a table; surviving paths and shadow rays are
+//                     written compacted (ballot ranks, one atomicAdd per warp), which
+//                     replaces the separate compaction pass                            (:82-134 + :267-300)
+//   traverse_shadow   persistent any-hit traversal + atomic film accumulation          (:47-80, :32-45)
+//
+// Streams are structure-of-arrays in HBM with 16-byte elements where fields travel
+// together (origin+tmin, direction+tmax, hit record, contribution+mis): 80 bytes per
+// primary ray and 52 per shadow ray, as in the reference (src/render/driver.impala:24-61).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "scene.h"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace rb200 {
+
+constexpr int kCapacity = 1 << 20;           // mapping_gpu.impala:319
+constexpr int kRBlock = 128;
+constexpr int kRSmemStack = 12;
+constexpr int kMaxBins = 1025;                // <= 1024 geometries + the miss bin (mapping_gpu.impala:202)
+
+struct PrimaryStream {                        // src/render/driver.impala:36-52
+    int* pixel;                               // rays.id
+    float4* ray_o;                            // org.xyz, tmin
+    float4* ray_d;                            // dir.xyz, tmax
+    float4* hit;                              // prim_id (bits), t, u, v
+    int* geom;                                // geom_id; num_geometries for a miss
+    float4* contrib_mis;                      // contrib.rgb, mis
+    uint2* rnd_depth;                         // rnd, depth
+};
+struct ShadowStream {                         // src/render/driver.impala:54-61
+    int* pixel;
+    float4* ray_o;
+    float4* ray_d;
+    float4* color;                            // rgb, unused
+};
+enum Counter { kWorkPrimary = 0, kWorkShadow, kHitCount, kSurvivors, kShadows, kNumCounters = 8 };
+
+struct SceneDev {
+    const Node8* nodes; const Tri4* tris;
+    const float4* normals; const float4* face_normals; const int4* indices; const int* light_ids;
+    const RodentMaterial* materials; const RodentLight* lights;
+    int num_materials, num_lights;
+};
+struct CameraDev { shade::V3 eye, dir, up, right; float w, h; };
+
+// ---- generate (gpu_generate_rays + make_camera_emitter, renderer.impala:26-40, camera.impala:35-44) ----
+__global__ void __launch_bounds__(256)
+generate_rays(PrimaryStream s, int first_ray_id, int first_dst, int n, CameraDev cam, int width, int height, int spp, int iter,
+              const int* __restrict__ rows) {
+    using namespace shade;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    const int ray_id = first_ray_id + gid, dst = first_dst + gid;
+    const int sample = ray_id % spp, local_pixel = ray_id / spp;
+    const int ly = local_pixel / width, x = local_pixel - ly * width;
+    const int y = __ldg(rows + ly);
+    unsigned rnd = fnv_hash(fnv_hash(fnv_hash(fnv_hash(0x811C9DC5u, unsigned(sample)), unsigned(iter)), unsigned(x)), unsigned(y));
+    const float kx = 2.0f * (float(x) + randf(rnd)) / float(width) - 1.0f;
+    const float ky = 1.0f - 2.0f * (float(y) + randf(rnd)) / float(height);
+    const V3 d = normalize(cam.right * (cam.w * kx) + cam.up * (cam.h * ky) + cam.dir);
+    s.pixel[dst] = y * width + x;
+    s.ray_o[dst] = make_float4(cam.eye.x, cam.eye.y, cam.eye.z, 0.0f);
+    s.ray_d[dst] = make_float4(d.x, d.y, d.z, kFltMax);
+    s.contrib_mis[dst] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    s.rnd_depth[dst] = make_uint2(rnd, 0u);
+}
+
+// ---- persistent traversal over a stream -----------------------------------------------------
+// SHADOW = false: closest hit, hit record + geometry id + per-material count.
+// SHADOW = true : any hit; unoccluded rays add their colour to the film.
+template <bool SHADOW>
+__global__ void __launch_bounds__(kRBlock, 6)
+traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
+                float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
+                const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
+                int* __restrict__ work_counter, int refill_below) {
+    __shared__ StackEntry smem_stack[kRSmemStack][kRBlock];
+    __shared__ int busy_lanes[kRBlock / 32];
+    __shared__ int hist[SHADOW ? 1 : kMaxBins];
+    const int num_rays = count_ptr ? min(*count_ptr, count_max) : count_max;
+    if (!SHADOW) {
+        for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
+        __syncthreads();
+    }
+    const unsigned lane = lane_id();
+    volatile int* busy = &busy_lanes[threadIdx.x >> 5];
+    Traversal<SHADOW, kRSmemStack, kRBlock> tr;
+    tr.st.smem = &smem_stack[0][threadIdx.x];
+    int ray_idx = -1;
+    bool drained = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
+        if (idle != 0 && !drained) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ray_idx < 0) {
+                const int i = base + __popc(idle & lanemask_lt());
+                if (i < num_rays) { ray_idx = i; tr.begin(__ldg(ray_o + i), __ldg(ray_d + i)); }
+            }
+            if (base + __popc(idle) >= num_rays) drained = true;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, ray_idx >= 0);
+        if (active == 0) break;
+        if (lane == 0) *busy = __popc(active);
+        __syncwarp();
+        if (ray_idx >= 0) {
+            const bool done = tr.template run<!SHADOW>(nodes, tris, [&] { return !drained && *busy < refill_below; });
+            if (done) {
+                if (SHADOW) {
+                    if (tr.hit.prim < 0) {                                     // gpu_accumulate, mapping_gpu.impala:32-45
+                        const int p = __ldg(pixels + ray_idx);
+                        const float4 c = __ldg(colors + ray_idx);
+                        atomicAdd(film + 3 * p + 0, c.x * inv_spp);
+                        atomicAdd(film + 3 * p + 1, c.y * inv_spp);
+                        atomicAdd(film + 3 * p + 2, c.z * inv_spp);
+                    }
+                } else {
+                    // make_primary_stream_hit_writer, driver.impala:106-115
+                    const int g = tr.hit.prim < 0 ? num_geoms : tr.hit.geom;
+                    hit_out[ray_idx] = make_float4(__int_as_float(tr.hit.prim), tr.hit.t, tr.hit.u, tr.hit.v);
+                    geom_out[ray_idx] = g;
+                    atomicAdd(&hist[g], 1);
+                }
+                ray_idx = -1;
+                atomicSub(const_cast<int*>(busy), 1);
+            }
+        }
+        __syncwarp();
+    }
+    if (!SHADOW) {
+        __syncthreads();
+        for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
+            if (hist[b]) atomicAdd(histogram + b, hist[b]);
+    }
+}
+
+// ---- scan: per-material begins, number of hit rays (the host scan of mapping_gpu.impala:201-208) ----
+__global__ void scan_bins(int* __restrict__ histogram, int* __restrict__ cursor, int num_geoms, int* __restrict__ counters) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for (int b = 0; b <= num_geoms; b++) {
+        cursor[b] = n;
+        if (b == num_geoms) counters[kHitCount] = n;     // the miss bin comes last and is not shaded (:357)
+        n += histogram[b];
+        histogram[b] = 0;
+    }
+}
+
+// ---- scatter: counting sort by material (gpu_sort_primary third pass + copy_primary_ray, :136-164, 210-220) ----
+__global__ void __launch_bounds__(256)
+scatter_by_material(PrimaryStream src, PrimaryStream dst, int size, int num_geoms, int* __restrict__ cursor) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = i < size ? src.geom[i] : num_geoms;
+    const bool live = g < num_geoms;
+    // one atomicAdd per (warp, material): peers with the same material take consecutive slots
+    const unsigned peers = __match_any_sync(0xffffffffu, live ? g : -1 - int(lane_id()));
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (live && int(lane_id()) == leader) base = atomicAdd(cursor + g, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!live) return;
+    const int d = base + __popc(peers & lanemask_lt());
+    dst.pixel[d] = src.pixel[i];
+    dst.ray_o[d] = src.ray_o[i];
+    dst.ray_d[d] = src.ray_d[i];
+    dst.hit[d] = src.hit[i];
+    dst.geom[d] = g;
+    dst.contrib_mis[d] = src.contrib_mis[i];
+    dst.rnd_depth[d] = src.rnd_depth[i];
+}
+
+// ---- shade (gpu_shade, mapping_gpu.impala:82-134, with the path tracer of renderer.impala:62-162) ----
+__global__ void __launch_bounds__(128)
+shade_rays(PrimaryStream in, PrimaryStream out, ShadowStream shadow, SceneDev sc, int* __restrict__ counters,
+           float* __restrict__ film, float inv_spp, int max_path_len) {
+    using namespace shade;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < counters[kHitCount];
+    bool emit_shadow = false, bounce = false;
+    int pixel = 0;
+    float4 sh_o, sh_d, sh_c, b_o, b_d, b_c;
+    uint2 b_r;
+    if (live) {
+        pixel = in.pixel[i];
+        const float4 ro = in.ray_o[i], rd = in.ray_d[i], h = in.hit[i], cm = in.contrib_mis[i];
+        const uint2 rdp = in.rnd_depth[i];
+        const RodentMaterial mat = sc.materials[in.geom[i]];
+        const V3 org = v3(ro.x, ro.y, ro.z), dir = v3(rd.x, rd.y, rd.z);
+        const int prim = __float_as_int(h.x);
+        const float t = h.y;
+        Col contrib = col(cm.x, cm.y, cm.z);
+        const float mis = cm.w;
+        unsigned rnd = rdp.x;
+        const int depth = int(rdp.y);
+        const Surf surf = surface_element(sc.normals, sc.face_normals, sc.indices, org, dir, prim, t, h.z, h.w);
+        const V3 out_dir = -dir;
+        const float pdf_lightpick = 1.0f / float(sc.num_lights);                              // renderer.impala:65
+
+        // on_hit, renderer.impala:111-127
+        if (mat.is_emissive && surf.is_entering) {
+            const RodentLight& l = sc.lights[sc.light_ids[prim]];
+            const float pdf_dir = cosine_hemisphere_pdf(dot(v3(l.n[0], l.n[1], l.n[2]), out_dir));
+            Col intensity = col(0, 0, 0); float pdf_area = 1.0f;                               // make_emission_value, light.impala:94-108
+            if (pdf_dir > 0.0f) { intensity = col(l.color[0], l.color[1], l.color[2]); pdf_area = l.inv_area; }
+            const float next_mis = mis * t * t / dot(out_dir, surf.local.c2);
+            const float w = 1.0f / (1.0f + next_mis * pdf_lightpick * pdf_area);
+            const Col c = (contrib * intensity) * w;
+            atomicAdd(film + 3 * pixel + 0, c.r * inv_spp);
+            atomicAdd(film + 3 * pixel + 1, c.g * inv_spp);
+            atomicAdd(film + 3 * pixel + 2, c.b * inv_spp);
+        }
+
+        // on_shadow, renderer.impala:69-109
+        if (!is_specular(mat) && sc.num_lights > 0) {
+            const int light_id = (xorshift(rnd) & 0x7FFFFFFF) % sc.num_lights;
+            const RodentLight& l = sc.lights[light_id];
+            float u = randf(rnd), v = randf(rnd);                                              // sample_triangle, random.impala:51-61
+            if (u + v > 1.0f) { u = 1.0f - u; v = 1.0f - v; }
+            const V3 pos = v3(l.v0[0], l.v0[1], l.v0[2]) * (1.0f - v - u) + v3(l.v1[0], l.v1[1], l.v1[2]) * u + v3(l.v2[0], l.v2[1], l.v2[2]) * v;
+            const V3 from_dir = surf.point - pos;
+            float cos_l = dot(from_dir, v3(l.n[0], l.n[1], l.n[2])) / length(from_dir);
+            Col intensity = col(l.color[0], l.color[1], l.color[2]);
+            float pdf_area = l.inv_area;
+            if (!(pdf_area > 0.0f && cosine_hemisphere_pdf(cos_l) > 0.0f && cos_l > 0.0f)) {   // make_direct_sample, light.impala:76-92
+                intensity = col(0, 0, 0); pdf_area = 1.0f; cos_l = 0.0f;
+            }
+            const V3 light_dir = pos - surf.point;
+            const float vis = dot(light_dir, surf.local.c2);
+            if (vis > 0.0f && cos_l > 0.0f) {
+                const float inv_d = 1.0f / length(light_dir), inv_d2 = inv_d * inv_d;
+                const V3 in_dir = light_dir * inv_d;
+                const float pdf_e = bsdf_pdf(mat, surf, in_dir, out_dir);
+                const float inv_pdf_l = 1.0f / (pdf_area * pdf_lightpick);
+                const float cos_e = vis * inv_d;
+                const float w = 1.0f / (1.0f + pdf_e * cos_l * inv_d2 * inv_pdf_l);
+                const float geom_factor = cos_e * cos_l * inv_d2 * inv_pdf_l;
+                const Col c = (intensity * (contrib * bsdf_eval(mat, surf, in_dir, out_dir))) * (geom_factor * w);
+                emit_shadow = true;
+                sh_o = make_float4(surf.point.x, surf.point.y, surf.point.z, kOffset);
+                sh_d = make_float4(light_dir.x, light_dir.y, light_dir.z, 1.0f - kOffset);
+                sh_c = make_float4(c.r, c.g, c.b, 0.0f);
+            }
+        }
+
+        // on_bounce, renderer.impala:129-152
+        float rr = 2.0f * luminance(contrib);                                                   // russian_roulette, random.impala:128-131
+        if (rr > 0.75f) rr = 0.75f;
+        if (!(depth >= max_path_len || randf(rnd) >= rr)) {
+            const BsdfSample bs = bsdf_sample(mat, surf, rnd, out_dir);
+            contrib = (contrib * bs.color) * (bs.cos / (bs.pdf * rr));
+            bounce = true;
+            b_o = make_float4(surf.point.x, surf.point.y, surf.point.z, kOffset);
+            b_d = make_float4(bs.in_dir.x, bs.in_dir.y, bs.in_dir.z, kFltMax);
+            b_c = make_float4(contrib.r, contrib.g, contrib.b, is_specular(mat) ? 0.0f : 1.0f / bs.pdf);
+            b_r = make_uint2(rnd, unsigned(depth + 1));
+        }
+    }
+    // compacted output: ranks from ballots, one atomicAdd per warp and stream
+    const unsigned lane = lane_id();
+    const unsigned mb = __ballot_sync(0xffffffffu, bounce), ms = __ballot_sync(0xffffffffu, emit_shadow);
+    int base_b = 0, base_s = 0;
+    if (lane == 0) {
+        if (mb) base_b = atomicAdd(counters + kSurvivors, __popc(mb));
+        if (ms) base_s = atomicAdd(counters + kShadows, __popc(ms));
+    }
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    base_s = __shfl_sync(0xffffffffu, base_s, 0);
+    if (bounce) {
+        const int d = base_b + __popc(mb & lanemask_lt());
+        out.pixel[d] = pixel; out.ray_o[d] = b_o; out.ray_d[d] = b_d; out.contrib_mis[d] = b_c; out.rnd_depth[d] = b_r;
+    }
+    if (emit_shadow) {
+        const int d = base_s + __popc(ms & lanemask_lt());
+        shadow.pixel[d] = pixel; shadow.ray_o[d] = sh_o; shadow.ray_d[d] = sh_d; shadow.color[d] = sh_c;
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+struct Renderer {
+    int dev = 0, width = 0, height = 0, spp = 1, max_path_len = 64;
+    std::vector<int> rows;                      // image rows owned by this renderer
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    PrimaryStream prim[2]{};
+    ShadowStream shadow{};
+    SceneDev scene{};
+    std::vector<void*> allocations;
+    int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr;
+    int* h_counters = nullptr;                  // pinned
+    float* film = nullptr; float* h_film = nullptr;
+    int sm_count = 0, occ_primary = 0, occ_shadow = 0;
+    int64_t stats[5] = {0, 0, 0, 0, 0};
+    double last_ms = 0.0;
+
+    template <typename T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        RB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+        allocations.push_back(p);
+        return static_cast<T*>(p);
+    }
+    template <typename T>
+    const T* upload(const T* src, size_t n) {
+        T* p = alloc<T>(n);
+        if (n) RB_CUDA_CHECK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+};
+
+static void alloc_stream(Renderer& r, PrimaryStream& s) {
+    s.pixel = r.alloc<int>(kCapacity); s.ray_o = r.alloc<float4>(kCapacity); s.ray_d = r.alloc<float4>(kCapacity);
+    s.hit = r.alloc<float4>(kCapacity); s.geom = r.alloc<int>(kCapacity); s.contrib_mis = r.alloc<float4>(kCapacity);
+    s.rnd_depth = r.alloc<uint2>(kCapacity);
+}
+
+static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
+    if (sc.materials.size() + 1 > size_t(kMaxBins)) { std::fprintf(stderr, "rodent_b200: more than 1024 materials\n"); return nullptr; }
+    if (width <= 0 || height <= 0 || spp <= 0 || num_parts <= 0 || part < 0 || part >= num_parts || band <= 0) return nullptr;
+    RB_CUDA_CHECK(cudaSetDevice(dev));
+    auto r = new Renderer();
+    r->dev = dev; r->width = width; r->height = height; r->spp = spp; r->max_path_len = max_path_len;
+    for (int y = 0; y < height; y++)
+        if ((y / band) % num_parts == part) r->rows.push_back(y);
+    cudaDeviceProp prop;
+    RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    r->sm_count = prop.multiProcessorCount;
+    RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
+    RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
+    alloc_stream(*r, r->prim[0]);
+    alloc_stream(*r, r->prim[1]);
+    r->shadow.pixel = r->alloc<int>(kCapacity); r->shadow.ray_o = r->alloc<float4>(kCapacity);
+    r->shadow.ray_d = r->alloc<float4>(kCapacity); r->shadow.color = r->alloc<float4>(kCapacity);
+    r->counters = r->alloc<int>(kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
+    RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
+    r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
+    r->film = r->alloc<float>(size_t(width) * height * 3);
+    RB_CUDA_CHECK(cudaMemset(r->film, 0, size_t(width) * height * 3 * sizeof(float)));
+    RB_CUDA_CHECK(cudaMallocHost(&r->h_film, size_t(width) * height * 3 * sizeof(float)));
+    std::memset(r->h_film, 0, size_t(width) * height * 3 * sizeof(float));
+    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, kNumCounters * sizeof(int)));
+    SceneDev& d = r->scene;
+    d.nodes = r->upload(sc.nodes.data(), sc.nodes.size());
+    d.tris = r->upload(sc.tris.data(), sc.tris.size());
+    d.normals = reinterpret_cast<const float4*>(r->upload(sc.normals.data(), sc.normals.size()));
+    d.face_normals = reinterpret_cast<const float4*>(r->upload(sc.face_normals.data(), sc.face_normals.size()));
+    d.indices = reinterpret_cast<const int4*>(r->upload(sc.indices.data(), sc.indices.size()));
+    d.light_ids = r->upload(sc.light_ids.data(), sc.light_ids.size());
+    d.materials = r->upload(sc.materials.data(), sc.materials.size());
+    d.lights = r->upload(sc.lights.data(), sc.lights.size());
+    d.num_materials = int(sc.materials.size()); d.num_lights = int(sc.lights.size());
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
+    return r;
+}
+
+static void destroy_renderer(Renderer* r) {
+    if (!r) return;
+    RB_CUDA_CHECK(cudaSetDevice(r->dev));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    for (void* p : r->allocations) RB_CUDA_CHECK(cudaFree(p));
+    RB_CUDA_CHECK(cudaFreeHost(r->h_film));
+    RB_CUDA_CHECK(cudaFreeHost(r->h_counters));
+    RB_CUDA_CHECK(cudaEventDestroy(r->ev0));
+    RB_CUDA_CHECK(cudaEventDestroy(r->ev1));
+    RB_CUDA_CHECK(cudaStreamDestroy(r->stream));
+    delete r;
+}
+
+// gpu_streaming_trace, mapping_gpu.impala:308-369
+static void render_device(Renderer& r, const Settings& st, int iter) {
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    const CameraDev cam{{st.eye.x, st.eye.y, st.eye.z}, {st.dir.x, st.dir.y, st.dir.z}, {st.up.x, st.up.y, st.up.z},
+                        {st.right.x, st.right.y, st.right.z}, st.width, st.height};
+    const int64_t total = int64_t(r.spp) * r.width * int64_t(r.rows.size());
+    const float inv_spp = 1.0f / float(r.spp);
+    const int num_geoms = r.scene.num_materials;
+    PrimaryStream& P = r.prim[0];
+    PrimaryStream& Q = r.prim[1];
+    int64_t id = 0; int size = 0;
+    int64_t n_primary = 0, n_shadow = 0, n_waves = 0, n_kernels = 0;
+    cudaStream_t s = r.stream;
+    RB_CUDA_CHECK(cudaEventRecord(r.ev0, s));
+    while (id < total || size > 0) {
+        if (size < kCapacity && id < total) {
+            const int n = int(std::min<int64_t>(total - id, kCapacity - size));
+            generate_rays<<<(n + 255) / 256, 256, 0, s>>>(P, int(id), size, n, cam, r.width, r.height, r.spp, iter, r.d_rows);
+            id += n; size += n; n_kernels++;
+        }
+        RB_CUDA_CHECK(cudaMemsetAsync(r.counters, 0, kNumCounters * sizeof(int), s));
+        const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
+        traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
+                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, r.counters + kWorkPrimary, 8);
+        scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, r.counters);
+        scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, Q, size, num_geoms, r.cursor);
+        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(Q, P, r.shadow, r.scene, r.counters, r.film, inv_spp, r.max_path_len);
+        const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
+        traverse_stream<true><<<grid_s, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, r.counters + kShadows, size,
+                                                         nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
+                                                         r.counters + kWorkShadow, 8);
+        RB_CUDA_CHECK(cudaGetLastError());
+        RB_CUDA_CHECK(cudaMemcpyAsync(r.h_counters, r.counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
+        RB_CUDA_CHECK(cudaStreamSynchronize(s));
+        n_primary += size; n_shadow += r.h_counters[kShadows]; n_waves++; n_kernels += 5;
+        size = r.h_counters[kSurvivors];
+    }
+    RB_CUDA_CHECK(cudaEventRecord(r.ev1, s));
+    RB_CUDA_CHECK(cudaEventSynchronize(r.ev1));
+    float ms = 0.0f;
+    RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+    r.last_ms = ms;
+    r.stats[0] = total; r.stats[1] = n_primary; r.stats[2] = n_shadow; r.stats[3] = n_waves; r.stats[4] = n_kernels;
+}
+
+static void present(Renderer& r) {
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    RB_CUDA_CHECK(cudaMemcpyAsync(r.h_film, r.film, size_t(r.width) * r.height * 3 * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r.stream));
+}
+
+// state behind the reference driver's global entry points
+static const Scene* g_bound_scene = nullptr;
+static int g_bound_dev = 0, g_bound_spp = 4, g_bound_max_path_len = 64;
+static Renderer* g_current = nullptr;
+
+}  // namespace rb200
+
+using namespace rb200;
+
+extern "C" {
+
+RodentRenderer* rodent_b200_renderer_create(const RodentScene* scene, int32_t dev, int32_t width, int32_t height, int32_t spp,
+                                            int32_t max_path_len, int32_t part, int32_t num_parts, int32_t band) {
+    return reinterpret_cast<RodentRenderer*>(create_renderer(*reinterpret_cast<const Scene*>(scene), dev, width, height, spp, max_path_len, part, num_parts, band));
+}
+void rodent_b200_renderer_free(RodentRenderer* r) { destroy_renderer(reinterpret_cast<Renderer*>(r)); }
+void rodent_b200_render(RodentRenderer* r, const Settings* settings, int32_t iter) {
+    render_device(*reinterpret_cast<Renderer*>(r), *settings, iter);
+    present(*reinterpret_cast<Renderer*>(r));
+}
+void rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int32_t iter) { render_device(*reinterpret_cast<Renderer*>(r), *settings, iter); }
+void rodent_b200_present(RodentRenderer* r) { present(*reinterpret_cast<Renderer*>(r)); }
+float* rodent_b200_film(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->h_film; }
+void* rodent_b200_film_device(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->film; }
+void rodent_b200_clear(RodentRenderer* rr) {
+    Renderer& r = *reinterpret_cast<Renderer*>(rr);
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    RB_CUDA_CHECK(cudaMemsetAsync(r.film, 0, size_t(r.width) * r.height * 3 * sizeof(float), r.stream));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r.stream));
+    std::memset(r.h_film, 0, size_t(r.width) * r.height * 3 * sizeof(float));
+}
+void rodent_b200_render_stats(const RodentRenderer* r, int64_t out[5]) { std::memcpy(out, reinterpret_cast<const Renderer*>(r)->stats, 5 * sizeof(int64_t)); }
+double rodent_b200_render_last_ms(const RodentRenderer* r) { return reinterpret_cast<const Renderer*>(r)->last_ms; }
+
+void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
+    g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;
+}
+void setup_interface(size_t width, size_t height) {
+    if (!g_bound_scene) { std::fprintf(stderr, "rodent_b200: setup_interface() without rodent_b200_bind()\n"); std::abort(); }
+    destroy_renderer(g_current);
+    g_current = create_renderer(*g_bound_scene, g_bound_dev, int(width), int(height), g_bound_spp, g_bound_max_path_len, 0, 1, 1);
+    if (!g_current) std::abort();
+}
+void cleanup_interface(void) { destroy_renderer(g_current); g_current = nullptr; }
+float* get_pixels(void) { return g_current ? g_current->h_film : nullptr; }
+void clear_pixels(void) { if (g_current) rodent_b200_clear(reinterpret_cast<RodentRenderer*>(g_current)); }
+int32_t get_spp(void) { return g_bound_spp; }
+void render(const Settings* settings, int32_t iter) {
+    if (!g_current) { std::fprintf(stderr, "rodent_b200: render() before setup_interface()\n"); std::abort(); }
+    rodent_b200_render(reinterpret_cast<RodentRenderer*>(g_current), settings, iter);
+}
+
+}  // extern "C"

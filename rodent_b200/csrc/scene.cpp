@@ -1,0 +1,564 @@
+// Runtime scene construction (host side): what the reference does at build time in
+// its scene compiler src/driver/converter.cpp, done when a scene is loaded.
+//
+//   OBJ / MTL parsing                 src/driver/obj.cpp:104-255, 257-371
+//   material clean-up, de-duplication src/driver/converter.cpp:440-557
+//   triangle mesh (dedup, normals)    src/driver/obj.cpp:412-509
+//   lights                            src/driver/converter.cpp:770-818
+//   material -> BSDF rules            src/driver/converter.cpp:857-913
+//   BVH8 / Tri4 emission              src/driver/converter.cpp:160-260 (node / leaf writers)
+//
+// The BVH itself is built with a binned-SAH top-down build followed by a collapse to
+// arity 8 (the reference uses an SBVH builder, src/driver/bvh.h; tree quality only
+// affects speed, not results).  The Impala code generation of the reference is replaced
+// by the RodentMaterial / RodentLight tables of include/rodent_b200.h.
+#include "scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <sstream>
+#include <unordered_map>
+
+namespace rb200 {
+namespace {
+
+struct F3 {
+    float x = 0, y = 0, z = 0;
+    bool operator==(const F3& o) const { return x == o.x && y == o.y && z == o.z; }
+    bool operator!=(const F3& o) const { return !(*this == o); }
+};
+F3 operator+(F3 a, F3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+F3 operator-(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+F3 operator*(F3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+F3 cross(F3 a, F3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+float length(F3 a) { return std::sqrt(dot(a, a)); }
+F3 normalize(F3 a) { return a * (1.0f / length(a)); }      // src/driver/float3.h:139-141
+F3 fmin3(F3 a, F3 b) { return {std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)}; }
+F3 fmax3(F3 a, F3 b) { return {std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)}; }
+
+struct ObjIndex { int v = 0, t = 0, n = 0; };
+struct ObjFace { std::vector<ObjIndex> idx; int material = 0; };
+struct ObjMaterial {                      // src/driver/obj.h:31-48
+    F3 ka, kd, ks, ke, tf;
+    float ns = 0, ni = 0, tr = 0, d = 0;
+    int illum = 0;
+    std::string map_ka, map_kd, map_ks, map_ke, map_bump, map_d;
+};
+struct ObjFile {
+    std::vector<std::vector<ObjFace>> objects;   // faces per `o` object (groups do not matter downstream)
+    std::vector<F3> vertices, normals;
+    std::vector<std::array<float, 2>> texcoords;
+    std::vector<std::string> materials, mtl_libs;
+};
+
+void warn(const std::string& m) { std::cerr << "rodent_b200: warning: " << m << std::endl; }
+bool fail(const std::string& m) { std::cerr << "rodent_b200: error: " << m << std::endl; return false; }
+
+const char* skip_ws(const char* p) { while (*p && std::isspace((unsigned char)*p)) p++; return p; }
+std::string first_word(const char* p) {
+    p = skip_ws(p);
+    const char* e = p;
+    while (*e && !std::isspace((unsigned char)*e)) e++;
+    return std::string(p, e);
+}
+std::string rest_of_line(const char* p) {
+    std::string s = skip_ws(p);
+    while (!s.empty() && std::isspace((unsigned char)s.back())) s.pop_back();
+    return s;
+}
+bool keyword(const char* p, const char* kw) {
+    const size_t n = std::strlen(kw);
+    return !std::strncmp(p, kw, n) && std::isspace((unsigned char)p[n]);
+}
+void read_floats(const char* p, float* out, int n) {
+    char* e;
+    for (int i = 0; i < n; i++) { out[i] = std::strtof(p, &e); p = e; }
+}
+
+// v, v/t, v//n, v/t/n with negative (relative) indices: obj.cpp:69-100
+bool read_index(const char*& p, ObjIndex& idx) {
+    p = skip_ws(p);
+    if (!std::isdigit((unsigned char)*p) && *p != '-') return false;
+    char* e;
+    idx = ObjIndex{};
+    idx.v = int(std::strtol(p, &e, 10)); p = skip_ws(e);
+    if (*p == '/') {
+        p++;
+        if (*p != '/') { idx.t = int(std::strtol(p, &e, 10)); p = e; }
+        p = skip_ws(p);
+        if (*p == '/') { p++; idx.n = int(std::strtol(p, &e, 10)); p = e; }
+    }
+    return true;
+}
+
+bool parse_obj(const std::string& path, ObjFile& file) {
+    std::ifstream in(path);
+    if (!in) return fail("cannot open OBJ file '" + path + "'");
+    file.objects.emplace_back();
+    file.materials.emplace_back("");                       // material 0 = the dummy material
+    file.vertices.emplace_back(); file.normals.emplace_back(); file.texcoords.push_back({0, 0});   // 1-based indices
+    int cur_mtl = 0, line_no = 0, errors = 0;
+    std::string line;
+    while (std::getline(in, line)) {
+        line_no++;
+        const char* p = skip_ws(line.c_str());
+        if (!*p || *p == '#') continue;
+        if (p[0] == 'v' && std::isspace((unsigned char)p[1])) {
+            float v[3]; read_floats(p + 1, v, 3); file.vertices.push_back({v[0], v[1], v[2]});
+        } else if (p[0] == 'v' && p[1] == 'n') {
+            float v[3]; read_floats(p + 2, v, 3); file.normals.push_back({v[0], v[1], v[2]});
+        } else if (p[0] == 'v' && p[1] == 't') {
+            float v[2]; read_floats(p + 2, v, 2); file.texcoords.push_back({v[0], v[1]});
+        } else if (p[0] == 'f' && std::isspace((unsigned char)p[1])) {
+            ObjFace f; f.material = cur_mtl;
+            const char* q = p + 2;
+            ObjIndex idx;
+            while (read_index(q, idx)) f.idx.push_back(idx);
+            bool ok = f.idx.size() >= 3;
+            for (auto& i : f.idx) {
+                if (i.v < 0) i.v += int(file.vertices.size());
+                if (i.t < 0) i.t += int(file.texcoords.size());
+                if (i.n < 0) i.n += int(file.normals.size());
+                ok = ok && i.v > 0 && i.t >= 0 && i.n >= 0 && i.v < int(file.vertices.size()) &&
+                     i.t < int(file.texcoords.size()) && i.n < int(file.normals.size());
+            }
+            if (ok) file.objects.back().push_back(f);
+            else { fail("invalid face (line " + std::to_string(line_no) + ")"); errors++; }
+        } else if (p[0] == 'g' && std::isspace((unsigned char)p[1])) {
+        } else if (p[0] == 'o' && std::isspace((unsigned char)p[1])) {
+            file.objects.emplace_back();
+        } else if (keyword(p, "usemtl")) {
+            const std::string name = first_word(p + 6);
+            cur_mtl = int(std::find(file.materials.begin(), file.materials.end(), name) - file.materials.begin());
+            if (cur_mtl == int(file.materials.size())) file.materials.push_back(name);
+        } else if (keyword(p, "mtllib")) {
+            file.mtl_libs.push_back(first_word(p + 6));
+        } else if (p[0] == 's' && std::isspace((unsigned char)p[1])) {
+        } else { fail("unknown OBJ command '" + std::string(p) + "' (line " + std::to_string(line_no) + ")"); errors++; }
+    }
+    return errors == 0;
+}
+
+bool parse_mtl(const std::string& path, std::map<std::string, ObjMaterial>& lib) {
+    std::ifstream in(path);
+    if (!in) return fail("cannot open MTL file '" + path + "'");
+    std::string line, name;
+    int errors = 0;
+    while (std::getline(in, line)) {
+        const char* p = skip_ws(line.c_str());
+        if (!*p || *p == '#') continue;
+        if (keyword(p, "newmtl")) {
+            name = first_word(p + 6);
+            if (lib.count(name)) { fail("material redefinition for '" + name + "'"); errors++; }
+            lib[name];
+            continue;
+        }
+        ObjMaterial& m = lib[name];
+        if (p[0] == 'K' && std::isspace((unsigned char)p[2]) && std::strchr("adse", p[1])) {
+            F3& c = p[1] == 'a' ? m.ka : p[1] == 'd' ? m.kd : p[1] == 's' ? m.ks : m.ke;
+            float v[3]; read_floats(p + 3, v, 3); c = {v[0], v[1], v[2]};
+        } else if (keyword(p, "Ns")) read_floats(p + 3, &m.ns, 1);
+        else if (keyword(p, "Ni")) read_floats(p + 3, &m.ni, 1);
+        else if (keyword(p, "Tf")) { float v[3]; read_floats(p + 3, v, 3); m.tf = {v[0], v[1], v[2]}; }
+        else if (keyword(p, "Tr")) read_floats(p + 3, &m.tr, 1);
+        else if (p[0] == 'd' && std::isspace((unsigned char)p[1])) read_floats(p + 2, &m.d, 1);
+        else if (keyword(p, "illum")) { float v; read_floats(p + 6, &v, 1); m.illum = int(v); }
+        else if (keyword(p, "map_Ka")) m.map_ka = rest_of_line(p + 6);
+        else if (keyword(p, "map_Kd")) m.map_kd = rest_of_line(p + 6);
+        else if (keyword(p, "map_Ks")) m.map_ks = rest_of_line(p + 6);
+        else if (keyword(p, "map_Ke")) m.map_ke = rest_of_line(p + 6);
+        else if (keyword(p, "map_bump")) m.map_bump = rest_of_line(p + 8);
+        else if (keyword(p, "bump")) m.map_bump = rest_of_line(p + 4);
+        else if (keyword(p, "map_d")) m.map_d = rest_of_line(p + 5);
+        else if (p[0] == 'K' || p[0] == 'N' || p[0] == 'T') { fail("invalid MTL command '" + std::string(p) + "'"); errors++; }
+        else warn("unknown MTL command '" + std::string(p) + "'");
+    }
+    return errors == 0;
+}
+
+// converter.cpp:440-458 (tr, d, map_ka, map_bump, map_d are ignored)
+bool same_material(const ObjMaterial& a, const ObjMaterial& b) {
+    return a.ka == b.ka && a.kd == b.kd && a.ks == b.ks && a.ke == b.ke && a.ns == b.ns && a.ni == b.ni && a.tf == b.tf &&
+           a.illum == b.illum && a.map_kd == b.map_kd && a.map_ks == b.map_ks && a.map_ke == b.map_ke;
+}
+// converter.cpp:460-465
+bool is_simple(const ObjMaterial& m) {
+    const F3 zero;
+    return m.illum != 5 && m.illum != 7 && m.ke == zero && m.map_ke.empty() && m.map_kd.empty() && m.map_ks.empty() &&
+           (m.kd != zero || m.ks != zero);
+}
+
+// cleanup_obj, converter.cpp:467-557: dummy material, missing -> dummy, identical -> first, unused removed,
+// "complex" materials before "simple" ones.
+void cleanup_materials(ObjFile& obj, std::map<std::string, ObjMaterial>& lib) {
+    ObjMaterial& dummy = lib[""];
+    dummy = ObjMaterial{};
+    dummy.kd = {0.0f, 1.0f, 1.0f}; dummy.ns = 1.0f; dummy.ni = 1.0f; dummy.tr = 1.0f; dummy.d = 1.0f; dummy.illum = 2;
+    for (auto& name : obj.materials)
+        if (!name.empty() && !lib.count(name)) { warn("missing material definition for '" + name + "', replaced by the dummy material"); name = ""; }
+    std::unordered_map<std::string, std::string> remap;
+    for (size_t i = 0; i < obj.materials.size(); i++) {
+        if (remap.count(obj.materials[i])) continue;
+        for (size_t j = i + 1; j < obj.materials.size(); j++)
+            if (same_material(lib[obj.materials[i]], lib[obj.materials[j]])) remap.emplace(obj.materials[j], obj.materials[i]);
+    }
+    auto canonical = [&](std::string n) { auto it = remap.find(n); return it == remap.end() ? n : it->second; };
+    std::vector<std::string> used;
+    for (auto& faces : obj.objects)
+        for (auto& f : faces) {
+            const std::string n = canonical(obj.materials[f.material]);
+            if (std::find(used.begin(), used.end(), n) == used.end()) used.push_back(n);
+        }
+    std::vector<std::string> kept;
+    for (auto& n : obj.materials)
+        if (std::find(used.begin(), used.end(), n) != used.end() && std::find(kept.begin(), kept.end(), n) == kept.end()) kept.push_back(n);
+    std::stable_partition(kept.begin(), kept.end(), [&](const std::string& n) { return !is_simple(lib[n]); });
+    std::vector<int> id_remap;
+    for (auto& n : obj.materials) id_remap.push_back(int(std::find(kept.begin(), kept.end(), canonical(n)) - kept.begin()));
+    for (auto& faces : obj.objects)
+        for (auto& f : faces) f.material = id_remap[f.material];
+    obj.materials = kept;
+}
+
+// converter.cpp:870-913 with constant colours (textured materials fall back to their constants)
+RodentMaterial make_material(const ObjMaterial& m) {
+    RodentMaterial r{};
+    const F3 zero;
+    r.ns = m.ns; r.ni = m.ni;
+    r.kd[0] = m.kd.x; r.kd[1] = m.kd.y; r.kd[2] = m.kd.z;
+    r.ks[0] = m.ks.x; r.ks[1] = m.ks.y; r.ks[2] = m.ks.z;
+    r.tf[0] = m.tf.x; r.tf[1] = m.tf.y; r.tf[2] = m.tf.z;
+    r.ke[0] = m.ke.x; r.ke[1] = m.ke.y; r.ke[2] = m.ke.z;
+    r.is_emissive = (m.ke != zero || !m.map_ke.empty()) ? 1 : 0;
+    if (m.illum == 5) r.bsdf = RODENT_BSDF_MIRROR;
+    else if (m.illum == 7) r.bsdf = RODENT_BSDF_GLASS;
+    else {
+        const bool diffuse = m.kd != zero || !m.map_kd.empty(), specular = m.ks != zero || !m.map_ks.empty();
+        if (diffuse && specular) {
+            // color_luminance, src/core/color.impala:33-35
+            const float lum_ks = m.ks.x * 0.2126f + m.ks.y * 0.7152f + m.ks.z * 0.0722f;
+            const float lum_kd = m.kd.x * 0.2126f + m.kd.y * 0.7152f + m.kd.z * 0.0722f;
+            r.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
+            r.bsdf = RODENT_BSDF_MIX;
+        } else r.bsdf = diffuse ? RODENT_BSDF_DIFFUSE : specular ? RODENT_BSDF_PHONG : RODENT_BSDF_BLACK;
+    }
+    return r;
+}
+
+// ---- BVH8 / Tri4 build ---------------------------------------------------------------
+struct Box {
+    F3 lo{std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    F3 hi{-std::numeric_limits<float>::max(), -std::numeric_limits<float>::max(), -std::numeric_limits<float>::max()};
+    void grow(F3 p) { lo = fmin3(lo, p); hi = fmax3(hi, p); }
+    void grow(const Box& b) { lo = fmin3(lo, b.lo); hi = fmax3(hi, b.hi); }
+    float half_area() const { const F3 e = hi - lo; return std::max(e.x, 0.f) * (std::max(e.y, 0.f) + std::max(e.z, 0.f)) + std::max(e.y, 0.f) * std::max(e.z, 0.f); }
+};
+struct Bvh2Node { Box box; int left = -1, right = -1, first = 0, count = 0; };
+
+struct Builder {
+    const std::vector<F3>& v0; const std::vector<F3>& v1; const std::vector<F3>& v2;
+    const std::vector<int>& geom;
+    std::vector<Box> boxes; std::vector<F3> centers; std::vector<int> order;
+    std::vector<Bvh2Node> n2;
+    std::vector<Node8>& nodes; std::vector<Tri4>& tris;
+    static constexpr int kBins = 16, kLeaf = 4;
+
+    int build2(int first, int count) {
+        Bvh2Node node; node.first = first; node.count = count;
+        Box cb;
+        for (int i = first; i < first + count; i++) { node.box.grow(boxes[order[i]]); cb.grow(centers[order[i]]); }
+        const int id = int(n2.size());
+        n2.push_back(node);
+        if (count <= kLeaf) return id;
+        // binned SAH over the three axes; leaves hold at most one Tri4
+        float best = std::numeric_limits<float>::max(); int best_axis = -1, best_bin = 0;
+        for (int axis = 0; axis < 3; axis++) {
+            const float lo = (&cb.lo.x)[axis], ext = (&cb.hi.x)[axis] - lo;
+            if (!(ext > 0)) continue;
+            Box bb[kBins]; int bc[kBins] = {};
+            for (int i = first; i < first + count; i++) {
+                const int b = std::min(kBins - 1, int(((&centers[order[i]].x)[axis] - lo) / ext * kBins));
+                bb[b].grow(boxes[order[i]]); bc[b]++;
+            }
+            float right_cost[kBins]; Box acc; int cnt = 0;
+            for (int b = kBins - 1; b > 0; b--) { acc.grow(bb[b]); cnt += bc[b]; right_cost[b] = cnt * acc.half_area(); }
+            acc = Box(); cnt = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                acc.grow(bb[b]); cnt += bc[b];
+                if (cnt == 0 || cnt == count) continue;
+                const float c = cnt * acc.half_area() + right_cost[b + 1];
+                if (c < best) { best = c; best_axis = axis; best_bin = b; }
+            }
+        }
+        int mid;
+        if (best_axis < 0) {
+            mid = first + count / 2;                   // all centroids coincide: split in the middle
+        } else {
+            const float lo = (&cb.lo.x)[best_axis], ext = (&cb.hi.x)[best_axis] - lo;
+            mid = int(std::partition(order.begin() + first, order.begin() + first + count, [&](int t) {
+                return std::min(kBins - 1, int(((&centers[t].x)[best_axis] - lo) / ext * kBins)) <= best_bin; }) - order.begin());
+        }
+        const int l = build2(first, mid - first), r = build2(mid, first + count - mid);
+        n2[id].left = l; n2[id].right = r;
+        return id;
+    }
+
+    // leaf writer of converter.cpp:207-259
+    int write_leaf(const Bvh2Node& leaf) {
+        const int first_tri4 = int(tris.size());
+        for (int i = 0; i < leaf.count; i += 4) {
+            Tri4 t; std::memset(&t, 0, sizeof t);
+            const int c = std::min(4, leaf.count - i);
+            for (int j = 0; j < c; j++) {
+                const int id = order[leaf.first + i + j];
+                const F3 e1 = v0[id] - v1[id], e2 = v2[id] - v0[id], n = cross(e1, e2);
+                t.v0[0][j] = v0[id].x; t.v0[1][j] = v0[id].y; t.v0[2][j] = v0[id].z;
+                t.e1[0][j] = e1.x; t.e1[1][j] = e1.y; t.e1[2][j] = e1.z;
+                t.e2[0][j] = e2.x; t.e2[1][j] = e2.y; t.e2[2][j] = e2.z;
+                t.n[0][j] = n.x; t.n[1][j] = n.y; t.n[2][j] = n.z;
+                t.prim_id[j] = id; t.geom_id[j] = geom[id];
+            }
+            for (int j = c; j < 4; j++) t.prim_id[j] = -1;
+            tris.push_back(t);
+        }
+        tris.back().prim_id[3] |= int32_t(0x80000000u);
+        return ~first_tri4;
+    }
+
+    // node writer of converter.cpp:160-204: collapse the binary tree to arity 8 by always opening
+    // the child with the largest area
+    int write_node(int root2) {
+        std::vector<int> kids{n2[root2].left, n2[root2].right};
+        while (kids.size() < 8) {
+            int pick = -1; float area = -1;
+            for (size_t i = 0; i < kids.size(); i++)
+                if (n2[kids[i]].left >= 0 && n2[kids[i]].box.half_area() > area) { area = n2[kids[i]].box.half_area(); pick = int(i); }
+            if (pick < 0) break;
+            const int k = kids[pick];
+            kids[pick] = n2[k].left;
+            kids.push_back(n2[k].right);
+        }
+        const int id = int(nodes.size());
+        nodes.emplace_back();
+        std::memset(&nodes[id], 0, sizeof(Node8));
+        for (int j = 0; j < 8; j++) {
+            const float inf = std::numeric_limits<float>::infinity();
+            if (j < int(kids.size())) {
+                const Box& b = n2[kids[j]].box;
+                nodes[id].bounds[0][j] = b.lo.x; nodes[id].bounds[1][j] = b.hi.x;
+                nodes[id].bounds[2][j] = b.lo.y; nodes[id].bounds[3][j] = b.hi.y;
+                nodes[id].bounds[4][j] = b.lo.z; nodes[id].bounds[5][j] = b.hi.z;
+            } else {
+                for (int r = 0; r < 6; r += 2) { nodes[id].bounds[r][j] = inf; nodes[id].bounds[r + 1][j] = -inf; }
+            }
+        }
+        for (size_t j = 0; j < kids.size(); j++) {
+            const int child = n2[kids[j]].left >= 0 ? write_node(kids[j]) + 1 : write_leaf(n2[kids[j]]);
+            nodes[id].child[j] = child;
+        }
+        return id;
+    }
+
+    void run() {
+        const int n = int(v0.size());
+        boxes.resize(n); centers.resize(n); order.resize(n);
+        std::iota(order.begin(), order.end(), 0);
+        for (int i = 0; i < n; i++) {
+            boxes[i].grow(v0[i]); boxes[i].grow(v1[i]); boxes[i].grow(v2[i]);
+            centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
+        }
+        const int root = build2(0, n);
+        if (n2[root].left < 0) {
+            // a single leaf: the root node (id 1) must still be an inner node
+            nodes.emplace_back();
+            std::memset(&nodes[0], 0, sizeof(Node8));
+            const float inf = std::numeric_limits<float>::infinity();
+            for (int j = 0; j < 8; j++)
+                for (int r = 0; r < 6; r += 2) { nodes[0].bounds[r][j] = inf; nodes[0].bounds[r + 1][j] = -inf; }
+            const Box& b = n2[root].box;
+            nodes[0].bounds[0][0] = b.lo.x; nodes[0].bounds[1][0] = b.hi.x; nodes[0].bounds[2][0] = b.lo.y;
+            nodes[0].bounds[3][0] = b.hi.y; nodes[0].bounds[4][0] = b.lo.z; nodes[0].bounds[5][0] = b.hi.z;
+            nodes[0].child[0] = write_leaf(n2[root]);
+        } else {
+            write_node(root);
+        }
+    }
+};
+
+void put4(std::vector<float>& dst, F3 v) { dst.push_back(v.x); dst.push_back(v.y); dst.push_back(v.z); dst.push_back(0.0f); }
+
+// lights + light ids from emissive materials: converter.cpp:770-818, 832
+void collect_lights(Scene& s, const std::vector<F3>& verts) {
+    const int num_tris = int(s.indices.size() / 4);
+    s.light_ids.assign(num_tris, 0);
+    for (int i = 0; i < num_tris; i++) {
+        const int m = s.indices[4 * i + 3];
+        if (!s.materials[m].is_emissive) continue;
+        const F3 a = verts[s.indices[4 * i]], b = verts[s.indices[4 * i + 1]], c = verts[s.indices[4 * i + 2]];
+        F3 n = cross(b - a, c - a);
+        RodentLight l{};
+        l.inv_area = 1.0f / (0.5f * length(n));
+        n = normalize(n);
+        l.v0[0] = a.x; l.v0[1] = a.y; l.v0[2] = a.z; l.v1[0] = b.x; l.v1[1] = b.y; l.v1[2] = b.z; l.v2[0] = c.x; l.v2[1] = c.y; l.v2[2] = c.z;
+        l.n[0] = n.x; l.n[1] = n.y; l.n[2] = n.z;
+        for (int k = 0; k < 3; k++) l.color[k] = s.materials[m].ke[k];
+        s.light_ids[i] = int(s.lights.size());
+        s.lights.push_back(l);
+    }
+}
+
+}  // namespace
+
+Scene* load_obj_scene(const std::string& path) {
+    ObjFile obj;
+    if (!parse_obj(path, obj)) return nullptr;
+    std::map<std::string, ObjMaterial> lib;
+    const size_t slash = path.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? "." : path.substr(0, slash);
+    for (auto& name : obj.mtl_libs)
+        if (!parse_mtl(dir + "/" + name, lib)) return nullptr;
+    cleanup_materials(obj, lib);
+
+    auto scene = new Scene();
+    for (auto& name : obj.materials) {
+        const ObjMaterial& m = lib[name];
+        if (!m.map_kd.empty() || !m.map_ks.empty() || !m.map_ke.empty())
+            warn("material '" + name + "' uses textures; constant colours are used instead");
+        scene->materials.push_back(make_material(m));
+        scene->material_names.push_back(name);
+    }
+
+    // compute_tri_mesh, obj.cpp:412-509: per object, vertices de-duplicated by (v, t, n) in order of first use
+    std::vector<F3> verts, normals, face_normals;
+    std::vector<std::array<float, 2>> uvs;
+    for (auto& faces : obj.objects) {
+        std::map<std::array<int, 3>, int> mapping;
+        std::vector<std::array<int, 3>> keys;
+        bool has_normals = false, has_uvs = false;
+        auto index_of = [&](const ObjIndex& i) {
+            const std::array<int, 3> k{i.v, i.t, i.n};
+            auto it = mapping.find(k);
+            if (it != mapping.end()) return it->second;
+            has_normals |= i.n != 0; has_uvs |= i.t != 0;
+            const int id = int(keys.size());
+            mapping.emplace(k, id); keys.push_back(k);
+            return id;
+        };
+        const size_t vtx_offset = verts.size(), tri_offset = scene->indices.size() / 4;
+        std::vector<std::array<int, 4>> tri_list;
+        for (auto& f : faces) {
+            std::vector<int> ids;
+            for (auto& i : f.idx) ids.push_back(index_of(i));
+            for (size_t i = 1; i + 1 < ids.size(); i++) tri_list.push_back({ids[0], ids[i], ids[i + 1], f.material});   // fan
+        }
+        if (tri_list.empty()) continue;
+        for (auto& k : keys) {
+            verts.push_back(obj.vertices[k[0]]);
+            uvs.push_back(has_uvs ? obj.texcoords[k[1]] : std::array<float, 2>{0, 0});
+            normals.push_back(has_normals ? obj.normals[k[2]] : F3{});
+        }
+        for (auto& t : tri_list) {
+            for (int c = 0; c < 3; c++) scene->indices.push_back(int(t[c] + vtx_offset));
+            scene->indices.push_back(t[3]);
+            const F3 a = verts[t[0] + vtx_offset], b = verts[t[1] + vtx_offset], c = verts[t[2] + vtx_offset];
+            face_normals.push_back(normalize(cross(b - a, c - a)));            // obj.cpp:385-395
+        }
+        if (!has_normals)                                                        // obj.cpp:397-410, 487-492
+            for (size_t i = 0; i < tri_list.size(); i++)
+                for (int c = 0; c < 3; c++) normals[tri_list[i][c] + vtx_offset] = normals[tri_list[i][c] + vtx_offset] + face_normals[tri_offset + i];
+    }
+    for (auto& n : normals) {                                                    // obj.cpp:495-504
+        const float len2 = dot(n, n);
+        if (len2 <= std::numeric_limits<float>::epsilon() || std::isnan(len2)) n = {0.0f, 1.0f, 0.0f};
+        else n = n * (1.0f / std::sqrt(len2));
+    }
+    if (scene->indices.empty()) { delete scene; fail("'" + path + "' contains no triangle"); return nullptr; }
+
+    for (auto& v : verts) put4(scene->vertices, v);
+    for (auto& n : normals) put4(scene->normals, n);
+    for (auto& n : face_normals) put4(scene->face_normals, n);
+    for (auto& t : uvs) { scene->texcoords.push_back(t[0]); scene->texcoords.push_back(t[1]); scene->texcoords.push_back(0); scene->texcoords.push_back(0); }
+    collect_lights(*scene, verts);
+
+    const int num_tris = int(scene->indices.size() / 4);
+    std::vector<F3> a(num_tris), b(num_tris), c(num_tris); std::vector<int> geom(num_tris);
+    for (int i = 0; i < num_tris; i++) {
+        a[i] = verts[scene->indices[4 * i]]; b[i] = verts[scene->indices[4 * i + 1]]; c[i] = verts[scene->indices[4 * i + 2]];
+        geom[i] = scene->indices[4 * i + 3];
+    }
+    Builder builder{a, b, c, geom, {}, {}, {}, {}, scene->nodes, scene->tris};
+    builder.run();
+    return scene;
+}
+
+Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
+                       const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims) {
+    auto scene = new Scene();
+    scene->nodes.assign(nodes, nodes + num_nodes);
+    scene->tris.assign(tris, tris + num_tri4);
+    scene->materials.assign(materials, materials + num_materials);
+    scene->material_names.resize(num_materials);
+    std::vector<F3> verts(size_t(num_prims) * 3), face_normals(num_prims);
+    std::vector<char> seen(num_prims, 0);
+    scene->indices.assign(size_t(num_prims) * 4, 0);
+    for (int k = 0; k < num_tri4; k++)
+        for (int j = 0; j < 4; j++) {
+            Tri4& t = scene->tris[k];
+            if (t.prim_id[j] == -1) continue;
+            const int p = t.prim_id[j] & 0x7FFFFFFF;
+            if (p >= num_prims) { delete scene; fail("prim_id out of range in BVH"); return nullptr; }
+            t.geom_id[j] = material_of_prim[p];
+            if (seen[p]) continue;
+            seen[p] = 1;
+            const F3 v0{t.v0[0][j], t.v0[1][j], t.v0[2][j]}, e1{t.e1[0][j], t.e1[1][j], t.e1[2][j]}, e2{t.e2[0][j], t.e2[1][j], t.e2[2][j]};
+            const F3 v1 = v0 - e1, v2 = v0 + e2;                                  // make_tri, intersection.impala:110-119
+            verts[3 * p] = v0; verts[3 * p + 1] = v1; verts[3 * p + 2] = v2;
+            const F3 n = cross(v1 - v0, v2 - v0);
+            const float len = length(n);
+            face_normals[p] = len > 0 ? n * (1.0f / len) : F3{0, 1, 0};
+            scene->indices[4 * p] = 3 * p; scene->indices[4 * p + 1] = 3 * p + 1; scene->indices[4 * p + 2] = 3 * p + 2;
+            scene->indices[4 * p + 3] = material_of_prim[p];
+        }
+    for (int p = 0; p < num_prims; p++) {
+        for (int c = 0; c < 3; c++) { put4(scene->vertices, verts[3 * p + c]); put4(scene->normals, face_normals[p]); }
+        put4(scene->face_normals, face_normals[p]);
+        if (!seen[p]) scene->indices[4 * p + 3] = material_of_prim[p];
+    }
+    scene->texcoords.assign(size_t(num_prims) * 12, 0.0f);
+    collect_lights(*scene, verts);
+    return scene;
+}
+
+}  // namespace rb200
+
+using rb200::Scene;
+
+extern "C" {
+
+RodentScene* rodent_b200_scene_load_obj(const char* obj_file) {
+    return reinterpret_cast<RodentScene*>(rb200::load_obj_scene(obj_file));
+}
+RodentScene* rodent_b200_scene_from_bvh8(const Node8* nodes, int32_t num_nodes, const Tri4* tris, int32_t num_tri4,
+                                         const RodentMaterial* materials, int32_t num_materials,
+                                         const int32_t* material_of_prim, int32_t num_prims) {
+    return reinterpret_cast<RodentScene*>(rb200::scene_from_bvh8(nodes, num_nodes, tris, num_tri4, materials, num_materials, material_of_prim, num_prims));
+}
+void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out) {
+    const Scene& s = *reinterpret_cast<const Scene*>(scene);
+    out->num_tris = int32_t(s.indices.size() / 4); out->num_vertices = int32_t(s.vertices.size() / 4);
+    out->num_materials = int32_t(s.materials.size()); out->num_lights = int32_t(s.lights.size());
+    out->num_nodes = int32_t(s.nodes.size()); out->num_tri4 = int32_t(s.tris.size());
+    out->vertices = s.vertices.data(); out->normals = s.normals.data(); out->face_normals = s.face_normals.data();
+    out->texcoords = s.texcoords.data(); out->indices = s.indices.data(); out->light_ids = s.light_ids.data();
+    out->materials = s.materials.data(); out->lights = s.lights.data(); out->nodes = s.nodes.data(); out->tris = s.tris.data();
+}
+void rodent_b200_scene_free(RodentScene* scene) { delete reinterpret_cast<Scene*>(scene); }
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// Host-side scene container behind the opaque RodentScene handle.
+#pragma once
+
+#include <array>
+#include <string>
+#include <vector>
+
+#include "../../include/rodent_b200.h"
+
+namespace rb200 {
+
+struct Scene {
+    std::vector<float> vertices, normals, face_normals, texcoords;   // float4 stride
+    std::vector<int32_t> indices;                                     // int4 per triangle
+    std::vector<int32_t> light_ids;
+    std::vector<RodentMaterial> materials;
+    std::vector<std::string> material_names;
+    std::vector<RodentLight> lights;
+    std::vector<Node8> nodes;
+    std::vector<Tri4> tris;
+};
+
+Scene* load_obj_scene(const std::string& path);
+Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
+                       const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims);
+
+}  // namespace rb200

@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's `rodent` driver (src/driver/driver.cpp): scene
+loading, camera set-up, the render loop and tone mapping, over the C ABI of
+include/rodent_b200.h (scene + wavefront path tracer)."""
+from __future__ import annotations
+
+import ctypes
+import math
+from ctypes import POINTER, c_float, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+from . import lib
+
+MATERIAL = np.dtype([("bsdf", "<i4"), ("is_emissive", "<i4"), ("ns", "<f4"), ("ni", "<f4"), ("kd", "<f4", (3,)), ("mix_k", "<f4"),
+                     ("ks", "<f4", (3,)), ("pad0", "<f4"), ("tf", "<f4", (3,)), ("pad1", "<f4"), ("ke", "<f4", (3,)), ("pad2", "<f4")])
+LIGHT = np.dtype([("v0", "<f4", (3,)), ("inv_area", "<f4"), ("v1", "<f4", (3,)), ("pad0", "<f4"), ("v2", "<f4", (3,)), ("pad1", "<f4"),
+                  ("n", "<f4", (3,)), ("pad2", "<f4"), ("color", "<f4", (3,)), ("pad3", "<f4")])
+assert MATERIAL.itemsize == 80 and LIGHT.itemsize == 80
+BSDF_BLACK, BSDF_DIFFUSE, BSDF_PHONG, BSDF_MIX, BSDF_MIRROR, BSDF_GLASS = range(6)
+
+
+class Vec3(ctypes.Structure):
+    _fields_ = [("x", c_float), ("y", c_float), ("z", c_float)]
+
+
+class Settings(ctypes.Structure):
+    """src/dummy_main.impala:3-13"""
+    _fields_ = [("eye", Vec3), ("dir", Vec3), ("up", Vec3), ("right", Vec3), ("width", c_float), ("height", c_float)]
+
+
+class SceneView(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("num_tris", "num_vertices", "num_materials", "num_lights", "num_nodes", "num_tri4")] + \
+               [(n, c_void_p) for n in ("vertices", "normals", "face_normals", "texcoords", "indices", "light_ids",
+                                        "materials", "lights", "nodes", "tris")]
+
+
+# symbol -> (restype, argtypes) of the scene / renderer part of include/rodent_b200.h
+SIGNATURES = {
+    "rodent_b200_scene_load_obj": (c_void_p, [ctypes.c_char_p]),
+    "rodent_b200_scene_from_bvh8": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32]),
+    "rodent_b200_scene_view": (None, [c_void_p, POINTER(SceneView)]),
+    "rodent_b200_scene_free": (None, [c_void_p]),
+    "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
+    "rodent_b200_renderer_free": (None, [c_void_p]),
+    "rodent_b200_render": (None, [c_void_p, POINTER(Settings), c_int32]),
+    "rodent_b200_render_device": (None, [c_void_p, POINTER(Settings), c_int32]),
+    "rodent_b200_present": (None, [c_void_p]),
+    "rodent_b200_film": (POINTER(c_float), [c_void_p]),
+    "rodent_b200_film_device": (c_void_p, [c_void_p]),
+    "rodent_b200_clear": (None, [c_void_p]),
+    "rodent_b200_render_stats": (None, [c_void_p, POINTER(c_int64)]),
+    "rodent_b200_render_last_ms": (ctypes.c_double, [c_void_p]),
+    "rodent_b200_bind": (None, [c_void_p, c_int32, c_int32, c_int32]),
+    "setup_interface": (None, [ctypes.c_size_t, ctypes.c_size_t]),
+    "cleanup_interface": (None, []),
+    "get_pixels": (POINTER(c_float), []),
+    "clear_pixels": (None, []),
+    "get_spp": (c_int32, []),
+    "render": (None, [POINTER(Settings), c_int32]),
+}
+
+
+def _bind(L):
+    if not getattr(L, "_render_bound", False):
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        L._render_bound = True
+    return L
+
+
+def camera(eye, direction, up, fov: float, width: int, height: int) -> Settings:
+    """Camera::Camera of src/driver/driver.cpp:31-38 in fp32."""
+    f = np.float32
+    d = np.asarray(direction, f)
+    u = np.asarray(up, f)
+
+    def norm(v):
+        return (v * (f(1.0) / np.sqrt((v * v).sum(dtype=f), dtype=f))).astype(f)
+
+    d = norm(d)
+    r = norm(np.cross(d, u).astype(f))
+    u = norm(np.cross(r, d).astype(f))
+    w = f(math.tan(float(f(fov) * f(3.14159265359) / f(360.0))))
+    h = f(w / f(f(width) / f(height)))
+    return Settings(Vec3(*map(float, eye)), Vec3(*map(float, d)), Vec3(*map(float, u)), Vec3(*map(float, r)), float(w), float(h))
+
+
+class Scene:
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("scene could not be created (see stderr)")
+        self.handle = c_void_p(handle)
+        self._view = SceneView()
+        _bind(lib.load()).rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+
+    @classmethod
+    def load_obj(cls, path) -> "Scene":
+        return cls(_bind(lib.load()).rodent_b200_scene_load_obj(str(path).encode()))
+
+    @classmethod
+    def from_bvh8(cls, nodes: np.ndarray, tris: np.ndarray, materials: np.ndarray, material_of_prim: np.ndarray) -> "Scene":
+        materials = np.ascontiguousarray(materials, MATERIAL)
+        mop = np.ascontiguousarray(material_of_prim, np.int32)
+        return cls(_bind(lib.load()).rodent_b200_scene_from_bvh8(nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris),
+                                                                  materials.ctypes.data, len(materials), mop.ctypes.data, len(mop)))
+
+    @property
+    def view(self) -> SceneView:
+        return self._view
+
+    def array(self, name: str) -> np.ndarray:
+        from . import formats
+        v = self._view
+        table = {"vertices": ((v.num_vertices, 4), np.float32), "normals": ((v.num_vertices, 4), np.float32),
+                 "face_normals": ((v.num_tris, 4), np.float32), "texcoords": ((v.num_vertices, 4), np.float32),
+                 "indices": ((v.num_tris, 4), np.int32), "light_ids": ((v.num_tris,), np.int32),
+                 "materials": ((v.num_materials,), MATERIAL), "lights": ((v.num_lights,), LIGHT),
+                 "nodes": ((v.num_nodes,), formats.NODE8), "tris": ((v.num_tri4,), formats.TRI4)}
+        shape, dt = table[name]
+        n = int(np.prod(shape)) * np.dtype(dt).itemsize
+        if n == 0:
+            return np.zeros(shape, dt)
+        buf = (ctypes.c_char * n).from_address(getattr(v, name))
+        return np.frombuffer(buf, dt).reshape(shape)
+
+    def free(self):
+        if self.handle:
+            lib.load().rodent_b200_scene_free(self.handle)
+            self.handle = None
+
+
+class Renderer:
+    """Wavefront path tracer on one device (rodent_b200_renderer_*)."""
+
+    def __init__(self, scene: Scene, dev: int, width: int, height: int, spp: int, max_path_len: int,
+                 part: int = 0, num_parts: int = 1, band: int = 8):
+        self.L = _bind(lib.load())
+        self.scene, self.width, self.height, self.spp = scene, width, height, spp
+        self.handle = c_void_p(self.L.rodent_b200_renderer_create(scene.handle, dev, width, height, spp, max_path_len, part, num_parts, band))
+        if not self.handle:
+            raise RuntimeError("renderer could not be created")
+
+    def render(self, settings: Settings, iteration: int, present: bool = True) -> float:
+        (self.L.rodent_b200_render if present else self.L.rodent_b200_render_device)(self.handle, ctypes.byref(settings), iteration)
+        return self.L.rodent_b200_render_last_ms(self.handle)
+
+    def present(self):
+        self.L.rodent_b200_present(self.handle)
+
+    def clear(self):
+        self.L.rodent_b200_clear(self.handle)
+
+    def film(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.L.rodent_b200_film(self.handle), (self.height, self.width, 3))
+
+    def film_device_ptr(self) -> int:
+        return self.L.rodent_b200_film_device(self.handle)
+
+    def stats(self) -> dict:
+        out = (c_int64 * 5)()
+        self.L.rodent_b200_render_stats(self.handle, out)
+        return dict(zip(("samples", "primary_rays", "shadow_rays", "wavefronts", "kernels"), map(int, out)))
+
+    def free(self):
+        if self.handle:
+            self.L.rodent_b200_renderer_free(self.handle)
+            self.handle = None
+
+
+def tonemap(film: np.ndarray, iterations: int) -> np.ndarray:
+    """save_image of src/driver/driver.cpp:138-162: clamp((film / iter) ^ (1/2.2)) * 255, truncated to 8 bit."""
+    f = np.float32
+    x = np.power(np.maximum(film.astype(f) * f(1.0 / iterations), f(0)), f(1.0 / 2.2), dtype=f)
+    return (np.clip(x, f(0), f(1)) * f(255.0)).astype(np.uint8)

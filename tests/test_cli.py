@@ -1,0 +1,81 @@
+"""bench_traversal / fbuf2png command lines (the reference's CTest procedure,
+cmake/test/run_traversal.cmake:1-12, README.md:33-40)."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from rodent_b200 import build, formats, testdata
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def tools():
+    build.build_cuda()
+    build.build_tools()
+    return ROOT / "tools" / "bin"
+
+
+def run(*cmd):
+    return subprocess.run([str(c) for c in cmd], capture_output=True, text=True)
+
+
+def test_bench_traversal_argument_errors(tools):
+    exe = tools / "bench_traversal"
+    assert run(exe, "--help").returncode == 0
+    for args, msg in ((["-ray", "x"], "No BVH file specified"), (["-bvh", "x"], "No ray file specified"),
+                      (["-bvh"], "Missing argument for -bvh"), (["--frobnicate"], "Unknown option '--frobnicate'"),
+                      (["stray"], "Invalid argument 'stray'"), (["-gpu", "opencl", "-bvh", "a", "-ray", "b"], "Unknown GPU platform 'opencl'"),
+                      (["-bvh", "a", "-ray", "b", "-gpu", "cuda", "-s"], "Options '--gpu' and '--single' are incompatible"),
+                      (["-bvh", "a", "-ray", "b", "-p", "-s"], "Options '--packet' and '--single' are incompatible"),
+                      (["-bvh", "a", "-ray", "b", "--bvh-width", "3"], "Invalid BVH width"),
+                      (["-bvh", "a", "-ray", "b", "--ray-width", "5"], "Invalid ray width"),
+                      (["-bvh", "/nonexistent", "-ray", "b", "-s", "--bvh-width", "8"], "Cannot load BVH file")):
+        r = run(exe, *args)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    # variants this library does not provide end like variant_not_available(): message + abort
+    r = run(exe, "-bvh", "a", "-ray", "b")
+    assert r.returncode < 0 and "cpu_intersect_hybrid_ray8_bvh4_tri4 is not provided" in r.stderr
+
+
+def test_fbuf2png_matches_reference_quantisation(tools, tmp_path, oracle_hits):
+    for name in ("primary", "random"):
+        formats.save_fbuf(tmp_path / f"{name}.fbuf", oracle_hits[name])
+        assert run(tools / "fbuf2png", "-n", tmp_path / f"{name}.fbuf", tmp_path / f"{name}.png").returncode == 0
+        got = np.array(Image.open(tmp_path / f"{name}.png"))
+        ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))
+        assert got.shape == ref.shape and int((got[..., 0] != ref[..., 0]).sum()) <= 2
+        assert (got[..., 3] == 255).all()
+    assert run(tools / "fbuf2png", tmp_path / "primary.fbuf").returncode == 1
+    (tmp_path / "short.fbuf").write_bytes(b"\0" * 100)
+    assert run(tools / "fbuf2png", tmp_path / "short.fbuf", tmp_path / "x.png").returncode == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [["-gpu", "cuda"], ["-s", "--bvh-width", "8"]])
+@pytest.mark.parametrize("name,tmin,tmax,hits", [("primary", "0.01", "5000", None), ("random", "0", "1", 959359)])
+def test_ctest_procedure_on_gpu(tools, tmp_path, mode, name, tmin, tmax, hits):
+    fbuf = tmp_path / "out.fbuf"
+    r = run(tools / "bench_traversal", "-bvh", testdata.sponza_bvh8(), "-ray", testdata.rays(name), "--bench", "3", "--warmup", "1",
+            "--tmin", tmin, "--tmax", tmax, "-o", fbuf, *mode)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "1048576 ray(s) in the distribution file." in out
+    assert re.search(r"ms for 3 iteration\(s\)\n[\d.e+]+ Mrays/sec\n# Average: .* ms\n# Median: .* ms\n# Min: .* ms\n(\d+) intersection\(s\)", out)
+    if hits is not None:
+        assert f"{hits} intersection(s)" in out
+    assert run(tools / "fbuf2png", "-n", fbuf, tmp_path / "out.png").returncode == 0
+    got = np.array(Image.open(tmp_path / "out.png"))[..., 0]
+    ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
+    assert int((got != ref).sum()) <= 2      # ImageMagick `compare -metric MSE` in the reference's CTest
+
+
+@pytest.mark.gpu
+def test_any_hit_cli(tools):
+    r = run(tools / "bench_traversal", "-bvh", testdata.sponza_bvh8(), "-ray", testdata.rays("random"), "--tmax", "1", "-gpu", "cuda", "-any")
+    assert r.returncode == 0 and "959359 intersection(s)" in r.stdout
