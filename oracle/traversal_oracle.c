@@ -31,6 +31,12 @@
 
 typedef struct { int32_t node; float tmin; } NodeRef;
 
+/* Optional step trace for scheduling studies (scripts/sim_sched.c defines it): one
+ * call per inner-node visit ('N') and per Tri4 packet ('L').  Empty in the oracle build. */
+#ifndef ORACLE_TRACE
+#define ORACLE_TRACE(kind) ((void)0)
+#endif
+
 /* Work counters, for the roofline's algorithmic bytes. */
 typedef struct OracleStats {
     uint64_t nodes;   /* inner nodes popped and box-tested  */
@@ -209,7 +215,7 @@ void traverse_single(const int N, const int any_hit,
 
     for (;;) {
         if (top_node == 0) break;                                        /* :168 */
-        if (!any_hit && top_t > tmax) { POP(); continue; }               /* :170-174 */
+        if (!any_hit && top_t > tmax) { POP(); ORACLE_TRACE('c'); continue; }   /* :170-174 */
 
         int restart = 0;
         while (top_node > 0) {                                           /* :177 */
@@ -217,6 +223,7 @@ void traverse_single(const int N, const int any_hit,
             const int32_t* child = (const int32_t*)(nb + 6 * N);
             POP();
             n_nodes++;
+            ORACLE_TRACE('N');
 
             /* intersect_ray_box ordered, intersection.impala:194-208, integer min/max */
             float tentry[8]; int mask = 0;
@@ -233,6 +240,7 @@ void traverse_single(const int N, const int any_hit,
                 mask |= (f2i(tx) < f2i(te) ? 0 : 1) << i;                /* :184 */
             }
             if (mask == 0) {                                             /* :189-191 */
+                ORACLE_TRACE('0');
                 if (any_hit) continue;
                 restart = 1; break;
             }
@@ -247,6 +255,7 @@ void traverse_single(const int N, const int any_hit,
                 else                      PUSH_AFTER(child_id, t);
             }
             if (ptr > max_ptr) max_ptr = ptr;
+            ORACLE_TRACE('0' + num_intrs);
 
             if (!any_hit && num_intrs >= 3) {                            /* :210-218, stack.impala:79-111 */
                 NodeRef* e = &st[ptr - num_intrs + 1];
@@ -268,6 +277,7 @@ void traverse_single(const int N, const int any_hit,
         for (;;) {
             const Tri4* tp = &tris[prim_id++];
             n_tri4++;
+            ORACLE_TRACE('L');
             float lt[4], lu[4], lv[4]; int hm = 0;
             for (int j = 0; j < 4; j++) {
                 lt[j] = FLT_MAX_; lu[j] = 0.0f; lv[j] = 0.0f;
