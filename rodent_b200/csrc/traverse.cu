@@ -17,6 +17,7 @@
 
 #include "traverse.cuh"
 #include "traverse_quad.cuh"
+#include "traverse_sched.cuh"
 
 namespace rb200 {
 
@@ -25,7 +26,10 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kSmemStackDepth = 16;  // stack levels kept in shared memory by the persistent thread-per-ray kernel
 
 struct Tuning {
-    int mapping = 1;         // lanes per ray: 4 = quad kernel (traverse_quad.cuh), 1 = thread per ray (traverse.cuh)
+    int mapping = 2;         // 2 = vote-scheduled thread per ray (traverse_sched.cuh), 1 = while-while thread per ray (traverse.cuh),
+                             // 4 = four lanes per ray (traverse_quad.cuh)
+    int refill_min = 16;     // (mapping 2) refill idle lanes once this many wait
+    int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
     int refill_below = 8;    // refill a warp when fewer than this many lanes are busy
@@ -107,6 +111,23 @@ traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict
 }
 
 
+// Vote-scheduled persistent kernel (traverse_sched.cuh): the default.
+constexpr int kVoteSmemDepth = 24;
+template <bool ANY, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
+traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                   int* __restrict__ work_counter, int refill_min) {
+    __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
+        [rays](int i, float4& r0, float4& r1) {
+            const float4* rp = reinterpret_cast<const float4*>(rays + i);
+            r0 = ldg4(rp); r1 = ldg4(rp + 1);
+        },
+        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); });
+}
+
 // Quad-per-ray persistent kernel: eight rays per warp (traverse_quad.cuh).  Idle quads are
 // refilled together: one atomicAdd per warp, ray index = base + rank of the quad among the
 // idle ones (ballot + popc).
@@ -174,6 +195,7 @@ struct DeviceState {
     double last_ms = 0.0;
     int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
     int occ_quad[2] = {0, 0};
+    int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
@@ -205,6 +227,12 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[1], traverse_bvh8_persistent<true>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[0], traverse_bvh8_quad<false>, kQuadBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[1], traverse_bvh8_quad<true>, kQuadBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[0][0], traverse_bvh8_vote<false, 4>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[0][1], traverse_bvh8_vote<true, 4>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][0], traverse_bvh8_vote<false, 5>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][1], traverse_bvh8_vote<true, 5>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][0], traverse_bvh8_vote<false, 6>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
             s.init = true;
         }
     }
@@ -215,7 +243,17 @@ template <bool ANY>
 static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
                    int num_rays, cudaStream_t stream, int* counter) {
     if (num_rays <= 0) return;
-    if (g_tuning.mapping == 4) {
+    if (g_tuning.mapping == 2) {
+        if (!counter) counter = s.counter;
+        RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        const int v = std::min(std::max(g_tuning.vote_min_blocks, 4), 6) - 4;
+        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_vote[v][ANY ? 1 : 0];
+        const int needed = (num_rays + kBlock - 1) / kBlock;
+        const int grid = std::min(needed, s.sm_count * per_sm);
+        if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
+        if (v == 1) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
+        if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
+    } else if (g_tuning.mapping == 4) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_quad[ANY ? 1 : 0];
@@ -390,6 +428,8 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "mapping")) g_tuning.mapping = value;
     else if (!std::strcmp(key, "quad_refill_below")) g_tuning.quad_refill_below = value;
     else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = value;
+    else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = value;
+    else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = value;
     else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }

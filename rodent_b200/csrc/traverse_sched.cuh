@@ -1,0 +1,240 @@
+// Vote-scheduled persistent BVH8/Tri4 traversal for sm_100a: one ray per lane, but the warp
+// decides together which kind of step runs next.
+//
+// The reference's single-ray loop (cpu_traverse_single_helper, src/traversal/mapping_cpu.impala:
+// 138-256) alternates between two bodies: an inner-node visit (8 slab tests, pushes, sort) and a
+// Tri4 test.  When 32 rays run it as 32 independent per-lane loops ("while-while", as in
+// tools/bench_aila/kepler_dynamic_fetch.cu:70-371), the hardware serialises the two bodies and
+// every nested loop exit; on the incoherent Sponza set that left 6.5 of 32 lanes active in the
+// node body and 1.9 in the leaf body (profiles/r01_traverse_thread_blocks.txt).  Here each ray
+// is an explicit state machine whose transitions are exactly the reference's, and the warp runs
+// ONE straight-line step per iteration, chosen by majority vote (__ballot_sync + __popc) between
+// the lanes that need a node step and those that need a Tri4 step; lanes of the other kind wait
+// with their state in registers.  Finished lanes are refilled from a global counter together
+// (one atomicAdd per warp, ranks from the ballot), as before.
+//
+// Per-ray order of node visits, pushes, sorts, Tri4 tests and tie-breaks is untouched, so hit
+// records stay bit-identical to the oracle; only the interleaving BETWEEN rays changes.
+#pragma once
+
+#include "traverse.cuh"
+
+namespace rb200 {
+
+// The memory part of the traversal stack (stack.impala:53-54: 64 entries): the first SMEM_DEPTH
+// levels in shared memory, [level][thread] so a warp's accesses to one level are conflict-free;
+// deeper levels (< 0.1 % of the accesses on Sponza at depth 24) go to a thread-local array that
+// is a separate object, so that the walker's scalar state stays in registers.
+template <int SMEM_DEPTH, int BLOCK>
+struct SplitStack {
+    StackEntry* smem;                                   // this thread's column
+    StackEntry* overflow;                               // kStackSize - SMEM_DEPTH thread-local entries
+    __device__ __forceinline__ StackEntry load(int i) const {
+        if (i < SMEM_DEPTH) return smem[i * BLOCK];
+        return overflow[i - SMEM_DEPTH];
+    }
+    __device__ __forceinline__ void store(int i, StackEntry e) {
+        if (i < SMEM_DEPTH) smem[i * BLOCK] = e;
+        else overflow[i - SMEM_DEPTH] = e;
+    }
+};
+
+template <bool ANY, int SMEM_DEPTH, int BLOCK>
+struct RayWalker {
+    RaySetup ray;
+    float tmax;
+    int top_node; float top_t; int ptr;
+    int leaf;                       // next Tri4 of the leaf being tested, -1 when not inside a leaf
+    HitRecord hit;
+    SplitStack<SMEM_DEPTH, BLOCK> st;
+
+    __device__ __forceinline__ void push(int n, float t) { ++ptr; st.store(ptr, StackEntry{top_node, top_t}); top_node = n; top_t = t; }
+    __device__ __forceinline__ void push_after(int n, float t) { ++ptr; st.store(ptr, StackEntry{n, t}); }
+    __device__ __forceinline__ void pop() { const StackEntry e = st.load(ptr); top_node = e.node; top_t = e.tmin; --ptr; }
+
+    // The head of the reference's outer loop (:168-174): drop entries that start behind the current hit.
+    __device__ __forceinline__ void cull() {
+        if (ANY) return;
+        while (top_node != 0 && top_t > tmax) pop();
+    }
+
+    __device__ __forceinline__ void begin(float4 r0, float4 r1) {
+        ray.init(r0, r1);
+        tmax = r1.w;
+        hit.prim = -1; hit.geom = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;   // empty_hit, intersection.impala:134-136
+        ptr = -1; top_node = 0; top_t = kFltMax; leaf = -1;
+        push(1, ray.tmin);                                                          // :153
+        cull();
+    }
+
+    __device__ __forceinline__ bool finished() const { return leaf < 0 && top_node == 0; }
+    __device__ __forceinline__ bool wants_node() const { return leaf < 0 && top_node > 0; }
+    __device__ __forceinline__ bool wants_leaf() const { return leaf >= 0 || top_node < 0; }
+
+    // One iteration of the inner `while (top_node > 0)` loop (:177-219).
+    template <bool X86_NAN>
+    __device__ __forceinline__ void node_step(const Node8* __restrict__ nodes) {
+        const float4* nb = reinterpret_cast<const float4*>(nodes + (top_node - 1));
+        pop();
+        const float4 nxa = ldg4(nb + ray.near_x), nxb = ldg4(nb + ray.near_x + 1);
+        const float4 nya = ldg4(nb + ray.near_y), nyb = ldg4(nb + ray.near_y + 1);
+        const float4 nza = ldg4(nb + ray.near_z), nzb = ldg4(nb + ray.near_z + 1);
+        const float4 fxa = ldg4(nb + ray.far_x), fxb = ldg4(nb + ray.far_x + 1);
+        const float4 fya = ldg4(nb + ray.far_y), fyb = ldg4(nb + ray.far_y + 1);
+        const float4 fza = ldg4(nb + ray.far_z), fzb = ldg4(nb + ray.far_z + 1);
+        const int4 ca = ldg4(reinterpret_cast<const int4*>(nb) + 12), cb = ldg4(reinterpret_cast<const int4*>(nb) + 13);
+
+        const float nx[8] = {nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w};
+        const float ny[8] = {nya.x, nya.y, nya.z, nya.w, nyb.x, nyb.y, nyb.z, nyb.w};
+        const float nz[8] = {nza.x, nza.y, nza.z, nza.w, nzb.x, nzb.y, nzb.z, nzb.w};
+        const float fx[8] = {fxa.x, fxa.y, fxa.z, fxa.w, fxb.x, fxb.y, fxb.z, fxb.w};
+        const float fy[8] = {fya.x, fya.y, fya.z, fya.w, fyb.x, fyb.y, fyb.z, fyb.w};
+        const float fz[8] = {fza.x, fza.y, fza.z, fza.w, fzb.x, fzb.y, fzb.z, fzb.w};
+        const int child[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+
+        // ordered slab test, intersection.impala:194-208 with integer min/max (:123-133, :184)
+        float tentry[8];
+        unsigned mask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float t0x = slab<X86_NAN>(ray.idx, nx[i], ray.iox);
+            const float t0y = slab<X86_NAN>(ray.idy, ny[i], ray.ioy);
+            const float t0z = slab<X86_NAN>(ray.idz, nz[i], ray.ioz);
+            const float t1x = slab<X86_NAN>(ray.idx, fx[i], ray.iox);
+            const float t1y = slab<X86_NAN>(ray.idy, fy[i], ray.ioy);
+            const float t1z = slab<X86_NAN>(ray.idz, fz[i], ray.ioz);
+            const float te = imax2(imax3(t0x, t0y, t0z), ray.tmin);
+            const float tx = imin2(imin3(t1x, t1y, t1z), tmax);
+            tentry[i] = te;
+            if (!(__float_as_int(tx) < __float_as_int(te))) mask |= 1u << i;
+        }
+        if (mask == 0) {
+            // :189-191.  Closest hit: back to the head of the outer loop (cull, then whatever is on top).
+            // Any hit: `continue` of the inner loop, no culling in that mode anyway.
+            cull();
+            return;
+        }
+        // pushes in lane order, :195-208
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (mask & (1u << i)) {
+                if (ANY || tentry[i] < top_t) push(child[i], tentry[i]);
+                else push_after(child[i], tentry[i]);
+            }
+        }
+        if (!ANY) {                                                                  // :210-218
+            const int n = __popc(mask);
+            if (n >= 3) sort_entries(st, ptr - n + 1, n);
+        }
+        // The reference goes on with the new top without a cull check (inner loop / :221-224).
+    }
+
+    // One Tri4 packet of the leaf loop (:224-249).  Returns true when an any-hit ray terminated (:252).
+    template <bool WANT_GEOM>
+    __device__ __forceinline__ bool leaf_step(const Tri4* __restrict__ tris) {
+        if (leaf < 0) { leaf = ~top_node; pop(); }                                   // :224-225
+        const float4* tp = reinterpret_cast<const float4*>(tris + leaf);
+        const int4 pid = ldg4(reinterpret_cast<const int4*>(tp) + 12);
+        const float4 v0x = ldg4(tp + 0), v0y = ldg4(tp + 1), v0z = ldg4(tp + 2);
+        const float4 e1x = ldg4(tp + 3), e1y = ldg4(tp + 4), e1z = ldg4(tp + 5);
+        const float4 e2x = ldg4(tp + 6), e2y = ldg4(tp + 7), e2z = ldg4(tp + 8);
+        const float4 nnx = ldg4(tp + 9), nny = ldg4(tp + 10), nnz = ldg4(tp + 11);
+
+        float lt[4], lu[4], lv[4];
+        unsigned hm = 0;
+#define RB_LANE(j, c)                                                                               \
+        lt[j] = kFltMax; lu[j] = 0.0f; lv[j] = 0.0f;                                                \
+        if (pid.c != -1 &&                                                                          \
+            intersect_tri_lane(ray, tmax, v0x.c, v0y.c, v0z.c, e1x.c, e1y.c, e1z.c,                 \
+                               e2x.c, e2y.c, e2z.c, nnx.c, nny.c, nnz.c, lt[j], lu[j], lv[j]))      \
+            hm |= 1u << j;
+        RB_LANE(0, x) RB_LANE(1, y) RB_LANE(2, z) RB_LANE(3, w)
+#undef RB_LANE
+        if (hm) {
+            int lane;
+            if (ANY) {
+                lane = __ffs(hm) - 1;                                                // :234-237 (hit.prim >= 0 is `terminated`)
+            } else {
+                // cpu_reduce with integer min, then first lane equal to it (:239-242)
+                const float mn = imin2(imin2(lt[0], lt[2]), imin2(lt[1], lt[3]));
+                lane = lt[0] == mn ? 0 : lt[1] == mn ? 1 : lt[2] == mn ? 2 : 3;
+            }
+            const int p = lane == 0 ? pid.x : lane == 1 ? pid.y : lane == 2 ? pid.z : pid.w;
+            hit.prim = p & 0x7FFFFFFF;                                               // mapping_cpu.impala:34
+            hit.t = lane == 0 ? lt[0] : lane == 1 ? lt[1] : lane == 2 ? lt[2] : lt[3];
+            hit.u = lane == 0 ? lu[0] : lane == 1 ? lu[1] : lane == 2 ? lu[2] : lu[3];
+            hit.v = lane == 0 ? lv[0] : lane == 1 ? lv[1] : lane == 2 ? lv[2] : lv[3];
+            if (WANT_GEOM) {
+                const int4 gid = ldg4(reinterpret_cast<const int4*>(tp) + 13);
+                hit.geom = lane == 0 ? gid.x : lane == 1 ? gid.y : lane == 2 ? gid.z : gid.w;
+            }
+            if (!ANY) tmax = hit.t;                                                  // :243
+        }
+        if (pid.w < 0) {                                                             // is_last, mapping_cpu.impala:40
+            leaf = -1;
+            if (ANY && hit.prim >= 0) { top_node = 0; return true; }                 // :252: the leaf is finished first
+            cull();                                                                  // back to the head of the outer loop
+        } else {
+            leaf++;
+        }
+        return false;
+    }
+};
+
+// The persistent loop shared by the bench_traversal kernels and the renderer's stream kernels.
+//   fetch(i, r0, r1)  loads ray i (origin+tmin, direction+tmax)
+//   sink(i, hit)      consumes the finished ray's record
+// `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
+template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
+__device__ __forceinline__ void traverse_vote_scheduled(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                                                        StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
+                                                        int refill_min, Fetch fetch, Sink sink) {
+    const unsigned lane = lane_id();
+    StackEntry overflow[kStackSize - SMEM_DEPTH];
+    RayWalker<ANY, SMEM_DEPTH, BLOCK> w;
+    w.st.smem = smem_column;
+    w.st.overflow = overflow;
+    w.leaf = -1; w.top_node = 0;
+    int ray_idx = -1;
+    bool drained = false;
+    for (;;) {
+        // a finished ray leaves its lane
+        if (ray_idx >= 0 && w.finished()) { sink(ray_idx, w.hit); ray_idx = -1; }
+        // ---- refill idle lanes: one atomicAdd per warp, ranks from ballot/popc ----
+        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
+        if (!drained && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ray_idx < 0) {
+                const int i = base + __popc(idle & lanemask_lt());
+                if (i < num_rays) {
+                    ray_idx = i;
+                    float4 r0, r1;
+                    fetch(i, r0, r1);
+                    w.begin(r0, r1);
+                }
+            }
+            if (base + __popc(idle) >= num_rays) drained = true;
+        }
+        const bool has = ray_idx >= 0;
+        const bool want_n = has && w.wants_node();
+        const bool want_l = has && w.wants_leaf();
+        const unsigned bn = __ballot_sync(0xffffffffu, want_n), bl = __ballot_sync(0xffffffffu, want_l);
+        if ((bn | bl) == 0) {
+            if (__ballot_sync(0xffffffffu, has) == 0 && drained) break;
+            continue;                       // only lanes whose fresh ray was culled at once; they leave next round
+        }
+        if (__popc(bn) >= __popc(bl)) {
+            // rays with a clamped axis need the x86 NaN pattern (RaySetup::degenerate); that variant is a
+            // superset of the plain one, so the whole warp takes it when any of its lanes does
+            if (__ballot_sync(0xffffffffu, want_n && w.ray.degenerate) != 0) { if (want_n) w.template node_step<true>(nodes); }
+            else                                                            { if (want_n) w.template node_step<false>(nodes); }
+        } else {
+            if (want_l) w.template leaf_step<WANT_GEOM>(tris);
+        }
+    }
+}
+
+}  // namespace rb200

@@ -40,9 +40,10 @@ def assert_records_equal(got, want):
         raise AssertionError(f"{len(bad)} of {len(got)} records differ, first: ray {bad[0]} got {got[bad[0]]} want {want[bad[0]]}")
 
 
-# kernel variants: the default quad-per-ray kernel, and the thread-per-ray kernels
-VARIANTS = {"quad": {"mapping": 4}, "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
-DEFAULTS = {"mapping": 1, "persistent": 1}
+# kernel variants: the default vote-scheduled kernel, the while-while thread-per-ray kernels and the quad-per-ray kernel
+VARIANTS = {"vote": {"mapping": 2}, "vote-refill1": {"mapping": 2, "refill_min": 1}, "quad": {"mapping": 4},
+            "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
+DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 16}
 
 
 @pytest.fixture(params=list(VARIANTS))
