@@ -28,7 +28,7 @@ constexpr int kSmemStackDepth = 16;  // stack levels kept in shared memory by th
 struct Tuning {
     int mapping = 2;         // 2 = vote-scheduled thread per ray (traverse_sched.cuh), 1 = while-while thread per ray (traverse.cuh),
                              // 4 = four lanes per ray (traverse_quad.cuh)
-    int refill_min = 16;     // (mapping 2) refill idle lanes once this many wait
+    int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
     int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy

@@ -14,9 +14,8 @@ def main():
         rays = formats.load_rays(testdata.rays(name), tmin, tmax)
         sets[name] = (traversal.DeviceArray.from_host(0, rays), traversal.DeviceArray(0, formats.HIT1, len(rays)))
     configs = [dict(mapping=1, persistent=1, refill_below=8), dict(mapping=4, blocks_per_sm=0, quad_refill_below=0)]
-    for mb in (4, 5, 6):
-        for rm in (16, 24):
-            configs.append(dict(mapping=2, refill_min=rm, vote_min_blocks=mb))
+    for rm in (8, 16, 24):
+        configs.append(dict(mapping=2, refill_min=rm))
     extra = [a for a in sys.argv[1:]]
     for cfg in configs:
         for k, v in cfg.items():

@@ -43,7 +43,7 @@ def assert_records_equal(got, want):
 # kernel variants: the default vote-scheduled kernel, the while-while thread-per-ray kernels and the quad-per-ray kernel
 VARIANTS = {"vote": {"mapping": 2}, "vote-refill1": {"mapping": 2, "refill_min": 1}, "quad": {"mapping": 4},
             "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
-DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 16}
+DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 24}
 
 
 @pytest.fixture(params=list(VARIANTS))
