@@ -25,13 +25,14 @@
 
 #include "scene.h"
 #include "shading.cuh"
-#include "traverse.cuh"
+#include "traverse_sched.cuh"
 
 namespace rb200 {
 
 constexpr int kCapacity = 1 << 20;           // mapping_gpu.impala:319
 constexpr int kRBlock = 128;
-constexpr int kRSmemStack = 12;
+constexpr int kRSmemStack = 24;
+constexpr int kRefillMin = 16;                // idle lanes that trigger a refill of the warp (traverse_sched.cuh)
 constexpr int kMaxBins = 1025;                // <= 1024 geometries + the miss bin (mapping_gpu.impala:202)
 
 struct PrimaryStream {                        // src/render/driver.impala:36-52
@@ -85,67 +86,41 @@ generate_rays(PrimaryStream s, int first_ray_id, int first_dst, int n, CameraDev
 // SHADOW = false: closest hit, hit record + geometry id + per-material count.
 // SHADOW = true : any hit; unoccluded rays add their colour to the film.
 template <bool SHADOW>
-__global__ void __launch_bounds__(kRBlock, 6)
+__global__ void __launch_bounds__(kRBlock, 5)
 traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                 const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
                 float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
                 const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
-                int* __restrict__ work_counter, int refill_below) {
+                int* __restrict__ work_counter, int refill_min) {
     __shared__ StackEntry smem_stack[kRSmemStack][kRBlock];
-    __shared__ int busy_lanes[kRBlock / 32];
     __shared__ int hist[SHADOW ? 1 : kMaxBins];
     const int num_rays = count_ptr ? min(*count_ptr, count_max) : count_max;
     if (!SHADOW) {
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
         __syncthreads();
     }
-    const unsigned lane = lane_id();
-    volatile int* busy = &busy_lanes[threadIdx.x >> 5];
-    Traversal<SHADOW, kRSmemStack, kRBlock> tr;
-    tr.st.smem = &smem_stack[0][threadIdx.x];
-    int ray_idx = -1;
-    bool drained = false;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
-        if (idle != 0 && !drained) {
-            const int leader = __ffs(idle) - 1;
-            int base = 0;
-            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (ray_idx < 0) {
-                const int i = base + __popc(idle & lanemask_lt());
-                if (i < num_rays) { ray_idx = i; tr.begin(__ldg(ray_o + i), __ldg(ray_d + i)); }
-            }
-            if (base + __popc(idle) >= num_rays) drained = true;
-        }
-        const unsigned active = __ballot_sync(0xffffffffu, ray_idx >= 0);
-        if (active == 0) break;
-        if (lane == 0) *busy = __popc(active);
-        __syncwarp();
-        if (ray_idx >= 0) {
-            const bool done = tr.template run<!SHADOW>(nodes, tris, [&] { return !drained && *busy < refill_below; });
-            if (done) {
-                if (SHADOW) {
-                    if (tr.hit.prim < 0) {                                     // gpu_accumulate, mapping_gpu.impala:32-45
-                        const int p = __ldg(pixels + ray_idx);
-                        const float4 c = __ldg(colors + ray_idx);
-                        atomicAdd(film + 3 * p + 0, c.x * inv_spp);
-                        atomicAdd(film + 3 * p + 1, c.y * inv_spp);
-                        atomicAdd(film + 3 * p + 2, c.z * inv_spp);
-                    }
-                } else {
-                    // make_primary_stream_hit_writer, driver.impala:106-115
-                    const int g = tr.hit.prim < 0 ? num_geoms : tr.hit.geom;
-                    hit_out[ray_idx] = make_float4(__int_as_float(tr.hit.prim), tr.hit.t, tr.hit.u, tr.hit.v);
-                    geom_out[ray_idx] = g;
-                    atomicAdd(&hist[g], 1);
+    int* const hist_bins = hist;
+    // the vote-scheduled persistent loop of traverse_sched.cuh, fed from / draining into the SoA streams
+    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
+        [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
+        [=](int i, const HitRecord& h) {
+            if (SHADOW) {
+                if (h.prim < 0) {                                              // gpu_accumulate, mapping_gpu.impala:32-45
+                    const int p = __ldg(pixels + i);
+                    const float4 c = __ldg(colors + i);
+                    atomicAdd(film + 3 * p + 0, c.x * inv_spp);
+                    atomicAdd(film + 3 * p + 1, c.y * inv_spp);
+                    atomicAdd(film + 3 * p + 2, c.z * inv_spp);
                 }
-                ray_idx = -1;
-                atomicSub(const_cast<int*>(busy), 1);
+            } else {
+                // make_primary_stream_hit_writer, driver.impala:106-115
+                const int g = h.prim < 0 ? num_geoms : h.geom;
+                hit_out[i] = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
+                geom_out[i] = g;
+                atomicAdd(hist_bins + g, 1);
             }
-        }
-        __syncwarp();
-    }
+        });
     if (!SHADOW) {
         __syncthreads();
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
@@ -409,14 +384,14 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
         RB_CUDA_CHECK(cudaMemsetAsync(r.counters, 0, kNumCounters * sizeof(int), s));
         const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
         traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, r.counters + kWorkPrimary, 8);
+                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, r.counters + kWorkPrimary, kRefillMin);
         scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, r.counters);
         scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, Q, size, num_geoms, r.cursor);
         shade_rays<<<(size + 127) / 128, 128, 0, s>>>(Q, P, r.shadow, r.scene, r.counters, r.film, inv_spp, r.max_path_len);
         const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
         traverse_stream<true><<<grid_s, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, r.counters + kShadows, size,
                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
-                                                         r.counters + kWorkShadow, 8);
+                                                         r.counters + kWorkShadow, kRefillMin);
         RB_CUDA_CHECK(cudaGetLastError());
         RB_CUDA_CHECK(cudaMemcpyAsync(r.h_counters, r.counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
         RB_CUDA_CHECK(cudaStreamSynchronize(s));
