@@ -12,7 +12,9 @@ Metric: Mrays/sec = rays / (1000 * ms), as tools/bench_traversal/bench_traversal
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line on rank 0.  `value`: rays resident in HBM, CUDA-event time of the
-traversal kernels.  `e2e`: the same passes through the host-pointer C ABI
+traversal kernels.  `path_trace`: the render configs of BASELINE.json (configs[2..4]) through
+the wavefront path tracer, image rows dealt out across the ranks, one NCCL reduce of the film
+inside the timed region (samples/s = spp*w*h / t, src/driver/driver.cpp:300 of the reference).  `e2e`: the same passes through the host-pointer C ABI
 (b200_intersect_single_ray1_bvh8_tri4) with pinned HOST buffers, copies in the timed
 region.  `roofline`: algorithmic bytes of the reference layout / kernel time against
 the measured HBM copy bandwidth.  `cpu_baseline` / `--impl reference`: the oracle
@@ -142,6 +144,75 @@ def config_dict(n_gpus: int):
             "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the timed events)"}
 
 
+def path_trace_bench(local: int, rank: int, world: int, barrier):
+    """BASELINE.json configs[2..4] through the wavefront path tracer.  Every rank owns the row bands
+    (y // 8) % world == rank, renders into a torch tensor bound as the renderer's film, and one
+    ncclReduce puts the image together on rank 0 inside the timed region.  Returns a dict on every rank."""
+    import torch
+    import torch.distributed as dist
+    from rodent_b200 import render as R, sharding, workloads
+    out = {}
+    names = ["cornell", "sponza"] + (["sponza4k"] if world >= 8 else [])
+    for name in names:
+        cfg = workloads.RENDER_CONFIGS[name]
+        W, H, spp, depth = cfg["width"], cfg["height"], cfg["spp"], cfg["max_path_len"]
+        scene = workloads.load_scene(name)
+        cam = workloads.camera(name)
+        film = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+        r = R.Renderer(scene, local, W, H, spp, depth, part=rank, num_parts=world, band=8)
+        r.bind_film(film.data_ptr())
+        iters = 3 if name == "cornell" else 1
+        if name != "sponza4k":                      # warm-up render (the 4K config is warmed by the 1080p one)
+            r.render(cam, 0, present=False)
+            film.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for it in range(iters):
+            dev_ms += r.render(cam, it, present=False)
+        if world > 1:
+            sharding.reduce_film(film)
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        st = r.stats()
+        stats = torch.tensor([ms, dev_ms, float(st["primary_rays"]), float(st["shadow_rays"]), float(st["kernels"])],
+                             dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms, dev_ms = float(mx[0]), float(mx[1])
+            rays = float(sm[2] + sm[3])
+            kernels = float(sm[4])
+        else:
+            rays, kernels = float(stats[2] + stats[3]), float(stats[4])
+        samples = float(W) * H * spp * iters
+        mean = float(film.mean()) / iters
+        out[name] = {"msamples_s": round(samples / ms / 1e3, 2), "ms_per_render": round(ms / iters, 2),
+                     "device_ms_per_render_max_rank": round(dev_ms / iters, 2),
+                     "mrays_s": round(rays * iters / ms / 1e3, 1),     # stats are those of the last render call
+                     "width": W, "height": H, "spp": spp, "max_path_len": depth, "renders": iters,
+                     "kernels_per_render_all_ranks": int(kernels), "film_mean": round(mean, 6),
+                     "sharding": f"row bands of 8 over {world} rank(s), film summed with one reduce"}
+        r.bind_film(None)
+        r.free()
+        del film
+    return out
+
+
+def cpu_path_trace_sample(threads: int):
+    """The CPU path-tracing oracle on a bounded Cornell sample (same scene and camera as configs[2])."""
+    from oracle import oracle
+    from rodent_b200 import workloads
+    scene = workloads.load_scene("cornell")
+    W, H, spp, depth = 256, 256, 16, 4
+    cam = workloads.camera("cornell", W, H)
+    oracle.render(scene.view, cam, 64, 64, 1, depth, 0, threads=threads)
+    t0 = time.perf_counter()
+    oracle.render(scene.view, cam, W, H, spp, depth, 0, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"msamples_s": round(W * H * spp / dt / 1e6, 3), "sample": f"cornell {W}x{H}, {spp} spp, {depth} bounces, {dt:.1f} s on {threads} threads"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,6 +241,7 @@ def run_reference(args):
                                  "cannot be produced here), gcc -O3 -march=x86-64-v3 -ffp-contract=off"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "path_trace": {"cornell_cpu_sample": cpu_path_trace_sample(threads)},
     }))
 
 
@@ -180,6 +252,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-path-trace", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -255,6 +328,11 @@ def main():
         e2e_ms += (time.perf_counter() - t0) * 1e3
     e2e_ok = all(int((pin_hits[n].array["tri_id"] >= 0).sum()) == hits_found[n] for n in names)
 
+    # ---- path tracing (configs[2..4]) ------------------------------------------------------------
+    for pa in list(pin_rays.values()) + list(pin_hits.values()):
+        pa.free()
+    path_trace = None if args.no_path_trace else path_trace_bench(local, rank, world, barrier)
+
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([kernel_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -287,17 +365,21 @@ def main():
         "wall_ms_per_step_incl_l2_flush": round(wall_ms / args.steps, 3),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "traverse_bvh8_persistent<false>",
+                     "kernel": "traverse_bvh8_vote<false, 5>",
                      "note": "algorithmic bytes of the reference layout (32+16+256*nodes+224*Tri4 per ray); the 19.8 MB BVH "
                              "is L2-resident, so frac > 1 means served from L2, not faster than HBM"},
         "clocks": clocks.summary(),
     }
+    if path_trace is not None:
+        out["path_trace"] = path_trace
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_value, passes, secs, visits = cpu_pass(nodes, tris, rays, threads, 4.0)
         out["cpu_baseline"] = {"value": round(cpu_value, 3), "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{passes} full passes over both ray sets in {secs:.1f} s wall on {threads} threads",
                                "visits_per_ray": {n: [round(v, 4) for v in visits[n]] for n in names}}
+        if path_trace is not None:
+            out["cpu_baseline"]["path_trace"] = cpu_path_trace_sample(threads)
         for n in names:   # the algorithmic bytes must come from the oracle's counters, not from a stale constant
             assert abs(bytes_per_ray(n, visits) - bytes_per_ray(n)) < 1.0, "VISITS constants are stale"
     print(json.dumps(out))

@@ -234,6 +234,10 @@ void  rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int
 void  rodent_b200_present(RodentRenderer* r);
 float* rodent_b200_film(RodentRenderer* r);            /* host film, width*height*3 floats (get_pixels, interface.cpp:520-522) */
 void*  rodent_b200_film_device(RodentRenderer* r);     /* device film, same layout                                          */
+/* Accumulate into a caller-owned device buffer (width*height*3 floats on the renderer's device) instead of
+ * the renderer's own film, e.g. a tensor that a collective reduces in place when the image rows are dealt out
+ * across GPUs; NULL switches back.  The reference has one film per process (interface.cpp:348). */
+void   rodent_b200_renderer_bind_film(RodentRenderer* r, float* device_film);
 void  rodent_b200_clear(RodentRenderer* r);            /* clear_pixels, interface.cpp:524-526                               */
 /* Work counters of the last render call: [0] camera samples, [1] closest-hit rays,
  * [2] shadow rays, [3] wavefronts, [4] kernels launched. */

@@ -281,7 +281,7 @@ struct Renderer {
     std::vector<void*> allocations;
     int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr;
     int* h_counters = nullptr;                  // pinned
-    float* film = nullptr; float* h_film = nullptr;
+    float* film = nullptr; float* own_film = nullptr; float* h_film = nullptr;
     int sm_count = 0, occ_primary = 0, occ_shadow = 0;
     int64_t stats[5] = {0, 0, 0, 0, 0};
     double last_ms = 0.0;
@@ -328,7 +328,7 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     r->counters = r->alloc<int>(kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
-    r->film = r->alloc<float>(size_t(width) * height * 3);
+    r->film = r->own_film = r->alloc<float>(size_t(width) * height * 3);
     RB_CUDA_CHECK(cudaMemset(r->film, 0, size_t(width) * height * 3 * sizeof(float)));
     RB_CUDA_CHECK(cudaMallocHost(&r->h_film, size_t(width) * height * 3 * sizeof(float)));
     std::memset(r->h_film, 0, size_t(width) * height * 3 * sizeof(float));
@@ -436,6 +436,12 @@ void rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int3
 void rodent_b200_present(RodentRenderer* r) { present(*reinterpret_cast<Renderer*>(r)); }
 float* rodent_b200_film(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->h_film; }
 void* rodent_b200_film_device(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->film; }
+void rodent_b200_renderer_bind_film(RodentRenderer* rr, float* device_film) {
+    Renderer& r = *reinterpret_cast<Renderer*>(rr);
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r.stream));
+    r.film = device_film ? device_film : r.own_film;
+}
 void rodent_b200_clear(RodentRenderer* rr) {
     Renderer& r = *reinterpret_cast<Renderer*>(rr);
     RB_CUDA_CHECK(cudaSetDevice(r.dev));

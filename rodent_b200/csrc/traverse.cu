@@ -34,6 +34,7 @@ struct Tuning {
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
     int refill_below = 8;    // refill a warp when fewer than this many lanes are busy
     int blocks_per_sm = 0;   // 0: occupancy API
+    int host_chunks = 4;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 4)
 };
 static Tuning g_tuning;
 
@@ -342,7 +343,8 @@ static void run_host(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit
     if (ANY)   // occluded leaves t/u/v untouched: round-trip the caller's records
         RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, s.streams[0]));
     if (ANY) RB_CUDA_CHECK(cudaStreamSynchronize(s.streams[0]));
-    const int chunk = std::max(1 << 16, (num_rays + 7) / 8);
+    const int pieces = std::max(1, g_tuning.host_chunks);
+    const int chunk = std::max(1 << 15, (num_rays + pieces - 1) / pieces);
     int k = 0;
     for (int first = 0; first < num_rays; first += chunk, k++) {
         const int n = std::min(chunk, num_rays - first);
@@ -431,6 +433,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = value;
     else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = value;
     else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
+    else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "rodent_b200_present": (None, [c_void_p]),
     "rodent_b200_film": (POINTER(c_float), [c_void_p]),
     "rodent_b200_film_device": (c_void_p, [c_void_p]),
+    "rodent_b200_renderer_bind_film": (None, [c_void_p, c_void_p]),
     "rodent_b200_clear": (None, [c_void_p]),
     "rodent_b200_render_stats": (None, [c_void_p, POINTER(c_int64)]),
     "rodent_b200_render_last_ms": (ctypes.c_double, [c_void_p]),
@@ -156,6 +157,10 @@ class Renderer:
 
     def film_device_ptr(self) -> int:
         return self.L.rodent_b200_film_device(self.handle)
+
+    def bind_film(self, device_ptr: int | None) -> None:
+        """Accumulate into caller-owned device memory (e.g. a torch tensor's data_ptr()); None: own film."""
+        self.L.rodent_b200_renderer_bind_film(self.handle, c_void_p(device_ptr) if device_ptr else None)
 
     def stats(self) -> dict:
         out = (c_int64 * 5)()
