@@ -21,7 +21,10 @@
 extern "C" {
 #endif
 
-/* ---- Layouts ------------------------------------------------------------ */
+/* ---- Layouts ------------------------------------------------------------ *
+ * Define RODENT_B200_NO_LAYOUTS before including this header when the reference's
+ * generated tools/common/traversal.h (same structs, same names) is included too. */
+#ifndef RODENT_B200_NO_LAYOUTS
 
 /* src/traversal/mapping_cpu.impala:18-22 (Impala [[f32*8]*6] == C float[6][8]).
  * bounds rows: lo_x, hi_x, lo_y, hi_y, lo_z, hi_z; child > 0: inner node id
@@ -68,6 +71,7 @@ typedef struct Hit1 {
     float   u;
     float   v;
 } Hit1;
+#endif /* RODENT_B200_NO_LAYOUTS */
 
 /* ---- Traversal, device pointers ----------------------------------------- *
  * Same contract as the reference's GPU exports
