@@ -48,7 +48,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_tools(force: bool = False) -> None:
-    """ray_gen, bench_traversal (linked against librodent_b200.so), fbuf2png."""
+    """ray_gen, bench_traversal and rodent (linked against librodent_b200.so), fbuf2png."""
     (TOOLS / "bin").mkdir(exist_ok=True)
     cxx = os.environ.get("CXX", "g++")
     common = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall"]
@@ -58,6 +58,9 @@ def build_tools(force: bool = False) -> None:
                      [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
     if (TOOLS / "fbuf2png.cpp").exists():
         jobs.append(("fbuf2png", ["fbuf2png.cpp"], ["-lz"]))
+    if (TOOLS / "rodent.cpp").exists():
+        jobs.append(("rodent", ["rodent.cpp"],
+                     [f"-L{PKG}", "-lrodent_b200", "-lz", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
     for name, srcs, extra in jobs:
         out = TOOLS / "bin" / name
         deps = [TOOLS / s for s in srcs] + [TOOLS / "formats.h", ROOT / "include" / "rodent_b200.h"]

@@ -79,3 +79,32 @@ def test_ctest_procedure_on_gpu(tools, tmp_path, mode, name, tmin, tmax, hits):
 def test_any_hit_cli(tools):
     r = run(tools / "bench_traversal", "-bvh", testdata.sponza_bvh8(), "-ray", testdata.rays("random"), "--tmax", "1", "-gpu", "cuda", "-any")
     assert r.returncode == 0 and "959359 intersection(s)" in r.stdout
+
+
+def test_rodent_argument_errors(tools, tmp_path):
+    """tools/rodent: the option handling of src/driver/driver.cpp:164-232 (messages on stderr, exit code 1)."""
+    exe = tools / "rodent"
+    r = run(exe, "--help")
+    assert r.returncode == 0 and "--bench  iterations" in r.stdout and "--eye    x y z" in r.stdout
+    for args, msg in ((["--frobnicate"], "Unknown option '--frobnicate'"), (["stray"], "Unexpected argument 'stray'"),
+                      (["--eye", "1", "2"], "Option '--eye' expects 3 arguments"), (["--width"], "Option '--width' expects 1 arguments"),
+                      ([], "No scene"), (["--scene", "x.obj"], "pass --bench"),
+                      (["--scene", tmp_path / "missing.obj", "--bench", "1"], "missing.obj")):
+        r = run(exe, *args)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+
+
+@pytest.mark.gpu
+def test_rodent_ctest_procedure_on_gpu(tools, tmp_path):
+    """cmake/test/run_rodent.cmake:1-8: rodent --bench 50 -o out.png --eye 0 1 2.7 --dir 0 0 -1 --up 0 1 0, compared
+    with testing/ref-cornell.png by MSE (defaults 1080x720, fov 60, SPP 4, MAX_PATH_LEN 64)."""
+    out = tmp_path / "cornell.png"
+    r = run(tools / "rodent", "--scene", GOLDEN / "cornell_box.obj", "--bench", "50", "-o", out,
+            "--eye", "0", "1", "2.7", "--dir", "0", "0", "-1", "--up", "0", "1", "0")
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"# ([\d.e+-]+)/([\d.e+-]+)/([\d.e+-]+) \(min/med/max Msamples/s\)", r.stdout)
+    assert m and 0 < float(m.group(1)) <= float(m.group(2)) <= float(m.group(3))
+    img = np.array(Image.open(out))[..., :3].astype(np.int32)
+    ref = np.array(Image.open(GOLDEN / "ref-cornell.png"))[..., :3].astype(np.int32)
+    assert img.shape == ref.shape
+    assert ((img - ref) ** 2).mean() < 0.5

@@ -72,4 +72,38 @@ inline bool write_fbuf(const std::string& path, const std::vector<Hit1>& hits) {
     return true;
 }
 
+// 8-bit RGBA PNG through zlib only (libpng headers are not available in this image); the translation unit
+// must link -lz and include <zlib.h> before this header to get it.
+#ifdef ZLIB_H
+inline bool write_png_rgba(const std::string& path, const std::vector<uint8_t>& rgba, uint32_t width, uint32_t height) {
+    auto put32 = [](std::vector<uint8_t>& v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back(uint8_t(x >> s)); };
+    File out(path, "wb");
+    if (!out || rgba.size() != size_t(width) * height * 4) return false;
+    auto chunk = [&](const char type[4], const std::vector<uint8_t>& data) {
+        std::vector<uint8_t> buf;
+        put32(buf, uint32_t(data.size()));
+        buf.insert(buf.end(), type, type + 4);
+        buf.insert(buf.end(), data.begin(), data.end());
+        put32(buf, uint32_t(crc32(0, buf.data() + 4, uInt(buf.size() - 4))));
+        return out.write(buf.data(), buf.size());
+    };
+    std::vector<uint8_t> raw;
+    raw.reserve(size_t(height) * (size_t(width) * 4 + 1));
+    for (uint32_t y = 0; y < height; y++) {
+        raw.push_back(0);   // filter: none
+        raw.insert(raw.end(), rgba.begin() + size_t(y) * width * 4, rgba.begin() + size_t(y + 1) * width * 4);
+    }
+    uLongf zlen = compressBound(uLong(raw.size()));
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), uLong(raw.size()), 6) != Z_OK) return false;
+    z.resize(zlen);
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    if (!out.write(sig, 8)) return false;
+    std::vector<uint8_t> ihdr;
+    put32(ihdr, width); put32(ihdr, height);
+    ihdr.insert(ihdr.end(), {8, 6, 0, 0, 0});   // 8 bit RGBA
+    return chunk("IHDR", ihdr) && chunk("IDAT", z) && chunk("IEND", {});
+}
+#endif
+
 }  // namespace rb200
