@@ -260,6 +260,39 @@ void   clear_pixels(void);
 int32_t get_spp(void);
 void   render(const Settings* settings, int32_t iter);
 
+
+
+/* ======================================================================== *
+ * Shading-interface micro-benchmark (tools/bench_interface)
+ * ======================================================================== */
+
+/* tools/bench_interface/bench_interface.impala:8-42 (the structs of the generated tools/common/interface.h). */
+typedef struct Vec2  { float x, y; } Vec2;
+typedef struct Color { float r, g, b; } Color;
+typedef struct Tex {
+    const Color* pixels;        /* device pointer, width * height */
+    Color    border_color;
+    uint32_t border;            /* 0 clamp, 1 repeat, 2 constant colour (:1-3) */
+    uint32_t sampler;           /* 0 nearest, 1 bilinear (:5-6)               */
+    int32_t  width, height;
+} Tex;
+typedef struct ShadedMesh {
+    const Vec3*     vertices;   /* device pointers */
+    const uint32_t* indices;    /* 4 per triangle  */
+    const Vec3*     normals;
+    const Vec2*     texcoords;
+    Tex tex_kd, tex_ks, tex_ns;
+} ShadedMesh;
+typedef struct TriHit { int32_t id; Vec2 uv; } TriHit;
+
+/* bench_interface(mesh, tri_hits, in_dirs, out_dirs, colors, n), tools/bench_interface/bench_interface.impala:137-143,
+ * called at tools/bench_interface/bench_interface.cpp:183: for every hit, the shader input (interpolated point, normals,
+ * texture coordinates, three texture look-ups, local frame: :91-123) and the diffuse BSDF evaluated on it (:125-135).
+ * `mesh` is a HOST struct holding DEVICE pointers; the four arrays are device pointers on device 0, as the reference's
+ * gpu_iterate (:56-65) has it; returns after the device finished. */
+void bench_interface(const ShadedMesh* mesh, const TriHit* tri_hits, const Vec3* in_dirs, const Vec3* out_dirs,
+                     Color* colors, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

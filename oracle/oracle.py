@@ -23,7 +23,7 @@ class OracleStats(ctypes.Structure):
 
 def build(force: bool = False) -> Path:
     so = _DIR / "liboracle.so"
-    newest = max((_DIR / f).stat().st_mtime for f in ("traversal_oracle.c", "render_oracle.c", "Makefile"))
+    newest = max((_DIR / f).stat().st_mtime for f in ("traversal_oracle.c", "render_oracle.c", "shading_bench_oracle.c", "Makefile"))
     if force or not so.exists() or so.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"] + (["-s"] if force else []), check=True)
     return so
@@ -95,3 +95,13 @@ def render(scene_view, settings, width: int, height: int, spp: int, max_path_len
     L.oracle_render(ctypes.byref(scene_view), ctypes.byref(settings), width, height, spp, max_path_len, iteration,
                     film.ctypes.data, threads or (os.cpu_count() or 1), ctypes.byref(stats))
     return film, stats
+
+
+def bench_interface(mesh, tri_hits: np.ndarray, in_dirs: np.ndarray, out_dirs: np.ndarray) -> np.ndarray:
+    """oracle_bench_interface: `mesh` is a rodent_b200.shading_bench.ShadedMesh whose pointers are HOST pointers."""
+    L = lib()
+    L.oracle_bench_interface.restype = None
+    L.oracle_bench_interface.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int32]
+    colors = np.zeros((len(tri_hits), 3), np.float32)
+    L.oracle_bench_interface(ctypes.byref(mesh), _ptr(tri_hits), _ptr(in_dirs), _ptr(out_dirs), _ptr(colors), len(tri_hits))
+    return colors

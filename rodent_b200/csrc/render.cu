@@ -27,6 +27,8 @@
 #include "shading.cuh"
 #include "traverse_sched.cuh"
 
+extern "C" void rodent_b200_count_launches(int64_t n);   // traverse.cu: the library-wide launch counter
+
 namespace rb200 {
 
 constexpr int kCapacity = 1 << 20;           // mapping_gpu.impala:319
@@ -403,6 +405,7 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
     float ms = 0.0f;
     RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
     r.last_ms = ms;
+    rodent_b200_count_launches(n_kernels);
     r.stats[0] = total; r.stats[1] = n_primary; r.stats[2] = n_shadow; r.stats[3] = n_waves; r.stats[4] = n_kernels;
 }
 

@@ -422,6 +422,7 @@ void rodent_b200_copy_to_host(int32_t dev, void* dst, const void* src, size_t by
 void rodent_b200_sync(int32_t dev) { device_state(dev); RB_CUDA_CHECK(cudaDeviceSynchronize()); }
 double rodent_b200_last_kernel_ms(int32_t dev) { return device_state(dev).last_ms; }
 int64_t rodent_b200_launch_count(void) { return g_launches.load(); }
+void rodent_b200_count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // for the other translation units
 const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }
 
 // Tuning knobs for experiments (not part of the drop-in surface).

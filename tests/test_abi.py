@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def declared_symbols():
     text = (ROOT / "include" / "rodent_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:cuda_|b200_|rodent_b200_|render|get_spp|get_pixels|clear_pixels|setup_interface|cleanup_interface)\w*)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:cuda_|b200_|rodent_b200_|bench_interface|render|get_spp|get_pixels|clear_pixels|setup_interface|cleanup_interface)\w*)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -21,8 +21,8 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for name in names:
         assert hasattr(L, name), f"{name} declared in include/rodent_b200.h but not exported"
-    from rodent_b200 import render
-    assert set(names) == set(lib.SIGNATURES) | set(render.SIGNATURES), "python bindings and header disagree"
+    from rodent_b200 import render, shading_bench
+    assert set(names) == set(lib.SIGNATURES) | set(render.SIGNATURES) | set(shading_bench.SIGNATURES), "python bindings and header disagree"
     assert L.rodent_b200_version().decode().startswith("rodent_b200")
 
 
