@@ -18,6 +18,7 @@
 #include "traverse.cuh"
 #include "traverse_quad.cuh"
 #include "traverse_sched.cuh"
+#include "traverse_pool.cuh"
 
 namespace rb200 {
 
@@ -26,13 +27,15 @@ constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kSmemStackDepth = 16;  // stack levels kept in shared memory by the persistent thread-per-ray kernel
 
 struct Tuning {
-    int mapping = 2;         // 2 = vote-scheduled thread per ray (traverse_sched.cuh), 1 = while-while thread per ray (traverse.cuh),
+    int mapping = 2;         // 3 = ray pool per warp (traverse_pool.cuh), 2 = vote-scheduled thread per ray (traverse_sched.cuh), 1 = while-while thread per ray (traverse.cuh),
                              // 4 = four lanes per ray (traverse_quad.cuh)
     int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
     int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
     int refill_below = 8;    // refill a warp when fewer than this many lanes are busy
+    int pool_prefetch = 1;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
+    int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_chunks = 4;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 4)
 };
@@ -129,6 +132,25 @@ traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
         [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); });
 }
 
+// Ray-pool kernel (traverse_pool.cuh): 64 rays per warp in shared memory, compacted onto the lanes per step.
+constexpr int kPoolBlock = 64;       // two warps (two pools, 29 KB) per CTA, seven CTAs per SM
+template <bool ANY>
+__global__ void __launch_bounds__(kPoolBlock, 7)
+traverse_bvh8_pool(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                   int* __restrict__ work_counter, int refill_min, StackEntry* __restrict__ overflow, int prefetch) {
+    __shared__ RayPool pools[kPoolBlock / 32];
+    const int warp = threadIdx.x >> 5;
+    const size_t global_warp = size_t(blockIdx.x) * (kPoolBlock / 32) + warp;
+    traverse_pooled<ANY, false>(
+        nodes, tris, pools[warp], overflow + global_warp * kPoolSlots * kPoolOverflow, num_rays, work_counter, refill_min, prefetch != 0,
+        [rays](int i, float4& r0, float4& r1) {
+            const float4* rp = reinterpret_cast<const float4*>(rays + i);
+            r0 = ldg4(rp); r1 = ldg4(rp + 1);
+        },
+        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); });
+}
+
 // Quad-per-ray persistent kernel: eight rays per warp (traverse_quad.cuh).  Idle quads are
 // refilled together: one atomicAdd per warp, ray index = base + rank of the quad among the
 // idle ones (ballot + popc).
@@ -196,6 +218,8 @@ struct DeviceState {
     double last_ms = 0.0;
     int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
     int occ_quad[2] = {0, 0};
+    int occ_pool[2] = {0, 0};
+    StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
     int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
@@ -234,6 +258,8 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][1], traverse_bvh8_vote<true, 5>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][0], traverse_bvh8_vote<false, 6>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[0], traverse_bvh8_pool<false>, kPoolBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[1], traverse_bvh8_pool<true>, kPoolBlock, 0));
             s.init = true;
         }
     }
@@ -244,7 +270,24 @@ template <bool ANY>
 static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
                    int num_rays, cudaStream_t stream, int* counter) {
     if (num_rays <= 0) return;
-    if (g_tuning.mapping == 2) {
+    if (g_tuning.mapping == 3) {
+        if (!counter) counter = s.counter;
+        RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_pool[ANY ? 1 : 0];
+        const int rays_per_block = kPoolBlock / 32 * kPoolSlots;
+        const int needed = (num_rays + rays_per_block - 1) / rays_per_block;
+        const int grid = std::min(needed, s.sm_count * per_sm);
+        const size_t warps = size_t(s.sm_count) * 16 * (kPoolBlock / 32);       // upper bound of any grid launched here
+        if (s.pool_overflow_warps < warps) {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            if (s.pool_overflow_warps < warps) {
+                if (s.pool_overflow) RB_CUDA_CHECK(cudaFree(s.pool_overflow));
+                RB_CUDA_CHECK(cudaMalloc(&s.pool_overflow, warps * kPoolSlots * kPoolOverflow * sizeof(StackEntry)));
+                s.pool_overflow_warps = warps;
+            }
+        }
+        traverse_bvh8_pool<ANY><<<std::min(grid, s.sm_count * 16), kPoolBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.pool_refill_min, s.pool_overflow, g_tuning.pool_prefetch);
+    } else if (g_tuning.mapping == 2) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
         const int v = std::min(std::max(g_tuning.vote_min_blocks, 4), 6) - 4;
@@ -434,6 +477,8 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = value;
     else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = value;
     else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
+    else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = value;
+    else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }
