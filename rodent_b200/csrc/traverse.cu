@@ -30,6 +30,7 @@ struct Tuning {
     int mapping = 2;         // 3 = ray pool per warp (traverse_pool.cuh), 2 = vote-scheduled thread per ray (traverse_sched.cuh), 1 = while-while thread per ray (traverse.cuh),
                              // 4 = four lanes per ray (traverse_quad.cuh)
     int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
+    int node_streak_min = 8;  // (mapping 2) consecutive node steps without re-voting while this many lanes want one (33: off)
     int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
@@ -121,7 +122,7 @@ template <bool ANY, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                    const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
-                   int* __restrict__ work_counter, int refill_min) {
+                   int* __restrict__ work_counter, int refill_min, int node_streak_min) {
     __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
     traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
@@ -129,7 +130,7 @@ traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
             const float4* rp = reinterpret_cast<const float4*>(rays + i);
             r0 = ldg4(rp); r1 = ldg4(rp + 1);
         },
-        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); });
+        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
 }
 
 // Ray-pool kernel (traverse_pool.cuh): 64 rays per warp in shared memory, compacted onto the lanes per step.
@@ -294,9 +295,9 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
         const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_vote[v][ANY ? 1 : 0];
         const int needed = (num_rays + kBlock - 1) / kBlock;
         const int grid = std::min(needed, s.sm_count * per_sm);
-        if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
-        if (v == 1) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
-        if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min);
+        if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 1) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
     } else if (g_tuning.mapping == 4) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -476,6 +477,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = value;
     else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = value;
     else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = value;
+    else if (!std::strcmp(key, "node_streak_min")) g_tuning.node_streak_min = value;
     else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
     else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = value;
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;

@@ -185,10 +185,11 @@ struct RayWalker {
 //   fetch(i, r0, r1)  loads ray i (origin+tmin, direction+tmax)
 //   sink(i, hit)      consumes the finished ray's record
 // `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
+// `node_streak_min`: see the node branch at the end of the loop (33: one step per vote).
 template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
 __device__ __forceinline__ void traverse_vote_scheduled(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                                                         StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
-                                                        int refill_min, Fetch fetch, Sink sink) {
+                                                        int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8) {
     const unsigned lane = lane_id();
     StackEntry overflow[kStackSize - SMEM_DEPTH];
     RayWalker<ANY, SMEM_DEPTH, BLOCK> w;
@@ -229,9 +230,20 @@ __device__ __forceinline__ void traverse_vote_scheduled(const Node8* __restrict_
         if (__popc(bn) >= __popc(bl)) {
             // rays with a clamped axis need the x86 NaN pattern (RaySetup::degenerate); that variant is a
             // superset of the plain one, so the whole warp takes it when any of its lanes does
-            if (__ballot_sync(0xffffffffu, want_n && w.ray.degenerate) != 0) { if (want_n) w.template node_step<true>(nodes); }
-            else                                                            { if (want_n) w.template node_step<false>(nodes); }
+            if (__ballot_sync(0xffffffffu, want_n && w.ray.degenerate) != 0) {
+                if (want_n) w.template node_step<true>(nodes);
+            } else {
+                // Node steps follow each other (most of a ray's steps are node steps): as long as at least
+                // `node_streak_min` lanes want another one right away, take it without going through the refill /
+                // finish / vote bookkeeping of the outer loop.  Lanes that reached a leaf or ran dry just wait.
+                bool go = want_n;
+                do {
+                    if (go) w.template node_step<false>(nodes);
+                    go = has && w.wants_node() && !w.ray.degenerate;
+                } while (__popc(__ballot_sync(0xffffffffu, go)) >= node_streak_min);
+            }
         } else {
+            // (streaks of Tri4 steps were measured too and do not pay: most leaves are one packet)
             if (want_l) w.template leaf_step<WANT_GEOM>(tris);
         }
     }

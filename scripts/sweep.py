@@ -13,11 +13,9 @@ def main():
     for name, (tmin, tmax) in testdata.RAY_SETS.items():
         rays = formats.load_rays(testdata.rays(name), tmin, tmax)
         sets[name] = (traversal.DeviceArray.from_host(0, rays), traversal.DeviceArray(0, formats.HIT1, len(rays)))
-    configs = [dict(mapping=1, persistent=1, refill_below=8), dict(mapping=4, blocks_per_sm=0, quad_refill_below=0)]
-    configs.append(dict(mapping=2, refill_min=24))
-    for pf in (0, 1):
-        for rm in (24, 32):
-            configs.append(dict(mapping=3, pool_refill_min=rm, pool_prefetch=pf))
+    configs = []
+    for ns in (33, 8):
+        configs.append(dict(mapping=2, refill_min=24, node_streak_min=ns))
     extra = [a for a in sys.argv[1:]]
     for cfg in configs:
         for k, v in cfg.items():

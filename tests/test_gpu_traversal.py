@@ -41,10 +41,11 @@ def assert_records_equal(got, want):
 
 
 # kernel variants: the default vote-scheduled kernel, the while-while thread-per-ray kernels and the quad-per-ray kernel
-VARIANTS = {"vote": {"mapping": 2}, "vote-refill1": {"mapping": 2, "refill_min": 1}, "pool": {"mapping": 3}, "pool-refill1": {"mapping": 3, "pool_refill_min": 1},
+VARIANTS = {"vote": {"mapping": 2}, "vote-refill1": {"mapping": 2, "refill_min": 1}, "vote-no-streaks": {"mapping": 2, "node_streak_min": 33},
+            "vote-long-streaks": {"mapping": 2, "node_streak_min": 1}, "pool": {"mapping": 3}, "pool-refill1": {"mapping": 3, "pool_refill_min": 1},
             "quad": {"mapping": 4},
             "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
-DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 24, "pool_refill_min": 24}
+DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 24, "pool_refill_min": 24, "node_streak_min": 8}
 
 
 @pytest.fixture(params=list(VARIANTS))
