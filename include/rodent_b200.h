@@ -117,7 +117,20 @@ void b200_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris,
                                           const Ray1* rays, Hit1* hits, int32_t num_packets);
 void b200_occluded_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris,
                                          const Ray1* rays, Hit1* hits, int32_t num_packets);
-void rodent_b200_forget_bvh(const Node8* nodes, const Tri4* tris);
+void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris);
+
+/* ---- The same four over a BVH4 -------------------------------------------- *
+ * cpu_{intersect,occluded}_single_ray1_bvh4_tri4 (tools/bench_traversal/bench_traversal.impala:279-305) is what
+ * `bench_traversal -s` runs at its default --bvh-width 4 (bench_traversal.cpp:147).  Node4 arrays, Tri4 leaves,
+ * the arity-4 sorting networks (bose_nelson_sort, src/core/sort.impala:3-32); contracts as above. */
+void cuda_intersect_single_ray1_bvh4_tri4(int32_t dev, const Node4* nodes, const Tri4* tris,
+                                          const Ray1* rays, Hit1* hits, int32_t num_rays);
+void cuda_occluded_single_ray1_bvh4_tri4(int32_t dev, const Node4* nodes, const Tri4* tris,
+                                         const Ray1* rays, Hit1* hits, int32_t num_rays);
+void b200_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris,
+                                          const Ray1* rays, Hit1* hits, int32_t num_packets);
+void b200_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris,
+                                         const Ray1* rays, Hit1* hits, int32_t num_packets);
 
 /* ---- Memory helpers (stand-ins for anydsl::Array / anydsl_alloc / anydsl_copy,
  * tools/common/load_bvh.h:58-68, load_rays.h:85-88) ------------------------ */

@@ -133,6 +133,24 @@ traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
         [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
 }
 
+// The same loop over a BVH4 (Node4: 6 rows of 4 floats, 4 children; leaves are Tri4 as well): the CPU single-ray
+// path of the reference at its default --bvh-width (cpu_{intersect,occluded}_single_ray1_bvh4_tri4,
+// tools/bench_traversal/bench_traversal.impala:279-305).
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 6)
+traverse_bvh4_vote(const Node4* __restrict__ nodes, const Tri4* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                   int* __restrict__ work_counter, int refill_min, int node_streak_min) {
+    __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 4>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
+        [rays](int i, float4& r0, float4& r1) {
+            const float4* rp = reinterpret_cast<const float4*>(rays + i);
+            r0 = ldg4(rp); r1 = ldg4(rp + 1);
+        },
+        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
+}
+
 // Ray-pool kernel (traverse_pool.cuh): 64 rays per warp in shared memory, compacted onto the lanes per step.
 constexpr int kPoolBlock = 64;       // two warps (two pools, 29 KB) per CTA, seven CTAs per SM
 template <bool ANY>
@@ -220,12 +238,13 @@ struct DeviceState {
     int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
     int occ_quad[2] = {0, 0};
     int occ_pool[2] = {0, 0};
+    int occ_bvh4[2] = {0, 0};
     StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
     int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
-    std::map<std::pair<const void*, const void*>, std::pair<Node8*, Tri4*>> bvh_cache;
+    std::map<std::pair<const void*, const void*>, std::pair<void*, Tri4*>> bvh_cache;
 };
 static DeviceState g_dev[64];
 static std::mutex g_mutex;
@@ -259,6 +278,8 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][1], traverse_bvh8_vote<true, 5>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][0], traverse_bvh8_vote<false, 6>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[0], traverse_bvh4_vote<false>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[1], traverse_bvh4_vote<true>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[0], traverse_bvh8_pool<false>, kPoolBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[1], traverse_bvh8_pool<true>, kPoolBlock, 0));
             s.init = true;
@@ -320,8 +341,22 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+// BVH4 input: the vote-scheduled kernel only.
 template <bool ANY>
-static void run_sync(int dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+static void launch(DeviceState& s, const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,
+                   int num_rays, cudaStream_t stream, int* counter) {
+    if (num_rays <= 0) return;
+    if (!counter) counter = s.counter;
+    RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_bvh4[ANY ? 1 : 0];
+    const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
+    traverse_bvh4_vote<ANY><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+    RB_CUDA_CHECK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <bool ANY, typename NodeT>
+static void run_sync(int dev, const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     DeviceState& s = device_state(dev);
     RB_CUDA_CHECK(cudaEventRecord(s.ev0, 0));
     launch<ANY>(s, nodes, tris, rays, hits, num_rays, 0, nullptr);
@@ -333,15 +368,16 @@ static void run_sync(int dev, const Node8* nodes, const Tri4* tris, const Ray1* 
 }
 
 // ---- host-pointer path ----------------------------------------------------------
-// Extent of a BVH8 given only its arrays: walk from the root (node 1).
-static void bvh8_extent(const Node8* nodes, const Tri4* tris, size_t& num_nodes, size_t& num_tri4) {
+// Extent of a BVH given only its arrays: walk from the root (node 1).
+template <typename NodeT>
+static void bvh_extent(const NodeT* nodes, const Tri4* tris, size_t& num_nodes, size_t& num_tri4) {
     std::vector<int> todo{1};
     num_nodes = 0; num_tri4 = 0;
     while (!todo.empty()) {
         const int id = todo.back(); todo.pop_back();
         num_nodes = std::max(num_nodes, size_t(id));
-        const Node8& n = nodes[id - 1];
-        for (int i = 0; i < 8; i++) {
+        const NodeT& n = nodes[id - 1];
+        for (int i = 0; i < int(sizeof(n.child) / sizeof(n.child[0])); i++) {
             const int c = n.child[i];
             if (c > 0) todo.push_back(c);
             else if (c < 0) {
@@ -353,25 +389,27 @@ static void bvh8_extent(const Node8* nodes, const Tri4* tris, size_t& num_nodes,
     }
 }
 
-static std::pair<Node8*, Tri4*> cached_bvh(DeviceState& s, const Node8* nodes, const Tri4* tris) {
+template <typename NodeT>
+static std::pair<NodeT*, Tri4*> cached_bvh(DeviceState& s, const NodeT* nodes, const Tri4* tris) {
     std::lock_guard<std::mutex> lock(g_mutex);
     auto key = std::make_pair((const void*)nodes, (const void*)tris);
     auto it = s.bvh_cache.find(key);
-    if (it != s.bvh_cache.end()) return it->second;
+    if (it != s.bvh_cache.end()) return std::make_pair(static_cast<NodeT*>(it->second.first), it->second.second);
     size_t nn, nt;
-    bvh8_extent(nodes, tris, nn, nt);
-    Node8* dn; Tri4* dt;
-    RB_CUDA_CHECK(cudaMalloc(&dn, nn * sizeof(Node8)));
+    bvh_extent(nodes, tris, nn, nt);
+    NodeT* dn; Tri4* dt;
+    RB_CUDA_CHECK(cudaMalloc(&dn, nn * sizeof(NodeT)));
     RB_CUDA_CHECK(cudaMalloc(&dt, std::max<size_t>(nt, 1) * sizeof(Tri4)));
-    RB_CUDA_CHECK(cudaMemcpy(dn, nodes, nn * sizeof(Node8), cudaMemcpyHostToDevice));
+    RB_CUDA_CHECK(cudaMemcpy(dn, nodes, nn * sizeof(NodeT), cudaMemcpyHostToDevice));
     RB_CUDA_CHECK(cudaMemcpy(dt, tris, nt * sizeof(Tri4), cudaMemcpyHostToDevice));
-    return s.bvh_cache[key] = std::make_pair(dn, dt);
+    s.bvh_cache[key] = std::make_pair(static_cast<void*>(dn), dt);
+    return std::make_pair(dn, dt);
 }
 
 // Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
 // transfers of one chunk overlap the traversal of another.
-template <bool ANY>
-static void run_host(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+template <bool ANY, typename NodeT>
+static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     if (num_rays <= 0) return;
     DeviceState& s = device_state(g_host_dev);
     auto bvh = cached_bvh(s, nodes, tris);
@@ -427,7 +465,19 @@ void b200_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, 
 void b200_occluded_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
     run_host<true>(nodes, tris, rays, hits, num_packets);
 }
-void rodent_b200_forget_bvh(const Node8* nodes, const Tri4* tris) {
+void cuda_intersect_single_ray1_bvh4_tri4(int32_t dev, const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<false>(dev, nodes, tris, rays, hits, num_rays);
+}
+void cuda_occluded_single_ray1_bvh4_tri4(int32_t dev, const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<true>(dev, nodes, tris, rays, hits, num_rays);
+}
+void b200_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    run_host<false>(nodes, tris, rays, hits, num_packets);
+}
+void b200_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
+    run_host<true>(nodes, tris, rays, hits, num_packets);
+}
+void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris) {
     DeviceState& s = device_state(g_host_dev);
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = s.bvh_cache.find(std::make_pair((const void*)nodes, (const void*)tris));

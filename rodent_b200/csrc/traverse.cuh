@@ -34,15 +34,17 @@ struct RaySetup {
     // rewrites generated NaNs to the x86 pattern.
     bool degenerate;
 
+    // ROW: float4 per bounds row, 2 for a Node8 (bounds[6][8]), 1 for a Node4 (bounds[6][4]).
+    template <int ROW = 2>
     __device__ __forceinline__ void init(float4 r0, float4 r1) {
         ox = r0.x; oy = r0.y; oz = r0.z; tmin = r0.w;
         dx = r1.x; dy = r1.y; dz = r1.z;
         idx = safe_rcp(dx); idy = safe_rcp(dy); idz = safe_rcp(dz);
         iox = -mul(ox, idx); ioy = -mul(oy, idy); ioz = -mul(oz, idz);
         const int px = dx > 0.0f, py = dy > 0.0f, pz = dz > 0.0f;
-        near_x = 2 * (1 - px); far_x = 2 * px;
-        near_y = 4 + 2 * (1 - py); far_y = 4 + 2 * py;
-        near_z = 8 + 2 * (1 - pz); far_z = 8 + 2 * pz;
+        near_x = ROW * (1 - px); far_x = ROW * px;
+        near_y = 2 * ROW + ROW * (1 - py); far_y = 2 * ROW + ROW * py;
+        near_z = 4 * ROW + ROW * (1 - pz); far_z = 4 * ROW + ROW * pz;
         const float big = kFltMax;
         degenerate = !(fabsf(iox) <= big && fabsf(ioy) <= big && fabsf(ioz) <= big) ||
                      idx == 0.0f || idy == 0.0f || idz == 0.0f;
@@ -121,6 +123,22 @@ __device__ __forceinline__ void sort_entries(Stack& st, int first, int n) {
         for (int k = 0; k < 8; k++)
             if (k < n) st.store(first + k, e[k]);
     }
+}
+// sort_n for a BVH4 (arity 4): bose_nelson_sort(n) of sort.impala:3-32, n = 3 or 4.  Its three-input network
+// is (1,2)(0,2)(0,1) -- not the (0,1)(0,2)(1,2) that Batcher's gives for an arity-8 node.
+template <typename Stack>
+__device__ __forceinline__ void sort_entries_bvh4(Stack& st, int first, int n) {
+    StackEntry e[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k < n) e[k] = st.load(first + k);
+        else { e[k].node = 0; e[k].tmin = -INFINITY; }
+    }
+    if (n == 3) { RB_CSWAP(1, 2) RB_CSWAP(0, 2) RB_CSWAP(0, 1) }
+    else        { RB_CSWAP(0, 1) RB_CSWAP(2, 3) RB_CSWAP(0, 2) RB_CSWAP(1, 3) RB_CSWAP(1, 2) }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n) st.store(first + k, e[k]);
 }
 #undef RB_CSWAP
 

@@ -39,7 +39,8 @@ struct SplitStack {
     }
 };
 
-template <bool ANY, int SMEM_DEPTH, int BLOCK>
+// ARITY: 8 for Node8 (BVH8), 4 for Node4 (BVH4); the leaves are Tri4 in both.
+template <bool ANY, int SMEM_DEPTH, int BLOCK, int ARITY = 8>
 struct RayWalker {
     RaySetup ray;
     float tmax;
@@ -59,7 +60,7 @@ struct RayWalker {
     }
 
     __device__ __forceinline__ void begin(float4 r0, float4 r1) {
-        ray.init(r0, r1);
+        ray.template init<ARITY / 4>(r0, r1);
         tmax = r1.w;
         hit.prim = -1; hit.geom = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;   // empty_hit, intersection.impala:134-136
         ptr = -1; top_node = 0; top_t = kFltMax; leaf = -1;
@@ -73,30 +74,32 @@ struct RayWalker {
 
     // One iteration of the inner `while (top_node > 0)` loop (:177-219).
     template <bool X86_NAN>
-    __device__ __forceinline__ void node_step(const Node8* __restrict__ nodes) {
-        const float4* nb = reinterpret_cast<const float4*>(nodes + (top_node - 1));
+    __device__ __forceinline__ void node_step(const void* __restrict__ nodes) {
+        constexpr int ROW = ARITY / 4;                       // float4 per bounds row
+        // a node is 6 rows of ARITY floats, ARITY child ids and ARITY ints of padding: 8 * ARITY float4 / 4
+        const float4* nb = reinterpret_cast<const float4*>(nodes) + size_t(top_node - 1) * (2 * ARITY);
         pop();
-        const float4 nxa = ldg4(nb + ray.near_x), nxb = ldg4(nb + ray.near_x + 1);
-        const float4 nya = ldg4(nb + ray.near_y), nyb = ldg4(nb + ray.near_y + 1);
-        const float4 nza = ldg4(nb + ray.near_z), nzb = ldg4(nb + ray.near_z + 1);
-        const float4 fxa = ldg4(nb + ray.far_x), fxb = ldg4(nb + ray.far_x + 1);
-        const float4 fya = ldg4(nb + ray.far_y), fyb = ldg4(nb + ray.far_y + 1);
-        const float4 fza = ldg4(nb + ray.far_z), fzb = ldg4(nb + ray.far_z + 1);
-        const int4 ca = ldg4(reinterpret_cast<const int4*>(nb) + 12), cb = ldg4(reinterpret_cast<const int4*>(nb) + 13);
-
-        const float nx[8] = {nxa.x, nxa.y, nxa.z, nxa.w, nxb.x, nxb.y, nxb.z, nxb.w};
-        const float ny[8] = {nya.x, nya.y, nya.z, nya.w, nyb.x, nyb.y, nyb.z, nyb.w};
-        const float nz[8] = {nza.x, nza.y, nza.z, nza.w, nzb.x, nzb.y, nzb.z, nzb.w};
-        const float fx[8] = {fxa.x, fxa.y, fxa.z, fxa.w, fxb.x, fxb.y, fxb.z, fxb.w};
-        const float fy[8] = {fya.x, fya.y, fya.z, fya.w, fyb.x, fyb.y, fyb.z, fyb.w};
-        const float fz[8] = {fza.x, fza.y, fza.z, fza.w, fzb.x, fzb.y, fzb.z, fzb.w};
-        const int child[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        float nx[ARITY], ny[ARITY], nz[ARITY], fx[ARITY], fy[ARITY], fz[ARITY];
+        int child[ARITY];
+#pragma unroll
+        for (int k = 0; k < ROW; k++) {                      // all loads of the node are issued before the first use
+            const float4 a = ldg4(nb + ray.near_x + k), b = ldg4(nb + ray.near_y + k), c = ldg4(nb + ray.near_z + k);
+            const float4 d = ldg4(nb + ray.far_x + k), e = ldg4(nb + ray.far_y + k), f = ldg4(nb + ray.far_z + k);
+            const int4 g = ldg4(reinterpret_cast<const int4*>(nb) + 6 * ROW + k);
+            nx[4 * k] = a.x; nx[4 * k + 1] = a.y; nx[4 * k + 2] = a.z; nx[4 * k + 3] = a.w;
+            ny[4 * k] = b.x; ny[4 * k + 1] = b.y; ny[4 * k + 2] = b.z; ny[4 * k + 3] = b.w;
+            nz[4 * k] = c.x; nz[4 * k + 1] = c.y; nz[4 * k + 2] = c.z; nz[4 * k + 3] = c.w;
+            fx[4 * k] = d.x; fx[4 * k + 1] = d.y; fx[4 * k + 2] = d.z; fx[4 * k + 3] = d.w;
+            fy[4 * k] = e.x; fy[4 * k + 1] = e.y; fy[4 * k + 2] = e.z; fy[4 * k + 3] = e.w;
+            fz[4 * k] = f.x; fz[4 * k + 1] = f.y; fz[4 * k + 2] = f.z; fz[4 * k + 3] = f.w;
+            child[4 * k] = g.x; child[4 * k + 1] = g.y; child[4 * k + 2] = g.z; child[4 * k + 3] = g.w;
+        }
 
         // ordered slab test, intersection.impala:194-208 with integer min/max (:123-133, :184)
-        float tentry[8];
+        float tentry[ARITY];
         unsigned mask = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < ARITY; i++) {
             const float t0x = slab<X86_NAN>(ray.idx, nx[i], ray.iox);
             const float t0y = slab<X86_NAN>(ray.idy, ny[i], ray.ioy);
             const float t0z = slab<X86_NAN>(ray.idz, nz[i], ray.ioz);
@@ -116,7 +119,7 @@ struct RayWalker {
         }
         // pushes in lane order, :195-208
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < ARITY; i++) {
             if (mask & (1u << i)) {
                 if (ANY || tentry[i] < top_t) push(child[i], tentry[i]);
                 else push_after(child[i], tentry[i]);
@@ -124,7 +127,10 @@ struct RayWalker {
         }
         if (!ANY) {                                                                  // :210-218
             const int n = __popc(mask);
-            if (n >= 3) sort_entries(st, ptr - n + 1, n);
+            if (n >= 3) {
+                if (ARITY == 8) sort_entries(st, ptr - n + 1, n);
+                else            sort_entries_bvh4(st, ptr - n + 1, n);
+            }
         }
         // The reference goes on with the new top without a cull check (inner loop / :221-224).
     }
@@ -186,13 +192,13 @@ struct RayWalker {
 //   sink(i, hit)      consumes the finished ray's record
 // `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
 // `node_streak_min`: see the node branch at the end of the loop (33: one step per vote).
-template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
-__device__ __forceinline__ void traverse_vote_scheduled(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, typename Fetch, typename Sink>
+__device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
                                                         StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
                                                         int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8) {
     const unsigned lane = lane_id();
     StackEntry overflow[kStackSize - SMEM_DEPTH];
-    RayWalker<ANY, SMEM_DEPTH, BLOCK> w;
+    RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY> w;
     w.st.smem = smem_column;
     w.st.overflow = overflow;
     w.leaf = -1; w.top_node = 0;

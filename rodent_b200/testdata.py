@@ -45,6 +45,15 @@ def sponza_bvh8() -> Path:
     return out
 
 
+def sponza_bvh4() -> Path:
+    out = DATA / "sponza_bvh4.bvh"
+    if not out.exists():
+        DATA.mkdir(exist_ok=True)
+        blob = lzma.decompress((GOLDEN / "sponza_bvh4.bvh.xz").read_bytes())
+        _atomic_write(out, lambda p: p.write_bytes(blob))
+    return out
+
+
 def rays(name: str) -> Path:
     out = DATA / f"sponza-{name}.rays"
     if not out.exists():

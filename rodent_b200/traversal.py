@@ -47,10 +47,11 @@ class DeviceArray:
 
 
 class Bvh8:
-    """BVH8/Tri4 resident on one device (load_bvh<Node8,Tri4>, load_bvh.h:46-74)."""
+    """BVH8/Tri4 -- or BVH4/Tri4 -- resident on one device (load_bvh<Node8,Tri4>, load_bvh.h:46-74)."""
 
     def __init__(self, dev: int, nodes: np.ndarray, tris: np.ndarray):
-        assert nodes.dtype == formats.NODE8 and tris.dtype == formats.TRI4
+        assert nodes.dtype in (formats.NODE8, formats.NODE4) and tris.dtype == formats.TRI4
+        self.arity = 8 if nodes.dtype == formats.NODE8 else 4
         self.dev = dev
         self.nodes = DeviceArray.from_host(dev, nodes)
         self.tris = DeviceArray.from_host(dev, tris)
@@ -65,7 +66,7 @@ def intersect(bvh: Bvh8, rays: DeviceArray, hits: DeviceArray, any_hit: bool = F
     time in ms (bench_gpu, bench_traversal.cpp:124-135)."""
     L = lib.load()
     n = rays.count if count is None else count
-    fn = L.cuda_occluded_single_ray1_bvh8_tri4 if any_hit else L.cuda_intersect_single_ray1_bvh8_tri4
+    fn = getattr(L, f"cuda_{'occluded' if any_hit else 'intersect'}_single_ray1_bvh{bvh.arity}_tri4")
     fn(bvh.dev, bvh.nodes.ptr, bvh.tris.ptr, rays.ptr, hits.ptr, n)
     return L.rodent_b200_last_kernel_ms(bvh.dev)
 
@@ -77,7 +78,8 @@ def intersect_host(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, hits: 
     L = lib.load()
     if hits is None:
         hits = np.zeros(len(rays), formats.HIT1)
-    fn = L.b200_occluded_single_ray1_bvh8_tri4 if any_hit else L.b200_intersect_single_ray1_bvh8_tri4
+    arity = 8 if nodes.dtype == formats.NODE8 else 4
+    fn = getattr(L, f"b200_{'occluded' if any_hit else 'intersect'}_single_ray1_bvh{arity}_tri4")
     fn(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, hits.ctypes.data, len(rays))
     return hits
 

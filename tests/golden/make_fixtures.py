@@ -4,8 +4,9 @@ the dev container where /root/reference exists):
     python tests/golden/make_fixtures.py
 
 * sponza_bvh8.bvh.xz  -- the BVH8_TRI4 block of testing/sponza.bvh re-wrapped as a
-                         single-block .bvh file and xz-compressed (the BVH4/BVH2
-                         blocks are not needed by the GPU path)
+                         single-block .bvh file and xz-compressed
+* sponza_bvh4.bvh.xz  -- the same for the BVH4_TRI4 block (the reference's default
+                         --bvh-width; the BVH2 block is not needed by the GPU path)
 * ref-primary.png, ref-random.png, ref-cornell.png -- the reference's golden images
 * cornell_box.obj/.mtl -- the reference's Cornell scene (test input data)
 * sponza_hits_sample.npz -- oracle hit records for a fixed sample of rays, so the
@@ -37,6 +38,11 @@ def main():
             blob = struct.pack("<I", F.BVH_MAGIC) + payload
             (HERE / "sponza_bvh8.bvh.xz").write_bytes(lzma.compress(blob, preset=9 | lzma.PRESET_EXTREME))
             print("sponza_bvh8.bvh.xz", n_nodes, n_tris, len(blob))
+        if typ == F.BVH4_TRI4:
+            payload = data[off - 20: off + n_nodes * 128 + n_tris * 224]
+            blob = struct.pack("<I", F.BVH_MAGIC) + payload
+            (HERE / "sponza_bvh4.bvh.xz").write_bytes(lzma.compress(blob, preset=9 | lzma.PRESET_EXTREME))
+            print("sponza_bvh4.bvh.xz", n_nodes, n_tris, len(blob))
     for name in ("ref-primary.png", "ref-random.png", "ref-cornell.png", "cornell_box.obj", "cornell_box.mtl"):
         shutil.copyfile(REF / name, HERE / name)
 

@@ -173,3 +173,46 @@ def test_kernel_launches_are_counted(gpu, ray_sets):
     run_gpu(gpu, np.ascontiguousarray(ray_sets["primary"][:1024]))
     assert L.rodent_b200_launch_count() == before + 1
     assert L.rodent_b200_last_kernel_ms(0) > 0
+
+
+# ---- BVH4 input (the reference's default --bvh-width) ---------------------------------------------------
+@pytest.fixture(scope="module")
+def sponza4():
+    from rodent_b200 import testdata
+    return formats.load_bvh(testdata.sponza_bvh4(), formats.BVH4_TRI4)
+
+
+@pytest.fixture(scope="module")
+def gpu4(sponza4):
+    from rodent_b200 import traversal
+    return traversal.Bvh8(0, *sponza4)
+
+
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_bvh4_closest_and_any_hit_bit_exact(name, gpu4, sponza4, ray_sets):
+    from oracle import oracle
+    nodes4, tris4 = sponza4
+    want = oracle.traverse(nodes4, tris4, ray_sets[name])
+    assert_records_equal(run_gpu(gpu4, ray_sets[name]), want)
+    occl = run_gpu(gpu4, ray_sets[name], any_hit=True)
+    assert np.array_equal(occl["tri_id"], oracle.traverse(nodes4, tris4, ray_sets[name], any_hit=True)["tri_id"])
+    ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
+    assert int((ref != formats.fbuf_to_gray(want["t"]).reshape(1024, 1024)).sum()) <= 2
+
+
+def test_bvh4_degenerate_rays_and_host_entry_point(gpu4, sponza4, ray_sets):
+    from oracle import oracle
+    from rodent_b200 import traversal
+    nodes4, tris4 = sponza4
+    rng = np.random.default_rng(11)
+    n = 10_000
+    od = np.empty((n, 6), np.float32)
+    od[:, :3] = rng.uniform([-1900, -100, -1100], [1800, 1400, 1100], (n, 3))
+    od[:, 3:] = rng.normal(size=(n, 3)) * 300
+    od[::7, 3] = 0.0; od[::11, 4] = 0.0; od[::13, 5] = -0.0; od[::77, 3:] = 0.0; od[::5, 3:] *= 1e-12
+    rays = formats.make_rays(od, 0.0, 10.0)
+    rays["tmin"][::3] = 0.25
+    rays["tmax"][::17] = 0.1
+    assert_records_equal(run_gpu(gpu4, rays), oracle.traverse(nodes4, tris4, rays))
+    some = np.ascontiguousarray(ray_sets["random"][:20_001])
+    assert_records_equal(traversal.intersect_host(nodes4, tris4, some), oracle.traverse(nodes4, tris4, some))

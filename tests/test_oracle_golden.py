@@ -124,13 +124,13 @@ def test_sorting_networks():
             assert k == sorted(k, reverse=True)
 
 
-@pytest.mark.skipif(not (REFERENCE / "testing/sponza.bvh").exists(), reason="reference tree not present")
 def test_bvh4_block_gives_same_records(ray_sets, oracle_hits):
     """The BVH4 block of the reference file carries the same triangles.  Records agree
     with the BVH8 traversal up to visit order: coplanar overlapping triangles (Sponza has
     many) are accepted through `t <= |det| * tmax` and the survivor depends on which was
     met first, which moves t by at most 1 ulp ("Ties")."""
-    nodes4, tris4 = formats.load_bvh(REFERENCE / "testing/sponza.bvh", formats.BVH4_TRI4)
+    from rodent_b200 import testdata
+    nodes4, tris4 = formats.load_bvh(testdata.sponza_bvh4(), formats.BVH4_TRI4)
     for name in ("primary", "random"):
         h4 = oracle.traverse(nodes4, tris4, ray_sets[name])
         h8 = oracle_hits[name]
@@ -138,3 +138,14 @@ def test_bvh4_block_gives_same_records(ray_sets, oracle_hits):
         assert (np.abs(h4["t"] - h8["t"]) <= np.spacing(np.maximum(h4["t"], h8["t"]))).all()
         assert (h4["t"] == h8["t"]).mean() > 0.998
         assert (h4["tri_id"] == h8["tri_id"]).mean() > 0.99
+
+
+def test_bvh4_hit_distance_matches_golden_png(ray_sets):
+    """The reference's CTest runs single_bvh4 against the same golden image (tools/CMakeLists.txt:26-31)."""
+    from PIL import Image
+    from rodent_b200 import testdata
+    nodes4, tris4 = formats.load_bvh(testdata.sponza_bvh4(), formats.BVH4_TRI4)
+    for name in ("primary", "random"):
+        h4 = oracle.traverse(nodes4, tris4, ray_sets[name])
+        ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
+        assert int((ref != formats.fbuf_to_gray(h4["t"]).reshape(1024, 1024)).sum()) <= 2
