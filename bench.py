@@ -79,6 +79,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.window = [None, None]          # timed region, perf_counter seconds
+
+    def mark_start(self):
+        self.window[0] = time.perf_counter()
+
+    def mark_end(self):
+        self.window[1] = time.perf_counter()
 
     def __enter__(self):
         try:
@@ -93,7 +100,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
         if self.proc:
@@ -102,12 +109,20 @@ class ClockSampler:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
-        if not sm:
+        """Samples taken inside the timed region (nvidia-smi is started before the warm-up so that it is up by then);
+        when the region was shorter than the sampling period, the sample nearest to it."""
+        rows = [r for r in self.rows if len(r) >= 7 and r[1].isdigit()]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        t0, t1 = self.window
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1 + 0.06]
+        if not inside and t0 is not None:
+            inside = [min(rows, key=lambda r: abs(r[0] - t0))]
+        rows = inside or rows
+        sm = [int(r[1]) for r in rows]
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k] == "Active" for r in rows)]
         return {"sm_mhz": int(statistics.median(sm)), "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -292,17 +307,19 @@ def main():
         torch.cuda.synchronize()
         return [traversal.intersect(bvh, d_rays[n], d_hits[n]) for n in names]
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = L.rodent_b200_launch_count()
-    per_set = []
-    t_wall0 = time.perf_counter()
     with ClockSampler(local) as clocks:
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        launches0 = L.rodent_b200_launch_count()
+        per_set = []
+        t_wall0 = time.perf_counter()
+        clocks.mark_start()
         for _ in range(args.steps):
             per_set.append(step())
         barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+        clocks.mark_end()
+        wall_ms = (time.perf_counter() - t_wall0) * 1e3
     launches = L.rodent_b200_launch_count() - launches0
     per_set = np.array(per_set)                      # steps x sets
     kernel_ms = float(per_set.sum())                 # timed region on the device: K steps
