@@ -9,8 +9,8 @@
 //   traverse_primary  persistent closest-hit traversal; writes the hit record and
 //                     counts rays per material in shared memory                       (:18-30 + count pass of :191-199)
 //   scan              exclusive scan of the per-material counts on the device          (host scan of :201-208)
-//   scatter           counting-sort scatter of the hit rays by material                (:210-220); misses are dropped here
-//   shade             surface element + emission + next-event estimation + bounce,
+//   scatter           counting sort of the hit rays by material -- of their INDICES     (:210-220); misses are dropped here
+//   shade             gathers its rays in material order; surface element + emission + next-event estimation + bounce,
 //                     material looked up in a table; surviving paths and shadow rays are
 //                     written compacted (ballot ranks, one atomicAdd per warp), which
 //                     replaces the separate compaction pass                            (:82-134 + :267-300)
@@ -64,13 +64,14 @@ struct CameraDev { shade::V3 eye, dir, up, right; float w, h; };
 
 // ---- generate (gpu_generate_rays + make_camera_emitter, renderer.impala:26-40, camera.impala:35-44) ----
 __global__ void __launch_bounds__(256)
-generate_rays(PrimaryStream s, int first_ray_id, int first_dst, int n, CameraDev cam, int width, int height, int spp, int iter,
+generate_rays(PrimaryStream s, long long first_ray_id, int first_dst, int n, CameraDev cam, int width, int height, int spp, int iter,
               const int* __restrict__ rows) {
     using namespace shade;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n) return;
-    const int ray_id = first_ray_id + gid, dst = first_dst + gid;
-    const int sample = ray_id % spp, local_pixel = ray_id / spp;
+    const long long ray_id = first_ray_id + gid;
+    const int dst = first_dst + gid;
+    const int sample = int(ray_id % spp), local_pixel = int(ray_id / spp);
     const int ly = local_pixel / width, x = local_pixel - ly * width;
     const int y = __ldg(rows + ly);
     unsigned rnd = fnv_hash(fnv_hash(fnv_hash(fnv_hash(0x811C9DC5u, unsigned(sample)), unsigned(iter)), unsigned(x)), unsigned(y));
@@ -142,9 +143,12 @@ __global__ void scan_bins(int* __restrict__ histogram, int* __restrict__ cursor,
     }
 }
 
-// ---- scatter: counting sort by material (gpu_sort_primary third pass + copy_primary_ray, :136-164, 210-220) ----
+// ---- scatter: counting sort by material (gpu_sort_primary third pass, :210-220) ----
+// The reference moves the whole 80-byte ray to its sorted position (copy_primary_ray, :136-164).  Here only the
+// ray's INDEX is moved: order[d] = i, 8 bytes of traffic per ray instead of 164, and the shade kernel gathers its
+// inputs through `order` (rays of one material keep their stream order, so the gather stays sector-friendly).
 __global__ void __launch_bounds__(256)
-scatter_by_material(PrimaryStream src, PrimaryStream dst, int size, int num_geoms, int* __restrict__ cursor) {
+scatter_by_material(PrimaryStream src, int* __restrict__ order, int size, int num_geoms, int* __restrict__ cursor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = i < size ? src.geom[i] : num_geoms;
     const bool live = g < num_geoms;
@@ -155,23 +159,17 @@ scatter_by_material(PrimaryStream src, PrimaryStream dst, int size, int num_geom
     if (live && int(lane_id()) == leader) base = atomicAdd(cursor + g, __popc(peers));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (!live) return;
-    const int d = base + __popc(peers & lanemask_lt());
-    dst.pixel[d] = src.pixel[i];
-    dst.ray_o[d] = src.ray_o[i];
-    dst.ray_d[d] = src.ray_d[i];
-    dst.hit[d] = src.hit[i];
-    dst.geom[d] = g;
-    dst.contrib_mis[d] = src.contrib_mis[i];
-    dst.rnd_depth[d] = src.rnd_depth[i];
+    order[base + __popc(peers & lanemask_lt())] = i;
 }
 
 // ---- shade (gpu_shade, mapping_gpu.impala:82-134, with the path tracer of renderer.impala:62-162) ----
 __global__ void __launch_bounds__(128)
-shade_rays(PrimaryStream in, PrimaryStream out, ShadowStream shadow, SceneDev sc, int* __restrict__ counters,
-           float* __restrict__ film, float inv_spp, int max_path_len) {
+shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, ShadowStream shadow, SceneDev sc,
+           int* __restrict__ counters, float* __restrict__ film, float inv_spp, int max_path_len) {
     using namespace shade;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < counters[kHitCount];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;       // position in material order
+    const bool live = k < counters[kHitCount];
+    const int i = live ? __ldg(order + k) : 0;                 // the ray's place in the stream
     bool emit_shadow = false, bounce = false;
     int pixel = 0;
     float4 sh_o, sh_d, sh_c, b_o, b_d, b_c;
@@ -281,7 +279,7 @@ struct Renderer {
     ShadowStream shadow{};
     SceneDev scene{};
     std::vector<void*> allocations;
-    int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr;
+    int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr; int* order = nullptr;
     int* h_counters = nullptr;                  // pinned
     float* film = nullptr; float* own_film = nullptr; float* h_film = nullptr;
     int sm_count = 0, occ_primary = 0, occ_shadow = 0;
@@ -328,6 +326,7 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     r->shadow.pixel = r->alloc<int>(kCapacity); r->shadow.ray_o = r->alloc<float4>(kCapacity);
     r->shadow.ray_d = r->alloc<float4>(kCapacity); r->shadow.color = r->alloc<float4>(kCapacity);
     r->counters = r->alloc<int>(kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
+    r->order = r->alloc<int>(kCapacity);
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
     r->film = r->own_film = r->alloc<float>(size_t(width) * height * 3);
@@ -380,7 +379,7 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
     while (id < total || size > 0) {
         if (size < kCapacity && id < total) {
             const int n = int(std::min<int64_t>(total - id, kCapacity - size));
-            generate_rays<<<(n + 255) / 256, 256, 0, s>>>(P, int(id), size, n, cam, r.width, r.height, r.spp, iter, r.d_rows);
+            generate_rays<<<(n + 255) / 256, 256, 0, s>>>(P, (long long)id, size, n, cam, r.width, r.height, r.spp, iter, r.d_rows);
             id += n; size += n; n_kernels++;
         }
         RB_CUDA_CHECK(cudaMemsetAsync(r.counters, 0, kNumCounters * sizeof(int), s));
@@ -388,8 +387,9 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
         traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
                                                           r.histogram, nullptr, nullptr, nullptr, 0.0f, r.counters + kWorkPrimary, kRefillMin);
         scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, r.counters);
-        scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, Q, size, num_geoms, r.cursor);
-        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(Q, P, r.shadow, r.scene, r.counters, r.film, inv_spp, r.max_path_len);
+        scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
+        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, r.counters, r.film, inv_spp, r.max_path_len);
+        std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
         const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
         traverse_stream<true><<<grid_s, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, r.counters + kShadows, size,
                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
