@@ -306,6 +306,38 @@ typedef struct TriHit { int32_t id; Vec2 uv; } TriHit;
 void bench_interface(const ShadedMesh* mesh, const TriHit* tri_hits, const Vec3* in_dirs, const Vec3* out_dirs,
                      Color* colors, int32_t n);
 
+/* ======================================================================== *
+ * Shading micro-benchmark (tools/bench_shading)
+ * ======================================================================== */
+
+/* src/render/driver.impala:24-52: one array per field, all of the same capacity. */
+typedef struct RayStream {
+    int32_t* id;
+    float *org_x, *org_y, *org_z, *dir_x, *dir_y, *dir_z, *tmin, *tmax;
+} RayStream;
+typedef struct PrimaryStream {
+    RayStream rays;
+    int32_t  *geom_id, *prim_id;
+    float    *t, *u, *v;
+    uint32_t *rnd;
+    float    *mis, *contrib_r, *contrib_g, *contrib_b;
+    int32_t  *depth;
+    int32_t  size, pad;
+} PrimaryStream;
+
+/* Drop-in for the call site of
+ *   cpu_bench_shading(primary_in, primary_out, vertices, normals, face_normals, texcoords, indices, pixels,
+ *                     width, height, begins, ends, num_tris, num_iters)
+ *   (tools/bench_shading/bench_shading.impala:22-104, called at tools/bench_shading/bench_shading.cpp:207-222):
+ * identical signature, HOST pointers.  For every ray of the four geometry ranges [begins[g], ends[g]) the surface
+ * element, a material made of a diffuse and a Phong lobe mixed by luminance (constant or bilinear, repeat-border
+ * texture colours depending on the geometry id), one BSDF sample, and the bounced ray + path state written to
+ * primary_out; repeated num_iters times.  Inputs are uploaded, outputs downloaded on every call. */
+void b200_bench_shading(const PrimaryStream* primary_in, PrimaryStream* primary_out,
+                        const Vec3* vertices, const Vec3* normals, const Vec3* face_normals, const Vec2* texcoords,
+                        const int32_t* indices, const uint32_t* pixels, int32_t width, int32_t height,
+                        const int32_t* begins, const int32_t* ends, int32_t num_tris, int32_t num_iters);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,8 @@ def bench_interface(mesh, tri_hits: np.ndarray, in_dirs: np.ndarray, out_dirs: n
     colors = np.zeros((len(tri_hits), 3), np.float32)
     L.oracle_bench_interface(ctypes.byref(mesh), _ptr(tri_hits), _ptr(in_dirs), _ptr(out_dirs), _ptr(colors), len(tri_hits))
     return colors
+
+
+def bench_shading_fn():
+    """oracle_bench_shading (render_oracle.c): same argument list as cpu_bench_shading."""
+    return lib().oracle_bench_shading

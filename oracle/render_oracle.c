@@ -389,3 +389,73 @@ void oracle_render(const RodentSceneView* sc, const Settings* cam, int width, in
     }
     free(jobs);
 }
+
+/* ---- cpu_bench_shading, tools/bench_shading/bench_shading.impala:22-104 ------------------------------------
+ * CPU restatement (same signature, host pointers).  Parity status: UNPINNED by the reference -- the tool prints a
+ * throughput and checks no value.  Known answers that follow from the source alone are asserted in
+ * tests/test_shading_bench.py (constant-colour geometry 0: a pure function of the BSDF sample; depth + 1; tmin = offset).
+ * The reference runs it with FTZ/DAZ set (bench_shading.cpp:57-59); no denormal occurs on its inputs. */
+static Col rgba32_texture(const uint32_t* pixels, int width, int height, float u, float v) {   /* image.impala:24-92: repeat border, bilinear */
+    u = u - floorf(u); v = v - floorf(v);
+    const float fu = u * (float)width, fv = v * (float)height;
+    int x0 = (int)fu; if (x0 > width - 1) x0 = width - 1;
+    int y0 = (int)fv; if (y0 > height - 1) y0 = height - 1;
+    const int x1 = x0 + 1 < width - 1 ? x0 + 1 : width - 1, y1 = y0 + 1 < height - 1 ? y0 + 1 : height - 1;
+    const float kx = fu - (float)(int)fu, ky = fv - (float)(int)fv;
+    Col p[4];
+    const int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+    for (int k = 0; k < 4; k++) {
+        const uint32_t q = pixels[ys[k] * width + xs[k]];
+        p[k] = col((float)(q & 0xFFu) * (1.0f / 255.0f), (float)((q >> 8) & 0xFFu) * (1.0f / 255.0f), (float)((q >> 16) & 0xFFu) * (1.0f / 255.0f));
+    }
+    return col(lerp1(lerp1(p[0].r, p[1].r, kx), lerp1(p[2].r, p[3].r, kx), ky),
+               lerp1(lerp1(p[0].g, p[1].g, kx), lerp1(p[2].g, p[3].g, kx), ky),
+               lerp1(lerp1(p[0].b, p[1].b, kx), lerp1(p[2].b, p[3].b, kx), ky));
+}
+
+void oracle_bench_shading(const PrimaryStream* in, PrimaryStream* out, const Vec3* vertices, const Vec3* normals,
+                          const Vec3* face_normals, const Vec2* texcoords, const int32_t* indices, const uint32_t* pixels,
+                          int32_t width, int32_t height, const int32_t* begins, const int32_t* ends, int32_t num_tris, int32_t num_iters) {
+    (void)vertices; (void)num_tris;
+    for (int iter = 0; iter < num_iters; iter++)
+        for (int geom_id = 0; geom_id < 4; geom_id++)                                   /* iterate_rays, :7-20 */
+            for (int i = begins[geom_id]; i < ends[geom_id]; i++) {
+                const V3 org = v3(in->rays.org_x[i], in->rays.org_y[i], in->rays.org_z[i]);
+                const V3 dir = v3(in->rays.dir_x[i], in->rays.dir_y[i], in->rays.dir_z[i]);
+                const int prim = in->prim_id[i];
+                const float t = in->t[i], hu = in->u[i], hv = in->v[i];
+                uint32_t rnd = in->rnd[i];
+                /* surface_element, geometry.impala:21-53 */
+                const int i0 = indices[prim * 4], i1 = indices[prim * 4 + 1], i2 = indices[prim * 4 + 2];
+                const V3 fn = v3(face_normals[prim].x, face_normals[prim].y, face_normals[prim].z);
+                const V3 normal = vnormalize(v3(lerp2(normals[i0].x, normals[i1].x, normals[i2].x, hu, hv),
+                                                lerp2(normals[i0].y, normals[i1].y, normals[i2].y, hu, hv),
+                                                lerp2(normals[i0].z, normals[i1].z, normals[i2].z, hu, hv)));
+                Surf surf;
+                surf.is_entering = vdot(dir, fn) <= 0.0f;
+                surf.point = vadd(org, vmulf(dir, t));
+                surf.face_normal = surf.is_entering ? fn : vneg(fn);
+                surf.local = orthonormal(vdot(dir, normal) <= 0.0f ? normal : vneg(normal));
+                const float tu = lerp2(texcoords[i0].x, texcoords[i1].x, texcoords[i2].x, hu, hv);
+                const float tv = lerp2(texcoords[i0].y, texcoords[i1].y, texcoords[i2].y, hu, hv);
+                /* shader, :45-62 */
+                const Col tex = rgba32_texture(pixels, width, height, tu, tv);
+                const Col kd = (geom_id & 1) == 0 ? col(0.0f, 1.0f, 0.0f) : tex;
+                const Col ks = (geom_id & 2) == 0 ? col(0.0f, 1.0f, 0.0f) : tex;
+                RodentMaterial mat;
+                memset(&mat, 0, sizeof mat);
+                mat.bsdf = RODENT_BSDF_MIX; mat.ns = (geom_id & 2) == 0 ? 96.0f : 12.0f; mat.ni = 1.0f;
+                mat.kd[0] = kd.r; mat.kd[1] = kd.g; mat.kd[2] = kd.b; mat.ks[0] = ks.r; mat.ks[1] = ks.g; mat.ks[2] = ks.b;
+                const float lum_ks = luminance(ks), lum_kd = luminance(kd);
+                mat.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
+                /* :84-98 */
+                const V3 out_dir = vneg(dir);
+                const BsdfSample smp = bsdf_sample(&mat, &surf, &rnd, out_dir);
+                const Col contrib = cmulf(cmul(col(in->contrib_r[i], in->contrib_g[i], in->contrib_b[i]), smp.color), smp.cos / smp.pdf);
+                out->rays.org_x[i] = surf.point.x; out->rays.org_y[i] = surf.point.y; out->rays.org_z[i] = surf.point.z;
+                out->rays.dir_x[i] = smp.in_dir.x; out->rays.dir_y[i] = smp.in_dir.y; out->rays.dir_z[i] = smp.in_dir.z;
+                out->rays.tmin[i] = 0.0001f; out->rays.tmax[i] = 3.4028234664e+38f;
+                out->rnd[i] = rnd; out->contrib_r[i] = contrib.r; out->contrib_g[i] = contrib.g; out->contrib_b[i] = contrib.b;
+                out->mis[i] = 1.0f / smp.pdf; out->depth[i] = in->depth[i] + 1;
+            }
+}

@@ -7,6 +7,9 @@
 // The kernel is a stream: 12 B TriHit in, 12 B Color out per hit (plus 24 B of directions the shader does
 // not read), the two triangles and the 12 MB kd texture stay in cache -- so it is HBM-bound, and it is laid
 // out for that: every thread handles four consecutive hits with 16-byte loads and stores, grid = one wave.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "shading.cuh"
 
@@ -98,6 +101,96 @@ bench_interface_kernel(ShadedMesh mesh, const TriHit* __restrict__ tri_hits, con
     }
 }
 
+// ---- bench_shading (tools/bench_shading/bench_shading.impala:22-104) ------------------------------------
+constexpr int kShadingGeoms = 4;                 // static num_geoms = 4 (:2)
+constexpr float kShadingOffset = 0.0001f;        // static offset (:3)
+
+struct ShadingArgs {
+    // input stream (device copies of the fields the benchmark reads) and output stream
+    const float *org_x, *org_y, *org_z, *dir_x, *dir_y, *dir_z;
+    const int* prim_id; const float *t, *u, *v; const unsigned* rnd; const float *contrib_r, *contrib_g, *contrib_b; const int* depth;
+    float *o_org_x, *o_org_y, *o_org_z, *o_dir_x, *o_dir_y, *o_dir_z, *o_tmin, *o_tmax, *o_mis, *o_contrib_r, *o_contrib_g, *o_contrib_b;
+    unsigned* o_rnd; int* o_depth;
+    const Vec3 *vertices, *normals, *face_normals; const Vec2* texcoords; const int* indices; const unsigned* pixels;
+    int width, height, num_iters;
+    int begins[kShadingGeoms], ends[kShadingGeoms];
+};
+
+// make_texture(repeat border, bilinear filter, make_image_rgba32), src/render/image.impala:24-92
+__device__ __forceinline__ shade::Col rgba32_texture(const unsigned* __restrict__ pixels, int width, int height, float u, float v) {
+    using namespace shade;
+    u = u - floorf(u); v = v - floorf(v);
+    const float fu = u * float(width), fv = v * float(height);
+    const int x0 = min(int(fu), width - 1), y0 = min(int(fv), height - 1);
+    const int x1 = min(x0 + 1, width - 1), y1 = min(y0 + 1, height - 1);
+    const float kx = fu - float(int(fu)), ky = fv - float(int(fv));
+    auto px = [&](int x, int y) {
+        const unsigned p = __ldg(pixels + y * width + x);
+        return col(float(p & 0xFFu) * (1.0f / 255.0f), float((p >> 8) & 0xFFu) * (1.0f / 255.0f), float((p >> 16) & 0xFFu) * (1.0f / 255.0f));
+    };
+    const Col p00 = px(x0, y0), p10 = px(x1, y0), p01 = px(x0, y1), p11 = px(x1, y1);
+    return col(lerp1(lerp1(p00.r, p10.r, kx), lerp1(p01.r, p11.r, kx), ky),
+               lerp1(lerp1(p00.g, p10.g, kx), lerp1(p01.g, p11.g, kx), ky),
+               lerp1(lerp1(p00.b, p10.b, kx), lerp1(p01.b, p11.b, kx), ky));
+}
+
+__global__ void __launch_bounds__(128)
+bench_shading_kernel(ShadingArgs a) {
+    using namespace shade;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int geom_id = -1;                                             // iterate_rays, sorted + specialized (:7-20)
+#pragma unroll
+    for (int g = 0; g < kShadingGeoms; g++)
+        if (i >= a.begins[g] && i < a.ends[g]) geom_id = g;
+    if (geom_id < 0) return;
+    for (int iter = 0; iter < a.num_iters; iter++) {
+        const V3 org = v3(a.org_x[i], a.org_y[i], a.org_z[i]), dir = v3(a.dir_x[i], a.dir_y[i], a.dir_z[i]);
+        const int prim = a.prim_id[i];
+        const float t = a.t[i], hu = a.u[i], hv = a.v[i];
+        unsigned rnd = a.rnd[i];
+        const Col contrib_in = col(a.contrib_r[i], a.contrib_g[i], a.contrib_b[i]);
+        const int depth = a.depth[i];
+
+        // make_tri_mesh_geometry(...).surface_element, src/render/geometry.impala:21-53
+        const int i0 = a.indices[prim * 4 + 0], i1 = a.indices[prim * 4 + 1], i2 = a.indices[prim * 4 + 2];
+        auto vec = [](const Vec3& q) { return v3(q.x, q.y, q.z); };
+        const V3 fn = vec(a.face_normals[prim]);
+        const V3 n0 = vec(a.normals[i0]), n1 = vec(a.normals[i1]), n2 = vec(a.normals[i2]);
+        const V3 normal = normalize(v3(lerp2(n0.x, n1.x, n2.x, hu, hv), lerp2(n0.y, n1.y, n2.y, hu, hv), lerp2(n0.z, n1.z, n2.z, hu, hv)));
+        Surf surf;
+        surf.is_entering = dot(dir, fn) <= 0.0f;
+        surf.point = org + dir * t;
+        surf.face_normal = surf.is_entering ? fn : -fn;
+        surf.local = orthonormal(dot(dir, normal) <= 0.0f ? normal : -normal);
+        const Vec2 t0 = a.texcoords[i0], t1 = a.texcoords[i1], t2 = a.texcoords[i2];
+        const float tu = lerp2(t0.x, t1.x, t2.x, hu, hv), tv = lerp2(t0.y, t1.y, t2.y, hu, hv);     // attr(0), vec4_lerp2
+
+        // shader (:45-62): diffuse + Phong mixed by luminance
+        const Col tex = rgba32_texture(a.pixels, a.width, a.height, tu, tv);
+        const Col kd = (geom_id & 1) == 0 ? col(0.0f, 1.0f, 0.0f) : tex;
+        const Col ks = (geom_id & 2) == 0 ? col(0.0f, 1.0f, 0.0f) : tex;
+        const float ns = (geom_id & 2) == 0 ? 96.0f : 12.0f;
+        const float lum_ks = luminance(ks), lum_kd = luminance(kd);
+        RodentMaterial mat;
+        mat.bsdf = RODENT_BSDF_MIX; mat.is_emissive = 0; mat.ns = ns; mat.ni = 1.0f;
+        mat.kd[0] = kd.r; mat.kd[1] = kd.g; mat.kd[2] = kd.b;
+        mat.ks[0] = ks.r; mat.ks[1] = ks.g; mat.ks[2] = ks.b;
+        mat.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
+
+        const V3 out_dir = -dir;
+        const BsdfSample smp = bsdf_sample(mat, surf, rnd, out_dir);
+        const Col contrib = (contrib_in * smp.color) * (smp.cos / smp.pdf);
+        const float mis = 1.0f / smp.pdf;                          // neither lobe is specular
+
+        a.o_org_x[i] = surf.point.x; a.o_org_y[i] = surf.point.y; a.o_org_z[i] = surf.point.z;
+        a.o_dir_x[i] = smp.in_dir.x; a.o_dir_y[i] = smp.in_dir.y; a.o_dir_z[i] = smp.in_dir.z;
+        a.o_tmin[i] = kShadingOffset; a.o_tmax[i] = kFltMax;
+        a.o_rnd[i] = rnd; a.o_contrib_r[i] = contrib.r; a.o_contrib_g[i] = contrib.g; a.o_contrib_b[i] = contrib.b;
+        a.o_mis[i] = mis; a.o_depth[i] = depth + 1;
+        asm volatile("" ::: "memory");                             // every iteration is carried out, as in the reference's loop
+    }
+}
+
 }  // namespace
 }  // namespace rb200
 
@@ -112,4 +205,68 @@ extern "C" void bench_interface(const ShadedMesh* mesh, const TriHit* tri_hits, 
     RB_CUDA_CHECK(cudaGetLastError());
     rodent_b200_count_launches(1);
     RB_CUDA_CHECK(cudaDeviceSynchronize());           // acc.sync(), :64
+}
+
+extern "C" void b200_bench_shading(const PrimaryStream* in, PrimaryStream* out, const Vec3* vertices, const Vec3* normals,
+                                   const Vec3* face_normals, const Vec2* texcoords, const int32_t* indices, const uint32_t* pixels,
+                                   int32_t width, int32_t height, const int32_t* begins, const int32_t* ends, int32_t num_tris,
+                                   int32_t num_iters) {
+    using namespace rb200;
+    int n = 0, num_vertices = 0;
+    for (int g = 0; g < kShadingGeoms; g++) n = std::max(n, ends[g]);
+    for (int k = 0; k < num_tris * 4; k++)
+        if (k % 4 != 3) num_vertices = std::max(num_vertices, indices[k] + 1);
+    if (n <= 0 || num_iters <= 0) return;
+    std::vector<void*> allocations;
+    auto upload = [&](const void* src, size_t bytes) {
+        void* p = nullptr;
+        RB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        RB_CUDA_CHECK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        allocations.push_back(p);
+        return p;
+    };
+    auto device = [&](size_t bytes) {
+        void* p = nullptr;
+        RB_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        allocations.push_back(p);
+        return p;
+    };
+    const size_t nb = size_t(n) * 4;
+    ShadingArgs a{};
+#define RB_IN(field, src) a.field = static_cast<decltype(a.field)>(upload(src, nb))
+    RB_IN(org_x, in->rays.org_x); RB_IN(org_y, in->rays.org_y); RB_IN(org_z, in->rays.org_z);
+    RB_IN(dir_x, in->rays.dir_x); RB_IN(dir_y, in->rays.dir_y); RB_IN(dir_z, in->rays.dir_z);
+    RB_IN(prim_id, in->prim_id); RB_IN(t, in->t); RB_IN(u, in->u); RB_IN(v, in->v); RB_IN(rnd, in->rnd);
+    RB_IN(contrib_r, in->contrib_r); RB_IN(contrib_g, in->contrib_g); RB_IN(contrib_b, in->contrib_b); RB_IN(depth, in->depth);
+#undef RB_IN
+#define RB_OUT(field) a.field = static_cast<decltype(a.field)>(device(nb))
+    RB_OUT(o_org_x); RB_OUT(o_org_y); RB_OUT(o_org_z); RB_OUT(o_dir_x); RB_OUT(o_dir_y); RB_OUT(o_dir_z); RB_OUT(o_tmin); RB_OUT(o_tmax);
+    RB_OUT(o_mis); RB_OUT(o_contrib_r); RB_OUT(o_contrib_g); RB_OUT(o_contrib_b); RB_OUT(o_rnd); RB_OUT(o_depth);
+#undef RB_OUT
+    a.vertices = static_cast<const Vec3*>(upload(vertices, size_t(num_vertices) * sizeof(Vec3)));
+    a.normals = static_cast<const Vec3*>(upload(normals, size_t(num_vertices) * sizeof(Vec3)));
+    a.face_normals = static_cast<const Vec3*>(upload(face_normals, size_t(num_tris) * sizeof(Vec3)));
+    a.texcoords = static_cast<const Vec2*>(upload(texcoords, size_t(num_vertices) * sizeof(Vec2)));
+    a.indices = static_cast<const int*>(upload(indices, size_t(num_tris) * 4 * sizeof(int)));
+    a.pixels = static_cast<const unsigned*>(upload(pixels, size_t(width) * height * sizeof(unsigned)));
+    a.width = width; a.height = height; a.num_iters = num_iters;
+    for (int g = 0; g < kShadingGeoms; g++) { a.begins[g] = begins[g]; a.ends[g] = ends[g]; }
+
+    bench_shading_kernel<<<(n + 127) / 128, 128>>>(a);
+    RB_CUDA_CHECK(cudaGetLastError());
+    rodent_b200_count_launches(1);
+    // only the rays of the four ranges were written; copy exactly those back
+    for (int g = 0; g < kShadingGeoms; g++) {
+        const int b = begins[g], cnt = ends[g] - begins[g];
+        if (cnt <= 0) continue;
+#define RB_BACK(dst, src) RB_CUDA_CHECK(cudaMemcpy((dst) + b, (src) + b, size_t(cnt) * 4, cudaMemcpyDeviceToHost))
+        RB_BACK(out->rays.org_x, a.o_org_x); RB_BACK(out->rays.org_y, a.o_org_y); RB_BACK(out->rays.org_z, a.o_org_z);
+        RB_BACK(out->rays.dir_x, a.o_dir_x); RB_BACK(out->rays.dir_y, a.o_dir_y); RB_BACK(out->rays.dir_z, a.o_dir_z);
+        RB_BACK(out->rays.tmin, a.o_tmin); RB_BACK(out->rays.tmax, a.o_tmax);
+        RB_BACK(out->rnd, a.o_rnd); RB_BACK(out->mis, a.o_mis);
+        RB_BACK(out->contrib_r, a.o_contrib_r); RB_BACK(out->contrib_g, a.o_contrib_g); RB_BACK(out->contrib_b, a.o_contrib_b);
+        RB_BACK(out->depth, a.o_depth);
+#undef RB_BACK
+    }
+    for (void* p : allocations) RB_CUDA_CHECK(cudaFree(p));
 }

@@ -1,5 +1,6 @@
-"""Host-side mirror of tools/bench_interface/bench_interface.cpp: the quad mesh, the three textures, the
-1 Mi random hits, and the call of `bench_interface` (include/rodent_b200.h)."""
+"""Host-side mirrors of tools/bench_interface/bench_interface.cpp (the quad mesh, the three textures, the 1 Mi random
+hits, the call of `bench_interface`) and of tools/bench_shading/bench_shading.cpp (streams, workload, the call of
+`b200_bench_shading`), over include/rodent_b200.h."""
 from __future__ import annotations
 
 import ctypes
@@ -98,3 +99,96 @@ def run_cuda(arrays, textures, width, height, hits, in_dirs, out_dirs, repeat: i
         L.bench_interface(ctypes.byref(mesh), d_hits, d_in, d_out, colors.ptr, len(hits))
     dt = (time.perf_counter() - t0) / repeat
     return colors.to_host().reshape(-1, 3), dt
+
+
+# ---- bench_shading (tools/bench_shading) ----------------------------------------------------------------
+class RayStream(ctypes.Structure):
+    """src/render/driver.impala:24-34"""
+    _fields_ = [(n, c_void_p) for n in ("id", "org_x", "org_y", "org_z", "dir_x", "dir_y", "dir_z", "tmin", "tmax")]
+
+
+class PrimaryStream(ctypes.Structure):
+    """src/render/driver.impala:36-52"""
+    _fields_ = [("rays", RayStream)] + [(n, c_void_p) for n in ("geom_id", "prim_id", "t", "u", "v", "rnd", "mis",
+                                                                  "contrib_r", "contrib_g", "contrib_b", "depth")] + \
+               [("size", c_int32), ("pad", c_int32)]
+
+
+assert ctypes.sizeof(PrimaryStream) == 20 * 8 + 8
+
+_SHADING_ARGS = [POINTER(PrimaryStream), POINTER(PrimaryStream)] + [c_void_p] * 6 + [c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32]
+SIGNATURES["b200_bench_shading"] = (None, _SHADING_ARGS)
+
+_FIELDS = ["id", "org_x", "org_y", "org_z", "dir_x", "dir_y", "dir_z", "tmin", "tmax", "geom_id", "prim_id", "t", "u", "v",
+           "rnd", "mis", "contrib_r", "contrib_g", "contrib_b", "depth"]
+_INT_FIELDS = {"id", "geom_id", "prim_id", "depth"}
+
+
+class HostStream:
+    """A primary stream carved out of one 20 * capacity float buffer (get_primary_stream, bench_shading.cpp:40-54)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = capacity
+        self.data = np.zeros(20 * capacity, np.float32)
+        self.struct = PrimaryStream()
+        for k, name in enumerate(_FIELDS):
+            addr = self.data.ctypes.data + 4 * k * capacity
+            setattr(self.struct.rays if k < 9 else self.struct, name, addr)
+        self.struct.size = 0
+
+    def field(self, name: str) -> np.ndarray:
+        k = _FIELDS.index(name)
+        view = self.data[k * self.capacity:(k + 1) * self.capacity]
+        return view.view(np.int32) if name in _INT_FIELDS else view.view(np.uint32) if name == "rnd" else view
+
+
+def shading_workload(num_rays: int = 4096, seed: int = 42, width: int = 1024, height: int = 1024):
+    """The benchmark's input (bench_shading.cpp:61-160): a quad, a checkerboard, rays from (0, 0, -1) onto the quad in
+    four geometry ranges.  numpy's generator instead of mt19937, same distribution."""
+    vertices, normals, texcoords, indices = quad_arrays()
+    face_normals = np.array([(0, 0, 1), (0, 0, 1)], np.float32)
+    yy, xx = np.mgrid[0:height, 0:width]
+    pixels = np.where((xx + yy) % 2 != 0, np.uint32(0xFFFFFFFF), np.uint32(0)).astype(np.uint32).reshape(-1)
+    rng = np.random.default_rng(seed)
+    s = HostStream(num_rays)
+    per = num_rays // 4
+    begins = np.arange(4, dtype=np.int32) * per
+    ends = begins + per
+    prim = (rng.random(num_rays) >= 0.5).astype(np.int32)
+    u, v = rng.random(num_rays, np.float32), rng.random(num_rays, np.float32)
+    flip = u + v > 1.0
+    u[flip], v[flip] = 1.0 - u[flip], 1.0 - v[flip]
+    tri = indices.reshape(-1, 4)[prim][:, :3]
+    p = ((1.0 - u - v)[:, None] * vertices[tri[:, 0]] + u[:, None] * vertices[tri[:, 1]] + v[:, None] * vertices[tri[:, 2]]).astype(np.float32)
+    org = np.array((0.0, 0.0, -1.0), np.float32)
+    d = p - org
+    geom = np.repeat(np.arange(4, dtype=np.int32), per)
+    s.field("id")[:] = np.arange(num_rays)
+    for k, name in enumerate(("org_x", "org_y", "org_z")):
+        s.field(name)[:] = org[k]
+    for k, name in enumerate(("dir_x", "dir_y", "dir_z")):
+        s.field(name)[:] = d[:, k]
+    s.field("tmin")[:] = 0.0
+    s.field("tmax")[:] = np.finfo(np.float32).max
+    s.field("geom_id")[:] = geom
+    s.field("prim_id")[:] = prim
+    s.field("t")[:] = 1.0
+    s.field("u")[:] = u
+    s.field("v")[:] = v
+    s.field("rnd")[:] = (33 * geom + np.tile(np.arange(per), 4)).astype(np.uint32)
+    s.field("mis")[:] = 0.5
+    for name in ("contrib_r", "contrib_g", "contrib_b"):
+        s.field(name)[:] = 1.0
+    s.field("depth")[:] = 0
+    s.struct.size = num_rays
+    mesh = dict(vertices=vertices, normals=normals, face_normals=face_normals, texcoords=texcoords, indices=indices, pixels=pixels,
+                width=width, height=height, begins=begins, ends=ends)
+    return s, mesh
+
+
+def call_bench_shading(fn, stream_in: HostStream, stream_out: HostStream, mesh: dict, num_iters: int) -> None:
+    """Calls `fn` (b200_bench_shading or the oracle's twin) with the reference's argument list (bench_shading.cpp:207-222)."""
+    fn.restype, fn.argtypes = None, _SHADING_ARGS
+    a = lambda name: mesh[name].ctypes.data
+    fn(ctypes.byref(stream_in.struct), ctypes.byref(stream_out.struct), a("vertices"), a("normals"), a("face_normals"), a("texcoords"),
+       a("indices"), a("pixels"), mesh["width"], mesh["height"], a("begins"), a("ends"), 2, num_iters)
