@@ -273,8 +273,8 @@ shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, S
 struct Renderer {
     int dev = 0, width = 0, height = 0, spp = 1, max_path_len = 64;
     std::vector<int> rows;                      // image rows owned by this renderer
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_shaded = nullptr, ev_shadow_done = nullptr;
     PrimaryStream prim[2]{};
     ShadowStream shadow{};
     SceneDev scene{};
@@ -319,13 +319,16 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     r->sm_count = prop.multiProcessorCount;
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_shaded, cudaEventDisableTiming));
+    RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_shadow_done, cudaEventDisableTiming));
     RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
     RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
     alloc_stream(*r, r->prim[0]);
     alloc_stream(*r, r->prim[1]);
     r->shadow.pixel = r->alloc<int>(kCapacity); r->shadow.ray_o = r->alloc<float4>(kCapacity);
     r->shadow.ray_d = r->alloc<float4>(kCapacity); r->shadow.color = r->alloc<float4>(kCapacity);
-    r->counters = r->alloc<int>(kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
+    r->counters = r->alloc<int>(2 * kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
     r->order = r->alloc<int>(kCapacity);
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
@@ -333,7 +336,7 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     RB_CUDA_CHECK(cudaMemset(r->film, 0, size_t(width) * height * 3 * sizeof(float)));
     RB_CUDA_CHECK(cudaMallocHost(&r->h_film, size_t(width) * height * 3 * sizeof(float)));
     std::memset(r->h_film, 0, size_t(width) * height * 3 * sizeof(float));
-    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, kNumCounters * sizeof(int)));
+    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, 2 * kNumCounters * sizeof(int)));
     SceneDev& d = r->scene;
     d.nodes = r->upload(sc.nodes.data(), sc.nodes.size());
     d.tris = r->upload(sc.tris.data(), sc.tris.size());
@@ -353,12 +356,16 @@ static void destroy_renderer(Renderer* r) {
     if (!r) return;
     RB_CUDA_CHECK(cudaSetDevice(r->dev));
     RB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r->stream2));
     for (void* p : r->allocations) RB_CUDA_CHECK(cudaFree(p));
     RB_CUDA_CHECK(cudaFreeHost(r->h_film));
     RB_CUDA_CHECK(cudaFreeHost(r->h_counters));
     RB_CUDA_CHECK(cudaEventDestroy(r->ev0));
     RB_CUDA_CHECK(cudaEventDestroy(r->ev1));
     RB_CUDA_CHECK(cudaStreamDestroy(r->stream));
+    RB_CUDA_CHECK(cudaStreamDestroy(r->stream2));
+    RB_CUDA_CHECK(cudaEventDestroy(r->ev_shaded));
+    RB_CUDA_CHECK(cudaEventDestroy(r->ev_shadow_done));
     delete r;
 }
 
@@ -374,32 +381,46 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
     PrimaryStream& Q = r.prim[1];
     int64_t id = 0; int size = 0;
     int64_t n_primary = 0, n_shadow = 0, n_waves = 0, n_kernels = 0;
-    cudaStream_t s = r.stream;
+    // Two streams: everything up to the shade kernel runs on `s`; the shadow-ray traversal of a wavefront runs on
+    // `s2` and overlaps the generation and closest-hit traversal of the NEXT wavefront.  Both traversals are
+    // persistent kernels whose last rays straggle (a few rays take ten times the median number of steps): the CTAs
+    // that drain early make room for the other kernel, so the tails are filled instead of waited for.  The two
+    // kernels only share the film (atomics); counters alternate between two sets so that a shadow pass still
+    // reading its set is never reset under it.
+    cudaStream_t s = r.stream, s2 = r.stream2;
     RB_CUDA_CHECK(cudaEventRecord(r.ev0, s));
     while (id < total || size > 0) {
+        const int parity = int(n_waves & 1);
+        int* counters = r.counters + parity * kNumCounters;
+        int* h_counters = r.h_counters + parity * kNumCounters;
         if (size < kCapacity && id < total) {
             const int n = int(std::min<int64_t>(total - id, kCapacity - size));
             generate_rays<<<(n + 255) / 256, 256, 0, s>>>(P, (long long)id, size, n, cam, r.width, r.height, r.spp, iter, r.d_rows);
             id += n; size += n; n_kernels++;
         }
-        RB_CUDA_CHECK(cudaMemsetAsync(r.counters, 0, kNumCounters * sizeof(int), s));
+        RB_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * sizeof(int), s));
         const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
         traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, r.counters + kWorkPrimary, kRefillMin);
-        scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, r.counters);
+                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
+        scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
         scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
-        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, r.counters, r.film, inv_spp, r.max_path_len);
+        RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
+        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, r.film, inv_spp, r.max_path_len);
+        RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));
+        RB_CUDA_CHECK(cudaMemcpyAsync(h_counters, counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
         std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
+        RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
         const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
-        traverse_stream<true><<<grid_s, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, r.counters + kShadows, size,
-                                                         nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
-                                                         r.counters + kWorkShadow, kRefillMin);
+        traverse_stream<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
+                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
+                                                          counters + kWorkShadow, kRefillMin);
+        RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
         RB_CUDA_CHECK(cudaGetLastError());
-        RB_CUDA_CHECK(cudaMemcpyAsync(r.h_counters, r.counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
-        RB_CUDA_CHECK(cudaStreamSynchronize(s));
-        n_primary += size; n_shadow += r.h_counters[kShadows]; n_waves++; n_kernels += 5;
-        size = r.h_counters[kSurvivors];
+        RB_CUDA_CHECK(cudaStreamSynchronize(s));                // survivors and shadow-ray count of this wavefront (the shadow pass runs on)
+        n_primary += size; n_shadow += h_counters[kShadows]; n_waves++; n_kernels += 5;
+        size = h_counters[kSurvivors];
     }
+    RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));
     RB_CUDA_CHECK(cudaEventRecord(r.ev1, s));
     RB_CUDA_CHECK(cudaEventSynchronize(r.ev1));
     float ms = 0.0f;
