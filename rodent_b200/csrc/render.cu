@@ -21,6 +21,7 @@
 // primary ray and 52 per shadow ray, as in the reference (src/render/driver.impala:24-61).
 #include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "scene.h"
@@ -285,6 +286,10 @@ struct Renderer {
     int sm_count = 0, occ_primary = 0, occ_shadow = 0;
     int64_t stats[5] = {0, 0, 0, 0, 0};
     double last_ms = 0.0;
+    // A renderer with several LANES drives that many independent wavefront pipelines (own streams, ray streams and
+    // counters, interleaved row bands, one host thread each) into the same film: see render_device.
+    std::vector<Renderer*> lanes;
+    Renderer* parent = nullptr;
 
     template <typename T>
     T* alloc(size_t n) {
@@ -307,17 +312,10 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
-static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
-    if (sc.materials.size() + 1 > size_t(kMaxBins)) { std::fprintf(stderr, "rodent_b200: more than 1024 materials\n"); return nullptr; }
-    if (width <= 0 || height <= 0 || spp <= 0 || num_parts <= 0 || part < 0 || part >= num_parts || band <= 0) return nullptr;
-    RB_CUDA_CHECK(cudaSetDevice(dev));
-    auto r = new Renderer();
-    r->dev = dev; r->width = width; r->height = height; r->spp = spp; r->max_path_len = max_path_len;
-    for (int y = 0; y < height; y++)
-        if ((y / band) % num_parts == part) r->rows.push_back(y);
-    cudaDeviceProp prop;
-    RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
-    r->sm_count = prop.multiProcessorCount;
+static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
+
+// Streams, events, ray streams and counters of one wavefront pipeline; `r->rows` must be set.
+static void alloc_pipeline(Renderer* r) {
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
     RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_shaded, cudaEventDisableTiming));
@@ -332,11 +330,24 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     r->order = r->alloc<int>(kCapacity);
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
+    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, 2 * kNumCounters * sizeof(int)));
+}
+
+static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
+    if (sc.materials.size() + 1 > size_t(kMaxBins)) { std::fprintf(stderr, "rodent_b200: more than 1024 materials\n"); return nullptr; }
+    if (width <= 0 || height <= 0 || spp <= 0 || num_parts <= 0 || part < 0 || part >= num_parts || band <= 0) return nullptr;
+    RB_CUDA_CHECK(cudaSetDevice(dev));
+    auto r = new Renderer();
+    r->dev = dev; r->width = width; r->height = height; r->spp = spp; r->max_path_len = max_path_len;
+    for (int y = 0; y < height; y++)
+        if ((y / band) % num_parts == part) r->rows.push_back(y);
+    cudaDeviceProp prop;
+    RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    r->sm_count = prop.multiProcessorCount;
     r->film = r->own_film = r->alloc<float>(size_t(width) * height * 3);
     RB_CUDA_CHECK(cudaMemset(r->film, 0, size_t(width) * height * 3 * sizeof(float)));
     RB_CUDA_CHECK(cudaMallocHost(&r->h_film, size_t(width) * height * 3 * sizeof(float)));
     std::memset(r->h_film, 0, size_t(width) * height * 3 * sizeof(float));
-    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, 2 * kNumCounters * sizeof(int)));
     SceneDev& d = r->scene;
     d.nodes = r->upload(sc.nodes.data(), sc.nodes.size());
     d.tris = r->upload(sc.tris.data(), sc.tris.size());
@@ -349,28 +360,76 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     d.num_materials = int(sc.materials.size()); d.num_lights = int(sc.lights.size());
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
+    // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
+    const int bands = int((r->rows.size() + 7) / 8);
+    const int num_lanes = std::max(1, std::min(g_render_lanes, bands / 4));
+    if (num_lanes == 1) {
+        alloc_pipeline(r);
+    } else {
+        RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));      // film copies, timing events
+        RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
+        RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
+        for (int j = 0; j < num_lanes; j++) {
+            auto lane = new Renderer();
+            lane->parent = r;
+            lane->dev = dev; lane->width = width; lane->height = height; lane->spp = spp; lane->max_path_len = max_path_len;
+            lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_shadow = r->occ_shadow;
+            lane->scene = r->scene;
+            for (size_t k = 0; k < r->rows.size(); k++)
+                if (int(k / 8) % num_lanes == j) lane->rows.push_back(r->rows[k]);
+            alloc_pipeline(lane);
+            r->lanes.push_back(lane);
+        }
+    }
     return r;
 }
 
 static void destroy_renderer(Renderer* r) {
     if (!r) return;
     RB_CUDA_CHECK(cudaSetDevice(r->dev));
-    RB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
-    RB_CUDA_CHECK(cudaStreamSynchronize(r->stream2));
+    for (Renderer* lane : r->lanes) destroy_renderer(lane);
+    if (r->stream) RB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    if (r->stream2) RB_CUDA_CHECK(cudaStreamSynchronize(r->stream2));
     for (void* p : r->allocations) RB_CUDA_CHECK(cudaFree(p));
-    RB_CUDA_CHECK(cudaFreeHost(r->h_film));
-    RB_CUDA_CHECK(cudaFreeHost(r->h_counters));
-    RB_CUDA_CHECK(cudaEventDestroy(r->ev0));
-    RB_CUDA_CHECK(cudaEventDestroy(r->ev1));
-    RB_CUDA_CHECK(cudaStreamDestroy(r->stream));
-    RB_CUDA_CHECK(cudaStreamDestroy(r->stream2));
-    RB_CUDA_CHECK(cudaEventDestroy(r->ev_shaded));
-    RB_CUDA_CHECK(cudaEventDestroy(r->ev_shadow_done));
+    if (r->h_film) RB_CUDA_CHECK(cudaFreeHost(r->h_film));
+    if (r->h_counters) RB_CUDA_CHECK(cudaFreeHost(r->h_counters));
+    if (r->ev0) RB_CUDA_CHECK(cudaEventDestroy(r->ev0));
+    if (r->ev1) RB_CUDA_CHECK(cudaEventDestroy(r->ev1));
+    if (r->ev_shaded) RB_CUDA_CHECK(cudaEventDestroy(r->ev_shaded));
+    if (r->ev_shadow_done) RB_CUDA_CHECK(cudaEventDestroy(r->ev_shadow_done));
+    if (r->stream) RB_CUDA_CHECK(cudaStreamDestroy(r->stream));
+    if (r->stream2) RB_CUDA_CHECK(cudaStreamDestroy(r->stream2));
     delete r;
 }
 
 // gpu_streaming_trace, mapping_gpu.impala:308-369
+static void render_pipeline(Renderer& r, float* film, const Settings& st, int iter);
+
+// One render(settings, iter) call.  With lanes, every lane runs its own wavefront loop on its own host thread and
+// streams; their kernels interleave on the device, so the stragglers at the end of one pipeline's traversal kernels
+// and the host round trip per wavefront are covered by the other pipelines' work.
 static void render_device(Renderer& r, const Settings& st, int iter) {
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    if (r.lanes.empty()) { render_pipeline(r, r.film, st, iter); return; }
+    RB_CUDA_CHECK(cudaEventRecord(r.ev0, r.stream));
+    std::vector<std::thread> threads;
+    for (Renderer* lane : r.lanes)
+        threads.emplace_back([lane, &r, &st, iter] { render_pipeline(*lane, r.film, st, iter); });
+    for (auto& t : threads) t.join();
+    RB_CUDA_CHECK(cudaEventRecord(r.ev1, r.stream));
+    RB_CUDA_CHECK(cudaEventSynchronize(r.ev1));
+    float ms = 0.0f;
+    RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+    r.last_ms = ms;
+    for (int k = 0; k < 5; k++) r.stats[k] = 0;
+    for (Renderer* lane : r.lanes) {
+        for (int k = 0; k < 5; k++) r.stats[k] += lane->stats[k];
+    }
+    r.stats[3] = 0;
+    for (Renderer* lane : r.lanes) r.stats[3] = std::max(r.stats[3], lane->stats[3]);     // wavefronts: the longest pipeline
+}
+
+static void render_pipeline(Renderer& r, float* film, const Settings& st, int iter) {
     RB_CUDA_CHECK(cudaSetDevice(r.dev));
     const CameraDev cam{{st.eye.x, st.eye.y, st.eye.z}, {st.dir.x, st.dir.y, st.dir.z}, {st.up.x, st.up.y, st.up.z},
                         {st.right.x, st.right.y, st.right.z}, st.width, st.height};
@@ -405,14 +464,14 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
         scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
         scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
         RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
-        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, r.film, inv_spp, r.max_path_len);
+        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
         RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));
         RB_CUDA_CHECK(cudaMemcpyAsync(h_counters, counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
         std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
         RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
         const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
         traverse_stream<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, r.film, inv_spp,
+                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
                                                           counters + kWorkShadow, kRefillMin);
         RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
         RB_CUDA_CHECK(cudaGetLastError());
@@ -476,6 +535,9 @@ void rodent_b200_clear(RodentRenderer* rr) {
 void rodent_b200_render_stats(const RodentRenderer* r, int64_t out[5]) { std::memcpy(out, reinterpret_cast<const Renderer*>(r)->stats, 5 * sizeof(int64_t)); }
 double rodent_b200_render_last_ms(const RodentRenderer* r) { return reinterpret_cast<const Renderer*>(r)->last_ms; }
 
+void rodent_b200_render_tune(const char* key, int32_t value) {
+    if (!std::strcmp(key, "render_lanes")) g_render_lanes = std::max(1, int(value));
+}
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;
 }

@@ -519,6 +519,8 @@ int64_t rodent_b200_launch_count(void) { return g_launches.load(); }
 void rodent_b200_count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // for the other translation units
 const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }
 
+void rodent_b200_render_tune(const char* key, int32_t value);   // render.cu
+
 // Tuning knobs for experiments (not part of the drop-in surface).
 void rodent_b200_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "persistent")) g_tuning.persistent = value;
@@ -532,6 +534,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = value;
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
+    else if (!std::strcmp(key, "render_lanes")) rodent_b200_render_tune(key, value);
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }
 

@@ -1,15 +1,17 @@
 """Developer helper: times the wavefront path tracer on the BASELINE.json render configs.
-usage: render_probe.py [cornell|sponza] [width height spp depth iters]"""
+usage: render_probe.py [cornell|sponza] [width height spp depth iters] [lanes]"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
-from rodent_b200 import render as R, workloads
+from rodent_b200 import lib, render as R, workloads
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cornell"
 cfg = workloads.RENDER_CONFIGS[name]
 W, H, spp, depth = (int(x) for x in sys.argv[2:6]) if len(sys.argv) >= 6 else (cfg["width"], cfg["height"], cfg["spp"], cfg["max_path_len"])
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+if len(sys.argv) > 7:
+    lib.tune("render_lanes", int(sys.argv[7]))
 scene = workloads.load_scene(name)
 cam = workloads.camera(name, W, H)
 r = R.Renderer(scene, 0, W, H, spp, depth)
