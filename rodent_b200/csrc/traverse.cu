@@ -425,15 +425,22 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     if (ANY)   // occluded leaves t/u/v untouched: round-trip the caller's records
         RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, s.streams[0]));
     if (ANY) RB_CUDA_CHECK(cudaStreamSynchronize(s.streams[0]));
-    const int pieces = std::max(1, g_tuning.host_chunks);
-    const int chunk = std::max(1 << 15, (num_rays + pieces - 1) / pieces);
+    // Pieces of decreasing size (k, k-1, ..., 1 parts of k(k+1)/2): the copy engine is the critical resource, and what
+    // follows the last byte of input is one piece's traversal -- including its stragglers -- and its copy out, so that
+    // last piece is kept small.
+    const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
+    const int64_t parts = int64_t(pieces) * (pieces + 1) / 2;
     int k = 0;
-    for (int first = 0; first < num_rays; first += chunk, k++) {
-        const int n = std::min(chunk, num_rays - first);
+    for (int first = 0; first < num_rays; k++) {
+        const int weight = std::max(1, pieces - k);
+        int n = int((int64_t(num_rays) * weight / parts + 3) & ~int64_t(3));
+        n = std::max(n, 1 << 14);
+        if (k >= pieces - 1 || n > num_rays - first) n = num_rays - first;
         cudaStream_t st = s.streams[k % 3];
         RB_CUDA_CHECK(cudaMemcpyAsync(s.d_rays + first, rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
         launch<ANY>(s, bvh.first, bvh.second, s.d_rays + first, s.d_hits + first, n, st, s.counter + 8 * (1 + k % 3));
         RB_CUDA_CHECK(cudaMemcpyAsync(hits + first, s.d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+        first += n;
     }
     for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
 }

@@ -12,7 +12,7 @@ for name, (tmin, tmax) in testdata.RAY_SETS.items():
     pr = traversal.PinnedArray(formats.RAY1, len(rays)); pr.array[:] = rays
     ph = traversal.PinnedArray(formats.HIT1, len(rays))
     sets[name] = (pr, ph)
-for chunks in (1, 2, 3, 4, 6, 8):
+for chunks in (3, 4, 5, 6, 8):
     lib.tune("host_chunks", chunks)
     for _ in range(3):
         for pr, ph in sets.values():
