@@ -9,7 +9,12 @@ lib.load()
 nodes, tris = formats.load_bvh(testdata.sponza_bvh8())
 bvh = traversal.Bvh8(0, nodes, tris)
 rays = formats.load_rays(testdata.rays("random"), 0.0, 1.0)
-steps = np.fromfile(Path(__file__).parent / "data" / "steps_random.u32", np.uint32)
+import subprocess, tempfile
+root = Path(__file__).resolve().parent.parent
+exe, out = Path(tempfile.gettempdir()) / "ray_steps", Path(tempfile.gettempdir()) / "steps_random.u32"
+subprocess.run(["gcc", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-o", str(exe), str(root / "scripts" / "ray_steps.c"), "-lpthread", "-lm"], check=True)
+subprocess.run([str(exe), str(testdata.sponza_bvh8()), str(testdata.rays("random")), "0", "1", str(out)], check=True)
+steps = np.fromfile(out, np.uint32)
 def timed(r, label):
     d_rays = traversal.DeviceArray.from_host(0, np.ascontiguousarray(r)); d_hits = traversal.DeviceArray(0, formats.HIT1, len(r))
     for _ in range(3): traversal.intersect(bvh, d_rays, d_hits)
