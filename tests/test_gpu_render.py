@@ -97,3 +97,44 @@ def test_reference_driver_entry_points(cornell):
     L.clear_pixels()
     assert not np.ctypeslib.as_array(L.get_pixels(), (H, W, 3)).any()
     L.cleanup_interface()
+
+
+def test_sponza_film_matches_oracle():
+    """configs[3] in small: the synthetic-material Sponza scene (diffuse and diffuse + Phong mixes, 271 triangle lights,
+    rodent_b200/workloads.py), three pipelines per renderer, against the CPU path-tracing oracle on the same samples."""
+    from rodent_b200 import workloads
+    scene = workloads.load_scene("sponza")
+    W, H, spp, depth = 192, 108, 2, 8
+    cam = workloads.camera("sponza", W, H)
+    r = R.Renderer(scene, 0, W, H, spp, depth)
+    want = np.zeros((H, W, 3), np.float32)
+    for it in range(2):
+        r.render(cam, it)
+        want, st = oracle.render(scene.view, cam, W, H, spp, depth, it, want)
+    got = r.film().copy()
+    stats = r.stats()
+    r.free()
+    e = rel_err(got, want)
+    # Phong lobes (fastpow with ns = 32) amplify the last-bit differences of sinf/cosf more than Cornell's diffuse walls do
+    assert np.median(e) < 1e-5 and (e < 1e-3).mean() > 0.98, (np.median(e), (e < 1e-3).mean())
+    assert abs(got.mean() - want.mean()) / want.mean() < 1e-2
+    assert stats["samples"] == W * H * spp
+    assert abs(stats["primary_rays"] - st.primary_rays) <= 0.002 * st.primary_rays + 4
+    assert abs(stats["shadow_rays"] - st.shadow_rays) <= 0.002 * st.shadow_rays + 4
+
+
+def test_lanes_do_not_change_the_film(cornell):
+    """One pipeline or four: same samples, same film (up to the order of the atomic adds)."""
+    from rodent_b200 import lib
+    W, H, spp = 256, 160, 3
+    cam = R.camera((0, 1, 2.7), (0, 0, -1), (0, 1, 0), 60.0, W, H)
+    films = []
+    for lanes in (1, 4):
+        lib.tune("render_lanes", lanes)
+        r = R.Renderer(cornell, 0, W, H, spp, 6)
+        r.render(cam, 0)
+        films.append(r.film().copy())
+        r.free()
+    lib.tune("render_lanes", 3)
+    e = rel_err(films[1], films[0])
+    assert np.median(e) < 1e-6 and (e < 1e-3).mean() > 0.999
