@@ -1,13 +1,15 @@
-// bench_traversal entry points: persistent-threads BVH8/Tri4 traversal kernels for
-// sm_100a and the C ABI around them (include/rodent_b200.h).
+// bench_traversal entry points: persistent BVH8/Tri4 (and BVH4/Tri4) traversal kernels for sm_100a and the C ABI
+// around them (include/rodent_b200.h).
 //
-// Kernel organisation (replaces gpu_traverse_single, src/traversal/mapping_gpu.impala:182-203,
-// and competes with the Aila-Laine kernel tools/bench_aila/kepler_dynamic_fetch.cu:70-371):
-//   * persistent CTAs, one resident set per SM (grid = SMs x occupancy);
-//   * each warp pulls rays from a global counter; lanes whose ray finished wait
-//     until the number of busy lanes in the warp drops below a threshold, then the
-//     idle lanes are refilled together with one atomicAdd (ballot + popc ranks);
-//   * while-while traversal of the reference's own order (traverse.cuh).
+// They replace gpu_traverse_single (src/traversal/mapping_gpu.impala:182-203) and compete with the Aila-Laine kernel
+// (tools/bench_aila/kepler_dynamic_fetch.cu:70-371).  All variants are persistent grids (SMs x resident CTAs) that pull
+// rays from a global counter with one atomicAdd per warp (ranks from ballot + popc) and follow the reference's own
+// per-ray order; they differ in how a warp's rays share its lanes:
+//   traverse_bvh8_vote / traverse_bvh4_vote   one ray per lane, the warp votes on the kind of step  (traverse_sched.cuh, default)
+//   traverse_bvh8_pool                        64 rays per warp in shared memory, compacted per step  (traverse_pool.cuh)
+//   traverse_bvh8_persistent / _grid          one ray per lane, per-lane while-while loops          (traverse.cuh)
+//   traverse_bvh8_quad                        four lanes per ray                                    (traverse_quad.cuh)
+// Measurements and what each experiment showed: profiles/r01_experiments.md.
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -35,7 +37,7 @@ struct Tuning {
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
     int refill_below = 8;    // refill a warp when fewer than this many lanes are busy
-    int pool_prefetch = 1;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
+    int pool_prefetch = 0;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_chunks = 4;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 4)
