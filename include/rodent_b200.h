@@ -132,6 +132,37 @@ void b200_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris,
 void b200_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris,
                                          const Ray1* rays, Hit1* hits, int32_t num_packets);
 
+/* ---- Packet interfaces ----------------------------------------------------- *
+ * tools/bench_traversal/bench_traversal.impala:32-65: structure-of-arrays packets of 4 or 8 rays / hits. */
+typedef struct Ray4 { float org[3][4]; float dir[3][4]; float tmin[4]; float tmax[4]; } Ray4;
+typedef struct Ray8 { float org[3][8]; float dir[3][8]; float tmin[8]; float tmax[8]; } Ray8;
+typedef struct Hit4 { int32_t tri_id[4]; float t[4]; float u[4]; float v[4]; } Hit4;
+typedef struct Hit8 { int32_t tri_id[8]; float t[8]; float u[8]; float v[8]; } Hit8;
+
+/* Drop-ins for the call sites of the reference's packet and hybrid variants,
+ *   cpu_{intersect,occluded}_{packet,hybrid}_ray{4,8}_bvh{4,8}_tri4(nodes, tris, rays, hits, num_packets)
+ *   (bench_traversal.impala:159-427, called at bench_traversal.cpp:44-74,84-122): identical signatures, HOST buffers.
+ * A GPU has no use for the CPU's packet traversal order, so every ray of a packet is traced by the single-ray kernel:
+ * each ray gets the closest hit (or an any-hit flag) exactly as cpu_*_single_ray1_* defines it.  The reference's packet
+ * kernels visit nodes in a per-packet order, which can pick another of several triangles hit at the same distance; `t`
+ * agrees (the reference's own test accepts every variant against one golden image, tools/CMakeLists.txt:26-31). */
+void b200_intersect_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_occluded_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_intersect_packet_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_occluded_packet_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_intersect_packet_ray4_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_occluded_packet_ray4_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_intersect_packet_ray8_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_occluded_packet_ray8_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_intersect_hybrid_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_occluded_hybrid_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_intersect_hybrid_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_occluded_hybrid_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_intersect_hybrid_ray4_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_occluded_hybrid_ray4_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
+void b200_intersect_hybrid_ray8_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+void b200_occluded_hybrid_ray8_bvh8_tri4(const Node8* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);
+
 /* ---- Memory helpers (stand-ins for anydsl::Array / anydsl_alloc / anydsl_copy,
  * tools/common/load_bvh.h:58-68, load_rays.h:85-88) ------------------------ */
 int32_t rodent_b200_device_count(void);

@@ -153,6 +153,28 @@ traverse_bvh4_vote(const Node4* __restrict__ nodes, const Tri4* __restrict__ tri
         [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
 }
 
+// Packet input (Ray4 / Ray8 in, Hit4 / Hit8 out, bench_traversal.impala:32-65): the same loop, fed from and draining
+// into the structure-of-arrays packets; ray i is lane i % W of packet i / W.
+template <bool ANY, int ARITY, int W>
+__global__ void __launch_bounds__(kBlock, 5)
+traverse_packets_vote(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
+                      const float* __restrict__ rays, float* __restrict__ hits, int num_rays,
+                      int* __restrict__ work_counter, int refill_min, int node_streak_min) {
+    __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, ARITY>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
+        [rays](int i, float4& r0, float4& r1) {
+            const float* p = rays + size_t(i / W) * (8 * W) + (i % W);          // org[3][W] dir[3][W] tmin[W] tmax[W]
+            r0 = make_float4(__ldg(p), __ldg(p + W), __ldg(p + 2 * W), __ldg(p + 6 * W));
+            r1 = make_float4(__ldg(p + 3 * W), __ldg(p + 4 * W), __ldg(p + 5 * W), __ldg(p + 7 * W));
+        },
+        [hits](int i, const HitRecord& h) {
+            float* p = hits + size_t(i / W) * (4 * W) + (i % W);                // tri_id[W] t[W] u[W] v[W]
+            p[0] = __int_as_float(h.prim);
+            if (!ANY) { p[W] = h.t; p[2 * W] = h.u; p[3 * W] = h.v; }           // make_cpu_hit4/8, bench_traversal.impala:133-157
+        }, node_streak_min);
+}
+
 // Ray-pool kernel (traverse_pool.cuh): 64 rays per warp in shared memory, compacted onto the lanes per step.
 constexpr int kPoolBlock = 64;       // two warps (two pools, 29 KB) per CTA, seven CTAs per SM
 template <bool ANY>
@@ -447,6 +469,38 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// Packet entry points: copy in, one launch, copy out.
+template <bool ANY, typename NodeT, int W>
+static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* rays, void* hits, int num_packets) {
+    if (num_packets <= 0) return;
+    constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
+    DeviceState& s = device_state(g_host_dev);
+    auto bvh = cached_bvh(s, nodes, tris);
+    if (!s.streams[0]) {
+        for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    }
+    const int num_rays = num_packets * W;
+    if (s.ray_capacity < size_t(num_rays)) {
+        if (s.d_rays) { RB_CUDA_CHECK(cudaFree(s.d_rays)); RB_CUDA_CHECK(cudaFree(s.d_hits)); }
+        RB_CUDA_CHECK(cudaMalloc(&s.d_rays, size_t(num_rays) * sizeof(Ray1)));
+        RB_CUDA_CHECK(cudaMalloc(&s.d_hits, size_t(num_rays) * sizeof(Hit1)));
+        s.ray_capacity = size_t(num_rays);
+    }
+    cudaStream_t st = s.streams[0];
+    int* counter = s.counter + 8;
+    RB_CUDA_CHECK(cudaMemcpyAsync(s.d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));     // a packet is W * 32 bytes
+    if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st)); // t/u/v stay the caller's
+    RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * s.occ_vote[1][ANY ? 1 : 0]);
+    traverse_packets_vote<ANY, ARITY, W><<<grid, kBlock, 0, st>>>(bvh.first, bvh.second, reinterpret_cast<const float*>(s.d_rays),
+                                                                  reinterpret_cast<float*>(s.d_hits), num_rays, counter,
+                                                                  g_tuning.refill_min, g_tuning.node_streak_min);
+    RB_CUDA_CHECK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    RB_CUDA_CHECK(cudaMemcpyAsync(hits, s.d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+    RB_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
 }  // namespace rb200
 
 using namespace rb200;
@@ -486,6 +540,17 @@ void b200_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, 
 void b200_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
     run_host<true>(nodes, tris, rays, hits, num_packets);
 }
+#define RB_PACKET_API(kind, W, B)                                                                                               \
+    void b200_intersect_##kind##_ray##W##_bvh##B##_tri4(const Node##B* n, const Tri4* t, const Ray##W* r, Hit##W* h, int32_t k) { \
+        run_host_packets<false, Node##B, W>(n, t, r, h, k);                                                                     \
+    }                                                                                                                           \
+    void b200_occluded_##kind##_ray##W##_bvh##B##_tri4(const Node##B* n, const Tri4* t, const Ray##W* r, Hit##W* h, int32_t k) {  \
+        run_host_packets<true, Node##B, W>(n, t, r, h, k);                                                                      \
+    }
+RB_PACKET_API(packet, 4, 4) RB_PACKET_API(packet, 8, 4) RB_PACKET_API(packet, 4, 8) RB_PACKET_API(packet, 8, 8)
+RB_PACKET_API(hybrid, 4, 4) RB_PACKET_API(hybrid, 8, 4) RB_PACKET_API(hybrid, 4, 8) RB_PACKET_API(hybrid, 8, 8)
+#undef RB_PACKET_API
+
 void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris) {
     DeviceState& s = device_state(g_host_dev);
     std::lock_guard<std::mutex> lock(g_mutex);

@@ -95,3 +95,32 @@ def fbuf_to_gray(t: np.ndarray, normalize: bool = True) -> np.ndarray:
     t = np.asarray(t, np.float32)
     tmax = t.max() if normalize else np.float32(1.0)
     return ((np.float32(255.0) * t) / np.float32(tmax)).astype(np.uint8)
+
+
+def packet_dtypes(width: int):
+    """(RayW, HitW) of tools/bench_traversal/bench_traversal.impala:32-65."""
+    ray = np.dtype([("org", "<f4", (3, width)), ("dir", "<f4", (3, width)), ("tmin", "<f4", (width,)), ("tmax", "<f4", (width,))])
+    hit = np.dtype([("tri_id", "<i4", (width,)), ("t", "<f4", (width,)), ("u", "<f4", (width,)), ("v", "<f4", (width,))])
+    assert ray.itemsize == 32 * width and hit.itemsize == 16 * width
+    return ray, hit
+
+
+def pack_rays(rays: np.ndarray, width: int) -> np.ndarray:
+    """Ray1 array -> packets, whole packets only (load_rays<RayW>, tools/common/load_rays.h:58-92)."""
+    ray_dt, _ = packet_dtypes(width)
+    n = len(rays) // width
+    r = rays[: n * width].reshape(n, width)
+    out = np.zeros(n, ray_dt)
+    out["org"] = r["org"].transpose(0, 2, 1)
+    out["dir"] = r["dir"].transpose(0, 2, 1)
+    out["tmin"] = r["tmin"]
+    out["tmax"] = r["tmax"]
+    return out
+
+
+def unpack_hits(hits: np.ndarray) -> np.ndarray:
+    """HitW packets -> Hit1 array in ray order."""
+    out = np.zeros(hits["tri_id"].size, HIT1)
+    for name in ("tri_id", "t", "u", "v"):
+        out[name] = hits[name].reshape(-1)
+    return out

@@ -40,6 +40,11 @@ SIGNATURES = {
     "rodent_b200_launch_count": (c_int64, []),
     "rodent_b200_version": (c_char_p, []),
 }
+for _kind in ("packet", "hybrid"):
+    for _w in (4, 8):
+        for _b in (4, 8):
+            for _op in ("intersect", "occluded"):
+                SIGNATURES[f"b200_{_op}_{_kind}_ray{_w}_bvh{_b}_tri4"] = (None, _TRAVERSE_HOST)
 # experiment knobs, not part of the drop-in surface
 _EXTRA = {"rodent_b200_tune": (None, [c_char_p, c_int32])}
 

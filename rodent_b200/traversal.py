@@ -99,3 +99,17 @@ class PinnedArray:
             self.array = None
             lib.load().rodent_b200_free_host(self.ptr)
             self.ptr = None
+
+
+def intersect_host_packets(nodes: np.ndarray, tris: np.ndarray, packets: np.ndarray, kind: str = "hybrid", any_hit: bool = False,
+                           hits: np.ndarray | None = None) -> np.ndarray:
+    """The host-buffer drop-in for cpu_{intersect,occluded}_{packet,hybrid}_ray{4,8}_bvh{4,8}_tri4
+    (bench_cpu_packet / bench_cpu_hybrid, bench_traversal.cpp:44-74,84-122)."""
+    L = lib.load()
+    width = packets.dtype["tmin"].shape[0]
+    arity = 8 if nodes.dtype == formats.NODE8 else 4
+    if hits is None:
+        hits = np.zeros(len(packets), formats.packet_dtypes(width)[1])
+    fn = getattr(L, f"b200_{'occluded' if any_hit else 'intersect'}_{kind}_ray{width}_bvh{arity}_tri4")
+    fn(nodes.ctypes.data, tris.ctypes.data, packets.ctypes.data, hits.ctypes.data, len(packets))
+    return hits

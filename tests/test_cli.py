@@ -38,9 +38,9 @@ def test_bench_traversal_argument_errors(tools):
                       (["-bvh", "/nonexistent", "-ray", "b", "-s", "--bvh-width", "8"], "Cannot load BVH file")):
         r = run(exe, *args)
         assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
-    # variants this library does not provide end like variant_not_available(): message + abort
-    r = run(exe, "-bvh", "a", "-ray", "b")
-    assert r.returncode < 0 and "cpu_intersect_hybrid_ray8_bvh4_tri4 is not provided" in r.stderr
+    # every CPU variant of the reference has a drop-in now: the default (hybrid, ray 8, BVH 4) gets as far as the file
+    r = run(exe, "-bvh", "/nonexistent", "-ray", "b")
+    assert r.returncode == 1 and "Cannot load BVH file" in r.stderr
 
 
 def test_fbuf2png_matches_reference_quantisation(tools, tmp_path, oracle_hits):
@@ -75,6 +75,21 @@ def test_ctest_procedure_on_gpu(tools, tmp_path, mode, name, tmin, tmax, hits):
     got = np.array(Image.open(tmp_path / "out.png"))[..., 0]
     ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
     assert int((got != ref).sum()) <= 2      # ImageMagick `compare -metric MSE` in the reference's CTest
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [[], ["-p"], ["--ray-width", "4"], ["-p", "--ray-width", "4", "--bvh-width", "8"], ["--bvh-width", "8"]])
+def test_packet_and_hybrid_variants_on_gpu(tools, tmp_path, mode):
+    """hybrid_bvh4 (the reference's default command line), packet_bvh4, ..., of tools/CMakeLists.txt:26-31."""
+    fbuf = tmp_path / "out.fbuf"
+    bvh = testdata.sponza_bvh8() if "8" in mode[-1:] and "--bvh-width" in mode else testdata.sponza_bvh4()
+    r = run(tools / "bench_traversal", "-bvh", bvh, "-ray", testdata.rays("primary"), "--bench", "2", "--tmin", "0.01", "--tmax", "5000", "-o", fbuf, *mode)
+    assert r.returncode == 0, r.stderr
+    assert "1048576 ray(s) in the distribution file." in r.stdout and "1026430 intersection(s)" in r.stdout
+    assert run(tools / "fbuf2png", "-n", fbuf, tmp_path / "out.png").returncode == 0
+    got = np.array(Image.open(tmp_path / "out.png"))[..., 0]
+    ref = np.array(Image.open(GOLDEN / "ref-primary.png"))[..., 0]
+    assert int((got != ref).sum()) <= 2
 
 
 @pytest.mark.gpu

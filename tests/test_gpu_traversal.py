@@ -216,3 +216,24 @@ def test_bvh4_degenerate_rays_and_host_entry_point(gpu4, sponza4, ray_sets):
     assert_records_equal(run_gpu(gpu4, rays), oracle.traverse(nodes4, tris4, rays))
     some = np.ascontiguousarray(ray_sets["random"][:20_001])
     assert_records_equal(traversal.intersect_host(nodes4, tris4, some), oracle.traverse(nodes4, tris4, some))
+
+
+# ---- packet / hybrid entry points ------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,width,arity", [("hybrid", 8, 4), ("packet", 4, 4), ("hybrid", 4, 8), ("packet", 8, 8)])
+def test_packet_entry_points(kind, width, arity, sponza, sponza4, ray_sets):
+    """Every ray of a packet gets the record the single-ray kernel (and oracle) gives it; occluded writes tri_id only."""
+    from oracle import oracle
+    from rodent_b200 import traversal
+    nodes, tris = sponza if arity == 8 else sponza4
+    rays = np.ascontiguousarray(ray_sets["random"][:100_003])
+    packets = formats.pack_rays(rays, width)
+    n = len(packets) * width
+    assert n == 100_003 // width * width
+    want = oracle.traverse(nodes, tris, np.ascontiguousarray(rays[:n]))
+    got = formats.unpack_hits(traversal.intersect_host_packets(nodes, tris, packets, kind))
+    assert_records_equal(got, want)
+    pre = np.zeros(len(packets), formats.packet_dtypes(width)[1])
+    pre["t"] = 3.0
+    occl = traversal.intersect_host_packets(nodes, tris, packets, kind, any_hit=True, hits=pre)
+    assert np.array_equal(formats.unpack_hits(occl)["tri_id"], oracle.traverse(nodes, tris, np.ascontiguousarray(rays[:n]), any_hit=True)["tri_id"])
+    assert (occl["t"] == 3.0).all()

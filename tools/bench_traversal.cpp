@@ -7,8 +7,9 @@
 //   -s [--bvh-width 4|8] the CPU single-ray call site (bench_cpu_single, :76-82 / :60-66) served by the
 //                        host-pointer drop-ins b200_{intersect,occluded}_single_ray1_bvh{4,8}_tri4,
 //                        timed with the host clock around the call, copies included
-// Packet/hybrid variants and BVH2 inputs are not provided by this library; asking for
-// them ends like the reference's variant_not_available() (bench_traversal.impala:15-21).
+//   (default) / -p       the hybrid / packet call sites (:44-74, :84-122) served by b200_*_{hybrid,packet}_ray{4,8}_bvh{4,8}_tri4:
+//                        every ray of a packet is traced by the single-ray kernel
+// BVH2 input is not provided by this library.
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -17,6 +18,8 @@
 #include <iostream>
 #include <numeric>
 #include <string>
+#include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "formats.h"
@@ -82,10 +85,8 @@ Options parse(int argc, char** argv) {
     return o;
 }
 
-[[noreturn]] void variant_not_available(const std::string& name) {
-    std::cerr << name << " is not provided by rodent_b200 (use -gpu cuda, or -s)" << std::endl;
-    std::abort();
-}
+template <typename F> struct FnArgs;
+template <typename R, typename... A> struct FnArgs<R (*)(A...)> { using type = std::tuple<A...>; };
 
 // The benchmark proper, for Node8 (BVH8) or Node4 (BVH4) input.
 template <typename NodeT, typename DevFn, typename HostFn>
@@ -144,15 +145,72 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
     return 0;
 }
 
+// Packet / hybrid variants: RayW packets in, HitW packets out (bench_cpu_packet / bench_cpu_hybrid, bench_traversal.cpp:44-122).
+template <typename NodeT, int W, typename Fn>
+int run_packets(const Options& o, rb200::BlockType block, Fn intersect, Fn occluded) {
+    std::vector<NodeT> nodes; std::vector<Tri4> tris; std::vector<Ray1> rays;
+    if (!rb200::read_bvh(o.bvh_file, block, nodes, tris)) fail("Cannot load BVH file");
+    if (!rb200::read_rays(o.ray_file, o.tmin, o.tmax, rays)) fail("Cannot load rays");
+    const size_t num_packets = rays.size() / W, ray_count = num_packets * W;        // whole packets only, load_rays.h:74-76
+    std::cout << ray_count << " ray(s) in the distribution file." << std::endl;
+    std::vector<float> packets(num_packets * 8 * W), hits(num_packets * 4 * W, 0.0f);
+    for (size_t p = 0; p < num_packets; p++)
+        for (int j = 0; j < W; j++) {
+            const Ray1& r = rays[p * W + j];
+            float* q = &packets[p * 8 * W + j];
+            for (int c = 0; c < 3; c++) { q[c * W] = r.org[c]; q[(3 + c) * W] = r.dir[c]; }
+            q[6 * W] = r.tmin; q[7 * W] = r.tmax;
+        }
+    rodent_b200_set_device(o.dev);
+    using RayW = std::remove_pointer_t<std::tuple_element_t<2, typename FnArgs<Fn>::type>>;
+    using HitW = std::remove_pointer_t<std::tuple_element_t<3, typename FnArgs<Fn>::type>>;
+    auto bench = [&] {
+        const auto t0 = std::chrono::steady_clock::now();
+        (o.any_hit ? occluded : intersect)(nodes.data(), tris.data(), reinterpret_cast<RayW*>(packets.data()),
+                                           reinterpret_cast<HitW*>(hits.data()), int32_t(num_packets));
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    for (int i = 0; i < o.warmup; i++) bench();
+    std::vector<double> timings;
+    for (int i = 0; i < o.iters; i++) timings.push_back(bench());
+    size_t intr = 0;
+    std::vector<Hit1> flat(ray_count);
+    for (size_t p = 0; p < num_packets; p++)
+        for (int j = 0; j < W; j++) {
+            const float* q = &hits[p * 4 * W + j];
+            int32_t id; std::memcpy(&id, q, 4);
+            flat[p * W + j] = Hit1{id, q[W], q[2 * W], q[3 * W]};
+            intr += id >= 0;
+        }
+    if (!o.out_file.empty() && !rb200::write_fbuf(o.out_file, flat)) fail("Cannot write output file");
+    std::sort(timings.begin(), timings.end());
+    const double sum = std::accumulate(timings.begin(), timings.end(), 0.0);
+    std::cout << sum << "ms for " << o.iters << " iteration(s)" << std::endl;
+    std::cout << ray_count * o.iters / (1000.0 * sum) << " Mrays/sec" << std::endl;
+    std::cout << "# Average: " << sum / timings.size() << " ms" << std::endl;
+    std::cout << "# Median: " << timings[timings.size() / 2] << " ms" << std::endl;
+    std::cout << "# Min: " << timings.front() << " ms" << std::endl;
+    std::cout << intr << " intersection(s)" << std::endl;
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     const Options o = parse(argc, argv);
     const bool use_gpu = !o.gpu.empty();
     if (!use_gpu && !o.single) {
-        const std::string kind = o.packet ? "packet" : "hybrid";
-        variant_not_available(std::string("cpu_") + (o.any_hit ? "occluded_" : "intersect_") + kind + "_ray" +
-                              std::to_string(o.ray_width) + "_bvh" + std::to_string(o.bvh_width) + "_tri4");
+        // the packet / hybrid call sites (the reference's default is hybrid, ray width 8, BVH width 4)
+        if (o.bvh_width == 4) {
+            if (o.packet) { if (o.ray_width == 4) return run_packets<Node4, 4>(o, rb200::kBvh4Tri4, b200_intersect_packet_ray4_bvh4_tri4, b200_occluded_packet_ray4_bvh4_tri4);
+                            return run_packets<Node4, 8>(o, rb200::kBvh4Tri4, b200_intersect_packet_ray8_bvh4_tri4, b200_occluded_packet_ray8_bvh4_tri4); }
+            if (o.ray_width == 4) return run_packets<Node4, 4>(o, rb200::kBvh4Tri4, b200_intersect_hybrid_ray4_bvh4_tri4, b200_occluded_hybrid_ray4_bvh4_tri4);
+            return run_packets<Node4, 8>(o, rb200::kBvh4Tri4, b200_intersect_hybrid_ray8_bvh4_tri4, b200_occluded_hybrid_ray8_bvh4_tri4);
+        }
+        if (o.packet) { if (o.ray_width == 4) return run_packets<Node8, 4>(o, rb200::kBvh8Tri4, b200_intersect_packet_ray4_bvh8_tri4, b200_occluded_packet_ray4_bvh8_tri4);
+                        return run_packets<Node8, 8>(o, rb200::kBvh8Tri4, b200_intersect_packet_ray8_bvh8_tri4, b200_occluded_packet_ray8_bvh8_tri4); }
+        if (o.ray_width == 4) return run_packets<Node8, 4>(o, rb200::kBvh8Tri4, b200_intersect_hybrid_ray4_bvh8_tri4, b200_occluded_hybrid_ray4_bvh8_tri4);
+        return run_packets<Node8, 8>(o, rb200::kBvh8Tri4, b200_intersect_hybrid_ray8_bvh8_tri4, b200_occluded_hybrid_ray8_bvh8_tri4);
     }
     // -gpu cuda traces the BVH8 block unless --bvh-width 4 is asked for; -s follows --bvh-width (default 4) as the reference does
     const int width = use_gpu && !o.bvh_width_given ? 8 : o.bvh_width;
