@@ -262,6 +262,9 @@ RodentScene* rodent_b200_scene_from_bvh8(const Node8* nodes, int32_t num_nodes, 
                                          const int32_t* material_of_prim, int32_t num_prims);
 void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out);
 void rodent_b200_scene_free(RodentScene* scene);
+/* The scene's triangles under a BVH4 as well (built on first use, owned by the scene), for writing .bvh files with both
+ * blocks as tools/bvh_extractor/extract_bvh4_8.cpp:9-42 does. */
+void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* num_nodes, const Tri4** tris, int32_t* num_tri4);
 
 typedef struct RodentRenderer RodentRenderer;
 

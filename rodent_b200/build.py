@@ -58,6 +58,9 @@ def build_tools(force: bool = False) -> None:
                      [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
     if (TOOLS / "fbuf2png.cpp").exists():
         jobs.append(("fbuf2png", ["fbuf2png.cpp"], ["-lz"]))
+    if (TOOLS / "bvh_extractor.cpp").exists():
+        jobs.append(("bvh_extractor", ["bvh_extractor.cpp"],
+                     [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
     if (TOOLS / "rodent.cpp").exists():
         jobs.append(("rodent", ["rodent.cpp"],
                      [f"-L{PKG}", "-lrodent_b200", "-lz", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))

@@ -262,13 +262,16 @@ struct Box {
 };
 struct Bvh2Node { Box box; int left = -1, right = -1, first = 0, count = 0; };
 
+// NodeT: Node8 or Node4 -- the binary tree is the same, the collapse stops at the node's arity.
+template <typename NodeT>
 struct Builder {
     const std::vector<F3>& v0; const std::vector<F3>& v1; const std::vector<F3>& v2;
     const std::vector<int>& geom;
     std::vector<Box> boxes; std::vector<F3> centers; std::vector<int> order;
     std::vector<Bvh2Node> n2;
-    std::vector<Node8>& nodes; std::vector<Tri4>& tris;
+    std::vector<NodeT>& nodes; std::vector<Tri4>& tris;
     static constexpr int kBins = 16, kLeaf = 4;
+    static constexpr int kArity = int(sizeof(NodeT::child) / sizeof(int32_t));
 
     int build2(int first, int count) {
         Bvh2Node node; node.first = first; node.count = count;
@@ -332,11 +335,11 @@ struct Builder {
         return ~first_tri4;
     }
 
-    // node writer of converter.cpp:160-204: collapse the binary tree to arity 8 by always opening
+    // node writer of converter.cpp:160-204: collapse the binary tree to the node's arity by always opening
     // the child with the largest area
     int write_node(int root2) {
         std::vector<int> kids{n2[root2].left, n2[root2].right};
-        while (kids.size() < 8) {
+        while (int(kids.size()) < kArity) {
             int pick = -1; float area = -1;
             for (size_t i = 0; i < kids.size(); i++)
                 if (n2[kids[i]].left >= 0 && n2[kids[i]].box.half_area() > area) { area = n2[kids[i]].box.half_area(); pick = int(i); }
@@ -347,8 +350,8 @@ struct Builder {
         }
         const int id = int(nodes.size());
         nodes.emplace_back();
-        std::memset(&nodes[id], 0, sizeof(Node8));
-        for (int j = 0; j < 8; j++) {
+        std::memset(&nodes[id], 0, sizeof(NodeT));
+        for (int j = 0; j < kArity; j++) {
             const float inf = std::numeric_limits<float>::infinity();
             if (j < int(kids.size())) {
                 const Box& b = n2[kids[j]].box;
@@ -378,9 +381,9 @@ struct Builder {
         if (n2[root].left < 0) {
             // a single leaf: the root node (id 1) must still be an inner node
             nodes.emplace_back();
-            std::memset(&nodes[0], 0, sizeof(Node8));
+            std::memset(&nodes[0], 0, sizeof(NodeT));
             const float inf = std::numeric_limits<float>::infinity();
-            for (int j = 0; j < 8; j++)
+            for (int j = 0; j < kArity; j++)
                 for (int r = 0; r < 6; r += 2) { nodes[0].bounds[r][j] = inf; nodes[0].bounds[r + 1][j] = -inf; }
             const Box& b = n2[root].box;
             nodes[0].bounds[0][0] = b.lo.x; nodes[0].bounds[1][0] = b.hi.x; nodes[0].bounds[2][0] = b.lo.y;
@@ -493,9 +496,24 @@ Scene* load_obj_scene(const std::string& path) {
         a[i] = verts[scene->indices[4 * i]]; b[i] = verts[scene->indices[4 * i + 1]]; c[i] = verts[scene->indices[4 * i + 2]];
         geom[i] = scene->indices[4 * i + 3];
     }
-    Builder builder{a, b, c, geom, {}, {}, {}, {}, scene->nodes, scene->tris};
+    Builder<Node8> builder{a, b, c, geom, {}, {}, {}, {}, scene->nodes, scene->tris};
     builder.run();
     return scene;
+}
+
+// The same triangles under a BVH4 (for the .bvh writer: the reference's files carry a BVH4 and a BVH8 block,
+// tools/bvh_extractor/extract_bvh4_8.cpp:9-42).
+void build_bvh4(Scene& scene) {
+    if (!scene.nodes4.empty()) return;
+    const int num_tris = int(scene.indices.size() / 4);
+    std::vector<F3> a(num_tris), b(num_tris), c(num_tris); std::vector<int> geom(num_tris);
+    for (int i = 0; i < num_tris; i++) {
+        const int* idx = &scene.indices[4 * i];
+        auto vert = [&](int k) { return F3{scene.vertices[4 * k], scene.vertices[4 * k + 1], scene.vertices[4 * k + 2]}; };
+        a[i] = vert(idx[0]); b[i] = vert(idx[1]); c[i] = vert(idx[2]); geom[i] = idx[3];
+    }
+    Builder<Node4> builder{a, b, c, geom, {}, {}, {}, {}, scene.nodes4, scene.tris4};
+    builder.run();
 }
 
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
@@ -560,5 +578,11 @@ void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out) {
     out->materials = s.materials.data(); out->lights = s.lights.data(); out->nodes = s.nodes.data(); out->tris = s.tris.data();
 }
 void rodent_b200_scene_free(RodentScene* scene) { delete reinterpret_cast<Scene*>(scene); }
+void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* num_nodes, const Tri4** tris, int32_t* num_tri4) {
+    Scene& s = *reinterpret_cast<Scene*>(scene);
+    rb200::build_bvh4(s);
+    *nodes = s.nodes4.data(); *num_nodes = int32_t(s.nodes4.size());
+    *tris = s.tris4.data(); *num_tri4 = int32_t(s.tris4.size());
+}
 
 }  // extern "C"

@@ -18,9 +18,12 @@ struct Scene {
     std::vector<RodentLight> lights;
     std::vector<Node8> nodes;
     std::vector<Tri4> tris;
+    std::vector<Node4> nodes4;            // built on demand (rodent_b200_scene_bvh4)
+    std::vector<Tri4> tris4;
 };
 
 Scene* load_obj_scene(const std::string& path);
+void build_bvh4(Scene& scene);
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
                        const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims);
 

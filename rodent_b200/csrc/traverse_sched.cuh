@@ -55,8 +55,9 @@ struct RayWalker {
 
     // The head of the reference's outer loop (:168-174): drop entries that start behind the current hit.
     __device__ __forceinline__ void cull() {
-        if (ANY) return;
-        while (top_node != 0 && top_t > tmax) pop();
+        if constexpr (!ANY) {
+            while (top_node != 0 && top_t > tmax) pop();
+        }
     }
 
     __device__ __forceinline__ void begin(float4 r0, float4 r1) {

@@ -40,6 +40,7 @@ SIGNATURES = {
     "rodent_b200_scene_from_bvh8": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_view": (None, [c_void_p, POINTER(SceneView)]),
     "rodent_b200_scene_free": (None, [c_void_p]),
+    "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
     "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
     "rodent_b200_renderer_free": (None, [c_void_p]),
     "rodent_b200_render": (None, [c_void_p, POINTER(Settings), c_int32]),
@@ -124,6 +125,14 @@ class Scene:
             return np.zeros(shape, dt)
         buf = (ctypes.c_char * n).from_address(getattr(v, name))
         return np.frombuffer(buf, dt).reshape(shape)
+
+    def bvh4(self):
+        """(nodes, tris) of the scene's triangles under a BVH4 (rodent_b200_scene_bvh4), as numpy copies."""
+        from . import formats
+        nodes, tris, nn, nt = c_void_p(), c_void_p(), c_int32(), c_int32()
+        _bind(lib.load()).rodent_b200_scene_bvh4(self.handle, ctypes.byref(nodes), ctypes.byref(nn), ctypes.byref(tris), ctypes.byref(nt))
+        view = lambda ptr, n, dt: np.frombuffer((ctypes.c_char * (n * dt.itemsize)).from_address(ptr), dt).copy()
+        return view(nodes.value, nn.value, formats.NODE4), view(tris.value, nt.value, formats.TRI4)
 
     def free(self):
         if self.handle:

@@ -125,3 +125,38 @@ def test_rodent_ctest_procedure_on_gpu(tools, tmp_path):
     ref = np.array(Image.open(GOLDEN / "ref-cornell.png"))[..., :3].astype(np.int32)
     assert img.shape == ref.shape
     assert ((img - ref) ** 2).mean() < 0.5
+
+
+def test_bvh_extractor_writes_both_blocks(tools, tmp_path):
+    """tools/bvh_extractor (the reference's extract_bvh4_8): an OBJ scene becomes a .bvh with a BVH8 and a BVH4 block that
+    the readers accept and that give the same closest hits as a brute-force search over the triangles."""
+    from oracle import oracle
+    out = tmp_path / "cornell.bvh"
+    r = run(tools / "bvh_extractor", GOLDEN / "cornell_box.obj", out)
+    assert r.returncode == 0 and "36 triangles" in r.stdout, r.stderr
+    n8, t8 = formats.load_bvh(out, formats.BVH8_TRI4)
+    n4, t4 = formats.load_bvh(out, formats.BVH4_TRI4)
+    assert len(n8) >= 1 and len(n4) >= len(n8) and len(t8) == len(t4)
+    prims = lambda t: sorted((t["prim_id"][t["prim_id"] != -1] & 0x7FFFFFFF).tolist())
+    assert prims(t8) == prims(t4) == list(range(36))
+    rng = np.random.default_rng(0)
+    od = np.concatenate([rng.uniform(-1, 2, (5000, 3)), rng.normal(size=(5000, 3))], 1).astype(np.float32)
+    rays = formats.make_rays(od, 0.0, 100.0)
+    h8, h4, hb = oracle.traverse(n8, t8, rays), oracle.traverse(n4, t4, rays), oracle.brute_force(t8, rays)
+    assert (h8["tri_id"] >= 0).sum() > 1000
+    assert np.array_equal(h8["t"], hb["t"]) and np.array_equal(h4["t"], hb["t"])
+    assert run(tools / "bvh_extractor", tmp_path / "missing.obj", out).returncode == 1
+    assert run(tools / "bvh_extractor").returncode == 1
+
+
+@pytest.mark.gpu
+def test_obj_to_bvh_to_bench_on_gpu(tools, tmp_path):
+    """The reference's tool chain on a scene of one's own: bvh_extractor -> ray_gen -> bench_traversal, both BVH widths."""
+    from oracle import oracle
+    bvh, rays = tmp_path / "cornell.bvh", tmp_path / "cornell.rays"
+    assert run(tools / "bvh_extractor", GOLDEN / "cornell_box.obj", bvh).returncode == 0
+    assert run(tools / "ray_gen", "random", bvh, "50000", "7", rays).returncode == 0
+    want = int((oracle.traverse(*formats.load_bvh(bvh, formats.BVH8_TRI4), formats.load_rays(rays, 0.0, 1.0))["tri_id"] >= 0).sum())
+    for mode in (["-gpu", "cuda"], ["-gpu", "cuda", "--bvh-width", "4"], ["-s"], []):
+        r = run(tools / "bench_traversal", "-bvh", bvh, "-ray", rays, "--tmax", "1", *mode)
+        assert r.returncode == 0 and f"{want} intersection(s)" in r.stdout, (mode, r.stdout, r.stderr)      # 50000 rays = 6250 whole packets
