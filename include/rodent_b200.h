@@ -214,10 +214,18 @@ typedef struct RodentMaterial {
     int32_t is_emissive;       /* make_emissive_material with lights(light_ids[prim]) (converter.cpp:915) */
     float   ns, ni;
     float   kd[3], mix_k;
-    float   ks[3], pad0;
-    float   tf[3], pad1;
+    float   ks[3]; int32_t map_kd;   /* 1 + index of the diffuse texture (MTL map_Kd), 0 = the constant kd  (converter.cpp:879-885) */
+    float   tf[3]; int32_t map_ks;   /* 1 + index of the specular texture (MTL map_Ks), 0 = the constant ks (converter.cpp:887-893) */
     float   ke[3], pad2;       /* emitted radiance of an emissive material (MTL Ke) */
 } RodentMaterial;
+
+/* One image of the scene as load_png leaves it (src/driver/image.cpp:10-93): RGBA8 packed little-endian in a uint32_t
+ * (r = bits 0-7: make_image_rgba32, src/render/image.impala:24-38), bottom row first, gamma 2.2 applied to r, g, b.
+ * Materials sample it with the repeat border and the bilinear filter (image.impala:48-92). */
+typedef struct RodentTexture {
+    int32_t width, height;
+    int64_t offset;            /* first pixel in RodentSceneView::texture_pixels */
+} RodentTexture;
 
 /* make_precomputed_triangle_light inputs (src/render/light.impala:147-154,
  * data/light_{verts,norms,areas,colors}.bin of converter.cpp:807-818) */
@@ -244,6 +252,10 @@ typedef struct RodentSceneView {
     const RodentLight*    lights;
     const Node8*          nodes;
     const Tri4*           tris;
+    const RodentTexture*  textures;       /* num_textures */
+    const uint32_t*       texture_pixels; /* num_texture_pixels, all images back to back */
+    int64_t               num_texture_pixels;
+    int32_t               num_textures, pad;
 } RodentSceneView;
 
 typedef struct RodentScene RodentScene;
@@ -260,6 +272,13 @@ RodentScene* rodent_b200_scene_load_obj(const char* obj_file);
 RodentScene* rodent_b200_scene_from_bvh8(const Node8* nodes, int32_t num_nodes, const Tri4* tris, int32_t num_tri4,
                                          const RodentMaterial* materials, int32_t num_materials,
                                          const int32_t* material_of_prim, int32_t num_prims);
+/* Appends an image (RGBA8 as in RodentTexture, already gamma-corrected, bottom row first) to the scene and returns the value
+ * to store in RodentMaterial::map_kd / map_ks (1 + its index).  What device.load_png hands the generated shaders
+ * (src/render/mapping_gpu.impala:518-525), for scenes that are not built from an OBJ file.  Call before creating renderers. */
+int32_t rodent_b200_scene_add_texture(RodentScene* scene, const uint32_t* rgba, int32_t width, int32_t height);
+/* Decodes a PNG file the way load_png does (image.cpp:25-93: 8-bit RGBA, palette / grey expanded, 16 bit stripped, rows
+ * flipped, gamma 2.2) and appends it; returns the map_kd / map_ks value or 0 on error (reason printed). */
+int32_t rodent_b200_scene_add_png(RodentScene* scene, const char* png_file);
 void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out);
 void rodent_b200_scene_free(RodentScene* scene);
 /* The scene's triangles under a BVH4 as well (built on first use, owned by the scene), for writing .bvh files with both

@@ -261,6 +261,50 @@ static inline void trace(const RodentSceneView* sc, int any, V3 org, V3 dir, flo
     else     traverse_single(8, 0, sc->nodes, sc->tris, &r, hit, st, geom);
 }
 
+/* make_texture(repeat border, bilinear filter, make_image_rgba32), src/render/image.impala:24-92 */
+static Col rgba32_texture(const uint32_t* pixels, int width, int height, float u, float v) {   /* image.impala:24-92: repeat border, bilinear */
+    u = u - floorf(u); v = v - floorf(v);
+    const float fu = u * (float)width, fv = v * (float)height;
+    int x0 = (int)fu; if (x0 > width - 1) x0 = width - 1;
+    int y0 = (int)fv; if (y0 > height - 1) y0 = height - 1;
+    const int x1 = x0 + 1 < width - 1 ? x0 + 1 : width - 1, y1 = y0 + 1 < height - 1 ? y0 + 1 : height - 1;
+    const float kx = fu - (float)(int)fu, ky = fv - (float)(int)fv;
+    Col p[4];
+    const int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+    for (int k = 0; k < 4; k++) {
+        const uint32_t q = pixels[ys[k] * width + xs[k]];
+        p[k] = col((float)(q & 0xFFu) * (1.0f / 255.0f), (float)((q >> 8) & 0xFFu) * (1.0f / 255.0f), (float)((q >> 16) & 0xFFu) * (1.0f / 255.0f));
+    }
+    return col(lerp1(lerp1(p[0].r, p[1].r, kx), lerp1(p[2].r, p[3].r, kx), ky),
+               lerp1(lerp1(p[0].g, p[1].g, kx), lerp1(p[2].g, p[3].g, kx), ky),
+               lerp1(lerp1(p[0].b, p[1].b, kx), lerp1(p[2].b, p[3].b, kx), ky));
+}
+
+/* The textured part of a material's shader, converter.cpp:876-903: kd / ks sampled at the hit's texture coordinates
+ * (surf.attr(0), geometry.impala:44-47), the mix weight recomputed from the sampled colours. */
+static RodentMaterial textured_material(const RodentSceneView* sc, int geom, int prim, float u, float v) {
+    RodentMaterial m = sc->materials[geom];
+    if ((m.map_kd | m.map_ks) == 0) return m;
+    const int i0 = sc->indices[prim * 4], i1 = sc->indices[prim * 4 + 1], i2 = sc->indices[prim * 4 + 2];
+    const float* tc = sc->texcoords;
+    const float tu = lerp2(tc[i0 * 4], tc[i1 * 4], tc[i2 * 4], u, v), tv = lerp2(tc[i0 * 4 + 1], tc[i1 * 4 + 1], tc[i2 * 4 + 1], u, v);
+    if (m.map_kd) {
+        const RodentTexture* t = &sc->textures[m.map_kd - 1];
+        const Col c = rgba32_texture(sc->texture_pixels + t->offset, t->width, t->height, tu, tv);
+        m.kd[0] = c.r; m.kd[1] = c.g; m.kd[2] = c.b;
+    }
+    if (m.map_ks) {
+        const RodentTexture* t = &sc->textures[m.map_ks - 1];
+        const Col c = rgba32_texture(sc->texture_pixels + t->offset, t->width, t->height, tu, tv);
+        m.ks[0] = c.r; m.ks[1] = c.g; m.ks[2] = c.b;
+    }
+    if (m.bsdf == RODENT_BSDF_MIX) {
+        const float lum_ks = luminance(col(m.ks[0], m.ks[1], m.ks[2])), lum_kd = luminance(col(m.kd[0], m.kd[1], m.kd[2]));
+        m.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
+    }
+    return m;
+}
+
 static void render_rows(RenderJob* job) {
     const RodentSceneView* sc = job->sc;
     const Settings* cam = job->cam;
@@ -287,7 +331,8 @@ static void render_rows(RenderJob* job) {
                     trace(sc, 0, org, dir, tmin, FLT_MAX_, &hit, &geom, &job->stats.trav);
                     job->stats.primary_rays++;
                     if (hit.tri_id < 0) break;                                       /* misses leave the stream, mapping_gpu.impala:357 */
-                    const RodentMaterial* mat = &sc->materials[geom];
+                    const RodentMaterial textured = textured_material(sc, geom, hit.tri_id, hit.u, hit.v);
+                    const RodentMaterial* mat = &textured;
                     const Surf surf = surface_element(sc, org, dir, hit.tri_id, hit.t, hit.u, hit.v);
                     const V3 out_dir = vneg(dir);
 
@@ -394,25 +439,8 @@ void oracle_render(const RodentSceneView* sc, const Settings* cam, int width, in
  * CPU restatement (same signature, host pointers).  Parity status: UNPINNED by the reference -- the tool prints a
  * throughput and checks no value.  Known answers that follow from the source alone are asserted in
  * tests/test_shading_bench.py (constant-colour geometry 0: a pure function of the BSDF sample; depth + 1; tmin = offset).
- * The reference runs it with FTZ/DAZ set (bench_shading.cpp:57-59); no denormal occurs on its inputs. */
-static Col rgba32_texture(const uint32_t* pixels, int width, int height, float u, float v) {   /* image.impala:24-92: repeat border, bilinear */
-    u = u - floorf(u); v = v - floorf(v);
-    const float fu = u * (float)width, fv = v * (float)height;
-    int x0 = (int)fu; if (x0 > width - 1) x0 = width - 1;
-    int y0 = (int)fv; if (y0 > height - 1) y0 = height - 1;
-    const int x1 = x0 + 1 < width - 1 ? x0 + 1 : width - 1, y1 = y0 + 1 < height - 1 ? y0 + 1 : height - 1;
-    const float kx = fu - (float)(int)fu, ky = fv - (float)(int)fv;
-    Col p[4];
-    const int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
-    for (int k = 0; k < 4; k++) {
-        const uint32_t q = pixels[ys[k] * width + xs[k]];
-        p[k] = col((float)(q & 0xFFu) * (1.0f / 255.0f), (float)((q >> 8) & 0xFFu) * (1.0f / 255.0f), (float)((q >> 16) & 0xFFu) * (1.0f / 255.0f));
-    }
-    return col(lerp1(lerp1(p[0].r, p[1].r, kx), lerp1(p[2].r, p[3].r, kx), ky),
-               lerp1(lerp1(p[0].g, p[1].g, kx), lerp1(p[2].g, p[3].g, kx), ky),
-               lerp1(lerp1(p[0].b, p[1].b, kx), lerp1(p[2].b, p[3].b, kx), ky));
-}
-
+ * The reference runs it with FTZ/DAZ set (bench_shading.cpp:57-59); no denormal occurs on its inputs.
+ * Its texture is rgba32_texture above. */
 void oracle_bench_shading(const PrimaryStream* in, PrimaryStream* out, const Vec3* vertices, const Vec3* normals,
                           const Vec3* face_normals, const Vec2* texcoords, const int32_t* indices, const uint32_t* pixels,
                           int32_t width, int32_t height, const int32_t* begins, const int32_t* ends, int32_t num_tris, int32_t num_iters) {

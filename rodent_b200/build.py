@@ -41,7 +41,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "rodent_b200.h"]
     if not force and _newer(LIB, deps):
         return LIB
-    cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+    cmd = [NVCC, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs), "-lz"]
     print("+", " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
     return LIB

@@ -59,6 +59,7 @@ struct SceneDev {
     const Node8* nodes; const Tri4* tris;
     const float4* normals; const float4* face_normals; const int4* indices; const int* light_ids;
     const RodentMaterial* materials; const RodentLight* lights;
+    const float4* texcoords; const RodentTexture* textures; const unsigned* texture_pixels;   // null without textured materials
     int num_materials, num_lights;
 };
 struct CameraDev { shade::V3 eye, dir, up, right; float w, h; };
@@ -179,7 +180,8 @@ shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, S
         pixel = in.pixel[i];
         const float4 ro = in.ray_o[i], rd = in.ray_d[i], h = in.hit[i], cm = in.contrib_mis[i];
         const uint2 rdp = in.rnd_depth[i];
-        const RodentMaterial mat = sc.materials[in.geom[i]];
+        RodentMaterial mat = sc.materials[in.geom[i]];
+        apply_textures(mat, sc.texcoords, sc.indices, sc.textures, sc.texture_pixels, __float_as_int(h.x), h.z, h.w);
         const V3 org = v3(ro.x, ro.y, ro.z), dir = v3(rd.x, rd.y, rd.z);
         const int prim = __float_as_int(h.x);
         const float t = h.y;
@@ -336,6 +338,14 @@ static void alloc_pipeline(Renderer* r) {
 static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
     if (sc.materials.size() + 1 > size_t(kMaxBins)) { std::fprintf(stderr, "rodent_b200: more than 1024 materials\n"); return nullptr; }
     if (width <= 0 || height <= 0 || spp <= 0 || num_parts <= 0 || part < 0 || part >= num_parts || band <= 0) return nullptr;
+    bool textured = false;
+    for (auto& m : sc.materials) {
+        if (m.map_kd < 0 || m.map_ks < 0 || size_t(m.map_kd) > sc.textures.size() || size_t(m.map_ks) > sc.textures.size()) {
+            std::fprintf(stderr, "rodent_b200: a material names texture %d / %d, the scene has %zu\n", m.map_kd, m.map_ks, sc.textures.size());
+            return nullptr;
+        }
+        textured |= (m.map_kd | m.map_ks) != 0;
+    }
     RB_CUDA_CHECK(cudaSetDevice(dev));
     auto r = new Renderer();
     r->dev = dev; r->width = width; r->height = height; r->spp = spp; r->max_path_len = max_path_len;
@@ -357,6 +367,11 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     d.light_ids = r->upload(sc.light_ids.data(), sc.light_ids.size());
     d.materials = r->upload(sc.materials.data(), sc.materials.size());
     d.lights = r->upload(sc.lights.data(), sc.lights.size());
+    if (textured) {
+        d.texcoords = reinterpret_cast<const float4*>(r->upload(sc.texcoords.data(), sc.texcoords.size()));
+        d.textures = r->upload(sc.textures.data(), sc.textures.size());
+        d.texture_pixels = r->upload(sc.texture_pixels.data(), sc.texture_pixels.size());
+    }
     d.num_materials = int(sc.materials.size()); d.num_lights = int(sc.lights.size());
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));

@@ -227,7 +227,7 @@ void cleanup_materials(ObjFile& obj, std::map<std::string, ObjMaterial>& lib) {
     obj.materials = kept;
 }
 
-// converter.cpp:870-913 with constant colours (textured materials fall back to their constants)
+// converter.cpp:870-913; map_kd / map_ks are filled in by the caller once the images are loaded
 RodentMaterial make_material(const ObjMaterial& m) {
     RodentMaterial r{};
     const F3 zero;
@@ -430,13 +430,42 @@ Scene* load_obj_scene(const std::string& path) {
     cleanup_materials(obj, lib);
 
     auto scene = new Scene();
+    // Images, converter.cpp:595-602, 748-768: one per distinct file name, relative to the OBJ's directory, '\\' -> '/';
+    // .png is decoded, an unknown extension gives the reference's 1x1 black dummy image.  (The reference registers map_Ks
+    // under map_Kd's name, :600, so a specular map silently samples image 0 there; here it samples its own file.)
+    std::unordered_map<std::string, int> images;
+    bool failed = false;
+    auto image_of = [&](std::string name, const std::string& material) -> int {
+        if (name.empty()) return 0;
+        std::replace(name.begin(), name.end(), '\\', '/');
+        auto it = images.find(name);
+        if (it != images.end()) return it->second;
+        auto ends_with = [&](const char* ext) { const size_t n = std::strlen(ext); return name.size() >= n && name.compare(name.size() - n, n, ext) == 0; };
+        int id = 0;
+        if (ends_with(".png")) {
+            int w = 0, h = 0; std::vector<uint32_t> px; std::string why;
+            if (load_png(dir + "/" + name, w, h, px, why)) id = scene->add_texture(px.data(), w, h);
+            else { fail("cannot load PNG file '" + dir + "/" + name + "': " + why); failed = true; }
+        } else if (ends_with(".jpg") || ends_with(".jpeg") || ends_with(".tga") || ends_with(".tiff")) {
+            warn("no decoder for '" + name + "' (material '" + material + "'): the material's constant colour is used instead");
+        } else {
+            const uint32_t black = 0xFF000000u;
+            id = scene->add_texture(&black, 1, 1);
+        }
+        return images[name] = id;
+    };
     for (auto& name : obj.materials) {
         const ObjMaterial& m = lib[name];
-        if (!m.map_kd.empty() || !m.map_ks.empty() || !m.map_ke.empty())
-            warn("material '" + name + "' uses textures; constant colours are used instead");
-        scene->materials.push_back(make_material(m));
+        if (!m.map_ke.empty()) warn("material '" + name + "': map_Ke is not sampled, the constant Ke is emitted");
+        RodentMaterial r = make_material(m);
+        if (r.bsdf == RODENT_BSDF_DIFFUSE || r.bsdf == RODENT_BSDF_PHONG || r.bsdf == RODENT_BSDF_MIX) {
+            r.map_kd = image_of(m.map_kd, name);
+            r.map_ks = image_of(m.map_ks, name);
+        }
+        scene->materials.push_back(r);
         scene->material_names.push_back(name);
     }
+    if (failed) { delete scene; return nullptr; }
 
     // compute_tri_mesh, obj.cpp:412-509: per object, vertices de-duplicated by (v, t, n) in order of first use
     std::vector<F3> verts, normals, face_normals;
@@ -554,6 +583,12 @@ Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int 
     return scene;
 }
 
+int Scene::add_texture(const uint32_t* rgba, int width, int height) {
+    textures.push_back({width, height, int64_t(texture_pixels.size())});
+    texture_pixels.insert(texture_pixels.end(), rgba, rgba + size_t(width) * height);
+    return int(textures.size());
+}
+
 }  // namespace rb200
 
 using rb200::Scene;
@@ -576,6 +611,20 @@ void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out) {
     out->vertices = s.vertices.data(); out->normals = s.normals.data(); out->face_normals = s.face_normals.data();
     out->texcoords = s.texcoords.data(); out->indices = s.indices.data(); out->light_ids = s.light_ids.data();
     out->materials = s.materials.data(); out->lights = s.lights.data(); out->nodes = s.nodes.data(); out->tris = s.tris.data();
+    out->textures = s.textures.data(); out->texture_pixels = s.texture_pixels.data();
+    out->num_texture_pixels = int64_t(s.texture_pixels.size()); out->num_textures = int32_t(s.textures.size()); out->pad = 0;
+}
+int32_t rodent_b200_scene_add_texture(RodentScene* scene, const uint32_t* rgba, int32_t width, int32_t height) {
+    if (!scene || !rgba || width <= 0 || height <= 0) return 0;
+    return reinterpret_cast<Scene*>(scene)->add_texture(rgba, width, height);
+}
+int32_t rodent_b200_scene_add_png(RodentScene* scene, const char* png_file) {
+    int w = 0, h = 0; std::vector<uint32_t> px; std::string why;
+    if (!scene || !rb200::load_png(png_file, w, h, px, why)) {
+        std::fprintf(stderr, "rodent_b200: cannot load PNG file '%s': %s\n", png_file, why.c_str());
+        return 0;
+    }
+    return reinterpret_cast<Scene*>(scene)->add_texture(px.data(), w, h);
 }
 void rodent_b200_scene_free(RodentScene* scene) { delete reinterpret_cast<Scene*>(scene); }
 void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* num_nodes, const Tri4** tris, int32_t* num_tri4) {

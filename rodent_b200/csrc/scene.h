@@ -20,7 +20,14 @@ struct Scene {
     std::vector<Tri4> tris;
     std::vector<Node4> nodes4;            // built on demand (rodent_b200_scene_bvh4)
     std::vector<Tri4> tris4;
+    std::vector<RodentTexture> textures;  // images of map_Kd / map_Ks, pixels back to back
+    std::vector<uint32_t> texture_pixels;
+
+    int add_texture(const uint32_t* rgba, int width, int height);   // returns 1 + index
 };
+
+// src/driver/image.cpp:25-93 (image.cpp of this directory)
+bool load_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 
 Scene* load_obj_scene(const std::string& path);
 void build_bvh4(Scene& scene);

@@ -125,6 +125,48 @@ __device__ __forceinline__ Surf surface_element(const float4* __restrict__ norma
     return s;
 }
 
+// make_texture(repeat border, bilinear filter, make_image_rgba32), src/render/image.impala:24-92
+__device__ __forceinline__ Col rgba32_texture(const unsigned* __restrict__ pixels, int width, int height, float u, float v) {
+    u = u - floorf(u); v = v - floorf(v);
+    const float fu = u * float(width), fv = v * float(height);
+    const int x0 = min(int(fu), width - 1), y0 = min(int(fv), height - 1);
+    const int x1 = min(x0 + 1, width - 1), y1 = min(y0 + 1, height - 1);
+    const float kx = fu - float(int(fu)), ky = fv - float(int(fv));
+    auto px = [&](int x, int y) {
+        const unsigned p = __ldg(pixels + y * width + x);
+        return col(float(p & 0xFFu) * (1.0f / 255.0f), float((p >> 8) & 0xFFu) * (1.0f / 255.0f), float((p >> 16) & 0xFFu) * (1.0f / 255.0f));
+    };
+    const Col p00 = px(x0, y0), p10 = px(x1, y0), p01 = px(x0, y1), p11 = px(x1, y1);
+    return col(lerp1(lerp1(p00.r, p10.r, kx), lerp1(p01.r, p11.r, kx), ky),
+               lerp1(lerp1(p00.g, p10.g, kx), lerp1(p01.g, p11.g, kx), ky),
+               lerp1(lerp1(p00.b, p10.b, kx), lerp1(p01.b, p11.b, kx), ky));
+}
+
+// The textured part of a material's shader (converter.cpp:876-903): kd / ks looked up at the hit's texture coordinates
+// (surf.attr(0), the lerp of the three vertices' uv: geometry.impala:44-47), the mix weight recomputed from them.
+__device__ __forceinline__ void apply_textures(RodentMaterial& m, const float4* __restrict__ texcoords, const int4* __restrict__ indices,
+                                               const RodentTexture* __restrict__ textures, const unsigned* __restrict__ texture_pixels,
+                                               int prim, float u, float v) {
+    if ((m.map_kd | m.map_ks) == 0) return;
+    const int4 idx = __ldg(indices + prim);
+    const float4 t0 = __ldg(texcoords + idx.x), t1 = __ldg(texcoords + idx.y), t2 = __ldg(texcoords + idx.z);
+    const float tu = lerp2(t0.x, t1.x, t2.x, u, v), tv = lerp2(t0.y, t1.y, t2.y, u, v);
+    if (m.map_kd) {
+        const RodentTexture t = textures[m.map_kd - 1];
+        const Col c = rgba32_texture(texture_pixels + t.offset, t.width, t.height, tu, tv);
+        m.kd[0] = c.r; m.kd[1] = c.g; m.kd[2] = c.b;
+    }
+    if (m.map_ks) {
+        const RodentTexture t = textures[m.map_ks - 1];
+        const Col c = rgba32_texture(texture_pixels + t.offset, t.width, t.height, tu, tv);
+        m.ks[0] = c.r; m.ks[1] = c.g; m.ks[2] = c.b;
+    }
+    if (m.bsdf == RODENT_BSDF_MIX) {
+        const float lum_ks = luminance(col(m.ks[0], m.ks[1], m.ks[2])), lum_kd = luminance(col(m.kd[0], m.kd[1], m.kd[2]));
+        m.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
+    }
+}
+
 // material.impala:54-192, interpreted from the RodentMaterial table
 struct BsdfSample { V3 in_dir; float pdf, cos; Col color; };
 

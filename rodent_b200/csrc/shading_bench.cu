@@ -116,24 +116,6 @@ struct ShadingArgs {
     int begins[kShadingGeoms], ends[kShadingGeoms];
 };
 
-// make_texture(repeat border, bilinear filter, make_image_rgba32), src/render/image.impala:24-92
-__device__ __forceinline__ shade::Col rgba32_texture(const unsigned* __restrict__ pixels, int width, int height, float u, float v) {
-    using namespace shade;
-    u = u - floorf(u); v = v - floorf(v);
-    const float fu = u * float(width), fv = v * float(height);
-    const int x0 = min(int(fu), width - 1), y0 = min(int(fv), height - 1);
-    const int x1 = min(x0 + 1, width - 1), y1 = min(y0 + 1, height - 1);
-    const float kx = fu - float(int(fu)), ky = fv - float(int(fv));
-    auto px = [&](int x, int y) {
-        const unsigned p = __ldg(pixels + y * width + x);
-        return col(float(p & 0xFFu) * (1.0f / 255.0f), float((p >> 8) & 0xFFu) * (1.0f / 255.0f), float((p >> 16) & 0xFFu) * (1.0f / 255.0f));
-    };
-    const Col p00 = px(x0, y0), p10 = px(x1, y0), p01 = px(x0, y1), p11 = px(x1, y1);
-    return col(lerp1(lerp1(p00.r, p10.r, kx), lerp1(p01.r, p11.r, kx), ky),
-               lerp1(lerp1(p00.g, p10.g, kx), lerp1(p01.g, p11.g, kx), ky),
-               lerp1(lerp1(p00.b, p10.b, kx), lerp1(p01.b, p11.b, kx), ky));
-}
-
 __global__ void __launch_bounds__(128)
 bench_shading_kernel(ShadingArgs a) {
     using namespace shade;

@@ -12,7 +12,8 @@ import numpy as np
 from . import lib
 
 MATERIAL = np.dtype([("bsdf", "<i4"), ("is_emissive", "<i4"), ("ns", "<f4"), ("ni", "<f4"), ("kd", "<f4", (3,)), ("mix_k", "<f4"),
-                     ("ks", "<f4", (3,)), ("pad0", "<f4"), ("tf", "<f4", (3,)), ("pad1", "<f4"), ("ke", "<f4", (3,)), ("pad2", "<f4")])
+                     ("ks", "<f4", (3,)), ("map_kd", "<i4"), ("tf", "<f4", (3,)), ("map_ks", "<i4"), ("ke", "<f4", (3,)), ("pad2", "<f4")])
+TEXTURE = np.dtype([("width", "<i4"), ("height", "<i4"), ("offset", "<i8")])
 LIGHT = np.dtype([("v0", "<f4", (3,)), ("inv_area", "<f4"), ("v1", "<f4", (3,)), ("pad0", "<f4"), ("v2", "<f4", (3,)), ("pad1", "<f4"),
                   ("n", "<f4", (3,)), ("pad2", "<f4"), ("color", "<f4", (3,)), ("pad3", "<f4")])
 assert MATERIAL.itemsize == 80 and LIGHT.itemsize == 80
@@ -31,7 +32,8 @@ class Settings(ctypes.Structure):
 class SceneView(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("num_tris", "num_vertices", "num_materials", "num_lights", "num_nodes", "num_tri4")] + \
                [(n, c_void_p) for n in ("vertices", "normals", "face_normals", "texcoords", "indices", "light_ids",
-                                        "materials", "lights", "nodes", "tris")]
+                                        "materials", "lights", "nodes", "tris", "textures", "texture_pixels")] + \
+               [("num_texture_pixels", c_int64), ("num_textures", c_int32), ("pad", c_int32)]
 
 
 # symbol -> (restype, argtypes) of the scene / renderer part of include/rodent_b200.h
@@ -40,6 +42,8 @@ SIGNATURES = {
     "rodent_b200_scene_from_bvh8": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_view": (None, [c_void_p, POINTER(SceneView)]),
     "rodent_b200_scene_free": (None, [c_void_p]),
+    "rodent_b200_scene_add_texture": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
+    "rodent_b200_scene_add_png": (c_int32, [c_void_p, ctypes.c_char_p]),
     "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
     "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
     "rodent_b200_renderer_free": (None, [c_void_p]),
@@ -107,6 +111,23 @@ class Scene:
         return cls(_bind(lib.load()).rodent_b200_scene_from_bvh8(nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris),
                                                                   materials.ctypes.data, len(materials), mop.ctypes.data, len(mop)))
 
+    def add_texture(self, rgba: np.ndarray) -> int:
+        """Appends an (height, width) uint32 image (RodentTexture layout: gamma-corrected, bottom row first); returns the
+        value for a material's map_kd / map_ks."""
+        rgba = np.ascontiguousarray(rgba, np.uint32)
+        L = _bind(lib.load())
+        tid = L.rodent_b200_scene_add_texture(self.handle, rgba.ctypes.data, rgba.shape[1], rgba.shape[0])
+        L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+        return tid
+
+    def add_png(self, path) -> int:
+        L = _bind(lib.load())
+        tid = L.rodent_b200_scene_add_png(self.handle, str(path).encode())
+        if not tid:
+            raise RuntimeError(f"cannot load {path} (see stderr)")
+        L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+        return tid
+
     @property
     def view(self) -> SceneView:
         return self._view
@@ -118,7 +139,8 @@ class Scene:
                  "face_normals": ((v.num_tris, 4), np.float32), "texcoords": ((v.num_vertices, 4), np.float32),
                  "indices": ((v.num_tris, 4), np.int32), "light_ids": ((v.num_tris,), np.int32),
                  "materials": ((v.num_materials,), MATERIAL), "lights": ((v.num_lights,), LIGHT),
-                 "nodes": ((v.num_nodes,), formats.NODE8), "tris": ((v.num_tri4,), formats.TRI4)}
+                 "nodes": ((v.num_nodes,), formats.NODE8), "tris": ((v.num_tri4,), formats.TRI4),
+                 "textures": ((v.num_textures,), TEXTURE), "texture_pixels": ((v.num_texture_pixels,), np.uint32)}
         shape, dt = table[name]
         n = int(np.prod(shape)) * np.dtype(dt).itemsize
         if n == 0:
