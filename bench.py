@@ -5,18 +5,22 @@ Workload (BASELINE.json configs[1]): `bench_traversal` on the Sponza BVH8 block 
 both reference ray sets, closest hit, single-ray semantics:
     sponza-primary.rays  1 048 576 rays, tmin 0, tmax 5000   (README.md:33-34 of the reference)
     sponza-random.rays   1 048 576 rays, tmin 0, tmax 1      (README.md:35-36)
-One "step" traces both sets once (2 kernel launches, 2 097 152 rays).
+One "step" traces both sets once (2 kernel launches, 2 097 152 rays).  The two launches go to two streams through
+the asynchronous entry points, the incoherent set first, so that the second launch fills the SMs the first one's
+stragglers leave idle (profiles/r01_experiments.md, "The tail of a launch"); `per_set` repeats the passes one
+launch at a time, as bench_traversal does.
 Metric: Mrays/sec = rays / (1000 * ms), as tools/bench_traversal/bench_traversal.cpp:386-387.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line on rank 0.  `value`: rays resident in HBM, CUDA-event time of the
-traversal kernels.  `path_trace`: the render configs of BASELINE.json (configs[2..4]) through
+steps (first launch's start to the last launch's end).  `path_trace`: the render configs of BASELINE.json (configs[2..4]) through
 the wavefront path tracer, image rows dealt out across the ranks, one NCCL reduce of the film
 inside the timed region (samples/s = spp*w*h / t, src/driver/driver.cpp:300 of the reference).  `e2e`: the same passes through the host-pointer C ABI
 (b200_intersect_single_ray1_bvh8_tri4) with pinned HOST buffers, copies in the timed
-region.  `roofline`: algorithmic bytes of the reference layout / kernel time against
+region; the two sets are submitted from two host threads (the entry points are reentrant, like the cpu_* functions
+they replace).  `roofline`: algorithmic bytes of the reference layout / kernel time against
 the measured HBM copy bandwidth.  `cpu_baseline` / `--impl reference`: the oracle
 (restated reference algorithm, oracle/traversal_oracle.c) on the box's host cores.
 """
@@ -219,13 +223,13 @@ def cpu_path_trace_sample(threads: int):
     from oracle import oracle
     from rodent_b200 import workloads
     scene = workloads.load_scene("cornell")
-    W, H, spp, depth = 256, 256, 16, 4
+    W, H, spp, depth = 1024, 1024, 32, 4                  # half of configs[2]'s samples: ~1 s on 16 threads
     cam = workloads.camera("cornell", W, H)
     oracle.render(scene.view, cam, 64, 64, 1, depth, 0, threads=threads)
     t0 = time.perf_counter()
     oracle.render(scene.view, cam, W, H, spp, depth, 0, threads=threads)
     dt = time.perf_counter() - t0
-    return {"msamples_s": round(W * H * spp / dt / 1e6, 3), "sample": f"cornell {W}x{H}, {spp} spp, {depth} bounces, {dt:.1f} s on {threads} threads"}
+    return {"msamples_s": round(W * H * spp / dt / 1e6, 3), "sample": f"cornell {W}x{H}, {spp} spp, {depth} bounces, {dt:.2f} s on {threads} threads"}
 
 
 def run_reference(args):
@@ -301,8 +305,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    order = sorted(names, key=lambda n: n != "random")          # the incoherent set first: its tail is the long one
+    streams = [torch.cuda.Stream() for _ in names]
+    counters = torch.zeros(16 * len(names), dtype=torch.int32, device="cuda")
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev_end = [torch.cuda.Event(enable_timing=True) for _ in names]
+
     def step():
-        """One pass over both ray sets; returns per-set kernel ms (CUDA events on the launch stream)."""
+        """One pass over both ray sets, the launches overlapping on two streams; returns the device time in ms from the
+        start of the first launch to the end of the last one (CUDA events on the launch streams)."""
+        flush.zero_()
+        torch.cuda.synchronize()
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        for k, n in enumerate(order):
+            traversal.intersect_async(bvh, d_rays[n], d_hits[n], streams[k].cuda_stream, counters.data_ptr() + 64 * k)
+            ev_end[k].record(streams[k])
+        torch.cuda.synchronize()
+        return max(ev0.elapsed_time(e) for e in ev_end)
+
+    def serial_step():
+        """The same passes one launch at a time; returns per-set kernel ms (bench_gpu, bench_traversal.cpp:124-135)."""
         flush.zero_()
         torch.cuda.synchronize()
         return [traversal.intersect(bvh, d_rays[n], d_hits[n]) for n in names]
@@ -312,18 +336,20 @@ def main():
             step()
         barrier()
         launches0 = L.rodent_b200_launch_count()
-        per_set = []
+        step_ms = []
         t_wall0 = time.perf_counter()
         clocks.mark_start()
         for _ in range(args.steps):
-            per_set.append(step())
+            step_ms.append(step())
         barrier()
         clocks.mark_end()
         wall_ms = (time.perf_counter() - t_wall0) * 1e3
     launches = L.rodent_b200_launch_count() - launches0
-    per_set = np.array(per_set)                      # steps x sets
-    kernel_ms = float(per_set.sum())                 # timed region on the device: K steps
+    kernel_ms = float(sum(step_ms))                  # timed region on the device: K steps
     hits_found = {n: int((d_hits[n].to_host()["tri_id"] >= 0).sum()) for n in names}
+    for _ in range(3):
+        serial_step()
+    per_set = np.array([serial_step() for _ in range(max(3, min(args.steps, 20)))])     # steps x sets, outside the timed region
 
     # ---- end to end: host buffers through the host-pointer C ABI -----------------------------
     pin_rays = {n: traversal.PinnedArray(formats.RAY1, len(rays[n])) for n in names}
@@ -331,18 +357,26 @@ def main():
     for n in names:
         pin_rays[n].array[:] = rays[n]
     e2e_steps = max(3, min(args.steps, 20))
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(len(names))
+
+    def e2e_step():
+        """Both sets through the host-pointer entry point, one host thread per set (ctypes drops the GIL in the call)."""
+        jobs = [pool.submit(traversal.intersect_host, nodes, tris, pin_rays[n].array, pin_hits[n].array) for n in order]
+        for j in jobs:
+            j.result()
+
     for _ in range(3):
-        for n in names:
-            traversal.intersect_host(nodes, tris, pin_rays[n].array, pin_hits[n].array)
+        e2e_step()
     barrier()
     e2e_ms = 0.0
     for _ in range(e2e_steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for n in names:
-            traversal.intersect_host(nodes, tris, pin_rays[n].array, pin_hits[n].array)
+        e2e_step()
         e2e_ms += (time.perf_counter() - t0) * 1e3
+    pool.shutdown()
     e2e_ok = all(int((pin_hits[n].array["tri_id"] >= 0).sum()) == hits_found[n] for n in names)
 
     # ---- path tracing (configs[2..4]) ------------------------------------------------------------
@@ -365,25 +399,32 @@ def main():
     per_set_ms = per_set.mean(axis=0)
     peak, peak_src = hbm_peak()
     algo_bytes = {n: bytes_per_ray(n) * len(rays[n]) for n in names}
-    achieved = sum(algo_bytes.values()) / (float(per_set_ms.sum()) * 1e-3) / 1e9
+    achieved = sum(algo_bytes.values()) / (kernel_ms / args.steps * 1e-3) / 1e9            # both launches / the step they share
+    achieved_serial = sum(algo_bytes.values()) / (float(per_set_ms.sum()) * 1e-3) / 1e9
     traffic = ncu_traffic()
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(kernel_ms / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(world),
+        "per_set_note": "one launch at a time, outside the timed region (bench_traversal's procedure)",
         "per_set": {n: {"mrays_s": round(len(rays[n]) / float(per_set_ms[k]) / 1e3, 2), "ms": round(float(per_set_ms[k]), 4),
                         "min_ms": round(float(per_set[:, k].min()), 4), "hits": hits_found[n],
                         "bytes_per_ray": round(bytes_per_ray(n), 1)} for k, n in enumerate(names)},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(sum(r.nbytes for r in rays.values())),
                 "d2h_bytes_per_step": int(16 * n_rays), "steps": e2e_steps, "results_match_device_path": e2e_ok,
-                "api": "b200_intersect_single_ray1_bvh8_tri4 (host pointers, pinned; BVH upload cached)"},
+                "api": "b200_intersect_single_ray1_bvh8_tri4 (host pointers, pinned; BVH upload cached), "
+                       "the two sets submitted from two host threads"},
         "gpu_launches": int(launches),
         "wall_ms_per_step_incl_l2_flush": round(wall_ms / args.steps, 3),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "kernel": "traverse_bvh8_vote<false, 5>",
-                     "note": "algorithmic bytes of the reference layout (32+16+256*nodes+224*Tri4 per ray); the 19.8 MB BVH "
+                     "launches_per_step": len(names), "achieved_one_launch_at_a_time": round(achieved_serial, 1),
+                     "note": "the step's two launches of this kernel overlap on two streams: achieved = algorithmic bytes of "
+                             "both / the step's device time (first start to last end); one launch at a time (per_set, what "
+                             "the ncu launch list serialises) gives achieved_one_launch_at_a_time.  "
+                             "algorithmic bytes of the reference layout (32+16+256*nodes+224*Tri4 per ray); the 19.8 MB BVH "
                              "is L2-resident, so frac > 1 means served from L2, not faster than HBM"},
         "clocks": clocks.summary(),
     }

@@ -111,7 +111,9 @@ void cuda_occluded_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, 
  * buffers.  The BVH is uploaded to the current device on first use and cached by
  * (nodes, tris) address; its extent is found by walking it from the root (node 1),
  * because the reference signature carries no sizes.  Rays are copied in and hits
- * copied out on every call.  rodent_b200_forget_bvh drops a cached copy (call it
+ * copied out on every call.  Like the cpu_* functions they replace, the calls are reentrant: each takes its own device
+ * staging buffers and streams, so calls from several host threads overlap on the device (one set's transfers under
+ * another set's traversal).  rodent_b200_forget_bvh drops a cached copy (call it
  * before freeing or rewriting a BVH that was passed here). */
 void b200_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris,
                                           const Ray1* rays, Hit1* hits, int32_t num_packets);

@@ -40,7 +40,7 @@ struct Tuning {
     int pool_prefetch = 0;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
-    int host_chunks = 4;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 4)
+    int host_chunks = 3;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 3..4)
 };
 static Tuning g_tuning;
 
@@ -265,10 +265,16 @@ struct DeviceState {
     int occ_bvh4[2] = {0, 0};
     StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
     int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
-    // host-pointer path
+    // host-pointer path: staging contexts (one per call in flight, reused) and the uploaded BVHs
+    std::vector<struct HostContext*> idle_contexts;
+    std::map<std::pair<const void*, const void*>, std::pair<void*, Tri4*>> bvh_cache;
+};
+// What one host-pointer call needs on the device.  The reference's cpu_* functions are reentrant, so their drop-ins are
+// too: every call takes a context of its own, and concurrent calls (from several host threads) overlap on the device.
+struct HostContext {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
-    std::map<std::pair<const void*, const void*>, std::pair<void*, Tri4*>> bvh_cache;
+    int* counters = nullptr;   // 3 x 8 ints: one work counter per stream
 };
 static DeviceState g_dev[64];
 static std::mutex g_mutex;
@@ -430,6 +436,35 @@ static std::pair<NodeT*, Tri4*> cached_bvh(DeviceState& s, const NodeT* nodes, c
     return std::make_pair(dn, dt);
 }
 
+static HostContext* acquire_host_context(DeviceState& s, size_t num_rays) {
+    HostContext* c = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        // prefer an idle context that is already large enough
+        for (size_t i = 0; i < s.idle_contexts.size(); i++)
+            if (s.idle_contexts[i]->ray_capacity >= num_rays) { c = s.idle_contexts[i]; s.idle_contexts.erase(s.idle_contexts.begin() + i); break; }
+        if (!c && !s.idle_contexts.empty()) { c = s.idle_contexts.back(); s.idle_contexts.pop_back(); }
+    }
+    if (!c) {
+        c = new HostContext();
+        for (auto& st : c->streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        RB_CUDA_CHECK(cudaMalloc(&c->counters, 3 * 8 * sizeof(int)));
+    }
+    if (c->ray_capacity < num_rays) {
+        if (c->d_rays) { RB_CUDA_CHECK(cudaFree(c->d_rays)); RB_CUDA_CHECK(cudaFree(c->d_hits)); }
+        RB_CUDA_CHECK(cudaMalloc(&c->d_rays, num_rays * sizeof(Ray1)));
+        RB_CUDA_CHECK(cudaMalloc(&c->d_hits, num_rays * sizeof(Hit1)));
+        c->ray_capacity = num_rays;
+    }
+    return c;
+}
+static void release_host_context(DeviceState& s, HostContext* c) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    s.idle_contexts.push_back(c);
+}
+// The ray-pool variant (mapping 3) indexes one per-device overflow buffer by warp: its launches must not overlap.
+static std::mutex g_pool_serial;
+
 // Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
 // transfers of one chunk overlap the traversal of another.
 template <bool ANY, typename NodeT>
@@ -437,18 +472,13 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     if (num_rays <= 0) return;
     DeviceState& s = device_state(g_host_dev);
     auto bvh = cached_bvh(s, nodes, tris);
-    if (!s.streams[0]) {
-        for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    std::unique_lock<std::mutex> serial(g_pool_serial, std::defer_lock);
+    if (g_tuning.mapping == 3) serial.lock();
+    HostContext* c = acquire_host_context(s, size_t(num_rays));
+    if (ANY) {  // occluded leaves t/u/v untouched: round-trip the caller's records
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, c->streams[0]));
+        RB_CUDA_CHECK(cudaStreamSynchronize(c->streams[0]));
     }
-    if (s.ray_capacity < size_t(num_rays)) {
-        if (s.d_rays) { RB_CUDA_CHECK(cudaFree(s.d_rays)); RB_CUDA_CHECK(cudaFree(s.d_hits)); }
-        RB_CUDA_CHECK(cudaMalloc(&s.d_rays, size_t(num_rays) * sizeof(Ray1)));
-        RB_CUDA_CHECK(cudaMalloc(&s.d_hits, size_t(num_rays) * sizeof(Hit1)));
-        s.ray_capacity = size_t(num_rays);
-    }
-    if (ANY)   // occluded leaves t/u/v untouched: round-trip the caller's records
-        RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, s.streams[0]));
-    if (ANY) RB_CUDA_CHECK(cudaStreamSynchronize(s.streams[0]));
     // Pieces of decreasing size (k, k-1, ..., 1 parts of k(k+1)/2): the copy engine is the critical resource, and what
     // follows the last byte of input is one piece's traversal -- including its stragglers -- and its copy out, so that
     // last piece is kept small.
@@ -460,13 +490,14 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
         int n = int((int64_t(num_rays) * weight / parts + 3) & ~int64_t(3));
         n = std::max(n, 1 << 14);
         if (k >= pieces - 1 || n > num_rays - first) n = num_rays - first;
-        cudaStream_t st = s.streams[k % 3];
-        RB_CUDA_CHECK(cudaMemcpyAsync(s.d_rays + first, rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
-        launch<ANY>(s, bvh.first, bvh.second, s.d_rays + first, s.d_hits + first, n, st, s.counter + 8 * (1 + k % 3));
-        RB_CUDA_CHECK(cudaMemcpyAsync(hits + first, s.d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+        cudaStream_t st = c->streams[k % 3];
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays + first, rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
+        launch<ANY>(s, bvh.first, bvh.second, c->d_rays + first, c->d_hits + first, n, st, c->counters + 8 * (k % 3));
+        RB_CUDA_CHECK(cudaMemcpyAsync(hits + first, c->d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
         first += n;
     }
-    for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (auto& st : c->streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
+    release_host_context(s, c);
 }
 
 // Packet entry points: copy in, one launch, copy out.
@@ -476,29 +507,22 @@ static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* r
     constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
     DeviceState& s = device_state(g_host_dev);
     auto bvh = cached_bvh(s, nodes, tris);
-    if (!s.streams[0]) {
-        for (auto& st : s.streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    }
     const int num_rays = num_packets * W;
-    if (s.ray_capacity < size_t(num_rays)) {
-        if (s.d_rays) { RB_CUDA_CHECK(cudaFree(s.d_rays)); RB_CUDA_CHECK(cudaFree(s.d_hits)); }
-        RB_CUDA_CHECK(cudaMalloc(&s.d_rays, size_t(num_rays) * sizeof(Ray1)));
-        RB_CUDA_CHECK(cudaMalloc(&s.d_hits, size_t(num_rays) * sizeof(Hit1)));
-        s.ray_capacity = size_t(num_rays);
-    }
-    cudaStream_t st = s.streams[0];
-    int* counter = s.counter + 8;
-    RB_CUDA_CHECK(cudaMemcpyAsync(s.d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));     // a packet is W * 32 bytes
-    if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(s.d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st)); // t/u/v stay the caller's
+    HostContext* c = acquire_host_context(s, size_t(num_rays));
+    cudaStream_t st = c->streams[0];
+    int* counter = c->counters;
+    RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));     // a packet is W * 32 bytes
+    if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st)); // t/u/v stay the caller's
     RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
     const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * s.occ_vote[1][ANY ? 1 : 0]);
-    traverse_packets_vote<ANY, ARITY, W><<<grid, kBlock, 0, st>>>(bvh.first, bvh.second, reinterpret_cast<const float*>(s.d_rays),
-                                                                  reinterpret_cast<float*>(s.d_hits), num_rays, counter,
+    traverse_packets_vote<ANY, ARITY, W><<<grid, kBlock, 0, st>>>(bvh.first, bvh.second, reinterpret_cast<const float*>(c->d_rays),
+                                                                  reinterpret_cast<float*>(c->d_hits), num_rays, counter,
                                                                   g_tuning.refill_min, g_tuning.node_streak_min);
     RB_CUDA_CHECK(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    RB_CUDA_CHECK(cudaMemcpyAsync(hits, s.d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+    RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
     RB_CUDA_CHECK(cudaStreamSynchronize(st));
+    release_host_context(s, c);
 }
 
 }  // namespace rb200

@@ -71,6 +71,18 @@ def intersect(bvh: Bvh8, rays: DeviceArray, hits: DeviceArray, any_hit: bool = F
     return L.rodent_b200_last_kernel_ms(bvh.dev)
 
 
+def intersect_async(bvh: Bvh8, rays: DeviceArray, hits: DeviceArray, stream: int, work_counter: int, any_hit: bool = False,
+                    count: int | None = None) -> None:
+    """Enqueue one traversal pass on `stream` (a cudaStream_t as an integer) without synchronising
+    (cuda_*_single_ray1_bvh8_tri4_async).  `work_counter`: device address of an int32 owned by the caller, one per stream
+    in flight."""
+    assert bvh.arity == 8
+    L = lib.load()
+    n = rays.count if count is None else count
+    fn = getattr(L, f"cuda_{'occluded' if any_hit else 'intersect'}_single_ray1_bvh8_tri4_async")
+    fn(bvh.dev, bvh.nodes.ptr, bvh.tris.ptr, rays.ptr, hits.ptr, n, stream, work_counter)
+
+
 def intersect_host(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, hits: np.ndarray | None = None,
                    any_hit: bool = False) -> np.ndarray:
     """The host-buffer drop-in for cpu_{intersect,occluded}_single_ray1_bvh8_tri4

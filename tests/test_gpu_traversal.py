@@ -145,6 +145,50 @@ def test_host_pointer_entry_points(sponza, ray_sets, oracle_hits):
     assert (occl["t"] == 3.0).all()
 
 
+def test_host_entry_points_are_reentrant(sponza, ray_sets, oracle_hits):
+    """The cpu_* functions are pure; their drop-ins may be called from several host threads at once -- different sets,
+    sizes and closest / any hit mixed, repeatedly (contexts are reused)."""
+    import threading
+    from rodent_b200 import traversal
+    nodes, tris = sponza
+    jobs = [("random", slice(None), False), ("primary", slice(None), False), ("random", slice(1000, 301000), False),
+            ("primary", slice(7, 50007), True), ("random", slice(0, 3), False), ("primary", slice(500000, 1048576), False)]
+    results = {}
+
+    def work(k, name, sl, any_hit):
+        rays = np.ascontiguousarray(ray_sets[name][sl])
+        for rep in range(3):
+            results[k, rep] = traversal.intersect_host(nodes, tris, rays, any_hit=any_hit)
+
+    threads = [threading.Thread(target=work, args=(k, *job)) for k, job in enumerate(jobs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k, (name, sl, any_hit) in enumerate(jobs):
+        for rep in range(3):
+            if any_hit:
+                assert ((results[k, rep]["tri_id"] >= 0) == (oracle_hits[name][sl]["tri_id"] >= 0)).all()
+            else:
+                assert_records_equal(results[k, rep], oracle_hits[name][sl])
+
+
+def test_async_launches_overlap_on_two_streams(gpu, ray_sets, oracle_hits):
+    """cuda_*_async: both sets in flight at once on two streams with their own work counters (what bench.py times)."""
+    import torch
+    from rodent_b200 import traversal
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    counters = torch.zeros(32, dtype=torch.int32, device="cuda")
+    d_rays = {n: traversal.DeviceArray.from_host(0, ray_sets[n]) for n in ("random", "primary")}
+    d_hits = {n: traversal.DeviceArray.from_host(0, np.zeros(len(ray_sets[n]), formats.HIT1)) for n in d_rays}
+    for rep in range(3):
+        for k, n in enumerate(d_rays):
+            traversal.intersect_async(gpu, d_rays[n], d_hits[n], streams[k].cuda_stream, counters.data_ptr() + 64 * k)
+        torch.cuda.synchronize()
+    for n in d_rays:
+        assert_records_equal(d_hits[n].to_host(), oracle_hits[n])
+
+
 def test_properties_full_size(gpu, ray_sets):
     """Size-independent properties on the full 1 Mi sets: order independence (a
     permutation of the rays permutes the records), idempotence, tmax clipping
