@@ -43,6 +43,20 @@ typedef struct Node4 {
     int32_t pad[4];
 } Node4;
 
+/* The layout of the reference's own GPU path, src/traversal/mapping_gpu.impala:3-16.  Node2: bounds = lo_x, hi_x,
+ * lo_y, hi_y, lo_z, hi_z of child 0, then of child 1; child as in Node8.  Tri1: one triangle, n is recomputed as
+ * cross(e1, e2); prim_id < 0: last triangle of its leaf, the reported id is prim_id & 0x7FFFFFFF. */
+typedef struct Node2 {
+    float   bounds[12];
+    int32_t child[2];
+    int32_t pad[2];
+} Node2;
+typedef struct Tri1 {
+    float   v0[3]; int32_t pad;
+    float   e1[3]; int32_t geom_id;
+    float   e2[3]; int32_t prim_id;
+} Tri1;
+
 /* src/traversal/mapping_cpu.impala:3-10.  e1 = v0 - v1, e2 = v2 - v0,
  * n = cross(e1, e2).  prim_id == -1: invalid lane; prim_id[3] < 0: last packet
  * of its leaf; the reported id is prim_id & 0x7FFFFFFF. */
@@ -89,6 +103,19 @@ typedef struct Hit1 {
 void cuda_intersect_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const Tri4* tris,
                                           const Ray1* rays, Hit1* hits, int32_t num_rays);
 void cuda_occluded_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const Tri4* tris,
+                                         const Ray1* rays, Hit1* hits, int32_t num_rays);
+
+/* The reference's GPU exports themselves, on their own BVH2 / Tri1 layout: drop-ins for
+ *   nvvm_{intersect,occluded}_single_ray1_bvh2_tri1(dev, nodes, tris, rays, hits, num_rays)
+ *   (tools/bench_traversal/bench_traversal.impala:459-493), i.e. `bench_traversal -gpu nvvm` unchanged up to the call.
+ * Semantics of gpu_traverse_single_helper (src/traversal/mapping_gpu.impala:94-178): unordered slab test with the
+ * video min/max instructions on the float bits (:74-85), both children hit -> nearer entry first, no culling of
+ * stacked entries, leaves of single triangles.  The hit writer stores all four fields in both modes
+ * (make_gpu_hit1, bench_traversal.impala:78-83): miss -> tri_id = -1, t = tmax, u = v = 0; `occluded` returns the first
+ * accepted triangle's record. */
+void cuda_intersect_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris,
+                                          const Ray1* rays, Hit1* hits, int32_t num_rays);
+void cuda_occluded_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris,
                                          const Ray1* rays, Hit1* hits, int32_t num_rays);
 
 /* Asynchronous forms: enqueue on `stream` (a cudaStream_t passed as void*; NULL

@@ -23,7 +23,7 @@ class OracleStats(ctypes.Structure):
 
 def build(force: bool = False) -> Path:
     so = _DIR / "liboracle.so"
-    newest = max((_DIR / f).stat().st_mtime for f in ("traversal_oracle.c", "render_oracle.c", "shading_bench_oracle.c", "Makefile"))
+    newest = max((_DIR / f).stat().st_mtime for f in ("traversal_oracle.c", "traversal_bvh2_oracle.c", "render_oracle.c", "shading_bench_oracle.c", "Makefile"))
     if force or not so.exists() or so.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_DIR), "-B" if force else "-s"] + (["-s"] if force else []), check=True)
     return so
@@ -63,6 +63,20 @@ def traverse(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit: boo
     lib().oracle_traverse(arity, int(any_hit), _ptr(nodes), _ptr(tris), _ptr(rays), _ptr(hits), len(rays),
                           threads, ctypes.byref(stats) if want_stats else None)
     return (hits, stats) if want_stats else hits
+
+
+def traverse_bvh2(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit: bool = False, threads: int | None = None,
+                  want_counters: bool = False):
+    """The reference's GPU traversal semantics on its BVH2 / Tri1 layout (oracle/traversal_bvh2_oracle.c)."""
+    from rodent_b200.formats import HIT1, NODE2, TRI1
+    assert nodes.dtype == NODE2 and tris.dtype == TRI1
+    hits = np.zeros(len(rays), HIT1)
+    counters = (ctypes.c_uint64 * 2)()
+    fn = lib().oracle_traverse_bvh2
+    fn.restype = None
+    fn.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p]
+    fn(int(any_hit), _ptr(nodes), _ptr(tris), _ptr(rays), _ptr(hits), len(rays), threads or (os.cpu_count() or 1), counters)
+    return (hits, (int(counters[0]), int(counters[1]))) if want_counters else hits
 
 
 def brute_force(tris: np.ndarray, rays: np.ndarray) -> np.ndarray:

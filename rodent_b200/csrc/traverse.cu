@@ -6,6 +6,7 @@
 // rays from a global counter with one atomicAdd per warp (ranks from ballot + popc) and follow the reference's own
 // per-ray order; they differ in how a warp's rays share its lanes:
 //   traverse_bvh8_vote / traverse_bvh4_vote   one ray per lane, the warp votes on the kind of step  (traverse_sched.cuh, default)
+//   traverse_bvh2_vote                        the reference's GPU semantics on its BVH2 / Tri1 layout (traverse_bvh2.cuh)
 //   traverse_bvh8_pool                        64 rays per warp in shared memory, compacted per step  (traverse_pool.cuh)
 //   traverse_bvh8_persistent / _grid          one ray per lane, per-lane while-while loops          (traverse.cuh)
 //   traverse_bvh8_quad                        four lanes per ray                                    (traverse_quad.cuh)
@@ -21,6 +22,7 @@
 #include "traverse_quad.cuh"
 #include "traverse_sched.cuh"
 #include "traverse_pool.cuh"
+#include "traverse_bvh2.cuh"
 
 namespace rb200 {
 
@@ -153,6 +155,27 @@ traverse_bvh4_vote(const Node4* __restrict__ nodes, const Tri4* __restrict__ tri
         [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
 }
 
+// The reference's GPU path on its own layout (nvvm_{intersect,occluded}_single_ray1_bvh2_tri1,
+// tools/bench_traversal/bench_traversal.impala:459-493): Node2 / Tri1 in, all four hit fields out in both modes
+// (make_gpu_hit1, :78-83).
+constexpr int kBvh2SmemDepth = 32;
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 8)
+traverse_bvh2_vote(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
+                   const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
+                   int* __restrict__ work_counter, int refill_min, int node_streak_min) {
+    __shared__ int smem_stack[kBvh2SmemDepth][kBlock];
+    traverse_bvh2_scheduled<ANY, kBvh2SmemDepth, kBlock>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, node_streak_min,
+        [rays](int i, float4& r0, float4& r1) {
+            const float4* rp = reinterpret_cast<const float4*>(rays + i);
+            r0 = ldg4(rp); r1 = ldg4(rp + 1);
+        },
+        [hits](int i, const HitRecord& h) {
+            *reinterpret_cast<float4*>(hits + i) = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
+        });
+}
+
 // Packet input (Ray4 / Ray8 in, Hit4 / Hit8 out, bench_traversal.impala:32-65): the same loop, fed from and draining
 // into the structure-of-arrays packets; ray i is lane i % W of packet i / W.
 template <bool ANY, int ARITY, int W>
@@ -254,7 +277,7 @@ traverse_bvh8_quad(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
 
 // ---- per-device state ---------------------------------------------------------
 struct DeviceState {
-    bool init = false;
+    std::atomic<bool> init{false};
     int sm_count = 0;
     int* counter = nullptr;    // 64 ints: slot 0 for the synchronous entry points, 8/16/24 for the host-path streams
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -263,6 +286,7 @@ struct DeviceState {
     int occ_quad[2] = {0, 0};
     int occ_pool[2] = {0, 0};
     int occ_bvh4[2] = {0, 0};
+    int occ_bvh2[2] = {0, 0};
     StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
     int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path: staging contexts (one per call in flight, reused) and the uploaded BVHs
@@ -285,9 +309,9 @@ static DeviceState& device_state(int dev) {
     if (dev < 0 || dev >= 64) { std::fprintf(stderr, "rodent_b200: bad device %d\n", dev); std::abort(); }
     DeviceState& s = g_dev[dev];
     RB_CUDA_CHECK(cudaSetDevice(dev));
-    if (!s.init) {
+    if (!s.init.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lock(g_mutex);
-        if (!s.init) {
+        if (!s.init.load(std::memory_order_relaxed)) {
             cudaDeviceProp prop;
             RB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
             if (prop.major != 10) {
@@ -310,9 +334,11 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[0], traverse_bvh4_vote<false>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[1], traverse_bvh4_vote<true>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[0], traverse_bvh2_vote<false>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[1], traverse_bvh2_vote<true>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[0], traverse_bvh8_pool<false>, kPoolBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[1], traverse_bvh8_pool<true>, kPoolBlock, 0));
-            s.init = true;
+            s.init.store(true, std::memory_order_release);
         }
     }
     return s;
@@ -385,8 +411,22 @@ static void launch(DeviceState& s, const Node4* nodes, const Tri4* tris, const R
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-template <bool ANY, typename NodeT>
-static void run_sync(int dev, const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+// BVH2 / Tri1 input.
+template <bool ANY>
+static void launch(DeviceState& s, const Node2* nodes, const Tri1* tris, const Ray1* rays, Hit1* hits,
+                   int num_rays, cudaStream_t stream, int* counter) {
+    if (num_rays <= 0) return;
+    if (!counter) counter = s.counter;
+    RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_bvh2[ANY ? 1 : 0];
+    const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
+    traverse_bvh2_vote<ANY><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+    RB_CUDA_CHECK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+template <bool ANY, typename NodeT, typename TriT>
+static void run_sync(int dev, const NodeT* nodes, const TriT* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     DeviceState& s = device_state(dev);
     RB_CUDA_CHECK(cudaEventRecord(s.ev0, 0));
     launch<ANY>(s, nodes, tris, rays, hits, num_rays, 0, nullptr);
@@ -535,6 +575,12 @@ void cuda_intersect_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const
     run_sync<false>(dev, nodes, tris, rays, hits, num_rays);
 }
 void cuda_occluded_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<true>(dev, nodes, tris, rays, hits, num_rays);
+}
+void cuda_intersect_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
+    run_sync<false>(dev, nodes, tris, rays, hits, num_rays);
+}
+void cuda_occluded_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris, const Ray1* rays, Hit1* hits, int32_t num_rays) {
     run_sync<true>(dev, nodes, tris, rays, hits, num_rays);
 }
 void cuda_intersect_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits,

@@ -1,0 +1,154 @@
+// The reference's GPU single-ray traversal on its own BVH2 / Tri1 layout, for sm_100a.
+//
+// Semantics: gpu_traverse_single_helper (src/traversal/mapping_gpu.impala:94-178) with the arity-2 branch, the NVVM
+// min/max set (make_nvvm_min_max, :74-85: fminf / fmaxf plus vmin / vmax on the float bits), the unordered slab test
+// (src/traversal/intersection.impala:194-208), the single-triangle leaves of make_gpu_bvh2_tri1 (:19-69, n = cross(e1, e2)
+// per test) and the register-top stack of src/traversal/stack.impala:52-123 (whose keys this path never reads).
+// The reference runs it as one thread per ray, block 64, one launch over the whole stream (:182-203).  Here the same
+// per-ray state machine runs under the vote scheduler of traverse_sched.cuh: the warp takes ONE straight-line step per
+// iteration -- a node step (4 x LDG.128, two slab tests, at most one push) or a triangle step (3 x LDG.128, one
+// Moeller-Trumbore test) -- chosen by majority, idle lanes refilled together from a global counter.
+// NaN handling needs no special path: the reference is NVIDIA code, and these are the same instructions.
+#pragma once
+
+#include "traverse.cuh"
+
+namespace rb200 {
+
+// Node ids only (the GPU path pushes undef keys): first SMEM_DEPTH levels in shared memory, [level][thread].
+template <int SMEM_DEPTH, int BLOCK>
+struct IdStack {
+    int* smem;
+    int* overflow;
+    __device__ __forceinline__ int load(int i) const { return i < SMEM_DEPTH ? smem[i * BLOCK] : overflow[i - SMEM_DEPTH]; }
+    __device__ __forceinline__ void store(int i, int v) {
+        if (i < SMEM_DEPTH) smem[i * BLOCK] = v;
+        else overflow[i - SMEM_DEPTH] = v;
+    }
+};
+
+template <bool ANY, int SMEM_DEPTH, int BLOCK>
+struct Bvh2Walker {
+    RaySetup ray;
+    float tmax;
+    int top, ptr;
+    int leaf;                       // next Tri1 of the leaf being tested, -1 when not inside a leaf
+    HitRecord hit;
+    IdStack<SMEM_DEPTH, BLOCK> st;
+
+    __device__ __forceinline__ void pop() { top = st.load(ptr); --ptr; }
+
+    __device__ __forceinline__ void begin(float4 r0, float4 r1) {
+        ray.template init<1>(r0, r1);                                      // make_gpu_ray1 + make_ray
+        tmax = r1.w;
+        hit.prim = -1; hit.geom = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;   // empty_hit
+        st.store(0, 0); ptr = 0; top = 1; leaf = -1;                       // stack.push(1, undef) on the empty stack, :103
+    }
+    __device__ __forceinline__ bool finished() const { return leaf < 0 && top == 0; }
+    __device__ __forceinline__ bool wants_node() const { return leaf < 0 && top > 0; }
+    __device__ __forceinline__ bool wants_leaf() const { return leaf >= 0 || top < 0; }
+
+    // intersect_ray_box(min_max, ordered = false, ...), intersection.impala:194-208
+    __device__ __forceinline__ bool hit_box(float lx, float hx, float ly, float hy, float lz, float hz, float& tentry) const {
+        const float t0x = add(mul(ray.idx, lx), ray.iox), t1x = add(mul(ray.idx, hx), ray.iox);
+        const float t0y = add(mul(ray.idy, ly), ray.ioy), t1y = add(mul(ray.idy, hy), ray.ioy);
+        const float t0z = add(mul(ray.idz, lz), ray.ioz), t1z = add(mul(ray.idz, hz), ray.ioz);
+        const int zmin = max(min(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(ray.tmin));      // fminmaxf
+        const int zmax = min(max(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(tmax));          // fmaxminf
+        tentry = __int_as_float(__vimax3_s32(__float_as_int(fminf(t0x, t1x)), __float_as_int(fminf(t0y, t1y)), zmin));
+        const float texit = __int_as_float(__vimin3_s32(__float_as_int(fmaxf(t0x, t1x)), __float_as_int(fmaxf(t0y, t1y)), zmax));
+        return tentry <= texit;                                            // mapping_gpu.impala:114
+    }
+
+    // One iteration of the outer loop up to the leaf loop (:106-135).
+    __device__ __forceinline__ void node_step(const Node2* __restrict__ nodes) {
+        const float4* p = reinterpret_cast<const float4*>(nodes + (top - 1));
+        const float4 b0 = ldg4(p), b1 = ldg4(p + 1), b2 = ldg4(p + 2);
+        const int4 ch = ldg4(reinterpret_cast<const int4*>(p + 3));
+        float t0, t1;
+        const bool h0 = hit_box(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, t0);   // box 0: lo/hi x, y, z (:33-36)
+        const bool h1 = hit_box(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, t1);   // box 1 (:37-40)
+        if (h0 && h1) {
+            const bool first0 = t0 < t1;                                   // :127-131
+            top = first0 ? ch.x : ch.y;
+            st.store(++ptr, first0 ? ch.y : ch.x);
+        } else if (h0 || h1) {
+            top = h0 ? ch.x : ch.y;                                        // :133
+        } else {
+            pop();                                                         // :122-123
+        }
+    }
+
+    // One triangle of the leaf loop (:155-174).
+    __device__ __forceinline__ void leaf_step(const Tri1* __restrict__ tris) {
+        if (leaf < 0) { leaf = ~top; pop(); }
+        const float4* p = reinterpret_cast<const float4*>(tris + leaf);
+        const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);       // v0 | e1, geom | e2, prim
+        const int prim = __float_as_int(c.w);
+        const float nx = sub(mul(b.y, c.z), mul(b.z, c.y));                // cross(e1, e2), vector.impala:62-66
+        const float ny = sub(mul(b.z, c.x), mul(b.x, c.z));
+        const float nz = sub(mul(b.x, c.y), mul(b.y, c.x));
+        float t, u, v;
+        if (intersect_tri_lane(ray, tmax, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, nx, ny, nz, t, u, v)) {
+            hit.prim = prim & 0x7FFFFFFF; hit.geom = __float_as_int(b.w); hit.t = t; hit.u = u; hit.v = v;
+            tmax = t;
+            if (ANY) { top = 0; leaf = -1; return; }                       // early_exit, :168
+        }
+        leaf = prim < 0 ? -1 : leaf + 1;                                   // is_last, :62
+    }
+};
+
+// The scheduler of traverse_vote_scheduled (traverse_sched.cuh) for this walker.
+template <bool ANY, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
+__device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris, int* smem_column,
+                                                        int num_rays, int* __restrict__ work_counter, int refill_min, int node_streak_min,
+                                                        Fetch fetch, Sink sink) {
+    const unsigned lane = lane_id();
+    int overflow[kStackSize - SMEM_DEPTH];
+    Bvh2Walker<ANY, SMEM_DEPTH, BLOCK> w;
+    w.st.smem = smem_column;
+    w.st.overflow = overflow;
+    w.leaf = -1; w.top = 0;
+    int ray_idx = -1;
+    bool drained = false;
+    for (;;) {
+        if (ray_idx >= 0 && w.finished()) { sink(ray_idx, w.hit); ray_idx = -1; }
+        const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
+        if (!drained && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (ray_idx < 0) {
+                const int i = base + __popc(idle & lanemask_lt());
+                if (i < num_rays) {
+                    ray_idx = i;
+                    float4 r0, r1;
+                    fetch(i, r0, r1);
+                    w.begin(r0, r1);
+                }
+            }
+            if (base + __popc(idle) >= num_rays) drained = true;
+        }
+        const bool has = ray_idx >= 0;
+        const bool want_n = has && w.wants_node();
+        const bool want_l = has && w.wants_leaf();
+        const unsigned bn = __ballot_sync(0xffffffffu, want_n), bl = __ballot_sync(0xffffffffu, want_l);
+        if ((bn | bl) == 0) break;                  // a fresh ray always wants a node step: nothing left and nothing to fetch
+        if (__popc(bn) >= __popc(bl)) {
+            bool go = want_n;
+            do {
+                if (go) w.node_step(nodes);
+                go = has && w.wants_node();
+            } while (__popc(__ballot_sync(0xffffffffu, go)) >= node_streak_min);
+        } else {
+            bool go = want_l;
+            do {
+                if (go) w.leaf_step(tris);
+                go = has && w.wants_leaf();
+            } while (__popc(__ballot_sync(0xffffffffu, go)) >= node_streak_min);
+        }
+    }
+}
+
+}  // namespace rb200

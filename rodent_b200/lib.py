@@ -20,6 +20,8 @@ SIGNATURES = {
     "cuda_occluded_single_ray1_bvh8_tri4": (None, _TRAVERSE_DEV),
     "cuda_intersect_single_ray1_bvh8_tri4_async": (None, _TRAVERSE_DEV + [c_void_p, c_void_p]),
     "cuda_occluded_single_ray1_bvh8_tri4_async": (None, _TRAVERSE_DEV + [c_void_p, c_void_p]),
+    "cuda_intersect_single_ray1_bvh2_tri1": (None, _TRAVERSE_DEV),
+    "cuda_occluded_single_ray1_bvh2_tri1": (None, _TRAVERSE_DEV),
     "cuda_intersect_single_ray1_bvh4_tri4": (None, _TRAVERSE_DEV),
     "cuda_occluded_single_ray1_bvh4_tri4": (None, _TRAVERSE_DEV),
     "b200_intersect_single_ray1_bvh4_tri4": (None, _TRAVERSE_HOST),

@@ -54,6 +54,16 @@ def sponza_bvh4() -> Path:
     return out
 
 
+def sponza_bvh2() -> Path:
+    """The BVH2 / Tri1 block of the reference's testing/sponza.bvh (the layout of its GPU path)."""
+    out = DATA / "sponza_bvh2.bvh"
+    if not out.exists():
+        DATA.mkdir(exist_ok=True)
+        blob = lzma.decompress((GOLDEN / "sponza_bvh2.bvh.xz").read_bytes())
+        _atomic_write(out, lambda p: p.write_bytes(blob))
+    return out
+
+
 def rays(name: str) -> Path:
     out = DATA / f"sponza-{name}.rays"
     if not out.exists():

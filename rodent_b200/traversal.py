@@ -47,11 +47,13 @@ class DeviceArray:
 
 
 class Bvh8:
-    """BVH8/Tri4 -- or BVH4/Tri4 -- resident on one device (load_bvh<Node8,Tri4>, load_bvh.h:46-74)."""
+    """BVH8/Tri4 -- or BVH4/Tri4, or the reference GPU path's BVH2/Tri1 -- resident on one device
+    (load_bvh<Node, Tri>, load_bvh.h:46-74)."""
 
     def __init__(self, dev: int, nodes: np.ndarray, tris: np.ndarray):
-        assert nodes.dtype in (formats.NODE8, formats.NODE4) and tris.dtype == formats.TRI4
-        self.arity = 8 if nodes.dtype == formats.NODE8 else 4
+        assert (nodes.dtype in (formats.NODE8, formats.NODE4) and tris.dtype == formats.TRI4) or \
+               (nodes.dtype == formats.NODE2 and tris.dtype == formats.TRI1)
+        self.arity = {formats.NODE8: 8, formats.NODE4: 4, formats.NODE2: 2}[nodes.dtype]
         self.dev = dev
         self.nodes = DeviceArray.from_host(dev, nodes)
         self.tris = DeviceArray.from_host(dev, tris)
@@ -66,7 +68,7 @@ def intersect(bvh: Bvh8, rays: DeviceArray, hits: DeviceArray, any_hit: bool = F
     time in ms (bench_gpu, bench_traversal.cpp:124-135)."""
     L = lib.load()
     n = rays.count if count is None else count
-    fn = getattr(L, f"cuda_{'occluded' if any_hit else 'intersect'}_single_ray1_bvh{bvh.arity}_tri4")
+    fn = getattr(L, f"cuda_{'occluded' if any_hit else 'intersect'}_single_ray1_bvh{bvh.arity}_tri{1 if bvh.arity == 2 else 4}")
     fn(bvh.dev, bvh.nodes.ptr, bvh.tris.ptr, rays.ptr, hits.ptr, n)
     return L.rodent_b200_last_kernel_ms(bvh.dev)
 

@@ -6,7 +6,8 @@ the dev container where /root/reference exists):
 * sponza_bvh8.bvh.xz  -- the BVH8_TRI4 block of testing/sponza.bvh re-wrapped as a
                          single-block .bvh file and xz-compressed
 * sponza_bvh4.bvh.xz  -- the same for the BVH4_TRI4 block (the reference's default
-                         --bvh-width; the BVH2 block is not needed by the GPU path)
+                         --bvh-width)
+* sponza_bvh2.bvh.xz  -- the same for the BVH2_TRI1 block, the layout of the reference's own GPU path
 * ref-primary.png, ref-random.png, ref-cornell.png -- the reference's golden images
 * cornell_box.obj/.mtl -- the reference's Cornell scene (test input data)
 * sponza_hits_sample.npz -- oracle hit records for a fixed sample of rays, so the
@@ -43,6 +44,11 @@ def main():
             blob = struct.pack("<I", F.BVH_MAGIC) + payload
             (HERE / "sponza_bvh4.bvh.xz").write_bytes(lzma.compress(blob, preset=9 | lzma.PRESET_EXTREME))
             print("sponza_bvh4.bvh.xz", n_nodes, n_tris, len(blob))
+        if typ == F.BVH2_TRI1:
+            payload = data[off - 20: off + n_nodes * 64 + n_tris * 48]
+            blob = struct.pack("<I", F.BVH_MAGIC) + payload
+            (HERE / "sponza_bvh2.bvh.xz").write_bytes(lzma.compress(blob, preset=9 | lzma.PRESET_EXTREME))
+            print("sponza_bvh2.bvh.xz", n_nodes, n_tris, len(blob))
     for name in ("ref-primary.png", "ref-random.png", "ref-cornell.png", "cornell_box.obj", "cornell_box.mtl"):
         shutil.copyfile(REF / name, HERE / name)
 

@@ -1,0 +1,169 @@
+"""The reference's own GPU traversal (BVH2 / Tri1, gpu_traverse_single_helper): the oracle restatement pinned to the golden
+images on the reference's BVH2 block, and cuda_{intersect,occluded}_single_ray1_bvh2_tri1 bit for bit against it."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import oracle
+from rodent_b200 import formats, testdata
+
+GOLDEN = Path(__file__).parent / "golden"
+HIT_COUNTS = {"primary": 1_026_430, "random": 959_359}
+
+
+@pytest.fixture(scope="module")
+def sponza2():
+    return formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
+
+
+@pytest.fixture(scope="module")
+def oracle2_hits(sponza2, ray_sets):
+    nodes, tris = sponza2
+    return {name: oracle.traverse_bvh2(nodes, tris, rays) for name, rays in ray_sets.items()}
+
+
+def axis_parallel_rays(n=20000, seed=5):
+    """Rays with one or two exactly-zero direction components, origins inside and on the planes of Sponza's boxes: the
+    slab terms become inf - inf there, and the integer min/max orders the NaN by its (NVIDIA) bit pattern."""
+    rng = np.random.default_rng(seed)
+    org = rng.uniform([-1900, -100, -1100], [1800, 1400, 1100], (n, 3))
+    d = rng.normal(size=(n, 3))
+    d[np.arange(n), rng.integers(0, 3, n)] = 0.0
+    d[: n // 4, 1] = 0.0
+    d[n // 4: n // 2][np.abs(d[n // 4: n // 2]) < 0.3] = 1e-9            # below the safe_rcp threshold, not zero
+    d[(d == 0).all(axis=1), 0] = 1.0
+    org[::7] = np.round(org[::7])
+    od = np.concatenate([org, d], axis=1).astype(np.float32)
+    od[::11, 0] = 0.0                                                    # org * FLT_MAX = 0: inv_org stays finite
+    return formats.make_rays(od, 0.0, 1e30)
+
+
+# ---- the oracle ------------------------------------------------------------------------------------------------
+def test_block_layout(sponza2):
+    """Node2 / Tri1 as mapping_gpu.impala:3-16 reads them: children are 1-based node ids or ~first triangle; every leaf run
+    ends with a sign-bit prim_id; boxes are ordered lo <= hi."""
+    nodes, tris = sponza2
+    assert (len(nodes), len(tris)) == (165658, 329634)
+    child = nodes["child"]
+    inner = child[child > 0]
+    assert inner.max() <= len(nodes) and len(np.unique(inner)) == len(inner)
+    leaves = ~child[child < 0]
+    assert leaves.min() == 0 and leaves.max() < len(tris)
+    assert (tris["prim_id"][-1] < 0)
+    b = nodes["bounds"].reshape(-1, 2, 3, 2)
+    assert (b[..., 0] <= b[..., 1]).all()
+    assert ((tris["prim_id"] & 0x7FFFFFFF).max()) == 262266               # the scene's 262 267 triangles, some referenced twice (SBVH)
+
+
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_oracle_matches_golden_png(name, oracle2_hits, oracle_hits):
+    """testing/ref-*.png pin t (8 bit after fbuf2png -n); same tolerance as for the BVH8 oracle.  Hit / miss agrees with the
+    CPU path ray for ray, t to rounding (n is recomputed here, stored in a Tri4)."""
+    hits = oracle2_hits[name]
+    ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
+    differ = int((ref != formats.fbuf_to_gray(hits["t"]).reshape(1024, 1024)).sum())
+    assert differ <= 2, f"{differ} pixels differ from ref-{name}.png"
+    assert int((hits["tri_id"] >= 0).sum()) == HIT_COUNTS[name]
+    cpu = oracle_hits[name]
+    assert ((hits["tri_id"] >= 0) == (cpu["tri_id"] >= 0)).all()
+    hit = cpu["tri_id"] >= 0
+    assert np.allclose(hits["t"][hit], cpu["t"][hit], rtol=2e-5, atol=0)
+    assert (hits["t"][~hit] == cpu["t"][~hit]).all()                      # misses report tmax
+
+
+def test_oracle_any_hit_and_counters(sponza2, ray_sets, oracle2_hits):
+    nodes, tris = sponza2
+    for name in ("primary", "random"):
+        rays = ray_sets[name][::16]
+        occl = oracle.traverse_bvh2(nodes, tris, np.ascontiguousarray(rays), any_hit=True)
+        want = oracle2_hits[name][::16]
+        assert ((occl["tri_id"] >= 0) == (want["tri_id"] >= 0)).all()
+        # the GPU hit writer stores the whole record in both modes (make_gpu_hit1): an accepted triangle, not farther than tmax
+        h = occl["tri_id"] >= 0
+        # (the acceptance test runs on t * |det| against tmax * |det|, so the closest hit is minimal only up to an ulp)
+        assert (occl["t"][h] >= want["t"][h] * np.float32(1 - 3e-7)).all() and (occl["t"][h] <= rays["tmax"][h]).all()
+        assert (occl["t"][~h] == rays["tmax"][~h]).all()
+    _, (n_nodes, n_tris) = oracle.traverse_bvh2(nodes, tris, ray_sets["primary"], want_counters=True, threads=3)
+    assert (n_nodes, n_tris) == (54029986, 4985482)                       # independent of the thread count
+
+
+def test_oracle_thread_invariance_and_nan_canonicalisation(sponza2):
+    nodes, tris = sponza2
+    rays = axis_parallel_rays(4000)
+    a = oracle.traverse_bvh2(nodes, tris, rays, threads=1)
+    b = oracle.traverse_bvh2(nodes, tris, rays, threads=7)
+    assert a.tobytes() == b.tobytes()
+    # Most of these rays miss, as they do in the reference: with org inside a slab of a zero-direction axis one plane term
+    # is inf - inf, fminf / fmaxf drop the NaN and leave texit = -inf on x and y (the z axis goes through the integer
+    # forms, where the NVIDIA NaN 0x7FFFFFFF orders above everything and the slab survives).
+    assert 0.02 < (a["tri_id"] >= 0).mean() < 0.5
+
+
+# ---- CUDA ------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gpu2(sponza2):
+    from rodent_b200 import traversal
+    return traversal.Bvh8(0, *sponza2)
+
+
+def run_gpu(bvh, rays, any_hit=False):
+    from rodent_b200 import traversal
+    d_rays = traversal.DeviceArray.from_host(0, rays)
+    d_hits = traversal.DeviceArray.from_host(0, np.full(len(rays), -7, np.int32).repeat(4).view(formats.HIT1))
+    traversal.intersect(bvh, d_rays, d_hits, any_hit=any_hit)
+    return d_hits.to_host()
+
+
+def assert_equal(got, want):
+    if got.tobytes() != want.tobytes():
+        bad = np.nonzero((got["tri_id"] != want["tri_id"]) | (got["t"].view("i4") != want["t"].view("i4")) |
+                         (got["u"].view("i4") != want["u"].view("i4")) | (got["v"].view("i4") != want["v"].view("i4")))[0]
+        raise AssertionError(f"{len(bad)} of {len(got)} records differ, first: ray {bad[0]} got {got[bad[0]]} want {want[bad[0]]}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["primary", "random"])
+def test_cuda_bit_exact_on_full_sets(name, gpu2, ray_sets, oracle2_hits, sponza2):
+    assert_equal(run_gpu(gpu2, ray_sets[name]), oracle2_hits[name])
+    nodes, tris = sponza2
+    assert_equal(run_gpu(gpu2, ray_sets[name], any_hit=True), oracle.traverse_bvh2(nodes, tris, ray_sets[name], any_hit=True))
+
+
+@pytest.mark.gpu
+def test_cuda_golden_png(gpu2, ray_sets):
+    hits = run_gpu(gpu2, ray_sets["primary"])
+    ref = np.array(Image.open(GOLDEN / "ref-primary.png"))[..., 0]
+    assert int((ref != formats.fbuf_to_gray(hits["t"]).reshape(1024, 1024)).sum()) <= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 4097])
+def test_cuda_ragged_sizes(n, gpu2, ray_sets, oracle2_hits):
+    rays = np.ascontiguousarray(ray_sets["random"][1000:1000 + n])
+    got = run_gpu(gpu2, rays) if n else np.zeros(0, formats.HIT1)
+    assert_equal(got, oracle2_hits["random"][1000:1000 + n])
+
+
+@pytest.mark.gpu
+def test_cuda_axis_parallel_rays_take_nvidia_nans(gpu2, sponza2):
+    """The oracle emulates NVIDIA's canonical NaN; on the device it is simply what the instructions return."""
+    nodes, tris = sponza2
+    rays = axis_parallel_rays()
+    assert_equal(run_gpu(gpu2, rays), oracle.traverse_bvh2(nodes, tris, rays))
+    assert_equal(run_gpu(gpu2, rays, any_hit=True), oracle.traverse_bvh2(nodes, tris, rays, any_hit=True))
+
+
+@pytest.mark.gpu
+def test_cuda_tuning_does_not_change_results(gpu2, ray_sets, oracle2_hits):
+    from rodent_b200 import lib
+    rays = np.ascontiguousarray(ray_sets["random"][:200000])
+    try:
+        for refill, streak in ((1, 33), (32, 1), (8, 4)):
+            lib.tune("refill_min", refill)
+            lib.tune("node_streak_min", streak)
+            assert_equal(run_gpu(gpu2, rays), oracle2_hits["random"][:200000])
+    finally:
+        lib.tune("refill_min", 24)
+        lib.tune("node_streak_min", 8)
