@@ -379,6 +379,27 @@ def main():
     pool.shutdown()
     e2e_ok = all(int((pin_hits[n].array["tri_id"] >= 0).sum()) == hits_found[n] for n in names)
 
+    # ---- the other surfaces of the same tool, one launch at a time, outside the timed region ------------------
+    # `-any` and the reference GPU path's own BVH2 / Tri1 block through cuda_*_bvh2_tri1
+    def median_ms(b, n, any_hit):
+        scratch = traversal.DeviceArray(local, formats.HIT1, len(rays[n]))
+        ms = []
+        for _ in range(7):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms.append(traversal.intersect(b, d_rays[n], scratch, any_hit=any_hit))
+        scratch.free()
+        return float(np.median(ms[2:]))
+
+    variants = {"bvh8_tri4_any_hit": {n: round(len(rays[n]) / median_ms(bvh, n, True) / 1e3, 1) for n in names}}
+    from rodent_b200 import testdata
+    nodes2, tris1 = formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
+    bvh2 = traversal.Bvh8(local, nodes2, tris1)
+    variants["bvh2_tri1"] = {n: round(len(rays[n]) / median_ms(bvh2, n, False) / 1e3, 1) for n in names}
+    variants["bvh2_tri1_any_hit"] = {n: round(len(rays[n]) / median_ms(bvh2, n, True) / 1e3, 1) for n in names}
+    variants["note"] = ("Mrays/s per set; bvh2_tri1 = the block and traversal semantics of the reference's own GPU path "
+                        "(nvvm_*_single_ray1_bvh2_tri1), whose records differ from the CPU single-ray path's in ties and rounding")
+
     # ---- path tracing (configs[2..4]) ------------------------------------------------------------
     for pa in list(pin_rays.values()) + list(pin_hits.values()):
         pa.free()
@@ -428,6 +449,7 @@ def main():
                              "is L2-resident, so frac > 1 means served from L2, not faster than HBM"},
         "clocks": clocks.summary(),
     }
+    out["variants"] = variants
     if path_trace is not None:
         out["path_trace"] = path_trace
     if world == 1 and not args.no_cpu_baseline:
@@ -436,6 +458,13 @@ def main():
         out["cpu_baseline"] = {"value": round(cpu_value, 3), "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"{passes} full passes over both ray sets in {secs:.1f} s wall on {threads} threads",
                                "visits_per_ray": {n: [round(v, 4) for v in visits[n]] for n in names}}
+        # configs[0]: the reference's CPU-runnable case, `bench_traversal -s` on the primary set, one thread
+        from oracle import oracle
+        t0 = time.perf_counter()
+        oracle.traverse(nodes, tris, rays["primary"], threads=1)
+        dt1 = time.perf_counter() - t0
+        out["cpu_baseline"]["single_thread_primary"] = {"value": round(len(rays["primary"]) / dt1 / 1e6, 3), "unit": UNIT,
+                                                        "sample": f"one pass over sponza-primary.rays in {dt1:.2f} s on 1 thread (configs[0])"}
         if path_trace is not None:
             out["cpu_baseline"]["path_trace"] = cpu_path_trace_sample(threads)
         for n in names:   # the algorithmic bytes must come from the oracle's counters, not from a stale constant

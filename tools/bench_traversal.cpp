@@ -2,7 +2,8 @@
 // tools/bench_traversal/bench_traversal.cpp (options :25-42, report :381-391), with the
 // traversal running on a B200 through the C ABI of include/rodent_b200.h.
 //
-//   -gpu cuda [-dev k]   device-resident arrays, cuda_{intersect,occluded}_single_ray1_bvh8_tri4,
+//   -gpu cuda [-dev k]   device-resident arrays, cuda_{intersect,occluded}_single_ray1_bvh8_tri4 (--bvh-width 4: _bvh4_tri4,
+//                        --bvh-width 2: _bvh2_tri1, the block and semantics of the reference's `-gpu nvvm`),
 //                        timed with CUDA events (the role of `-gpu nvvm` + anydsl_get_kernel_time)
 //   -s [--bvh-width 4|8] the CPU single-ray call site (bench_cpu_single, :76-82 / :60-66) served by the
 //                        host-pointer drop-ins b200_{intersect,occluded}_single_ray1_bvh{4,8}_tri4,
@@ -45,7 +46,7 @@ void usage() {
                  "  -dev  k            CUDA device index\n"
                  "  -any               exit at the first intersection\n"
                  "  -s    --single     host-buffer single-ray entry point\n"
-                 "        --bvh-width  4 or 8 (default 4) ; --ray-width 4 or 8 (default 8)\n"
+                 "        --bvh-width  4 or 8 (default 4; 2 with -gpu: the reference GPU path's BVH2 block) ; --ray-width 4 or 8 (default 8)\n"
                  "  -o    --output     write hit distances as .fbuf\n";
 }
 
@@ -80,7 +81,7 @@ Options parse(int argc, char** argv) {
     if (o.ray_file.empty()) fail("No ray file specified");
     if (!o.gpu.empty() && o.single) fail("Options '--gpu' and '--single' are incompatible");
     if (o.single && o.packet) fail("Options '--packet' and '--single' are incompatible");
-    if (o.bvh_width != 4 && o.bvh_width != 8) fail("Invalid BVH width");
+    if (o.bvh_width != 4 && o.bvh_width != 8 && !(o.bvh_width == 2 && !o.gpu.empty())) fail("Invalid BVH width");
     if (o.ray_width != 4 && o.ray_width != 8) fail("Invalid ray width");
     return o;
 }
@@ -88,11 +89,11 @@ Options parse(int argc, char** argv) {
 template <typename F> struct FnArgs;
 template <typename R, typename... A> struct FnArgs<R (*)(A...)> { using type = std::tuple<A...>; };
 
-// The benchmark proper, for Node8 (BVH8) or Node4 (BVH4) input.
-template <typename NodeT, typename DevFn, typename HostFn>
+// The benchmark proper, for Node8 (BVH8), Node4 (BVH4) or -- the reference GPU path's own layout -- Node2 / Tri1 input.
+template <typename NodeT, typename TriT = Tri4, typename DevFn, typename HostFn>
 int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev_occluded, HostFn host_intersect, HostFn host_occluded) {
     const bool use_gpu = !o.gpu.empty();
-    std::vector<NodeT> nodes; std::vector<Tri4> tris; std::vector<Ray1> rays;
+    std::vector<NodeT> nodes; std::vector<TriT> tris; std::vector<Ray1> rays;
     if (!rb200::read_bvh(o.bvh_file, block, nodes, tris)) fail("Cannot load BVH file");
     if (!rb200::read_rays(o.ray_file, o.tmin, o.tmax, rays)) fail("Cannot load rays");
     const size_t ray_count = rays.size();
@@ -100,7 +101,7 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
     std::vector<Hit1> hits(ray_count, Hit1{-1, 0.0f, 0.0f, 0.0f});
 
     std::function<double()> bench;
-    NodeT* d_nodes = nullptr; Tri4* d_tris = nullptr; Ray1* d_rays = nullptr; Hit1* d_hits = nullptr;
+    NodeT* d_nodes = nullptr; TriT* d_tris = nullptr; Ray1* d_rays = nullptr; Hit1* d_hits = nullptr;
     if (use_gpu) {
         if (o.dev < 0 || o.dev >= rodent_b200_device_count()) fail("Invalid GPU device");
         auto upload = [&](const void* src, size_t bytes) {
@@ -109,7 +110,7 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
             return p;
         };
         d_nodes = static_cast<NodeT*>(upload(nodes.data(), nodes.size() * sizeof(NodeT)));
-        d_tris = static_cast<Tri4*>(upload(tris.data(), tris.size() * sizeof(Tri4)));
+        d_tris = static_cast<TriT*>(upload(tris.data(), tris.size() * sizeof(TriT)));
         d_rays = static_cast<Ray1*>(upload(rays.data(), rays.size() * sizeof(Ray1)));
         d_hits = static_cast<Hit1*>(upload(hits.data(), hits.size() * sizeof(Hit1)));
         bench = [&] {
@@ -214,6 +215,11 @@ int main(int argc, char** argv) {
     }
     // -gpu cuda traces the BVH8 block unless --bvh-width 4 is asked for; -s follows --bvh-width (default 4) as the reference does
     const int width = use_gpu && !o.bvh_width_given ? 8 : o.bvh_width;
+    if (width == 2) {       // what `-gpu nvvm` traces in the reference: the BVH2 / Tri1 block (bench_traversal.cpp:250-262)
+        using HostFn = void (*)(const Node2*, const Tri1*, const Ray1*, Hit1*, int32_t);
+        return run<Node2, Tri1>(o, rb200::kBvh2Tri1, cuda_intersect_single_ray1_bvh2_tri1, cuda_occluded_single_ray1_bvh2_tri1,
+                                HostFn(nullptr), HostFn(nullptr));
+    }
     if (width == 8)
         return run<Node8>(o, rb200::kBvh8Tri4, cuda_intersect_single_ray1_bvh8_tri4, cuda_occluded_single_ray1_bvh8_tri4,
                           b200_intersect_single_ray1_bvh8_tri4, b200_occluded_single_ray1_bvh8_tri4);
