@@ -35,6 +35,8 @@ struct Tuning {
                              // 4 = four lanes per ray (traverse_quad.cuh)
     int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
     int node_streak_min = 8;  // (mapping 2) consecutive node steps without re-voting while this many lanes want one (33: off)
+    int bvh2_streak_min = 4; // BVH2 / Tri1 kernel: consecutive steps of one kind while this many lanes want one (measured 4 > 8 > 16)
+    int bvh2_min_blocks = 8; // BVH2 / Tri1 kernel: __launch_bounds__ min blocks per SM of the variant launched: 8, 10 or 12
     int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
     int persistent = 1;      // (mapping 1) 0: one thread per ray, plain grid
     int quad_refill_below = 6;   // (mapping 4) refill a warp when fewer than this many quads are busy
@@ -158,14 +160,15 @@ traverse_bvh4_vote(const Node4* __restrict__ nodes, const Tri4* __restrict__ tri
 // The reference's GPU path on its own layout (nvvm_{intersect,occluded}_single_ray1_bvh2_tri1,
 // tools/bench_traversal/bench_traversal.impala:459-493): Node2 / Tri1 in, all four hit fields out in both modes
 // (make_gpu_hit1, :78-83).
-constexpr int kBvh2SmemDepth = 32;
-template <bool ANY>
-__global__ void __launch_bounds__(kBlock, 8)
+// MIN_BLOCKS: resident CTAs per SM asked of ptxas (8: 53 registers, 10: 48, 12: 40 with 24..36 bytes of spills); the
+// incoherent set is bound by L2 latency and wants warps, the coherent one by issue slots (profiles/r01_traverse_bvh2_ncu.txt).
+template <bool ANY, int MIN_BLOCKS, int SMEM_DEPTH>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 traverse_bvh2_vote(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
                    const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
                    int* __restrict__ work_counter, int refill_min, int node_streak_min) {
-    __shared__ int smem_stack[kBvh2SmemDepth][kBlock];
-    traverse_bvh2_scheduled<ANY, kBvh2SmemDepth, kBlock>(
+    __shared__ int smem_stack[SMEM_DEPTH][kBlock];
+    traverse_bvh2_scheduled<ANY, SMEM_DEPTH, kBlock>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, node_streak_min,
         [rays](int i, float4& r0, float4& r1) {
             const float4* rp = reinterpret_cast<const float4*>(rays + i);
@@ -286,7 +289,7 @@ struct DeviceState {
     int occ_quad[2] = {0, 0};
     int occ_pool[2] = {0, 0};
     int occ_bvh4[2] = {0, 0};
-    int occ_bvh2[2] = {0, 0};
+    int occ_bvh2[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 8, 10, 12][closest, any]
     StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
     int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path: staging contexts (one per call in flight, reused) and the uploaded BVHs
@@ -334,8 +337,12 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[0], traverse_bvh4_vote<false>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[1], traverse_bvh4_vote<true>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[0], traverse_bvh2_vote<false>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[1], traverse_bvh2_vote<true>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[0][0], traverse_bvh2_vote<false, 8, 32>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[0][1], traverse_bvh2_vote<true, 8, 32>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[1][0], traverse_bvh2_vote<false, 10, 24>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[1][1], traverse_bvh2_vote<true, 10, 24>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[2][0], traverse_bvh2_vote<false, 12, 24>, kBlock, 0));
+            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[2][1], traverse_bvh2_vote<true, 12, 24>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[0], traverse_bvh8_pool<false>, kPoolBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_pool[1], traverse_bvh8_pool<true>, kPoolBlock, 0));
             s.init.store(true, std::memory_order_release);
@@ -418,9 +425,12 @@ static void launch(DeviceState& s, const Node2* nodes, const Tri1* tris, const R
     if (num_rays <= 0) return;
     if (!counter) counter = s.counter;
     RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_bvh2[ANY ? 1 : 0];
+    const int v = g_tuning.bvh2_min_blocks >= 12 ? 2 : g_tuning.bvh2_min_blocks >= 10 ? 1 : 0;
+    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_bvh2[v][ANY ? 1 : 0];
     const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
-    traverse_bvh2_vote<ANY><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+    if (v == 0) traverse_bvh2_vote<ANY, 8, 32><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.bvh2_streak_min);
+    if (v == 1) traverse_bvh2_vote<ANY, 10, 24><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.bvh2_streak_min);
+    if (v == 2) traverse_bvh2_vote<ANY, 12, 24><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.bvh2_streak_min);
     RB_CUDA_CHECK(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
@@ -678,6 +688,8 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = value;
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
+    else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = value;
+    else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = value;
     else if (!std::strcmp(key, "render_lanes")) rodent_b200_render_tune(key, value);
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }

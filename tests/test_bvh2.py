@@ -160,10 +160,12 @@ def test_cuda_tuning_does_not_change_results(gpu2, ray_sets, oracle2_hits):
     from rodent_b200 import lib
     rays = np.ascontiguousarray(ray_sets["random"][:200000])
     try:
-        for refill, streak in ((1, 33), (32, 1), (8, 4)):
+        for refill, streak, blocks in ((1, 33, 8), (32, 1, 10), (8, 8, 12)):
             lib.tune("refill_min", refill)
-            lib.tune("node_streak_min", streak)
+            lib.tune("bvh2_streak_min", streak)
+            lib.tune("bvh2_min_blocks", blocks)
             assert_equal(run_gpu(gpu2, rays), oracle2_hits["random"][:200000])
     finally:
         lib.tune("refill_min", 24)
-        lib.tune("node_streak_min", 8)
+        lib.tune("bvh2_streak_min", 4)
+        lib.tune("bvh2_min_blocks", 8)
