@@ -285,6 +285,9 @@ typedef struct RodentSceneView {
     const uint32_t*       texture_pixels; /* num_texture_pixels, all images back to back */
     int64_t               num_texture_pixels;
     int32_t               num_textures, pad;
+    const Node2*          nodes2;         /* the same triangles under a BVH2 / Tri1 (NULL until built or set), */
+    const Tri1*           tris1;          /* the layout of the reference's GPU renderer (mapping_gpu.impala:19-69) */
+    int32_t               num_nodes2, num_tri1;
 } RodentSceneView;
 
 typedef struct RodentScene RodentScene;
@@ -313,6 +316,13 @@ void rodent_b200_scene_free(RodentScene* scene);
 /* The scene's triangles under a BVH4 as well (built on first use, owned by the scene), for writing .bvh files with both
  * blocks as tools/bvh_extractor/extract_bvh4_8.cpp:9-42 does. */
 void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* num_nodes, const Tri4** tris, int32_t* num_tri4);
+/* BVH2 / Tri1 over the scene's triangles -- what the reference's GPU device renders from (device.load_bvh2_tri1,
+ * src/render/mapping_gpu.impala:505-509).  `build` makes one from the scene's own builder; `set` adopts a caller's arrays
+ * (e.g. the BVH2 block of a .bvh file over the same triangles; copied, Tri1::geom_id rewritten to the scene's material
+ * ids; returns 0 if a prim_id is out of range).  Renderers created afterwards trace their closest-hit rays through it with
+ * the reference GPU path's traversal and keep the BVH8 for shadow rays (any hit is faster there: DESIGN.md 4.2). */
+void    rodent_b200_scene_build_bvh2(RodentScene* scene);
+int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1);
 
 typedef struct RodentRenderer RodentRenderer;
 

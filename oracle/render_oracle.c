@@ -21,6 +21,9 @@
  * (tests/test_render_oracle.py).  Bit parity with the reference is not defined for this
  * path: it calls libm sinf/cosf/sqrtf and is compiled -ffast-math.
  */
+#ifdef ORACLE_DEBUG_PIXEL   /* developer aid: -DORACLE_DEBUG_PIXEL, then ORACLE_DEBUG_X / _Y print that pixel's closest-hit rays */
+#include <stdio.h>
+#endif
 #include <math.h>
 
 #include "traversal_oracle.c"
@@ -255,8 +258,14 @@ typedef struct {
     OracleRenderStats stats;
 } RenderJob;
 
+void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom);   /* traversal_bvh2_oracle.c */
+
+/* Closest hit through the scene's BVH2 / Tri1 when it carries one -- the reference GPU device's layout and traversal
+ * (gpu_traverse_primary, mapping_gpu.impala:18-30) -- otherwise, and for shadow rays always, the BVH8 single-ray kernel:
+ * the same split as the CUDA render loop (rodent_b200/csrc/render.cu). */
 static inline void trace(const RodentSceneView* sc, int any, V3 org, V3 dir, float tmin, float tmax, Hit1* hit, int32_t* geom, OracleStats* st) {
     Ray1 r = {{org.x, org.y, org.z}, tmin, {dir.x, dir.y, dir.z}, tmax};
+    if (!any && sc->nodes2) { oracle_bvh2_trace_one(0, sc->nodes2, sc->tris1, &r, hit, geom); return; }
     if (any) traverse_single(8, 1, sc->nodes, sc->tris, &r, hit, st, geom);
     else     traverse_single(8, 0, sc->nodes, sc->tris, &r, hit, st, geom);
 }
@@ -330,6 +339,11 @@ static void render_rows(RenderJob* job) {
                     Hit1 hit; int32_t geom;
                     trace(sc, 0, org, dir, tmin, FLT_MAX_, &hit, &geom, &job->stats.trav);
                     job->stats.primary_rays++;
+#ifdef ORACLE_DEBUG_PIXEL
+                    if (getenv("ORACLE_DEBUG_X") && x == atoi(getenv("ORACLE_DEBUG_X")) && y == atoi(getenv("ORACLE_DEBUG_Y")))
+                        fprintf(stderr, "RAY %d %d %d %08x %08x %08x %08x %08x %08x %08x -> %d %g geom %d\n", sample, depth,
+                                0, f2i(org.x), f2i(org.y), f2i(org.z), f2i(tmin), f2i(dir.x), f2i(dir.y), f2i(dir.z), hit.tri_id, hit.t, geom);
+#endif
                     if (hit.tri_id < 0) break;                                       /* misses leave the stream, mapping_gpu.impala:357 */
                     const RodentMaterial textured = textured_material(sc, geom, hit.tri_id, hit.u, hit.v);
                     const RodentMaterial* mat = &textured;

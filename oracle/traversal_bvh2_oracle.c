@@ -80,7 +80,7 @@ static inline int hit_tri(const Ray* r, const Tri1* tp, float* out_t, float* out
 
 /* gpu_traverse_single_helper, mapping_gpu.impala:94-178, arity 2.  The stack keeps its top in a register and never
  * looks at the entry distances on this path (stack.impala:52-123 with undef keys). */
-static void traverse_bvh2(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* rp, Hit1* hp, uint64_t* counters) {
+static void traverse_bvh2(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* rp, Hit1* hp, uint64_t* counters, int32_t* geom_out) {
     Ray ray;
     for (int a = 0; a < 3; a++) {                                        /* make_gpu_ray1 + make_ray, intersection.impala:88-99 */
         ray.org[a] = rp->org[a]; ray.dir[a] = rp->dir[a];
@@ -89,6 +89,7 @@ static void traverse_bvh2(int any_hit, const Node2* nodes, const Tri1* tris, con
     }
     ray.tmin = rp->tmin; ray.tmax = rp->tmax;
     Hit1 hit = { -1, ray.tmax, 0.0f, 0.0f };                             /* empty_hit, :134-136 (u, v undefined there) */
+    int32_t geom = -1;
 
     int32_t mem[STACK_SIZE + 8];
     int ptr = 0; int32_t top = 1; mem[0] = 0;                            /* push(root) onto the empty stack, :103 */
@@ -112,21 +113,27 @@ static void traverse_bvh2(int any_hit, const Node2* nodes, const Tri1* tris, con
                 if (counters) counters[1]++;
                 float t, u, v;
                 if (hit_tri(&ray, tp, &t, &u, &v)) {
-                    hit.tri_id = tp->prim_id & 0x7FFFFFFF; hit.t = t; hit.u = u; hit.v = v;
+                    hit.tri_id = tp->prim_id & 0x7FFFFFFF; hit.t = t; hit.u = u; hit.v = v; geom = tp->geom_id;
                     ray.tmax = t;
-                    if (any_hit) { *hp = hit; return; }                  /* :168 */
+                    if (any_hit) { *hp = hit; if (geom_out) *geom_out = geom; return; }   /* :168 */
                 }
                 if (tp->prim_id < 0) break;                              /* is_last, :62 */
             }
         }
     }
     *hp = hit;                                                           /* make_gpu_hit1, bench_traversal.impala:78-83 */
+    if (geom_out) *geom_out = geom;
+}
+
+/* One ray, with the geometry id of the hit (make_hit(geom_id, ...), mapping_gpu.impala:60): for the path-tracing oracle. */
+void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom) {
+    traverse_bvh2(any_hit, nodes, tris, ray, hit, NULL, geom);
 }
 
 typedef struct { int any_hit; const Node2* nodes; const Tri1* tris; const Ray1* rays; Hit1* hits; int32_t begin, end; uint64_t counters[2]; } Job;
 static void* run_range(void* p) {
     Job* j = (Job*)p;
-    for (int32_t i = j->begin; i < j->end; i++) traverse_bvh2(j->any_hit, j->nodes, j->tris, &j->rays[i], &j->hits[i], j->counters);
+    for (int32_t i = j->begin; i < j->end; i++) traverse_bvh2(j->any_hit, j->nodes, j->tris, &j->rays[i], &j->hits[i], j->counters, NULL);
     return NULL;
 }
 

@@ -27,6 +27,7 @@
 #include "scene.h"
 #include "shading.cuh"
 #include "traverse_sched.cuh"
+#include "traverse_bvh2.cuh"
 
 extern "C" void rodent_b200_count_launches(int64_t n);   // traverse.cu: the library-wide launch counter
 
@@ -57,6 +58,7 @@ enum Counter { kWorkPrimary = 0, kWorkShadow, kHitCount, kSurvivors, kShadows, k
 
 struct SceneDev {
     const Node8* nodes; const Tri4* tris;
+    const Node2* nodes2; const Tri1* tris1;          // null unless the scene carries a BVH2 (closest-hit rays then use it)
     const float4* normals; const float4* face_normals; const int4* indices; const int* light_ids;
     const RodentMaterial* materials; const RodentLight* lights;
     const float4* texcoords; const RodentTexture* textures; const unsigned* texture_pixels;   // null without textured materials
@@ -131,6 +133,33 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
             if (hist[b]) atomicAdd(histogram + b, hist[b]);
     }
+}
+
+// Closest hit through the scene's BVH2 / Tri1 -- the layout and traversal of the reference's GPU renderer
+// (gpu_traverse_primary over make_gpu_bvh2_tri1, mapping_gpu.impala:18-30,505-509) -- same stream contract as above.
+constexpr int kRBvh2Stack = 32;
+__global__ void __launch_bounds__(kRBlock, 8)
+traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
+                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int num_rays,
+                     float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
+                     int* __restrict__ work_counter, int refill_min, int streak_min) {
+    __shared__ int smem_stack[kRBvh2Stack][kRBlock];
+    __shared__ int hist[kMaxBins];
+    for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
+    __syncthreads();
+    int* const hist_bins = hist;
+    traverse_bvh2_scheduled<false, kRBvh2Stack, kRBlock>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, streak_min,
+        [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
+        [=](int i, const HitRecord& h) {
+            const int g = h.prim < 0 ? num_geoms : h.geom;
+            hit_out[i] = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
+            geom_out[i] = g;
+            atomicAdd(hist_bins + g, 1);
+        });
+    __syncthreads();
+    for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
+        if (hist[b]) atomicAdd(histogram + b, hist[b]);
 }
 
 // ---- scan: per-material begins, number of hit rays (the host scan of mapping_gpu.impala:201-208) ----
@@ -285,7 +314,7 @@ struct Renderer {
     int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr; int* order = nullptr;
     int* h_counters = nullptr;                  // pinned
     float* film = nullptr; float* own_film = nullptr; float* h_film = nullptr;
-    int sm_count = 0, occ_primary = 0, occ_shadow = 0;
+    int sm_count = 0, occ_primary = 0, occ_shadow = 0, occ_primary2 = 0;
     int64_t stats[5] = {0, 0, 0, 0, 0};
     double last_ms = 0.0;
     // A renderer with several LANES drives that many independent wavefront pipelines (own streams, ray streams and
@@ -314,6 +343,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
+static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
 
 // Streams, events, ray streams and counters of one wavefront pipeline; `r->rows` must be set.
@@ -373,6 +403,11 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         d.texture_pixels = r->upload(sc.texture_pixels.data(), sc.texture_pixels.size());
     }
     d.num_materials = int(sc.materials.size()); d.num_lights = int(sc.lights.size());
+    if (!sc.nodes2.empty() && g_render_bvh2) {
+        d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
+        d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
+    }
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
     // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
@@ -388,7 +423,7 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
             auto lane = new Renderer();
             lane->parent = r;
             lane->dev = dev; lane->width = width; lane->height = height; lane->spp = spp; lane->max_path_len = max_path_len;
-            lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_shadow = r->occ_shadow;
+            lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_primary2 = r->occ_primary2; lane->occ_shadow = r->occ_shadow;
             lane->scene = r->scene;
             for (size_t k = 0; k < r->rows.size(); k++)
                 if (int(k / 8) % num_lanes == j) lane->rows.push_back(r->rows[k]);
@@ -473,9 +508,15 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
             id += n; size += n; n_kernels++;
         }
         RB_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * sizeof(int), s));
-        const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
-        traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
+        if (r.scene.nodes2) {
+            const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
+            traverse_stream_bvh2<<<grid_p, kRBlock, 0, s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, size, P.hit, P.geom, num_geoms,
+                                                            r.histogram, counters + kWorkPrimary, kRefillMin, 4);
+        } else {
+            const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
+            traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
+                                                              r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
+        }
         scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
         scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
         RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
@@ -552,6 +593,7 @@ double rodent_b200_render_last_ms(const RodentRenderer* r) { return reinterpret_
 
 void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_lanes")) g_render_lanes = std::max(1, int(value));
+    if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;

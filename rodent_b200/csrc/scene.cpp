@@ -369,6 +369,63 @@ struct Builder {
         return id;
     }
 
+    // The binary tree itself as Node2 / Tri1 (src/traversal/mapping_gpu.impala:3-16): one Tri1 per triangle, the last of
+    // a leaf flagged in prim_id's sign bit; node ids are 1-based, the root is node 1 and always an inner node.
+    int emit2_leaf(const Bvh2Node& leaf, std::vector<Tri1>& out) const {
+        const int first = int(out.size());
+        for (int i = 0; i < leaf.count; i++) {
+            const int id = order[leaf.first + i];
+            const F3 e1 = v0[id] - v1[id], e2 = v2[id] - v0[id];
+            Tri1 t{};
+            t.v0[0] = v0[id].x; t.v0[1] = v0[id].y; t.v0[2] = v0[id].z;
+            t.e1[0] = e1.x; t.e1[1] = e1.y; t.e1[2] = e1.z; t.e2[0] = e2.x; t.e2[1] = e2.y; t.e2[2] = e2.z;
+            t.geom_id = geom[id]; t.prim_id = id;
+            out.push_back(t);
+        }
+        out.back().prim_id |= int32_t(0x80000000u);
+        return ~first;
+    }
+    int emit2_node(int k, std::vector<Node2>& out_nodes, std::vector<Tri1>& out_tris) const {
+        const int id = int(out_nodes.size());
+        out_nodes.emplace_back();
+        const int kids[2] = {n2[k].left, n2[k].right};
+        for (int j = 0; j < 2; j++) {
+            const Box& b = n2[kids[j]].box;
+            float* dst = out_nodes[id].bounds + 6 * j;
+            dst[0] = b.lo.x; dst[1] = b.hi.x; dst[2] = b.lo.y; dst[3] = b.hi.y; dst[4] = b.lo.z; dst[5] = b.hi.z;
+        }
+        for (int j = 0; j < 2; j++) {
+            const int c = n2[kids[j]].left >= 0 ? emit2_node(kids[j], out_nodes, out_tris) + 1 : emit2_leaf(n2[kids[j]], out_tris);
+            out_nodes[id].child[j] = c;
+            out_nodes[id].pad[j] = 0;
+        }
+        return id;
+    }
+    void run2(std::vector<Node2>& out_nodes, std::vector<Tri1>& out_tris) {
+        const int n = int(v0.size());
+        boxes.resize(n); centers.resize(n); order.resize(n);
+        std::iota(order.begin(), order.end(), 0);
+        for (int i = 0; i < n; i++) {
+            boxes[i].grow(v0[i]); boxes[i].grow(v1[i]); boxes[i].grow(v2[i]);
+            centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
+        }
+        const int root = build2(0, n);
+        if (n2[root].left < 0) {
+            // a scene of one leaf: the root points at it twice (a triangle found twice is found at the same t)
+            Node2 node{};
+            for (int j = 0; j < 2; j++) {
+                const Box& b = n2[root].box;
+                float* dst = node.bounds + 6 * j;
+                dst[0] = b.lo.x; dst[1] = b.hi.x; dst[2] = b.lo.y; dst[3] = b.hi.y; dst[4] = b.lo.z; dst[5] = b.hi.z;
+            }
+            out_nodes.push_back(node);
+            const int leaf = emit2_leaf(n2[root], out_tris);
+            out_nodes[0].child[0] = out_nodes[0].child[1] = leaf;
+        } else {
+            emit2_node(root, out_nodes, out_tris);
+        }
+    }
+
     void run() {
         const int n = int(v0.size());
         boxes.resize(n); centers.resize(n); order.resize(n);
@@ -545,6 +602,34 @@ void build_bvh4(Scene& scene) {
     builder.run();
 }
 
+void build_bvh2(Scene& scene) {
+    if (!scene.nodes2.empty()) return;
+    const int num_tris = int(scene.indices.size() / 4);
+    std::vector<F3> a(num_tris), b(num_tris), c(num_tris); std::vector<int> geom(num_tris);
+    for (int i = 0; i < num_tris; i++) {
+        const int* idx = &scene.indices[4 * i];
+        auto vert = [&](int k) { return F3{scene.vertices[4 * k], scene.vertices[4 * k + 1], scene.vertices[4 * k + 2]}; };
+        a[i] = vert(idx[0]); b[i] = vert(idx[1]); c[i] = vert(idx[2]); geom[i] = idx[3];
+    }
+    std::vector<Node8> unused_nodes; std::vector<Tri4> unused_tris;
+    Builder<Node8> builder{a, b, c, geom, {}, {}, {}, {}, unused_nodes, unused_tris};
+    builder.run2(scene.nodes2, scene.tris1);
+}
+
+bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris, int num_tri1) {
+    const int num_prims = int(scene.indices.size() / 4);
+    if (num_nodes <= 0 || num_tri1 <= 0) return fail("empty BVH2");
+    std::vector<Tri1> t(tris, tris + num_tri1);
+    for (auto& tri : t) {
+        const int p = tri.prim_id & 0x7FFFFFFF;
+        if (p >= num_prims) return fail("prim_id out of range in BVH2");
+        tri.geom_id = scene.indices[4 * p + 3];
+    }
+    scene.nodes2.assign(nodes, nodes + num_nodes);
+    scene.tris1 = std::move(t);
+    return true;
+}
+
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
                        const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims) {
     auto scene = new Scene();
@@ -613,6 +698,12 @@ void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out) {
     out->materials = s.materials.data(); out->lights = s.lights.data(); out->nodes = s.nodes.data(); out->tris = s.tris.data();
     out->textures = s.textures.data(); out->texture_pixels = s.texture_pixels.data();
     out->num_texture_pixels = int64_t(s.texture_pixels.size()); out->num_textures = int32_t(s.textures.size()); out->pad = 0;
+    out->nodes2 = s.nodes2.empty() ? nullptr : s.nodes2.data(); out->tris1 = s.tris1.empty() ? nullptr : s.tris1.data();
+    out->num_nodes2 = int32_t(s.nodes2.size()); out->num_tri1 = int32_t(s.tris1.size());
+}
+void rodent_b200_scene_build_bvh2(RodentScene* scene) { rb200::build_bvh2(*reinterpret_cast<Scene*>(scene)); }
+int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1) {
+    return rb200::set_bvh2(*reinterpret_cast<Scene*>(scene), nodes, num_nodes, tris, num_tri1) ? 1 : 0;
 }
 int32_t rodent_b200_scene_add_texture(RodentScene* scene, const uint32_t* rgba, int32_t width, int32_t height) {
     if (!scene || !rgba || width <= 0 || height <= 0) return 0;

@@ -20,6 +20,8 @@ struct Scene {
     std::vector<Tri4> tris;
     std::vector<Node4> nodes4;            // built on demand (rodent_b200_scene_bvh4)
     std::vector<Tri4> tris4;
+    std::vector<Node2> nodes2;            // built or set on demand (rodent_b200_scene_{build,set}_bvh2)
+    std::vector<Tri1> tris1;
     std::vector<RodentTexture> textures;  // images of map_Kd / map_Ks, pixels back to back
     std::vector<uint32_t> texture_pixels;
 
@@ -31,6 +33,8 @@ bool load_png(const std::string& path, int& width, int& height, std::vector<uint
 
 Scene* load_obj_scene(const std::string& path);
 void build_bvh4(Scene& scene);
+void build_bvh2(Scene& scene);
+bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris, int num_tri1);
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
                        const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims);
 

@@ -33,7 +33,8 @@ class SceneView(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("num_tris", "num_vertices", "num_materials", "num_lights", "num_nodes", "num_tri4")] + \
                [(n, c_void_p) for n in ("vertices", "normals", "face_normals", "texcoords", "indices", "light_ids",
                                         "materials", "lights", "nodes", "tris", "textures", "texture_pixels")] + \
-               [("num_texture_pixels", c_int64), ("num_textures", c_int32), ("pad", c_int32)]
+               [("num_texture_pixels", c_int64), ("num_textures", c_int32), ("pad", c_int32)] + \
+               [("nodes2", c_void_p), ("tris1", c_void_p), ("num_nodes2", c_int32), ("num_tri1", c_int32)]
 
 
 # symbol -> (restype, argtypes) of the scene / renderer part of include/rodent_b200.h
@@ -44,6 +45,8 @@ SIGNATURES = {
     "rodent_b200_scene_free": (None, [c_void_p]),
     "rodent_b200_scene_add_texture": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "rodent_b200_scene_add_png": (c_int32, [c_void_p, ctypes.c_char_p]),
+    "rodent_b200_scene_build_bvh2": (None, [c_void_p]),
+    "rodent_b200_scene_set_bvh2": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
     "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
     "rodent_b200_renderer_free": (None, [c_void_p]),
@@ -111,6 +114,22 @@ class Scene:
         return cls(_bind(lib.load()).rodent_b200_scene_from_bvh8(nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris),
                                                                   materials.ctypes.data, len(materials), mop.ctypes.data, len(mop)))
 
+    def build_bvh2(self) -> None:
+        """A BVH2 / Tri1 over the scene's triangles from the scene's own builder; renderers created afterwards trace their
+        closest-hit rays through it (rodent_b200_scene_build_bvh2)."""
+        L = _bind(lib.load())
+        L.rodent_b200_scene_build_bvh2(self.handle)
+        L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+
+    def set_bvh2(self, nodes: np.ndarray, tris: np.ndarray) -> None:
+        """Adopts a BVH2 / Tri1 over the same triangles, e.g. the BVH2 block of the .bvh file the scene came from."""
+        from . import formats
+        nodes, tris = np.ascontiguousarray(nodes, formats.NODE2), np.ascontiguousarray(tris, formats.TRI1)
+        L = _bind(lib.load())
+        if not L.rodent_b200_scene_set_bvh2(self.handle, nodes.ctypes.data, len(nodes), tris.ctypes.data, len(tris)):
+            raise RuntimeError("BVH2 rejected (see stderr)")
+        L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+
     def add_texture(self, rgba: np.ndarray) -> int:
         """Appends an (height, width) uint32 image (RodentTexture layout: gamma-corrected, bottom row first); returns the
         value for a material's map_kd / map_ks."""
@@ -140,7 +159,8 @@ class Scene:
                  "indices": ((v.num_tris, 4), np.int32), "light_ids": ((v.num_tris,), np.int32),
                  "materials": ((v.num_materials,), MATERIAL), "lights": ((v.num_lights,), LIGHT),
                  "nodes": ((v.num_nodes,), formats.NODE8), "tris": ((v.num_tri4,), formats.TRI4),
-                 "textures": ((v.num_textures,), TEXTURE), "texture_pixels": ((v.num_texture_pixels,), np.uint32)}
+                 "textures": ((v.num_textures,), TEXTURE), "texture_pixels": ((v.num_texture_pixels,), np.uint32),
+                 "nodes2": ((v.num_nodes2,), formats.NODE2), "tris1": ((v.num_tri1,), formats.TRI1)}
         shape, dt = table[name]
         n = int(np.prod(shape)) * np.dtype(dt).itemsize
         if n == 0:

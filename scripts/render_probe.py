@@ -1,5 +1,5 @@
 """Developer helper: times the wavefront path tracer on the BASELINE.json render configs.
-usage: render_probe.py [cornell|sponza] [width height spp depth iters] [lanes]"""
+usage: render_probe.py [cornell|sponza] [width height spp depth iters] [lanes] [render_bvh2]"""
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -12,6 +12,8 @@ W, H, spp, depth = (int(x) for x in sys.argv[2:6]) if len(sys.argv) >= 6 else (c
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 3
 if len(sys.argv) > 7:
     lib.tune("render_lanes", int(sys.argv[7]))
+if len(sys.argv) > 8:
+    lib.tune("render_bvh2", int(sys.argv[8]))
 scene = workloads.load_scene(name)
 cam = workloads.camera(name, W, H)
 r = R.Renderer(scene, 0, W, H, spp, depth)

@@ -98,3 +98,35 @@ def test_oracle_render_is_schedule_independent(cornell):
     assert a.tobytes() == b.tobytes()
     c, _ = oracle.render(cornell.view, cam, W, H, 3, 8, 6, threads=7)
     assert a.tobytes() != c.tobytes()                                       # iter feeds the RNG seed
+
+
+def test_scene_bvh2_built_and_adopted():
+    """rodent_b200_scene_build_bvh2: the scene's own binary tree as Node2 / Tri1 finds what the BVH8 finds (Cornell: no ties,
+    so even the records agree except for the recomputed normal's rounding); the oracle's film through it is the BVH8 film.
+    rodent_b200_scene_set_bvh2: the reference's BVH2 block over Sponza, geometry ids rewritten to the scene's materials."""
+    from rodent_b200 import testdata, workloads
+    scene = R.Scene.load_obj(GOLDEN / "cornell_box.obj")
+    assert scene.view.num_nodes2 == 0 and not scene.view.nodes2
+    W, H = 96, 72
+    cam = R.camera((0, 1, 2.7), (0, 0, -1), (0, 1, 0), 60.0, W, H)
+    before, _ = oracle.render(scene.view, cam, W, H, 4, 8, 0)
+    scene.build_bvh2()
+    n2, t1 = scene.array("nodes2").copy(), scene.array("tris1").copy()
+    assert len(t1) == 36 and sorted((t1["prim_id"] & 0x7FFFFFFF).tolist()) == list(range(36))
+    assert (t1["geom_id"] == scene.array("indices")[t1["prim_id"] & 0x7FFFFFFF, 3]).all()
+    rng = np.random.default_rng(2)
+    od = np.concatenate([rng.uniform(-1, 2, (20000, 3)), rng.normal(size=(20000, 3))], axis=1).astype(np.float32)
+    rays = formats.make_rays(od, 0.0, 100.0)
+    a = oracle.traverse_bvh2(n2, t1, rays)
+    b = oracle.traverse(scene.array("nodes").copy(), scene.array("tris").copy(), rays)
+    assert ((a["tri_id"] >= 0) == (b["tri_id"] >= 0)).all() and np.allclose(a["t"], b["t"], rtol=1e-5)
+    after, _ = oracle.render(scene.view, cam, W, H, 4, 8, 0)
+    e = np.abs(after - before) / (np.abs(before) + 1e-3)
+    assert np.median(e) < 1e-6 and (e < 1e-3).mean() > 0.995
+
+    sponza = workloads.load_scene("sponza")
+    t1 = sponza.array("tris1")
+    assert (t1["geom_id"] == sponza.array("indices")[t1["prim_id"] & 0x7FFFFFFF, 3]).all()
+    bad = formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
+    with pytest.raises(RuntimeError):
+        scene.set_bvh2(*bad)                                   # Sponza's prim ids do not exist in the Cornell box
