@@ -319,8 +319,8 @@ void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* nu
 /* BVH2 / Tri1 over the scene's triangles -- what the reference's GPU device renders from (device.load_bvh2_tri1,
  * src/render/mapping_gpu.impala:505-509).  `build` makes one from the scene's own builder; `set` adopts a caller's arrays
  * (e.g. the BVH2 block of a .bvh file over the same triangles; copied, Tri1::geom_id rewritten to the scene's material
- * ids; returns 0 if a prim_id is out of range).  Renderers created afterwards trace their closest-hit rays through it with
- * the reference GPU path's traversal and keep the BVH8 for shadow rays (any hit is faster there: DESIGN.md 4.2). */
+ * ids; returns 0 if a prim_id is out of range).  Renderers created afterwards trace their rays through it with the
+ * reference GPU path's traversal (Sponza: 1.7x the samples/s of the BVH8 walk). */
 void    rodent_b200_scene_build_bvh2(RodentScene* scene);
 int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1);
 

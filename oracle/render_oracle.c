@@ -260,12 +260,12 @@ typedef struct {
 
 void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom);   /* traversal_bvh2_oracle.c */
 
-/* Closest hit through the scene's BVH2 / Tri1 when it carries one -- the reference GPU device's layout and traversal
- * (gpu_traverse_primary, mapping_gpu.impala:18-30) -- otherwise, and for shadow rays always, the BVH8 single-ray kernel:
- * the same split as the CUDA render loop (rodent_b200/csrc/render.cu). */
+/* Through the scene's BVH2 / Tri1 when it carries one -- the reference GPU device's layout and traversal
+ * (gpu_traverse_primary / gpu_traverse_secondary, mapping_gpu.impala:18-80) -- otherwise the BVH8 single-ray kernel: the
+ * same choice as the CUDA render loop (rodent_b200/csrc/render.cu). */
 static inline void trace(const RodentSceneView* sc, int any, V3 org, V3 dir, float tmin, float tmax, Hit1* hit, int32_t* geom, OracleStats* st) {
     Ray1 r = {{org.x, org.y, org.z}, tmin, {dir.x, dir.y, dir.z}, tmax};
-    if (!any && sc->nodes2) { oracle_bvh2_trace_one(0, sc->nodes2, sc->tris1, &r, hit, geom); return; }
+    if (sc->nodes2) { oracle_bvh2_trace_one(any, sc->nodes2, sc->tris1, &r, hit, geom); return; }
     if (any) traverse_single(8, 1, sc->nodes, sc->tris, &r, hit, st, geom);
     else     traverse_single(8, 0, sc->nodes, sc->tris, &r, hit, st, geom);
 }

@@ -135,31 +135,49 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
     }
 }
 
-// Closest hit through the scene's BVH2 / Tri1 -- the layout and traversal of the reference's GPU renderer
-// (gpu_traverse_primary over make_gpu_bvh2_tri1, mapping_gpu.impala:18-30,505-509) -- same stream contract as above.
+// The same two kernels on the scene's BVH2 / Tri1 -- the layout and traversal of the reference's GPU renderer
+// (gpu_traverse_primary / gpu_traverse_secondary over make_gpu_bvh2_tri1, mapping_gpu.impala:18-80,505-509) -- same stream
+// contract as above.
 constexpr int kRBvh2Stack = 32;
+template <bool SHADOW>
 __global__ void __launch_bounds__(kRBlock, 8)
 traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
-                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, int num_rays,
+                     const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
                      float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
+                     const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
                      int* __restrict__ work_counter, int refill_min, int streak_min) {
     __shared__ int smem_stack[kRBvh2Stack][kRBlock];
-    __shared__ int hist[kMaxBins];
-    for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
-    __syncthreads();
+    __shared__ int hist[SHADOW ? 1 : kMaxBins];
+    const int num_rays = count_ptr ? min(*count_ptr, count_max) : count_max;
+    if (!SHADOW) {
+        for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
+        __syncthreads();
+    }
     int* const hist_bins = hist;
-    traverse_bvh2_scheduled<false, kRBvh2Stack, kRBlock>(
+    traverse_bvh2_scheduled<SHADOW, kRBvh2Stack, kRBlock>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, streak_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
-            const int g = h.prim < 0 ? num_geoms : h.geom;
-            hit_out[i] = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
-            geom_out[i] = g;
-            atomicAdd(hist_bins + g, 1);
+            if (SHADOW) {
+                if (h.prim < 0) {
+                    const int p = __ldg(pixels + i);
+                    const float4 c = __ldg(colors + i);
+                    atomicAdd(film + 3 * p + 0, c.x * inv_spp);
+                    atomicAdd(film + 3 * p + 1, c.y * inv_spp);
+                    atomicAdd(film + 3 * p + 2, c.z * inv_spp);
+                }
+            } else {
+                const int g = h.prim < 0 ? num_geoms : h.geom;
+                hit_out[i] = make_float4(__int_as_float(h.prim), h.t, h.u, h.v);
+                geom_out[i] = g;
+                atomicAdd(hist_bins + g, 1);
+            }
         });
-    __syncthreads();
-    for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
-        if (hist[b]) atomicAdd(histogram + b, hist[b]);
+    if (!SHADOW) {
+        __syncthreads();
+        for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
+            if (hist[b]) atomicAdd(histogram + b, hist[b]);
+    }
 }
 
 // ---- scan: per-material begins, number of hit rays (the host scan of mapping_gpu.impala:201-208) ----
@@ -314,7 +332,7 @@ struct Renderer {
     int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr; int* order = nullptr;
     int* h_counters = nullptr;                  // pinned
     float* film = nullptr; float* own_film = nullptr; float* h_film = nullptr;
-    int sm_count = 0, occ_primary = 0, occ_shadow = 0, occ_primary2 = 0;
+    int sm_count = 0, occ_primary = 0, occ_shadow = 0, occ_primary2 = 0, occ_shadow2 = 0;
     int64_t stats[5] = {0, 0, 0, 0, 0};
     double last_ms = 0.0;
     // A renderer with several LANES drives that many independent wavefront pipelines (own streams, ray streams and
@@ -343,6 +361,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
+static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
 
@@ -407,7 +426,8 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
         d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
     }
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2, kRBlock, 0));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false>, kRBlock, 0));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
     // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
@@ -423,7 +443,7 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
             auto lane = new Renderer();
             lane->parent = r;
             lane->dev = dev; lane->width = width; lane->height = height; lane->spp = spp; lane->max_path_len = max_path_len;
-            lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_primary2 = r->occ_primary2; lane->occ_shadow = r->occ_shadow;
+            lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_primary2 = r->occ_primary2; lane->occ_shadow2 = r->occ_shadow2; lane->occ_shadow = r->occ_shadow;
             lane->scene = r->scene;
             for (size_t k = 0; k < r->rows.size(); k++)
                 if (int(k / 8) % num_lanes == j) lane->rows.push_back(r->rows[k]);
@@ -510,8 +530,8 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
         RB_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * sizeof(int), s));
         if (r.scene.nodes2) {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
-            traverse_stream_bvh2<<<grid_p, kRBlock, 0, s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, size, P.hit, P.geom, num_geoms,
-                                                            r.histogram, counters + kWorkPrimary, kRefillMin, 4);
+            traverse_stream_bvh2<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
+                                                                   r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin, 4);
         } else {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
             traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
@@ -525,10 +545,17 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
         RB_CUDA_CHECK(cudaMemcpyAsync(h_counters, counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
         std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
         RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
-        const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
-        traverse_stream<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                          counters + kWorkShadow, kRefillMin);
+        if (r.scene.nodes2 && g_render_shadow_bvh2) {
+            const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
+            traverse_stream_bvh2<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
+                                                                   nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+                                                                   counters + kWorkShadow, kRefillMin, 4);
+        } else {
+            const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
+            traverse_stream<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
+                                                              nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+                                                              counters + kWorkShadow, kRefillMin);
+        }
         RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
         RB_CUDA_CHECK(cudaGetLastError());
         RB_CUDA_CHECK(cudaStreamSynchronize(s));                // survivors and shadow-ray count of this wavefront (the shadow pass runs on)
@@ -594,6 +621,7 @@ double rodent_b200_render_last_ms(const RodentRenderer* r) { return reinterpret_
 void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_lanes")) g_render_lanes = std::max(1, int(value));
     if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value;
+    if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;

@@ -101,8 +101,8 @@ def load_scene(name: str) -> render.Scene:
     key = "sponza" if name.startswith("sponza") else name
     if key not in _scene_cache:
         # Sponza carries a BVH2 / Tri1 as well -- the BVH2 block of the reference's own file, the layout its GPU device
-        # renders from: closest-hit rays go through it (+36 % samples/s), shadow rays through the BVH8.
-        # The 36-triangle Cornell box gains nothing from it (2 028 against 2 075 Msamples/s) and keeps the BVH8.
+        # renders from: the renderer then traces through it (1.7x the samples/s of the BVH8 walk).
+        # The 36-triangle Cornell box gains nothing from it (2.01 .. 2.06 Gsamples/s either way) and keeps the BVH8.
         if key == "cornell":
             _scene_cache[key] = render.Scene.load_obj(ROOT / "tests" / "golden" / "cornell_box.obj")
         elif key == "sponza":

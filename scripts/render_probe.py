@@ -14,7 +14,11 @@ if len(sys.argv) > 7:
     lib.tune("render_lanes", int(sys.argv[7]))
 if len(sys.argv) > 8:
     lib.tune("render_bvh2", int(sys.argv[8]))
+if len(sys.argv) > 9:
+    lib.tune("render_shadow_bvh2", int(sys.argv[9]))
 scene = workloads.load_scene(name)
+if len(sys.argv) > 10 and int(sys.argv[10]):
+    scene.build_bvh2()
 cam = workloads.camera(name, W, H)
 r = R.Renderer(scene, 0, W, H, spp, depth)
 for it in range(iters):

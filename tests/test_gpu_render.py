@@ -145,7 +145,7 @@ def test_lanes_do_not_change_the_film(cornell):
 
 
 def test_closest_hit_through_the_scene_bvh2():
-    """A scene that carries a BVH2 / Tri1 (the reference GPU device's layout) traces its closest-hit rays through it, with
+    """A scene that carries a BVH2 / Tri1 (the reference GPU device's layout) traces its rays through it, with
     that path's traversal; the oracle does the same (render_oracle.c: trace), so the films agree to the usual tolerance --
     for the scene's own binary tree (Cornell) and for the reference's BVH2 block (Sponza, covered by
     test_sponza_film_matches_oracle since workloads.load_scene attaches it).  Switching it off (`render_bvh2` = 0) traces
