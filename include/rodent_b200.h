@@ -112,7 +112,7 @@ void cuda_occluded_single_ray1_bvh8_tri4(int32_t dev, const Node8* nodes, const 
  * video min/max instructions on the float bits (:74-85), both children hit -> nearer entry first, no culling of
  * stacked entries, leaves of single triangles.  The hit writer stores all four fields in both modes
  * (make_gpu_hit1, bench_traversal.impala:78-83): miss -> tri_id = -1, t = tmax, u = v = 0; `occluded` returns the first
- * accepted triangle's record. */
+ * accepted triangle's record.  `nodes` must be 32-byte aligned (device allocations are). */
 void cuda_intersect_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris,
                                           const Ray1* rays, Hit1* hits, int32_t num_rays);
 void cuda_occluded_single_ray1_bvh2_tri1(int32_t dev, const Node2* nodes, const Tri1* tris,

@@ -59,6 +59,19 @@ __device__ __forceinline__ float imax2(float a, float b) { return __int_as_float
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ int4 ldg4(const int4* p) { return __ldg(p); }
 
+// One 256-bit load (LDG.E.256 on sm_100a): a whole row of a Node8, half a Node2, two rows of a Tri4.  On the divergent
+// record fetches of the traversal kernels a load instruction costs the L1 data pipe about one wavefront per lane whatever
+// its width (profiles/r01_microbench_pipes.txt), so half as many instructions is half as many wavefronts.
+// `p` must be 32-byte aligned.
+struct F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg8(const float4* p) {
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 

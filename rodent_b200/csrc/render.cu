@@ -108,7 +108,7 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
     }
     int* const hist_bins = hist;
     // the vote-scheduled persistent loop of traverse_sched.cuh, fed from / draining into the SoA streams
-    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock>(
+    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock, 8, true>(      // 256-bit record loads: the scene arrays are cudaMalloc'ed
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {

@@ -35,6 +35,7 @@ struct Tuning {
                              // 4 = four lanes per ray (traverse_quad.cuh)
     int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
     int node_streak_min = 8;  // (mapping 2) consecutive node steps without re-voting while this many lanes want one (33: off)
+    int wide_loads = 1;      // (mapping 2, 5 blocks) 256-bit record loads when the arrays are 32-byte aligned
     int bvh2_streak_min = 4; // BVH2 / Tri1 kernel: consecutive steps of one kind while this many lanes want one (measured 4 > 8 > 16)
     int bvh2_min_blocks = 8; // BVH2 / Tri1 kernel: __launch_bounds__ min blocks per SM of the variant launched: 8, 10 or 12
     int vote_min_blocks = 5; // (mapping 2) __launch_bounds__ min blocks per SM of the variant launched: 4, 5 or 6
@@ -124,13 +125,14 @@ traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict
 
 // Vote-scheduled persistent kernel (traverse_sched.cuh): the default.
 constexpr int kVoteSmemDepth = 24;
-template <bool ANY, int MIN_BLOCKS>
+// WIDE: 256-bit record loads (needs 32-byte aligned nodes / tris: the launcher checks).
+template <bool ANY, int MIN_BLOCKS, bool WIDE = false>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                    const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
                    int* __restrict__ work_counter, int refill_min, int node_streak_min) {
     __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
-    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock>(
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 8, WIDE>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [rays](int i, float4& r0, float4& r1) {
             const float4* rp = reinterpret_cast<const float4*>(rays + i);
@@ -380,7 +382,9 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
         const int needed = (num_rays + kBlock - 1) / kBlock;
         const int grid = std::min(needed, s.sm_count * per_sm);
         if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        if (v == 1) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        const bool wide = g_tuning.wide_loads && ((reinterpret_cast<uintptr_t>(nodes) | reinterpret_cast<uintptr_t>(tris)) & 31) == 0;
+        if (v == 1 && wide) traverse_bvh8_vote<ANY, 5, true><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 1 && !wide) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
         if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
     } else if (g_tuning.mapping == 4) {
         if (!counter) counter = s.counter;
@@ -423,6 +427,10 @@ template <bool ANY>
 static void launch(DeviceState& s, const Node2* nodes, const Tri1* tris, const Ray1* rays, Hit1* hits,
                    int num_rays, cudaStream_t stream, int* counter) {
     if (num_rays <= 0) return;
+    if (reinterpret_cast<uintptr_t>(nodes) & 31) {
+        std::fprintf(stderr, "rodent_b200: the Node2 array must be 32-byte aligned (cudaMalloc / rodent_b200_alloc_device give 256)\n");
+        std::abort();
+    }
     if (!counter) counter = s.counter;
     RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     const int v = g_tuning.bvh2_min_blocks >= 12 ? 2 : g_tuning.bvh2_min_blocks >= 10 ? 1 : 0;
@@ -689,6 +697,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = value;
+    else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value;
     else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = value;
     else if (!std::strcmp(key, "render_lanes") || !std::strcmp(key, "render_bvh2") || !std::strcmp(key, "render_shadow_bvh2")) rodent_b200_render_tune(key, value);
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }

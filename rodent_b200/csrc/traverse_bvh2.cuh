@@ -6,7 +6,7 @@
 // per test) and the register-top stack of src/traversal/stack.impala:52-123 (whose keys this path never reads).
 // The reference runs it as one thread per ray, block 64, one launch over the whole stream (:182-203).  Here the same
 // per-ray state machine runs under the vote scheduler of traverse_sched.cuh: the warp takes ONE straight-line step per
-// iteration -- a node step (4 x LDG.128, two slab tests, at most one push) or a triangle step (3 x LDG.128, one
+// iteration -- a node step (2 x LDG.256, two slab tests, at most one push) or a triangle step (3 x LDG.128, one
 // Moeller-Trumbore test) -- chosen by majority, idle lanes refilled together from a global counter.
 // NaN handling needs no special path: the reference is NVIDIA code, and these are the same instructions.
 #pragma once
@@ -63,8 +63,9 @@ struct Bvh2Walker {
     // One iteration of the outer loop up to the leaf loop (:106-135).
     __device__ __forceinline__ void node_step(const Node2* __restrict__ nodes) {
         const float4* p = reinterpret_cast<const float4*>(nodes + (top - 1));
-        const float4 b0 = ldg4(p), b1 = ldg4(p + 1), b2 = ldg4(p + 2);
-        const int4 ch = ldg4(reinterpret_cast<const int4*>(p + 3));
+        const F8 lo = ldg8(p), hi = ldg8(p + 2);                           // a Node2 is two 256-bit loads (32-byte aligned array)
+        const float4 b0 = lo.lo, b1 = lo.hi, b2 = hi.lo;
+        const int4 ch = make_int4(__float_as_int(hi.hi.x), __float_as_int(hi.hi.y), __float_as_int(hi.hi.z), __float_as_int(hi.hi.w));
         float t0, t1;
         const bool h0 = hit_box(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, t0);   // box 0: lo/hi x, y, z (:33-36)
         const bool h1 = hit_box(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, t1);   // box 1 (:37-40)

@@ -40,7 +40,9 @@ struct SplitStack {
 };
 
 // ARITY: 8 for Node8 (BVH8), 4 for Node4 (BVH4); the leaves are Tri4 in both.
-template <bool ANY, int SMEM_DEPTH, int BLOCK, int ARITY = 8>
+// WIDE: fetch records with 256-bit loads (7 per Node8 instead of 14 x 128 bit, 7 per Tri4 instead of 13);
+// needs 32-byte aligned arrays.
+template <bool ANY, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false>
 struct RayWalker {
     RaySetup ray;
     float tmax;
@@ -82,6 +84,18 @@ struct RayWalker {
         pop();
         float nx[ARITY], ny[ARITY], nz[ARITY], fx[ARITY], fy[ARITY], fz[ARITY];
         int child[ARITY];
+        if constexpr (WIDE && ARITY == 8) {                  // a bounds row of a Node8 is one 256-bit load
+            const F8 a = ldg8(nb + ray.near_x), b = ldg8(nb + ray.near_y), c = ldg8(nb + ray.near_z);
+            const F8 d = ldg8(nb + ray.far_x), e = ldg8(nb + ray.far_y), f = ldg8(nb + ray.far_z);
+            const F8 g = ldg8(nb + 6 * ROW);
+#define RB_ROW(dst, src)                                                                             \
+            dst[0] = src.lo.x; dst[1] = src.lo.y; dst[2] = src.lo.z; dst[3] = src.lo.w;              \
+            dst[4] = src.hi.x; dst[5] = src.hi.y; dst[6] = src.hi.z; dst[7] = src.hi.w;
+            RB_ROW(nx, a) RB_ROW(ny, b) RB_ROW(nz, c) RB_ROW(fx, d) RB_ROW(fy, e) RB_ROW(fz, f)
+#undef RB_ROW
+            child[0] = __float_as_int(g.lo.x); child[1] = __float_as_int(g.lo.y); child[2] = __float_as_int(g.lo.z); child[3] = __float_as_int(g.lo.w);
+            child[4] = __float_as_int(g.hi.x); child[5] = __float_as_int(g.hi.y); child[6] = __float_as_int(g.hi.z); child[7] = __float_as_int(g.hi.w);
+        } else
 #pragma unroll
         for (int k = 0; k < ROW; k++) {                      // all loads of the node are issued before the first use
             const float4 a = ldg4(nb + ray.near_x + k), b = ldg4(nb + ray.near_y + k), c = ldg4(nb + ray.near_z + k);
@@ -141,11 +155,23 @@ struct RayWalker {
     __device__ __forceinline__ bool leaf_step(const Tri4* __restrict__ tris) {
         if (leaf < 0) { leaf = ~top_node; pop(); }                                   // :224-225
         const float4* tp = reinterpret_cast<const float4*>(tris + leaf);
-        const int4 pid = ldg4(reinterpret_cast<const int4*>(tp) + 12);
-        const float4 v0x = ldg4(tp + 0), v0y = ldg4(tp + 1), v0z = ldg4(tp + 2);
-        const float4 e1x = ldg4(tp + 3), e1y = ldg4(tp + 4), e1z = ldg4(tp + 5);
-        const float4 e2x = ldg4(tp + 6), e2y = ldg4(tp + 7), e2z = ldg4(tp + 8);
-        const float4 nnx = ldg4(tp + 9), nny = ldg4(tp + 10), nnz = ldg4(tp + 11);
+        int4 pid, gid_wide;
+        float4 v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, nnx, nny, nnz;
+        if constexpr (WIDE) {                                                         // a Tri4 is seven 256-bit loads
+            const F8 p6 = ldg8(tp + 12);
+            const F8 p0 = ldg8(tp + 0), p1 = ldg8(tp + 2), p2 = ldg8(tp + 4), p3 = ldg8(tp + 6), p4 = ldg8(tp + 8), p5 = ldg8(tp + 10);
+            pid = make_int4(__float_as_int(p6.lo.x), __float_as_int(p6.lo.y), __float_as_int(p6.lo.z), __float_as_int(p6.lo.w));
+            gid_wide = make_int4(__float_as_int(p6.hi.x), __float_as_int(p6.hi.y), __float_as_int(p6.hi.z), __float_as_int(p6.hi.w));
+            v0x = p0.lo; v0y = p0.hi; v0z = p1.lo; e1x = p1.hi; e1y = p2.lo; e1z = p2.hi;
+            e2x = p3.lo; e2y = p3.hi; e2z = p4.lo; nnx = p4.hi; nny = p5.lo; nnz = p5.hi;
+        } else {
+            pid = ldg4(reinterpret_cast<const int4*>(tp) + 12);
+            v0x = ldg4(tp + 0); v0y = ldg4(tp + 1); v0z = ldg4(tp + 2);
+            e1x = ldg4(tp + 3); e1y = ldg4(tp + 4); e1z = ldg4(tp + 5);
+            e2x = ldg4(tp + 6); e2y = ldg4(tp + 7); e2z = ldg4(tp + 8);
+            nnx = ldg4(tp + 9); nny = ldg4(tp + 10); nnz = ldg4(tp + 11);
+            gid_wide = make_int4(0, 0, 0, 0);
+        }
 
         float lt[4], lu[4], lv[4];
         unsigned hm = 0;
@@ -172,7 +198,7 @@ struct RayWalker {
             hit.u = lane == 0 ? lu[0] : lane == 1 ? lu[1] : lane == 2 ? lu[2] : lu[3];
             hit.v = lane == 0 ? lv[0] : lane == 1 ? lv[1] : lane == 2 ? lv[2] : lv[3];
             if (WANT_GEOM) {
-                const int4 gid = ldg4(reinterpret_cast<const int4*>(tp) + 13);
+                const int4 gid = WIDE ? gid_wide : ldg4(reinterpret_cast<const int4*>(tp) + 13);
                 hit.geom = lane == 0 ? gid.x : lane == 1 ? gid.y : lane == 2 ? gid.z : gid.w;
             }
             if (!ANY) tmax = hit.t;                                                  // :243
@@ -193,13 +219,13 @@ struct RayWalker {
 //   sink(i, hit)      consumes the finished ray's record
 // `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
 // `node_streak_min`: see the node branch at the end of the loop (33: one step per vote).
-template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, typename Fetch, typename Sink>
+template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, typename Fetch, typename Sink>
 __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
                                                         StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
                                                         int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8) {
     const unsigned lane = lane_id();
     StackEntry overflow[kStackSize - SMEM_DEPTH];
-    RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY> w;
+    RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY, WIDE> w;
     w.st.smem = smem_column;
     w.st.overflow = overflow;
     w.leaf = -1; w.top_node = 0;
