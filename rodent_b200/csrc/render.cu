@@ -92,7 +92,7 @@ generate_rays(PrimaryStream s, long long first_ray_id, int first_dst, int n, Cam
 // ---- persistent traversal over a stream -----------------------------------------------------
 // SHADOW = false: closest hit, hit record + geometry id + per-material count.
 // SHADOW = true : any hit; unoccluded rays add their colour to the film.
-template <bool SHADOW>
+template <bool SHADOW, bool WIDE = false>
 __global__ void __launch_bounds__(kRBlock, 5)
 traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                 const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
@@ -108,7 +108,7 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
     }
     int* const hist_bins = hist;
     // the vote-scheduled persistent loop of traverse_sched.cuh, fed from / draining into the SoA streams
-    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock, 8, true>(      // 256-bit record loads: the scene arrays are cudaMalloc'ed
+    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock, 8, WIDE>(      // WIDE: 256-bit record loads (the scene arrays are cudaMalloc'ed)
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
@@ -361,6 +361,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
+static int g_render_wide = 0;          // 256-bit record loads in the BVH8 stream kernels (rodent_b200_tune "render_wide")
 static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
@@ -534,8 +535,9 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
                                                                    r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin, 4);
         } else {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
-            traverse_stream<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                              r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
+            auto kernel = g_render_wide ? traverse_stream<false, true> : traverse_stream<false, false>;
+            kernel<<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
+                                              r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
         }
         scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
         scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
@@ -552,9 +554,10 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
                                                                    counters + kWorkShadow, kRefillMin, 4);
         } else {
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
-            traverse_stream<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                                              nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                              counters + kWorkShadow, kRefillMin);
+            auto kernel = g_render_wide ? traverse_stream<true, true> : traverse_stream<true, false>;
+            kernel<<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
+                                               nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+                                               counters + kWorkShadow, kRefillMin);
         }
         RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
         RB_CUDA_CHECK(cudaGetLastError());
@@ -622,6 +625,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_lanes")) g_render_lanes = std::max(1, int(value));
     if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value;
     if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value;
+    if (!std::strcmp(key, "render_wide")) g_render_wide = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;

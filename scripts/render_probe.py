@@ -16,6 +16,8 @@ if len(sys.argv) > 8:
     lib.tune("render_bvh2", int(sys.argv[8]))
 if len(sys.argv) > 9:
     lib.tune("render_shadow_bvh2", int(sys.argv[9]))
+if len(sys.argv) > 11:
+    lib.tune("render_wide", int(sys.argv[11]))
 scene = workloads.load_scene(name)
 if len(sys.argv) > 10 and int(sys.argv[10]):
     scene.build_bvh2()
