@@ -361,6 +361,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
+static int g_render_refill_min = 20, g_render_streak_min = 8;   // BVH2 stream kernels: refill threshold, step-streak threshold (swept: profiles/r01_experiments.md)
 static int g_render_wide = 0;          // 256-bit record loads in the BVH8 stream kernels (rodent_b200_tune "render_wide")
 static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
@@ -532,7 +533,7 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
         if (r.scene.nodes2) {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
             traverse_stream_bvh2<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                                   r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin, 4);
+                                                                   r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min);
         } else {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
             auto kernel = g_render_wide ? traverse_stream<false, true> : traverse_stream<false, false>;
@@ -551,7 +552,7 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
             traverse_stream_bvh2<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
                                                                    nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                                   counters + kWorkShadow, kRefillMin, 4);
+                                                                   counters + kWorkShadow, g_render_refill_min, g_render_streak_min);
         } else {
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
             auto kernel = g_render_wide ? traverse_stream<true, true> : traverse_stream<true, false>;
@@ -626,6 +627,8 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value;
     if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value;
     if (!std::strcmp(key, "render_wide")) g_render_wide = value;
+    if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = value;
+    if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;
