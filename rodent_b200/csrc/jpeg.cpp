@@ -1,0 +1,336 @@
+// JPEG -> the RGBA8 image the reference's load_jpg produces (src/driver/image.cpp:186-238).
+//
+// The reference decodes with libjpeg at its defaults and copies `output_components` bytes per pixel into a zero-filled
+// RGBA image, bottom row first, then applies gamma 2.2 (:10-18): colour images come out as (r, g, b, 0), grey ones as
+// (grey, 0, 0, 0).  libjpeg is not part of this image, so the decoder is written here from the JPEG specification
+// (ITU-T T.81: baseline / extended sequential Huffman, 8 bit, restart intervals) with libjpeg's default choices for the
+// parts the standard leaves open, so that pixels come out the same: the slow-but-accurate integer IDCT (jidctint.c),
+// "fancy" triangle-filter chroma upsampling for 2x1 and 2x2 subsampling (jdsample.c) and the fixed-point YCbCr -> RGB
+// tables (jdcolor.c).  tests/test_textures.py checks it pixel for pixel against PIL, which wraps libjpeg-turbo.
+// Progressive and arithmetic-coded files are reported as unsupported.
+#include "scene.h"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iterator>
+
+namespace rb200 {
+namespace {
+
+struct Huffman {
+    uint8_t bits[17] = {0}, vals[256] = {0};
+    int mincode[17], maxcode[18], valptr[17];
+    bool present = false;
+    void build() {
+        int code = 0, k = 0;
+        for (int l = 1; l <= 16; l++) {
+            valptr[l] = k; mincode[l] = code;
+            code += bits[l]; k += bits[l];
+            maxcode[l] = bits[l] ? code - 1 : -1;
+            code <<= 1;
+        }
+        maxcode[17] = 0x7FFFFFFF;
+    }
+};
+
+struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0; int blocks_w = 0, blocks_h = 0; std::vector<uint8_t> plane; int stride = 0, rows = 0; };
+
+struct BitReader {
+    const uint8_t* p; const uint8_t* end;
+    uint32_t acc = 0; int count = 0; bool hit_marker = false;
+    void fill() {
+        while (count <= 24) {
+            int b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0x00) p += 2;             // stuffed zero
+                    else { hit_marker = true; b = 0; }                   // a marker: feed zeros, as libjpeg does
+                } else p++;
+            }
+            acc |= uint32_t(b) << (24 - count);
+            count += 8;
+        }
+    }
+    int bit() { if (count == 0) fill(); const int b = acc >> 31; acc <<= 1; count--; return b; }
+    int bits(int n) { if (n == 0) return 0; if (count < n) fill(); const int v = int(acc >> (32 - n)); acc <<= n; count -= n; return v; }
+    void reset() { acc = 0; count = 0; hit_marker = false; }
+};
+
+int decode_symbol(BitReader& br, const Huffman& h, bool& ok) {
+    int code = 0;
+    for (int l = 1; l <= 16; l++) {
+        code = (code << 1) | br.bit();
+        if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) return h.vals[h.valptr[l] + code - h.mincode[l]];
+    }
+    ok = false;
+    return 0;
+}
+int extend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v; }
+
+const uint8_t kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                             35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+inline uint8_t range_limit(int x) {                      // libjpeg's IDCT range-limit table: clamp(x + 128) with 10-bit wrap-around
+    x = ((x + 512) & 1023) - 512;
+    x += 128;
+    return uint8_t(x < 0 ? 0 : x > 255 ? 255 : x);
+}
+inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// jpeg_idct_islow (jidctint.c): 13-bit constants, 2 extra bits kept between the passes.
+void idct_islow(const int* in /* dequantised, natural order */, uint8_t* out, int stride) {
+    constexpr int C = 13, P = 2;
+    constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
+                  F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+    int ws[64];
+    auto pass = [&](int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, int* o) {
+        int z2 = d2, z3 = d6;
+        int z1 = (z2 + z3) * F_0_541;
+        int tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+        z2 = d0; z3 = d4;
+        int tmp0 = (z2 + z3) << C, tmp1 = (z2 - z3) << C;
+        const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = d7; tmp1 = d5; tmp2 = d3; tmp3 = d1;
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; int z4 = tmp1 + tmp3;
+        const int z5 = (z3 + z4) * F_1_175;
+        tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+        z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+        z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        o[0] = tmp10 + tmp3; o[7] = tmp10 - tmp3; o[1] = tmp11 + tmp2; o[6] = tmp11 - tmp2;
+        o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1; o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
+    };
+    for (int c = 0; c < 8; c++) {                        // pass 1: columns
+        int o[8];
+        pass(in[c], in[8 + c], in[16 + c], in[24 + c], in[32 + c], in[40 + c], in[48 + c], in[56 + c], o);
+        for (int r = 0; r < 8; r++) ws[8 * r + c] = descale(o[r], C - P);
+    }
+    for (int r = 0; r < 8; r++) {                        // pass 2: rows
+        int o[8];
+        const int* w = ws + 8 * r;
+        pass(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], o);
+        for (int c = 0; c < 8; c++) out[r * stride + c] = range_limit(descale(o[c], C + P + 3));
+    }
+}
+
+uint16_t be16(const uint8_t* p) { return uint16_t(p[0] << 8 | p[1]); }
+
+}  // namespace
+
+bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { why = "cannot open file"; return false; }
+    const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (file.size() < 4 || file[0] != 0xFF || file[1] != 0xD8) { why = "not a JPEG file"; return false; }
+
+    uint16_t qt[4][64] = {};
+    Huffman dc[4], ac[4];
+    std::vector<Component> comps;
+    int w = 0, h = 0, restart_interval = 0, hmax = 1, vmax = 1;
+    bool have_frame = false, adobe_rgb = false;
+    size_t pos = 2, scan_start = 0;
+    while (pos + 4 <= file.size()) {
+        if (file[pos] != 0xFF) { why = "marker expected"; return false; }
+        const int m = file[pos + 1];
+        if (m == 0xFF) { pos++; continue; }                                  // fill bytes
+        pos += 2;
+        if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0xD9) break;
+        if (pos + 2 > file.size()) { why = "truncated segment"; return false; }
+        const size_t len = be16(&file[pos]);
+        if (len < 2 || pos + len > file.size()) { why = "truncated segment"; return false; }
+        const uint8_t* s = &file[pos + 2];
+        const size_t n = len - 2;
+        if (m == 0xDB) {                                                     // DQT
+            for (size_t i = 0; i < n;) {
+                const int pq = s[i] >> 4, tq = s[i] & 15;
+                if (tq > 3 || i + 1 + (pq ? 128 : 64) > n) { why = "bad DQT"; return false; }
+                for (int k = 0; k < 64; k++) qt[tq][kZigzag[k]] = pq ? be16(&s[i + 1 + 2 * k]) : s[i + 1 + k];
+                i += 1 + (pq ? 128 : 64);
+            }
+        } else if (m == 0xC4) {                                              // DHT
+            for (size_t i = 0; i < n;) {
+                const int tc = s[i] >> 4, th = s[i] & 15;
+                if (tc > 1 || th > 3 || i + 17 > n) { why = "bad DHT"; return false; }
+                Huffman& t = tc ? ac[th] : dc[th];
+                int total = 0;
+                for (int l = 1; l <= 16; l++) { t.bits[l] = s[i + l]; total += t.bits[l]; }
+                if (total > 256 || i + 17 + total > n) { why = "bad DHT"; return false; }
+                std::memcpy(t.vals, &s[i + 17], total);
+                t.build(); t.present = true;
+                i += 17 + total;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {                                 // SOF0 / SOF1: sequential Huffman
+            if (n < 6 || s[0] != 8) { why = "only 8-bit samples are supported"; return false; }
+            h = be16(&s[1]); w = be16(&s[3]);
+            const int nc = s[5];
+            if ((nc != 1 && nc != 3) || n < size_t(6 + 3 * nc) || w == 0 || h == 0) { why = "unsupported number of components"; return false; }
+            comps.resize(nc);
+            for (int c = 0; c < nc; c++) {
+                comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c] & 3;
+                hmax = std::max(hmax, comps[c].h); vmax = std::max(vmax, comps[c].v);
+            }
+            have_frame = true;
+        } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
+            why = m == 0xC2 ? "progressive JPEG is not supported" : "this JPEG coding process is not supported";
+            return false;
+        } else if (m == 0xDD) {
+            if (n >= 2) restart_interval = be16(s);
+        } else if (m == 0xEE) {                                              // Adobe: transform 0 with three components = RGB
+            if (n >= 12 && !std::memcmp(s, "Adobe", 5)) adobe_rgb = s[11] == 0;
+        } else if (m == 0xDA) {                                              // SOS
+            if (!have_frame) { why = "SOS before SOF"; return false; }
+            const int ns = s[0];
+            if (ns != int(comps.size()) || n < size_t(1 + 2 * ns + 3)) { why = "non-interleaved scans are not supported"; return false; }
+            for (int k = 0; k < ns; k++) {
+                Component* c = nullptr;
+                for (auto& cc : comps) if (cc.id == s[1 + 2 * k]) c = &cc;
+                if (!c) { why = "bad SOS"; return false; }
+                c->td = s[2 + 2 * k] >> 4; c->ta = s[2 + 2 * k] & 15;
+                if (c->td > 3 || c->ta > 3 || !dc[c->td].present || !ac[c->ta].present) { why = "missing Huffman table"; return false; }
+            }
+            scan_start = pos + len;
+            break;
+        }
+        pos += len;
+    }
+    if (!scan_start) { why = "no scan found"; return false; }
+    if (comps.size() == 3) {
+        const bool ok = comps[1].h == 1 && comps[1].v == 1 && comps[2].h == 1 && comps[2].v == 1 &&
+                        (comps[0].h == 1 || comps[0].h == 2) && (comps[0].v == 1 || comps[0].v == 2) && !(comps[0].h == 1 && comps[0].v == 2);
+        if (!ok) { why = "unsupported chroma subsampling"; return false; }
+    } else { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }                 // a single component is never interleaved
+
+    // ---- entropy decoding + IDCT into component planes (padded to whole MCUs) ----
+    const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
+    const int mcus_x = (w + mcu_w - 1) / mcu_w, mcus_y = (h + mcu_h - 1) / mcu_h;
+    for (auto& c : comps) {
+        c.blocks_w = mcus_x * c.h; c.blocks_h = mcus_y * c.v;
+        c.stride = c.blocks_w * 8; c.rows = c.blocks_h * 8;
+        c.plane.assign(size_t(c.stride) * c.rows, 0);
+    }
+    BitReader br{&file[scan_start], file.data() + file.size()};
+    int restarts_left = restart_interval;
+    for (int my = 0; my < mcus_y; my++)
+        for (int mx = 0; mx < mcus_x; mx++) {
+            if (restart_interval && restarts_left == 0) {
+                // skip to the RSTn marker, reset predictors
+                const uint8_t* p = br.p;
+                while (p + 1 < br.end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) p++;
+                if (p + 1 >= br.end) { why = "missing restart marker"; return false; }
+                br.p = p + 2; br.reset();
+                for (auto& c : comps) c.dc_pred = 0;
+                restarts_left = restart_interval;
+            }
+            for (auto& c : comps)
+                for (int by = 0; by < c.v; by++)
+                    for (int bx = 0; bx < c.h; bx++) {
+                        int coef[64] = {0};
+                        bool ok = true;
+                        const int t = decode_symbol(br, dc[c.td], ok);
+                        if (!ok || t > 11) { why = "corrupt entropy-coded data"; return false; }
+                        c.dc_pred += t ? extend(br.bits(t), t) : 0;
+                        coef[0] = c.dc_pred * qt[c.tq][0];
+                        for (int k = 1; k < 64;) {
+                            const int rs = decode_symbol(br, ac[c.ta], ok);
+                            if (!ok) { why = "corrupt entropy-coded data"; return false; }
+                            const int r = rs >> 4, sz = rs & 15;
+                            if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
+                            k += r;
+                            if (k > 63) { why = "corrupt entropy-coded data"; return false; }
+                            coef[kZigzag[k]] = extend(br.bits(sz), sz) * qt[c.tq][kZigzag[k]];
+                            k++;
+                        }
+                        uint8_t* dst = c.plane.data() + size_t((my * c.v + by) * 8) * c.stride + (mx * c.h + bx) * 8;
+                        idct_islow(coef, dst, c.stride);
+                    }
+            restarts_left--;
+        }
+
+    // ---- upsampling (jdsample.c, fancy) + colour conversion (jdcolor.c) ----
+    width = w; height = h;
+    pixels.assign(size_t(w) * h, 0);
+    uint32_t gamma_lut[256];
+    for (int v = 0; v < 256; v++) gamma_lut[v] = uint32_t(uint8_t(std::pow(float(v) * (1.0f / 255.0f), 2.2f) * 255.0f));   // image.cpp:10-18
+    if (comps.size() == 1) {
+        for (int y = 0; y < h; y++) {
+            uint32_t* dst = pixels.data() + size_t(h - 1 - y) * w;           // bottom row first, image.cpp:223
+            for (int x = 0; x < w; x++) dst[x] = gamma_lut[comps[0].plane[size_t(y) * comps[0].stride + x]];   // (grey, 0, 0, 0): :226-227
+        }
+        return true;
+    }
+    const int H = comps[0].h, V = comps[0].v;                                // chroma is (1, 1): subsampled by H x V
+    const int cw = (w + H - 1) / H, chh = (h + V - 1) / V;                   // downsampled_width / height of the chroma planes
+    std::vector<uint8_t> up[2];
+    for (int k = 0; k < 2; k++) {
+        const Component& c = comps[1 + k];
+        std::vector<uint8_t>& o = up[k];
+        const int ow = cw * H;
+        o.assign(size_t(ow) * h, 0);
+        auto row = [&](int r) { return c.plane.data() + size_t(std::min(std::max(r, 0), chh - 1)) * c.stride; };
+        if (H == 1 && V == 1) {
+            for (int y = 0; y < h; y++) std::memcpy(&o[size_t(y) * ow], row(y), cw);
+        } else if (cw <= 2) {                                                // jinit_upsampler: fancy only if downsampled_width > 2, else replication
+            for (int y = 0; y < h; y++)
+                for (int x = 0; x < ow; x++) o[size_t(y) * ow + x] = row(y / V)[x / H];
+        } else if (H == 2 && V == 1) {                                       // h2v1_fancy_upsample
+            for (int y = 0; y < h; y++) {
+                const uint8_t* in_row = row(y); uint8_t* out = &o[size_t(y) * ow];
+                out[0] = in_row[0]; out[1] = uint8_t((in_row[0] * 3 + in_row[1] + 2) >> 2);
+                for (int x = 1; x < cw - 1; x++) {
+                    const int v3 = in_row[x] * 3;
+                    out[2 * x] = uint8_t((v3 + in_row[x - 1] + 1) >> 2); out[2 * x + 1] = uint8_t((v3 + in_row[x + 1] + 2) >> 2);
+                }
+                out[2 * (cw - 1)] = uint8_t((in_row[cw - 1] * 3 + in_row[cw - 2] + 1) >> 2); out[2 * (cw - 1) + 1] = in_row[cw - 1];
+            }
+        } else {                                                             // h2v2_fancy_upsample
+            for (int y = 0; y < h; y++) {
+                const int r = y >> 1;
+                const uint8_t* near_row = row(r);
+                const uint8_t* far_row = row((y & 1) ? r + 1 : r - 1);        // the context rows replicate at the image edges (jdmainct.c)
+                uint8_t* out = &o[size_t(y) * ow];
+                auto colsum = [&](int x) { return near_row[x] * 3 + far_row[x]; };
+                int last = colsum(0), cur = last, next = colsum(1);
+                out[0] = uint8_t((cur * 4 + 8) >> 4); out[1] = uint8_t((cur * 3 + next + 7) >> 4);
+                for (int x = 1; x < cw - 1; x++) {
+                    last = cur; cur = next; next = colsum(x + 1);
+                    out[2 * x] = uint8_t((cur * 3 + last + 8) >> 4); out[2 * x + 1] = uint8_t((cur * 3 + next + 7) >> 4);
+                }
+                last = cur; cur = next;
+                out[2 * (cw - 1)] = uint8_t((cur * 3 + last + 8) >> 4); out[2 * (cw - 1) + 1] = uint8_t((cur * 4 + 7) >> 4);
+            }
+        }
+    }
+    // build_ycc_rgb_table / ycc_rgb_convert
+    int cr_r[256], cb_b[256], cr_g[256], cb_g[256];
+    for (int i = 0; i < 256; i++) {
+        const int x = i - 128;
+        cr_r[i] = (91881 * x + 32768) >> 16;            // FIX(1.40200)
+        cb_b[i] = (116130 * x + 32768) >> 16;           // FIX(1.77200)
+        cr_g[i] = -46802 * x;                           // FIX(0.71414)
+        cb_g[i] = -22554 * x + 32768;                   // FIX(0.34414)
+    }
+    auto clamp8 = [](int v) { return v < 0 ? 0 : v > 255 ? 255 : v; };
+    const int ow = cw * H;
+    for (int y = 0; y < h; y++) {
+        uint32_t* dst = pixels.data() + size_t(h - 1 - y) * w;
+        const uint8_t* yr = comps[0].plane.data() + size_t(y) * comps[0].stride;
+        const uint8_t* cb = &up[0][size_t(y) * ow];
+        const uint8_t* cr = &up[1][size_t(y) * ow];
+        for (int x = 0; x < w; x++) {
+            int r, g, b;
+            if (adobe_rgb) { r = yr[x]; g = cb[x]; b = cr[x]; }
+            else {
+                r = clamp8(yr[x] + cr_r[cr[x]]);
+                g = clamp8(yr[x] + ((cb_g[cb[x]] + cr_g[cr[x]]) >> 16));
+                b = clamp8(yr[x] + cb_b[cb[x]]);
+            }
+            dst[x] = gamma_lut[r] | gamma_lut[g] << 8 | gamma_lut[b] << 16;  // alpha stays 0 (:213, :226-227)
+        }
+    }
+    return true;
+}
+
+}  // namespace rb200

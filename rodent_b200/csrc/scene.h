@@ -30,6 +30,8 @@ struct Scene {
 
 // src/driver/image.cpp:25-93 (image.cpp of this directory)
 bool load_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
+// src/driver/image.cpp:186-238 (jpeg.cpp of this directory)
+bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 
 Scene* load_obj_scene(const std::string& path);
 void build_bvh4(Scene& scene);

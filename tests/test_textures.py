@@ -164,6 +164,68 @@ def test_png_loader_rejects_bad_files(tmp_path, capfd):
     assert scene.view.num_textures == 1                                     # only the dummy of "none.xyz"
 
 
+# ---- the JPEG loader ------------------------------------------------------------------------------------------
+def photo(h, w, seed=0):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 100 * np.sin(x / 7.0) * np.cos(y / 5.0), 128 + 90 * np.cos(x / 3.0 + y / 11.0), 60 + x * 2 % 200], 2)
+    return np.clip(img + rng.normal(0, 20, img.shape), 0, 255).astype(np.uint8)
+
+
+def jpg_expected(path):
+    """What load_jpg leaves (image.cpp:186-238) from libjpeg's pixels, which PIL (libjpeg-turbo) provides: rows bottom-up,
+    gamma on the colour bytes, alpha 0; a grey file fills only the first byte of each pixel."""
+    lut = gamma_lut().astype(np.uint32)
+    im = Image.open(path)
+    px = np.array(im)[::-1].astype(np.uint32)
+    return lut[px] if im.mode == "L" else lut[px[..., 0]] | lut[px[..., 1]] << 8 | lut[px[..., 2]] << 16
+
+
+@pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (8, 8), (1, 1), (17, 16), (100, 3), (3, 100), (33, 2), (250, 130)])
+def test_jpg_loader_matches_libjpeg(tmp_path, h, w):
+    """Pixel for pixel: integer IDCT, fancy chroma upsampling (replication when the chroma plane is at most two samples
+    wide), fixed-point colour conversion; 4:4:4 / 4:2:2 / 4:2:0, custom Huffman tables, restart intervals."""
+    scene = R.Scene.load_obj(write_scene(tmp_path, "none.xyz", "none.xyz"))
+    for sub in (0, 1, 2):
+        for k, kw in enumerate((dict(quality=50), dict(quality=95, optimize=True), dict(quality=75, restart_marker_blocks=3),
+                                dict(quality=30, restart_marker_rows=1))):
+            path = tmp_path / f"s{sub}_{k}.jpg"
+            Image.fromarray(photo(h, w, sub * 4 + k)).save(path, subsampling=sub, **kw)
+            if k >= 2:
+                assert b"\xff\xdd" in path.read_bytes()                     # a DRI segment: the restart path is exercised
+            tid = scene.add_png(path)
+            tex = scene.array("textures")[tid - 1]
+            assert (tex["width"], tex["height"]) == (w, h)
+            got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + w * h].reshape(h, w)
+            assert np.array_equal(got, jpg_expected(path)), (sub, kw)
+
+
+def test_jpg_grey_progressive_and_errors(tmp_path, capfd):
+    scene = R.Scene.load_obj(write_scene(tmp_path, "none.xyz", "none.xyz"))
+    Image.fromarray(photo(40, 50)[..., 0]).save(tmp_path / "grey.jpg", quality=80)
+    tid = scene.add_png(tmp_path / "grey.jpg")
+    tex = scene.array("textures")[tid - 1]
+    got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + 2000].reshape(40, 50)
+    assert np.array_equal(got, jpg_expected(tmp_path / "grey.jpg")) and (got >> 8 == 0).all()      # (grey, 0, 0, 0): image.cpp:226-227
+    Image.fromarray(photo(40, 50)).save(tmp_path / "prog.jpg", progressive=True)
+    (tmp_path / "cut.jpg").write_bytes((tmp_path / "grey.jpg").read_bytes()[:300])
+    (tmp_path / "not.jpg").write_bytes(b"GIF89a" + bytes(100))
+    for name in ("prog.jpg", "cut.jpg", "not.jpg", "missing.jpg"):
+        with pytest.raises(RuntimeError):
+            scene.add_png(tmp_path / name)
+    err = capfd.readouterr().err
+    assert "progressive JPEG is not supported" in err and err.count("cannot load JPG file") == 4
+    # through an OBJ: a file this decoder cannot read falls back to the constant with a warning, a missing one fails the load
+    Image.fromarray(photo(16, 16)).save(tmp_path / "floor.jpg", quality=90)
+    scene = R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "prog.jpg"))
+    mats = scene.array("materials")
+    assert mats["map_kd"].tolist()[0] == 1 and mats["map_ks"].tolist()[1] == 0
+    assert np.array_equal(scene.array("texture_pixels").reshape(16, 16), jpg_expected(tmp_path / "floor.jpg"))
+    assert "progressive JPEG is not supported; the material's constant colour is used instead" in capfd.readouterr().err
+    with pytest.raises(RuntimeError):
+        R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "nowhere.jpeg"))
+
+
 # ---- binding images to materials --------------------------------------------------------------------------------
 def test_obj_binds_images_to_materials(tmp_path, capfd):
     Image.fromarray(checker()).save(tmp_path / "floor.png")
@@ -186,9 +248,9 @@ def test_obj_binds_images_to_materials(tmp_path, capfd):
     scene = R.Scene.load_obj(write_scene(tmp_path, "floor.png", "floor.png"))
     assert scene.array("materials")["map_kd"].tolist()[0] == 1 and scene.array("materials")["map_ks"].tolist()[1] == 1
     assert scene.view.num_textures == 1
-    scene = R.Scene.load_obj(write_scene(tmp_path, "floor.bmp", "wall.jpg"))
+    scene = R.Scene.load_obj(write_scene(tmp_path, "floor.bmp", "wall.tga"))
     err = capfd.readouterr().err
-    assert "no decoder for 'wall.jpg'" in err
+    assert "no decoder for 'wall.tga'" in err
     assert scene.array("materials")["map_kd"].tolist()[0] == 1 and scene.array("materials")["map_ks"].tolist()[1] == 0
     assert scene.array("texture_pixels").tolist() == [0xFF000000]
     # a PNG that cannot be read fails the load, as the reference's load_png does at start-up (interface.cpp:476-477)
@@ -268,7 +330,7 @@ def test_textured_film_matches_oracle(tmp_path, size, spp, depth):
     assert abs(got.mean() - want.mean()) / want.mean() < 2e-3
     assert abs(stats["primary_rays"] - st.primary_rays) <= 0.001 * st.primary_rays + 4
     # and the texture matters: the same scene without its images renders something else
-    flat = R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "wall.jpg"))
+    flat = R.Scene.load_obj(write_scene(tmp_path, "floor.tga", "wall.tga"))
     r = R.Renderer(flat, 0, W, H, spp, depth)
     for it in range(2):
         r.render(cam, it)
