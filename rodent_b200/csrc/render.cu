@@ -138,23 +138,25 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
 // The same two kernels on the scene's BVH2 / Tri1 -- the layout and traversal of the reference's GPU renderer
 // (gpu_traverse_primary / gpu_traverse_secondary over make_gpu_bvh2_tri1, mapping_gpu.impala:18-80,505-509) -- same stream
 // contract as above.
-constexpr int kRBvh2Stack = 32;
-template <bool SHADOW>
+// STACK: levels of the id stack kept in shared memory (deeper ones go to a thread-local array).  The per-material counts
+// live in dynamic shared memory, (num_geoms + 1) ints for the closest-hit form: what a CTA does not take as shared memory
+// the SM keeps as L1, which serves two thirds of this kernel's record reads.
+template <bool SHADOW, int STACK>
 __global__ void __launch_bounds__(kRBlock, 8)
 traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
                      float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
                      const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
                      int* __restrict__ work_counter, int refill_min, int streak_min) {
-    __shared__ int smem_stack[kRBvh2Stack][kRBlock];
-    __shared__ int hist[SHADOW ? 1 : kMaxBins];
+    __shared__ int smem_stack[STACK][kRBlock];
+    extern __shared__ int hist[];
     const int num_rays = count_ptr ? min(*count_ptr, count_max) : count_max;
     if (!SHADOW) {
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock) hist[b] = 0;
         __syncthreads();
     }
     int* const hist_bins = hist;
-    traverse_bvh2_scheduled<SHADOW, kRBvh2Stack, kRBlock>(
+    traverse_bvh2_scheduled<SHADOW, STACK, kRBlock>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, streak_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
@@ -362,6 +364,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
 }
 
 static int g_render_refill_min = 20, g_render_streak_min = 8;   // BVH2 stream kernels: refill threshold, step-streak threshold (swept: profiles/r01_experiments.md)
+static int g_render_bvh2_stack = 16;   // BVH2 stream kernels: stack levels in shared memory (8, 16, 24, 32; measured 518 / 518 / 518 / 513 Msamples/s)
 static int g_render_wide = 0;          // 256-bit record loads in the BVH8 stream kernels (rodent_b200_tune "render_wide")
 static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
@@ -428,8 +431,8 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
         d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
     }
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false>, kRBlock, 0));
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true>, kRBlock, 0));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, 32>, kRBlock, (sc.materials.size() + 1) * sizeof(int)));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, 32>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
     // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
@@ -532,8 +535,10 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
         RB_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * sizeof(int), s));
         if (r.scene.nodes2) {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
-            traverse_stream_bvh2<false><<<grid_p, kRBlock, 0, s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                                   r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min);
+            auto kernel = g_render_bvh2_stack <= 8 ? traverse_stream_bvh2<false, 8> : g_render_bvh2_stack <= 16 ? traverse_stream_bvh2<false, 16> :
+                          g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<false, 24> : traverse_stream_bvh2<false, 32>;
+            kernel<<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
+                                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min);
         } else {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
             auto kernel = g_render_wide ? traverse_stream<false, true> : traverse_stream<false, false>;
@@ -550,9 +555,11 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
         RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
         if (r.scene.nodes2 && g_render_shadow_bvh2) {
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
-            traverse_stream_bvh2<true><<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                                                   nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                                   counters + kWorkShadow, g_render_refill_min, g_render_streak_min);
+            auto kernel = g_render_bvh2_stack <= 8 ? traverse_stream_bvh2<true, 8> : g_render_bvh2_stack <= 16 ? traverse_stream_bvh2<true, 16> :
+                          g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<true, 24> : traverse_stream_bvh2<true, 32>;
+            kernel<<<grid_s, kRBlock, sizeof(int), s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
+                                                         nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+                                                         counters + kWorkShadow, g_render_refill_min, g_render_streak_min);
         } else {
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
             auto kernel = g_render_wide ? traverse_stream<true, true> : traverse_stream<true, false>;
@@ -628,6 +635,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value;
     if (!std::strcmp(key, "render_wide")) g_render_wide = value;
     if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = value;
+    if (!std::strcmp(key, "render_bvh2_stack")) g_render_bvh2_stack = value;
     if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {

@@ -6,9 +6,9 @@ from rodent_b200 import lib, render as R, workloads
 scene = workloads.load_scene("sponza")
 W, H, spp, depth = 1920, 1080, 16, 8
 cam = workloads.camera("sponza", W, H)
-for refill in (16, 20, 24):
-    for streak in (8, 12, 16, 33):
-        lib.tune("render_refill_min", refill); lib.tune("render_streak_min", streak)
+for refill in (20,):
+    for streak in (32, 24, 16, 8):          # here: stack levels in shared memory
+        lib.tune("render_bvh2_stack", streak)
         r = R.Renderer(scene, 0, W, H, spp, depth)
         ms = [r.render(cam, it, present=False) for it in range(4)]
         r.free()
