@@ -35,6 +35,7 @@ struct Tuning {
                              // 4 = four lanes per ray (traverse_quad.cuh)
     int refill_min = 24;     // (mapping 2) refill idle lanes once this many wait
     int node_streak_min = 8;  // (mapping 2) consecutive node steps without re-voting while this many lanes want one (33: off)
+    int vote_smem_depth = 24; // (mapping 2, 5 blocks, wide) stack levels in shared memory: 24, 16 or 12
     int wide_loads = 1;      // (mapping 2, 5 blocks) 256-bit record loads when the arrays are 32-byte aligned
     int bvh2_streak_min = 4; // BVH2 / Tri1 kernel: consecutive steps of one kind while this many lanes want one (measured 4 > 8 > 16)
     int bvh2_min_blocks = 8; // BVH2 / Tri1 kernel: __launch_bounds__ min blocks per SM of the variant launched: 8, 10 or 12
@@ -126,13 +127,13 @@ traverse_bvh8_persistent(const Node8* __restrict__ nodes, const Tri4* __restrict
 // Vote-scheduled persistent kernel (traverse_sched.cuh): the default.
 constexpr int kVoteSmemDepth = 24;
 // WIDE: 256-bit record loads (needs 32-byte aligned nodes / tris: the launcher checks).
-template <bool ANY, int MIN_BLOCKS, bool WIDE = false>
+template <bool ANY, int MIN_BLOCKS, bool WIDE = false, int DEPTH = kVoteSmemDepth>
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS)
 traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                    const Ray1* __restrict__ rays, Hit1* __restrict__ hits, int num_rays,
                    int* __restrict__ work_counter, int refill_min, int node_streak_min) {
-    __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
-    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 8, WIDE>(
+    __shared__ StackEntry smem_stack[DEPTH][kBlock];
+    traverse_vote_scheduled<ANY, false, DEPTH, kBlock, 8, WIDE>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [rays](int i, float4& r0, float4& r1) {
             const float4* rp = reinterpret_cast<const float4*>(rays + i);
@@ -383,7 +384,9 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
         const int grid = std::min(needed, s.sm_count * per_sm);
         if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
         const bool wide = g_tuning.wide_loads && ((reinterpret_cast<uintptr_t>(nodes) | reinterpret_cast<uintptr_t>(tris)) & 31) == 0;
-        if (v == 1 && wide) traverse_bvh8_vote<ANY, 5, true><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 1 && wide && g_tuning.vote_smem_depth >= 24) traverse_bvh8_vote<ANY, 5, true><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 1 && wide && g_tuning.vote_smem_depth < 24 && g_tuning.vote_smem_depth >= 16) traverse_bvh8_vote<ANY, 5, true, 16><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        if (v == 1 && wide && g_tuning.vote_smem_depth < 16) traverse_bvh8_vote<ANY, 5, true, 12><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
         if (v == 1 && !wide) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
         if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
     } else if (g_tuning.mapping == 4) {
@@ -698,6 +701,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = value;
     else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value;
+    else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = value;
     else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = value;
     else if (!std::strcmp(key, "render_lanes") || !std::strcmp(key, "render_bvh2") || !std::strcmp(key, "render_shadow_bvh2") || !std::strcmp(key, "render_wide") ||
              !std::strcmp(key, "render_refill_min") || !std::strcmp(key, "render_streak_min") || !std::strcmp(key, "render_bvh2_stack")) rodent_b200_render_tune(key, value);

@@ -11,12 +11,12 @@ for name, (tmin, tmax) in testdata.RAY_SETS.items():
     rays = formats.load_rays(testdata.rays(name), tmin, tmax)
     want = oracle.traverse(nodes, tris, rays)
     d_rays = traversal.DeviceArray.from_host(0, rays); d_hits = traversal.DeviceArray(0, formats.HIT1, len(rays))
-    for wide in (0, 1, 0, 1):
-        lib.tune("wide_loads", wide)
+    for wide in (24, 16, 12, 24, 16, 12):
+        lib.tune("vote_smem_depth", wide)
         out = []
         for any_hit in (False, True):
             ts = sorted(traversal.intersect(bvh, d_rays, d_hits, any_hit=any_hit) for _ in range(13))
             out.append(f"{'any' if any_hit else 'closest'} {len(rays) / ts[6] / 1e3:.0f} Mrays/s")
         traversal.intersect(bvh, d_rays, d_hits)
         ok = d_hits.to_host().tobytes() == want.tobytes()
-        print(name, "wide" if wide else "narrow", out, "bit-exact" if ok else "DIFFERENT", flush=True)
+        print(name, "smem depth", wide, out, "bit-exact" if ok else "DIFFERENT", flush=True)
