@@ -295,7 +295,8 @@ typedef struct RodentScene RodentScene;
 /* Runtime replacement of the reference's scene compiler (src/driver/converter.cpp:
  * convert_obj): OBJ/MTL parsing, material clean-up and de-duplication (:440-557),
  * triangle mesh (src/driver/obj.cpp:412-509), light extraction (:778-818), material
- * rules (:857-913) and a BVH8/Tri4 build.  Returns NULL and prints the reason on error. */
+ * rules (:857-913) and a BVH8/Tri4 build (plus the BVH2/Tri1 of the reference's GPU device for scenes of 4096 triangles and
+ * more, see rodent_b200_scene_build_bvh2).  Returns NULL and prints the reason on error. */
 RodentScene* rodent_b200_scene_load_obj(const char* obj_file);
 /* A scene whose geometry is an existing BVH8/Tri4 (e.g. the Sponza block of
  * testing/sponza.bvh, which carries no materials): triangles are recovered as

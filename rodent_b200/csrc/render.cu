@@ -33,7 +33,7 @@ extern "C" void rodent_b200_count_launches(int64_t n);   // traverse.cu: the lib
 
 namespace rb200 {
 
-constexpr int kCapacity = 1 << 20;           // mapping_gpu.impala:319
+static int kCapacity = 1 << 20;              // rays per stream: mapping_gpu.impala:319 (rodent_b200_tune "render_capacity", before a renderer is created)
 constexpr int kRBlock = 128;
 constexpr int kRSmemStack = 24;
 constexpr int kRefillMin = 16;                // idle lanes that trigger a refill of the warp (traverse_sched.cuh)
@@ -636,6 +636,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_wide")) g_render_wide = value;
     if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = value;
     if (!std::strcmp(key, "render_bvh2_stack")) g_render_bvh2_stack = value;
+    if (!std::strcmp(key, "render_capacity") && value >= 1024) kCapacity = value;
     if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {

@@ -130,3 +130,28 @@ def test_scene_bvh2_built_and_adopted():
     bad = formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
     with pytest.raises(RuntimeError):
         scene.set_bvh2(*bad)                                   # Sponza's prim ids do not exist in the Cornell box
+
+
+def test_large_obj_scenes_get_a_bvh2(tmp_path):
+    """rodent_b200_scene_load_obj builds the BVH2 / Tri1 as well from 4096 triangles on (the Cornell box stays without)."""
+    n = 48                                                     # a wavy (n x n) grid: 2 n^2 = 4608 triangles
+    lines = ["mtllib g.mtl", "usemtl m"]
+    for j in range(n + 1):
+        for i in range(n + 1):
+            lines.append(f"v {i / n} {0.05 * np.sin(i * 0.7) * np.cos(j * 0.5):.6f} {j / n}")
+    for j in range(n):
+        for i in range(n):
+            a = j * (n + 1) + i + 1
+            lines.append(f"f {a} {a + 1} {a + n + 2} {a + n + 1}")
+    (tmp_path / "g.obj").write_text("\n".join(lines) + "\n")
+    (tmp_path / "g.mtl").write_text("newmtl m\nKd 0.5 0.5 0.5\nillum 2\n")
+    scene = R.Scene.load_obj(tmp_path / "g.obj")
+    assert scene.view.num_tris == 2 * n * n and scene.view.num_tri1 == 2 * n * n and scene.view.num_nodes2 > 0
+    n2, t1 = scene.array("nodes2").copy(), scene.array("tris1").copy()
+    rng = np.random.default_rng(4)
+    od = np.concatenate([rng.uniform([0, 0.3, 0], [1, 1, 1], (20000, 3)), rng.normal(size=(20000, 3)) * [1, 0.3, 1] - [0, 1, 0]], axis=1).astype(np.float32)
+    rays = formats.make_rays(od, 0.0, 100.0)
+    a = oracle.traverse_bvh2(n2, t1, rays)
+    b = oracle.traverse(scene.array("nodes").copy(), scene.array("tris").copy(), rays)
+    assert ((a["tri_id"] >= 0) == (b["tri_id"] >= 0)).all() and (a["tri_id"] >= 0).mean() > 0.2
+    assert np.allclose(a["t"], b["t"], rtol=1e-4)
