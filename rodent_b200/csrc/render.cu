@@ -431,8 +431,8 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
         d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
     }
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, 32>, kRBlock, (sc.materials.size() + 1) * sizeof(int)));
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, 32>, kRBlock, 0));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, 16>, kRBlock, (sc.materials.size() + 1) * sizeof(int)));
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, 16>, kRBlock, sizeof(int)));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
     RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
     // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
