@@ -164,3 +164,25 @@ def test_obj_to_bvh_to_bench_on_gpu(tools, tmp_path):
     for mode in (["-gpu", "cuda"], ["-gpu", "cuda", "--bvh-width", "4"], ["-s"], []):
         r = run(tools / "bench_traversal", "-bvh", bvh, "-ray", rays, "--tmax", "1", *mode)
         assert r.returncode == 0 and f"{want} intersection(s)" in r.stdout, (mode, r.stdout, r.stderr)      # 50000 rays = 6250 whole packets
+
+
+def test_shading_tools_argument_errors(tools):
+    for tool in ("bench_interface", "bench_shading"):
+        r = run(tools / tool, "--bogus")
+        assert r.returncode == 1 and "Invalid argument '--bogus'" in r.stderr
+
+
+@pytest.mark.gpu
+def test_bench_interface_and_bench_shading_tools(tools):
+    """tools/bench_interface and tools/bench_shading of the reference: no arguments, one line "<x> Mrays/s"
+    (bench_interface.cpp:188, bench_shading.cpp:227).  The reference's workload has constant images, so every hit's colour is
+    kd / pi = (0.1, 0.2, 0.3) / pi."""
+    r = run(tools / "bench_interface", "--iters", "20", "--check")
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert re.fullmatch(r"[\d.e+]+ Mrays/s", lines[0]) and float(lines[0].split()[0]) > 100
+    for line in lines[1:5]:
+        assert np.allclose([float(x) for x in line.split()], np.array([0.1, 0.2, 0.3]) / np.pi, rtol=1e-5)
+    r = run(tools / "bench_shading", "--bench", "5", "--iters", "50")
+    assert r.returncode == 0, r.stderr
+    assert re.fullmatch(r"[\d.e+]+ Mrays/s", r.stdout.strip()) and float(r.stdout.split()[0]) > 1
