@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <new>
 
 #include <zlib.h>
 
@@ -54,7 +55,12 @@ bool unfilter(uint8_t* data, size_t rows, size_t stride, size_t bpp) {
 
 }  // namespace
 
+static bool decode_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 bool load_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why) {
+    try { return decode_png(path, width, height, pixels, why); }
+    catch (const std::bad_alloc&) { why = "out of memory"; return false; }
+}
+static bool decode_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why) {
     std::ifstream in(path, std::ios::binary);
     if (!in) { why = "cannot open file"; return false; }
     const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());

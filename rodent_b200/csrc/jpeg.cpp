@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <iterator>
+#include <new>
 
 namespace rb200 {
 namespace {
@@ -119,7 +120,12 @@ uint16_t be16(const uint8_t* p) { return uint16_t(p[0] << 8 | p[1]); }
 
 }  // namespace
 
+static bool decode_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why) {
+    try { return decode_jpg(path, width, height, pixels, why); }
+    catch (const std::bad_alloc&) { why = "out of memory"; return false; }
+}
+static bool decode_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why) {
     std::ifstream in(path, std::ios::binary);
     if (!in) { why = "cannot open file"; return false; }
     const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
@@ -167,6 +173,7 @@ bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint
             h = be16(&s[1]); w = be16(&s[3]);
             const int nc = s[5];
             if ((nc != 1 && nc != 3) || n < size_t(6 + 3 * nc) || w == 0 || h == 0) { why = "unsupported number of components"; return false; }
+            if (uint64_t(w) * uint64_t(h) > (uint64_t(1) << 28)) { why = "unreasonable image size"; return false; }
             comps.resize(nc);
             for (int c = 0; c < nc; c++) {
                 comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c] & 3;
