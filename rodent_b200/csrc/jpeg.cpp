@@ -73,12 +73,12 @@ int extend(int v, int n) { return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v; }
 const uint8_t kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                              35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-inline uint8_t range_limit(int x) {                      // libjpeg's IDCT range-limit table: clamp(x + 128) with 10-bit wrap-around
+inline uint8_t range_limit(int x) {                      // libjpeg's IDCT range-limit table: clamp(x + 128), indexed with x & RANGE_MASK (10 bits)
     x = ((x + 512) & 1023) - 512;
     x += 128;
     return uint8_t(x < 0 ? 0 : x > 255 ? 255 : x);
 }
-inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+inline int64_t descale(int64_t x, int n) { return (x + (int64_t(1) << (n - 1))) >> n; }
 
 // jpeg_idct_islow (jidctint.c): 13-bit constants, 2 extra bits kept between the passes.
 void idct_islow(const int* in /* dequantised, natural order */, uint8_t* out, int stride) {
@@ -86,16 +86,18 @@ void idct_islow(const int* in /* dequantised, natural order */, uint8_t* out, in
     constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
                   F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
     int ws[64];
-    auto pass = [&](int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, int* o) {
-        int z2 = d2, z3 = d6;
-        int z1 = (z2 + z3) * F_0_541;
-        int tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
+    // 64-bit intermediates, as libjpeg's JLONG (long) is on the reference's platform: corrupt coefficients cannot overflow
+    using L = int64_t;
+    auto pass = [&](L d0, L d1, L d2, L d3, L d4, L d5, L d6, L d7, L* o) {
+        L z2 = d2, z3 = d6;
+        L z1 = (z2 + z3) * F_0_541;
+        L tmp2 = z1 + z3 * (-F_1_847), tmp3 = z1 + z2 * F_0_765;
         z2 = d0; z3 = d4;
-        int tmp0 = (z2 + z3) << C, tmp1 = (z2 - z3) << C;
-        const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        L tmp0 = (z2 + z3) * (1 << C), tmp1 = (z2 - z3) * (1 << C);
+        const L tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
         tmp0 = d7; tmp1 = d5; tmp2 = d3; tmp3 = d1;
-        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; int z4 = tmp1 + tmp3;
-        const int z5 = (z3 + z4) * F_1_175;
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; L z4 = tmp1 + tmp3;
+        const L z5 = (z3 + z4) * F_1_175;
         tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
         z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
         z3 += z5; z4 += z5;
@@ -104,15 +106,15 @@ void idct_islow(const int* in /* dequantised, natural order */, uint8_t* out, in
         o[2] = tmp12 + tmp1; o[5] = tmp12 - tmp1; o[3] = tmp13 + tmp0; o[4] = tmp13 - tmp0;
     };
     for (int c = 0; c < 8; c++) {                        // pass 1: columns
-        int o[8];
+        L o[8];
         pass(in[c], in[8 + c], in[16 + c], in[24 + c], in[32 + c], in[40 + c], in[48 + c], in[56 + c], o);
-        for (int r = 0; r < 8; r++) ws[8 * r + c] = descale(o[r], C - P);
+        for (int r = 0; r < 8; r++) ws[8 * r + c] = int(descale(o[r], C - P));
     }
     for (int r = 0; r < 8; r++) {                        // pass 2: rows
-        int o[8];
+        L o[8];
         const int* w = ws + 8 * r;
         pass(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], o);
-        for (int c = 0; c < 8; c++) out[r * stride + c] = range_limit(descale(o[c], C + P + 3));
+        for (int c = 0; c < 8; c++) out[r * stride + c] = range_limit(int(descale(o[c], C + P + 3) & 0x3FF));
     }
 }
 
@@ -238,8 +240,8 @@ static bool decode_jpg(const std::string& path, int& width, int& height, std::ve
                         bool ok = true;
                         const int t = decode_symbol(br, dc[c.td], ok);
                         if (!ok || t > 11) { why = "corrupt entropy-coded data"; return false; }
-                        c.dc_pred += t ? extend(br.bits(t), t) : 0;
-                        coef[0] = c.dc_pred * qt[c.tq][0];
+                        c.dc_pred = int(uint32_t(c.dc_pred) + uint32_t(t ? extend(br.bits(t), t) : 0));
+                        coef[0] = int16_t(c.dc_pred) * qt[c.tq][0];                      // a coefficient is a JCOEF (short) in libjpeg
                         for (int k = 1; k < 64;) {
                             const int rs = decode_symbol(br, ac[c.ta], ok);
                             if (!ok) { why = "corrupt entropy-coded data"; return false; }
