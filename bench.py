@@ -440,7 +440,7 @@ def main():
         "wall_ms_per_step_incl_l2_flush": round(wall_ms / args.steps, 3),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "traverse_bvh8_vote<false, 5, true>",
+                     "kernel": "traverse_bvh8_vote<false, 5, true, 24>",
                      "launches_per_step": len(names), "achieved_one_launch_at_a_time": round(achieved_serial, 1),
                      "note": "the step's two launches of this kernel overlap on two streams: achieved = algorithmic bytes of "
                              "both / the step's device time (first start to last end); one launch at a time (per_set, what "
