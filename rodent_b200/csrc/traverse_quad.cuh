@@ -74,7 +74,8 @@ struct QuadTraversal {
     unsigned qmask; int s;
 
     __device__ __forceinline__ Entry& slot(int i) { return sp[i * kQuadsPerWarp]; }
-    __device__ __forceinline__ void pop() { top = slot(ptr); --ptr; }
+    // (the quad's lanes all read the slot; one of them may overwrite it with a push right after: order the two)
+    __device__ __forceinline__ void pop() { top = slot(ptr); __syncwarp(qmask); --ptr; }
 
     __device__ __forceinline__ void begin(float4 r0, float4 r1) {
         ox = r0.x; oy = r0.y; oz = r0.z; tmin = r0.w;
