@@ -42,6 +42,32 @@ def overlapped(order, priorities=(0, 0)):
     return run
 
 
+class Slice:
+    """A contiguous part of a device array, for launching a set in pieces."""
+    def __init__(self, arr, first, count):
+        self.ptr, self.count = arr.ptr + first * arr.dtype.itemsize, count
+
+
+def pieces(plan):
+    """plan: [(set name, first fraction, last fraction), ...], one stream per entry, launched in this order."""
+    streams = [torch.cuda.Stream() for _ in plan]
+    ev0, ev = torch.cuda.Event(enable_timing=True), [torch.cuda.Event(enable_timing=True) for _ in plan]
+
+    def run():
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
+        for k, (name, a, b) in enumerate(plan):
+            n = d_rays[name].count
+            first, last = int(n * a), int(n * b)
+            traversal.intersect_async(bvh, Slice(d_rays[name], first, last - first), Slice(d_hits[name], first, last - first),
+                                      streams[k].cuda_stream, counters.data_ptr() + 32 * k)
+            ev[k].record(streams[k])
+        torch.cuda.synchronize()
+        return max(ev0.elapsed_time(e) for e in ev)
+    return run
+
+
 def measure(label, fn, reps=12):
     times = []
     for i in range(reps + 3):
@@ -56,8 +82,11 @@ def measure(label, fn, reps=12):
 measure("one after the other (sync entry points)", serial)
 measure("two streams, random first", overlapped(("random", "primary")))
 measure("two streams, primary first", overlapped(("primary", "random")))
-measure("two streams, random first + high priority", overlapped(("random", "primary"), (-1, 0)))
-measure("two streams, random first, primary high prio", overlapped(("random", "primary"), (0, -1)))
+measure("random, primary halves", pieces([("random", 0, 1), ("primary", 0, 0.5), ("primary", 0.5, 1)]))
+measure("random halves, primary", pieces([("random", 0, 0.5), ("random", 0.5, 1), ("primary", 0, 1)]))
+measure("random, primary 3/4 + 1/4", pieces([("random", 0, 1), ("primary", 0, 0.75), ("primary", 0.75, 1)]))
+measure("random 1/2, primary, random 1/2", pieces([("random", 0, 0.5), ("primary", 0, 1), ("random", 0.5, 1)]))
+measure("random, primary 1/4 x 4", pieces([("random", 0, 1)] + [("primary", k / 4, (k + 1) / 4) for k in range(4)]))
 want = {n: d_hits[n].to_host().copy() for n in rays}
 
 # host-pointer entry points
@@ -86,7 +115,7 @@ def host_threads(order):
     return run
 
 
-for chunks in (4, 3, 2, 6):
+for chunks in (3,):
     lib.tune("host_chunks", chunks)
     measure(f"host pointers, one thread, {chunks} pieces", host_serial)
     measure(f"host pointers, two threads (random first), {chunks}", host_threads(("random", "primary")))
