@@ -313,7 +313,7 @@ int32_t rodent_b200_scene_add_texture(RodentScene* scene, const uint32_t* rgba, 
  * flipped, gamma 2.2) and appends it; returns the map_kd / map_ks value or 0 on error (reason printed). */
 int32_t rodent_b200_scene_add_png(RodentScene* scene, const char* png_file);
 /* The same for a JPEG file, as load_jpg leaves it (image.cpp:186-238: libjpeg defaults, (r, g, b, 0) or (grey, 0, 0, 0),
- * rows flipped, gamma 2.2).  Baseline / extended sequential Huffman files; progressive ones are reported as unsupported. */
+ * rows flipped, gamma 2.2).  Sequential and progressive Huffman files; arithmetic-coded ones are reported as unsupported. */
 int32_t rodent_b200_scene_add_jpg(RodentScene* scene, const char* jpg_file);
 void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out);
 void rodent_b200_scene_free(RodentScene* scene);

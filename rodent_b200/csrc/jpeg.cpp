@@ -3,11 +3,12 @@
 // The reference decodes with libjpeg at its defaults and copies `output_components` bytes per pixel into a zero-filled
 // RGBA image, bottom row first, then applies gamma 2.2 (:10-18): colour images come out as (r, g, b, 0), grey ones as
 // (grey, 0, 0, 0).  libjpeg is not part of this image, so the decoder is written here from the JPEG specification
-// (ITU-T T.81: baseline / extended sequential Huffman, 8 bit, restart intervals) with libjpeg's default choices for the
+// (ITU-T T.81: baseline / extended sequential and progressive Huffman, 8 bit, interleaved or one scan per component,
+// restart intervals) with libjpeg's default choices for the
 // parts the standard leaves open, so that pixels come out the same: the slow-but-accurate integer IDCT (jidctint.c),
 // "fancy" triangle-filter chroma upsampling for 2x1 and 2x2 subsampling (jdsample.c) and the fixed-point YCbCr -> RGB
 // tables (jdcolor.c).  tests/test_textures.py checks it pixel for pixel against PIL, which wraps libjpeg-turbo.
-// Progressive and arithmetic-coded files are reported as unsupported.
+// Arithmetic-coded, lossless and 12-bit files are reported as unsupported.
 #include "scene.h"
 
 #include <cmath>
@@ -35,7 +36,7 @@ struct Huffman {
     }
 };
 
-struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0; int blocks_w = 0, blocks_h = 0; std::vector<uint8_t> plane; int stride = 0, rows = 0; };
+struct Component { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, dc_pred = 0; int blocks_w = 0, blocks_h = 0; std::vector<int16_t> coef; std::vector<uint8_t> plane; int stride = 0, rows = 0; };
 
 struct BitReader {
     const uint8_t* p; const uint8_t* end;
@@ -136,21 +137,22 @@ static bool decode_jpg(const std::string& path, int& width, int& height, std::ve
     uint16_t qt[4][64] = {};
     Huffman dc[4], ac[4];
     std::vector<Component> comps;
-    int w = 0, h = 0, restart_interval = 0, hmax = 1, vmax = 1;
-    bool have_frame = false, adobe_rgb = false;
-    size_t pos = 2, scan_start = 0;
+    int w = 0, h = 0, restart_interval = 0, hmax = 1, vmax = 1, mcus_x = 0, mcus_y = 0;
+    bool have_frame = false, progressive = false, adobe_rgb = false, saw_scan = false;
+    size_t pos = 2;
     while (pos + 4 <= file.size()) {
-        if (file[pos] != 0xFF) { why = "marker expected"; return false; }
+        if (file[pos] != 0xFF) { pos++; continue; }                          // (garbage between segments is skipped, as libjpeg does)
         const int m = file[pos + 1];
         if (m == 0xFF) { pos++; continue; }                                  // fill bytes
         pos += 2;
-        if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0x00 || m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
         if (m == 0xD9) break;
         if (pos + 2 > file.size()) { why = "truncated segment"; return false; }
         const size_t len = be16(&file[pos]);
         if (len < 2 || pos + len > file.size()) { why = "truncated segment"; return false; }
         const uint8_t* s = &file[pos + 2];
         const size_t n = len - 2;
+        pos += len;
         if (m == 0xDB) {                                                     // DQT
             for (size_t i = 0; i < n;) {
                 const int pq = s[i] >> 4, tq = s[i] & 15;
@@ -170,8 +172,10 @@ static bool decode_jpg(const std::string& path, int& width, int& height, std::ve
                 t.build(); t.present = true;
                 i += 17 + total;
             }
-        } else if (m == 0xC0 || m == 0xC1) {                                 // SOF0 / SOF1: sequential Huffman
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {                    // SOF0 / SOF1: sequential, SOF2: progressive (Huffman)
+            if (have_frame) { why = "more than one frame"; return false; }
             if (n < 6 || s[0] != 8) { why = "only 8-bit samples are supported"; return false; }
+            progressive = m == 0xC2;
             h = be16(&s[1]); w = be16(&s[3]);
             const int nc = s[5];
             if ((nc != 1 && nc != 3) || n < size_t(6 + 3 * nc) || w == 0 || h == 0) { why = "unsupported number of components"; return false; }
@@ -179,84 +183,152 @@ static bool decode_jpg(const std::string& path, int& width, int& height, std::ve
             comps.resize(nc);
             for (int c = 0; c < nc; c++) {
                 comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c] & 3;
-                hmax = std::max(hmax, comps[c].h); vmax = std::max(vmax, comps[c].v);
+            }
+            if (nc == 3) {
+                const bool ok = comps[1].h == 1 && comps[1].v == 1 && comps[2].h == 1 && comps[2].v == 1 &&
+                                (comps[0].h == 1 || comps[0].h == 2) && (comps[0].v == 1 || comps[0].v == 2) && !(comps[0].h == 1 && comps[0].v == 2);
+                if (!ok) { why = "unsupported chroma subsampling"; return false; }
+            } else comps[0].h = comps[0].v = 1;                              // a single component is never interleaved
+            for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
+            mcus_x = (w + 8 * hmax - 1) / (8 * hmax); mcus_y = (h + 8 * vmax - 1) / (8 * vmax);
+            for (auto& c : comps) {                                          // planes and coefficients padded to whole MCUs
+                c.blocks_w = mcus_x * c.h; c.blocks_h = mcus_y * c.v;
+                c.stride = c.blocks_w * 8; c.rows = c.blocks_h * 8;
+                c.coef.assign(size_t(c.blocks_w) * c.blocks_h * 64, 0);
             }
             have_frame = true;
-        } else if (m == 0xC2 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
-            why = m == 0xC2 ? "progressive JPEG is not supported" : "this JPEG coding process is not supported";
+        } else if (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC) {
+            why = "this JPEG coding process is not supported";
             return false;
         } else if (m == 0xDD) {
             if (n >= 2) restart_interval = be16(s);
         } else if (m == 0xEE) {                                              // Adobe: transform 0 with three components = RGB
             if (n >= 12 && !std::memcmp(s, "Adobe", 5)) adobe_rgb = s[11] == 0;
-        } else if (m == 0xDA) {                                              // SOS
+        } else if (m == 0xDA) {                                              // SOS: one scan
             if (!have_frame) { why = "SOS before SOF"; return false; }
             const int ns = s[0];
-            if (ns != int(comps.size()) || n < size_t(1 + 2 * ns + 3)) { why = "non-interleaved scans are not supported"; return false; }
+            if (ns < 1 || ns > int(comps.size()) || n < size_t(1 + 2 * ns + 3)) { why = "bad SOS"; return false; }
+            Component* sc[3];
             for (int k = 0; k < ns; k++) {
-                Component* c = nullptr;
-                for (auto& cc : comps) if (cc.id == s[1 + 2 * k]) c = &cc;
-                if (!c) { why = "bad SOS"; return false; }
-                c->td = s[2 + 2 * k] >> 4; c->ta = s[2 + 2 * k] & 15;
-                if (c->td > 3 || c->ta > 3 || !dc[c->td].present || !ac[c->ta].present) { why = "missing Huffman table"; return false; }
+                sc[k] = nullptr;
+                for (auto& cc : comps) if (cc.id == s[1 + 2 * k]) sc[k] = &cc;
+                if (!sc[k]) { why = "bad SOS"; return false; }
+                sc[k]->td = (s[2 + 2 * k] >> 4) & 3; sc[k]->ta = s[2 + 2 * k] & 3;
             }
-            scan_start = pos + len;
-            break;
-        }
-        pos += len;
-    }
-    if (!scan_start) { why = "no scan found"; return false; }
-    if (comps.size() == 3) {
-        const bool ok = comps[1].h == 1 && comps[1].v == 1 && comps[2].h == 1 && comps[2].v == 1 &&
-                        (comps[0].h == 1 || comps[0].h == 2) && (comps[0].v == 1 || comps[0].v == 2) && !(comps[0].h == 1 && comps[0].v == 2);
-        if (!ok) { why = "unsupported chroma subsampling"; return false; }
-    } else { comps[0].h = comps[0].v = 1; hmax = vmax = 1; }                 // a single component is never interleaved
+            const int Ss = s[1 + 2 * ns], Se = s[2 + 2 * ns], Ah = s[3 + 2 * ns] >> 4, Al = s[3 + 2 * ns] & 15;
+            if (!progressive && (Ss != 0 || Se != 63 || Ah != 0 || Al != 0)) { why = "bad SOS"; return false; }
+            if (progressive && (Ss > Se || Se > 63 || Al > 13 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1))) { why = "bad progressive scan"; return false; }
+            const bool need_dc = Ss == 0 && Ah == 0, need_ac = Se > 0;
+            for (int k = 0; k < ns; k++)
+                if ((need_dc && !dc[sc[k]->td].present) || (need_ac && !ac[sc[k]->ta].present)) { why = "missing Huffman table"; return false; }
 
-    // ---- entropy decoding + IDCT into component planes (padded to whole MCUs) ----
-    const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
-    const int mcus_x = (w + mcu_w - 1) / mcu_w, mcus_y = (h + mcu_h - 1) / mcu_h;
-    for (auto& c : comps) {
-        c.blocks_w = mcus_x * c.h; c.blocks_h = mcus_y * c.v;
-        c.stride = c.blocks_w * 8; c.rows = c.blocks_h * 8;
-        c.plane.assign(size_t(c.stride) * c.rows, 0);
-    }
-    BitReader br{&file[scan_start], file.data() + file.size()};
-    int restarts_left = restart_interval;
-    for (int my = 0; my < mcus_y; my++)
-        for (int mx = 0; mx < mcus_x; mx++) {
-            if (restart_interval && restarts_left == 0) {
-                // skip to the RSTn marker, reset predictors
-                const uint8_t* p = br.p;
-                while (p + 1 < br.end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) p++;
-                if (p + 1 >= br.end) { why = "missing restart marker"; return false; }
-                br.p = p + 2; br.reset();
-                for (auto& c : comps) c.dc_pred = 0;
-                restarts_left = restart_interval;
-            }
-            for (auto& c : comps)
-                for (int by = 0; by < c.v; by++)
-                    for (int bx = 0; bx < c.h; bx++) {
-                        int coef[64] = {0};
-                        bool ok = true;
-                        const int t = decode_symbol(br, dc[c.td], ok);
-                        if (!ok || t > 11) { why = "corrupt entropy-coded data"; return false; }
-                        c.dc_pred = int(uint32_t(c.dc_pred) + uint32_t(t ? extend(br.bits(t), t) : 0));
-                        coef[0] = int16_t(c.dc_pred) * qt[c.tq][0];                      // a coefficient is a JCOEF (short) in libjpeg
-                        for (int k = 1; k < 64;) {
-                            const int rs = decode_symbol(br, ac[c.ta], ok);
-                            if (!ok) { why = "corrupt entropy-coded data"; return false; }
-                            const int r = rs >> 4, sz = rs & 15;
-                            if (sz == 0) { if (r == 15) { k += 16; continue; } break; }
-                            k += r;
-                            if (k > 63) { why = "corrupt entropy-coded data"; return false; }
-                            coef[kZigzag[k]] = extend(br.bits(sz), sz) * qt[c.tq][kZigzag[k]];
-                            k++;
-                        }
-                        uint8_t* dst = c.plane.data() + size_t((my * c.v + by) * 8) * c.stride + (mx * c.h + bx) * 8;
-                        idct_islow(coef, dst, c.stride);
+            // blocks of this scan: interleaved MCUs, or (one component) its own blocks row by row, T.81 A.2.2 / A.2.3
+            const int scan_w = ns > 1 ? mcus_x : ((w * sc[0]->h + hmax - 1) / hmax + 7) / 8;
+            const int scan_h = ns > 1 ? mcus_y : ((h * sc[0]->v + vmax - 1) / vmax + 7) / 8;
+            BitReader br{&file[pos], file.data() + file.size()};
+            int restarts_left = restart_interval, eobrun = 0;
+            for (auto& c : comps) c.dc_pred = 0;
+            for (int my = 0; my < scan_h; my++)
+                for (int mx = 0; mx < scan_w; mx++) {
+                    if (restart_interval && restarts_left == 0) {            // skip to the RSTn marker, reset the predictors
+                        const uint8_t* q = br.p;
+                        while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+                        if (q + 1 >= br.end) { why = "missing restart marker"; return false; }
+                        br.p = q + 2; br.reset();
+                        for (auto& c : comps) c.dc_pred = 0;
+                        eobrun = 0;
+                        restarts_left = restart_interval;
                     }
-            restarts_left--;
+                    for (int k = 0; k < ns; k++) {
+                        Component& c = *sc[k];
+                        const int nbx = ns > 1 ? c.h : 1, nby = ns > 1 ? c.v : 1;
+                        for (int by = 0; by < nby; by++)
+                            for (int bx = 0; bx < nbx; bx++) {
+                                int16_t* blk = c.coef.data() + (size_t(my * nby + by) * c.blocks_w + (mx * nbx + bx)) * 64;
+                                bool ok = true;
+                                if (!progressive) {                          // sequential: T.81 F.2.2
+                                    const int t = decode_symbol(br, dc[c.td], ok);
+                                    if (!ok || t > 11) { why = "corrupt entropy-coded data"; return false; }
+                                    c.dc_pred = int(uint32_t(c.dc_pred) + uint32_t(t ? extend(br.bits(t), t) : 0));
+                                    blk[0] = int16_t(c.dc_pred);             // a coefficient is a JCOEF (short) in libjpeg
+                                    for (int kk = 1; kk < 64;) {
+                                        const int rs = decode_symbol(br, ac[c.ta], ok);
+                                        if (!ok) { why = "corrupt entropy-coded data"; return false; }
+                                        const int r = rs >> 4, sz = rs & 15;
+                                        if (sz == 0) { if (r == 15) { kk += 16; continue; } break; }
+                                        kk += r;
+                                        if (kk > 63) { why = "corrupt entropy-coded data"; return false; }
+                                        blk[kZigzag[kk]] = int16_t(extend(br.bits(sz), sz));
+                                        kk++;
+                                    }
+                                } else if (Ss == 0) {                        // progressive DC: G.1.2.1
+                                    if (Ah == 0) {
+                                        const int t = decode_symbol(br, dc[c.td], ok);
+                                        if (!ok || t > 11) { why = "corrupt entropy-coded data"; return false; }
+                                        c.dc_pred = int(uint32_t(c.dc_pred) + uint32_t(t ? extend(br.bits(t), t) : 0));
+                                        blk[0] = int16_t(c.dc_pred * (1 << Al));
+                                    } else if (br.bit()) blk[0] = int16_t(blk[0] | (1 << Al));
+                                } else if (Ah == 0) {                        // progressive AC, first pass: G.1.2.2
+                                    if (eobrun > 0) { eobrun--; continue; }
+                                    for (int kk = Ss; kk <= Se; kk++) {
+                                        const int rs = decode_symbol(br, ac[c.ta], ok);
+                                        if (!ok) { why = "corrupt entropy-coded data"; return false; }
+                                        const int r = rs >> 4, sz = rs & 15;
+                                        if (sz) {
+                                            kk += r;
+                                            if (kk > Se) { why = "corrupt entropy-coded data"; return false; }
+                                            blk[kZigzag[kk]] = int16_t(extend(br.bits(sz), sz) * (1 << Al));
+                                        } else if (r == 15) kk += 15;
+                                        else { eobrun = (1 << r) + (r ? br.bits(r) : 0) - 1; break; }
+                                    }
+                                } else {                                     // progressive AC, refinement: G.1.2.3
+                                    const int p1 = 1 << Al, m1 = -(1 << Al);
+                                    auto refine = [&](int16_t& coef) {       // one correction bit for a coefficient that is already non-zero
+                                        if (br.bit() && (coef & p1) == 0) coef = int16_t(coef >= 0 ? coef + p1 : coef + m1);
+                                    };
+                                    int kk = Ss;
+                                    if (eobrun == 0) {
+                                        for (; kk <= Se; kk++) {
+                                            const int rs = decode_symbol(br, ac[c.ta], ok);
+                                            if (!ok) { why = "corrupt entropy-coded data"; return false; }
+                                            int r = rs >> 4, value = 0;
+                                            if (rs & 15) value = br.bit() ? p1 : m1;          // the size must be 1
+                                            else if (r != 15) { eobrun = (1 << r) + (r ? br.bits(r) : 0); break; }
+                                            for (; kk <= Se; kk++) {          // pass the non-zero history, stop at the r-th zero
+                                                int16_t& coef = blk[kZigzag[kk]];
+                                                if (coef != 0) refine(coef);
+                                                else if (--r < 0) break;
+                                            }
+                                            if (value && kk <= Se) blk[kZigzag[kk]] = int16_t(value);
+                                        }
+                                    }
+                                    if (eobrun > 0) {
+                                        for (; kk <= Se; kk++) { int16_t& coef = blk[kZigzag[kk]]; if (coef != 0) refine(coef); }
+                                        eobrun--;
+                                    }
+                                }
+                            }
+                    }
+                    restarts_left--;
+                }
+            saw_scan = true;
+            pos = size_t(br.p - file.data());                                // the reader stopped at the next marker (or the end)
         }
+    }
+    if (!saw_scan) { why = "no scan found"; return false; }
+
+    // ---- dequantisation + IDCT into the component planes ----
+    for (auto& c : comps) {
+        c.plane.assign(size_t(c.stride) * c.rows, 0);
+        for (int by = 0; by < c.blocks_h; by++)
+            for (int bx = 0; bx < c.blocks_w; bx++) {
+                const int16_t* blk = c.coef.data() + (size_t(by) * c.blocks_w + bx) * 64;
+                int coef[64];
+                for (int k = 0; k < 64; k++) coef[k] = int(blk[k]) * qt[c.tq][k];
+                idct_islow(coef, c.plane.data() + size_t(by) * 8 * c.stride + bx * 8, c.stride);
+            }
+        std::vector<int16_t>().swap(c.coef);
+    }
 
     // ---- upsampling (jdsample.c, fancy) + colour conversion (jdcolor.c) ----
     width = w; height = h;

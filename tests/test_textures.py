@@ -184,15 +184,19 @@ def jpg_expected(path):
 @pytest.mark.parametrize("h,w", [(64, 64), (37, 53), (8, 8), (1, 1), (17, 16), (100, 3), (3, 100), (33, 2), (250, 130)])
 def test_jpg_loader_matches_libjpeg(tmp_path, h, w):
     """Pixel for pixel: integer IDCT, fancy chroma upsampling (replication when the chroma plane is at most two samples
-    wide), fixed-point colour conversion; 4:4:4 / 4:2:2 / 4:2:0, custom Huffman tables, restart intervals."""
+    wide), fixed-point colour conversion; 4:4:4 / 4:2:2 / 4:2:0, custom Huffman tables, restart intervals, sequential and
+    progressive (spectral selection + successive approximation, one AC scan per component)."""
     scene = R.Scene.load_obj(write_scene(tmp_path, "none.xyz", "none.xyz"))
     for sub in (0, 1, 2):
         for k, kw in enumerate((dict(quality=50), dict(quality=95, optimize=True), dict(quality=75, restart_marker_blocks=3),
-                                dict(quality=30, restart_marker_rows=1))):
+                                dict(quality=30, restart_marker_rows=1), dict(quality=60, progressive=True),
+                                dict(quality=92, progressive=True, restart_marker_blocks=2), dict(quality=15, progressive=True))):
             path = tmp_path / f"s{sub}_{k}.jpg"
             Image.fromarray(photo(h, w, sub * 4 + k)).save(path, subsampling=sub, **kw)
-            if k >= 2:
+            if k in (2, 3, 5):
                 assert b"\xff\xdd" in path.read_bytes()                     # a DRI segment: the restart path is exercised
+            if k >= 4:
+                assert b"\xff\xc2" in path.read_bytes()                     # SOF2
             tid = scene.add_png(path)
             tex = scene.array("textures")[tid - 1]
             assert (tex["width"], tex["height"]) == (w, h)
@@ -200,28 +204,30 @@ def test_jpg_loader_matches_libjpeg(tmp_path, h, w):
             assert np.array_equal(got, jpg_expected(path)), (sub, kw)
 
 
-def test_jpg_grey_progressive_and_errors(tmp_path, capfd):
+def test_jpg_grey_and_errors(tmp_path, capfd):
     scene = R.Scene.load_obj(write_scene(tmp_path, "none.xyz", "none.xyz"))
-    Image.fromarray(photo(40, 50)[..., 0]).save(tmp_path / "grey.jpg", quality=80)
-    tid = scene.add_png(tmp_path / "grey.jpg")
-    tex = scene.array("textures")[tid - 1]
-    got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + 2000].reshape(40, 50)
-    assert np.array_equal(got, jpg_expected(tmp_path / "grey.jpg")) and (got >> 8 == 0).all()      # (grey, 0, 0, 0): image.cpp:226-227
-    Image.fromarray(photo(40, 50)).save(tmp_path / "prog.jpg", progressive=True)
-    (tmp_path / "cut.jpg").write_bytes((tmp_path / "grey.jpg").read_bytes()[:300])
+    for k, kw in enumerate((dict(quality=80), dict(quality=80, progressive=True))):
+        Image.fromarray(photo(40, 50)[..., 0]).save(tmp_path / "grey.jpg", **kw)
+        tid = scene.add_png(tmp_path / "grey.jpg")
+        tex = scene.array("textures")[tid - 1]
+        got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + 2000].reshape(40, 50)
+        assert np.array_equal(got, jpg_expected(tmp_path / "grey.jpg")) and (got >> 8 == 0).all()  # (grey, 0, 0, 0): image.cpp:226-227
+    blob = (tmp_path / "grey.jpg").read_bytes()
+    (tmp_path / "prog.jpg").write_bytes(blob.replace(b"\xff\xc2", b"\xff\xc9", 1))      # SOF9: arithmetic coding, no decoder here
+    (tmp_path / "cut.jpg").write_bytes(blob[:blob.index(b"\xff\xda")])              # no scan at all (a scan cut short decodes, as in libjpeg)
     (tmp_path / "not.jpg").write_bytes(b"GIF89a" + bytes(100))
     for name in ("prog.jpg", "cut.jpg", "not.jpg", "missing.jpg"):
         with pytest.raises(RuntimeError):
             scene.add_png(tmp_path / name)
     err = capfd.readouterr().err
-    assert "progressive JPEG is not supported" in err and err.count("cannot load JPG file") == 4
+    assert "this JPEG coding process is not supported" in err and err.count("cannot load JPG file") == 4
     # through an OBJ: a file this decoder cannot read falls back to the constant with a warning, a missing one fails the load
     Image.fromarray(photo(16, 16)).save(tmp_path / "floor.jpg", quality=90)
     scene = R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "prog.jpg"))
     mats = scene.array("materials")
     assert mats["map_kd"].tolist()[0] == 1 and mats["map_ks"].tolist()[1] == 0
     assert np.array_equal(scene.array("texture_pixels").reshape(16, 16), jpg_expected(tmp_path / "floor.jpg"))
-    assert "progressive JPEG is not supported; the material's constant colour is used instead" in capfd.readouterr().err
+    assert "this JPEG coding process is not supported; the material's constant colour is used instead" in capfd.readouterr().err
     with pytest.raises(RuntimeError):
         R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "nowhere.jpeg"))
 
