@@ -147,7 +147,7 @@ traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ t
                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
                      float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
                      const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
-                     int* __restrict__ work_counter, int refill_min, int streak_min) {
+                     int* __restrict__ work_counter, int refill_min, int streak_min, int leaf_streak_min) {
     __shared__ int smem_stack[STACK][kRBlock];
     extern __shared__ int hist[];
     const int num_rays = count_ptr ? min(*count_ptr, count_max) : count_max;
@@ -174,7 +174,7 @@ traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ t
                 geom_out[i] = g;
                 atomicAdd(hist_bins + g, 1);
             }
-        });
+        }, leaf_streak_min);
     if (!SHADOW) {
         __syncthreads();
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
@@ -363,6 +363,7 @@ static void alloc_stream(Renderer& r, PrimaryStream& s) {
     s.rnd_depth = r.alloc<uint2>(kCapacity);
 }
 
+static int g_render_leaf_streak_min = 2;                        // triangle steps follow each other while this many lanes want one (0: as for node steps)
 static int g_render_refill_min = 20, g_render_streak_min = 8;   // BVH2 stream kernels: refill threshold, step-streak threshold (swept: profiles/r01_experiments.md)
 static int g_render_bvh2_stack = 16;   // BVH2 stream kernels: stack levels in shared memory (8, 16, 24, 32; measured 518 / 518 / 518 / 513 Msamples/s)
 static int g_render_wide = 0;          // 256-bit record loads in the BVH8 stream kernels (rodent_b200_tune "render_wide")
@@ -538,7 +539,7 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
             auto kernel = g_render_bvh2_stack <= 8 ? traverse_stream_bvh2<false, 8> : g_render_bvh2_stack <= 16 ? traverse_stream_bvh2<false, 16> :
                           g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<false, 24> : traverse_stream_bvh2<false, 32>;
             kernel<<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min);
+                                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
         } else {
             const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
             auto kernel = g_render_wide ? traverse_stream<false, true> : traverse_stream<false, false>;
@@ -559,7 +560,7 @@ static void render_pipeline(Renderer& r, float* film, const Settings& st, int it
                           g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<true, 24> : traverse_stream_bvh2<true, 32>;
             kernel<<<grid_s, kRBlock, sizeof(int), s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
                                                          nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                         counters + kWorkShadow, g_render_refill_min, g_render_streak_min);
+                                                         counters + kWorkShadow, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
         } else {
             const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
             auto kernel = g_render_wide ? traverse_stream<true, true> : traverse_stream<true, false>;
@@ -638,6 +639,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     if (!std::strcmp(key, "render_bvh2_stack")) g_render_bvh2_stack = value;
     if (!std::strcmp(key, "render_capacity") && value >= 1024) kCapacity = value;
     if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = value;
+    if (!std::strcmp(key, "render_leaf_streak_min")) g_render_leaf_streak_min = value;
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;

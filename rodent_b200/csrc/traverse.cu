@@ -704,7 +704,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = value;
     else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = value;
     else if (!std::strcmp(key, "render_lanes") || !std::strcmp(key, "render_bvh2") || !std::strcmp(key, "render_shadow_bvh2") || !std::strcmp(key, "render_wide") ||
-             !std::strcmp(key, "render_refill_min") || !std::strcmp(key, "render_streak_min") || !std::strcmp(key, "render_bvh2_stack") ||
+             !std::strcmp(key, "render_refill_min") || !std::strcmp(key, "render_streak_min") || !std::strcmp(key, "render_leaf_streak_min") || !std::strcmp(key, "render_bvh2_stack") ||
              !std::strcmp(key, "render_capacity")) rodent_b200_render_tune(key, value);
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }

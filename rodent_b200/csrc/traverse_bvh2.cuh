@@ -103,7 +103,8 @@ struct Bvh2Walker {
 template <bool ANY, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
 __device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris, int* smem_column,
                                                         int num_rays, int* __restrict__ work_counter, int refill_min, int node_streak_min,
-                                                        Fetch fetch, Sink sink) {
+                                                        Fetch fetch, Sink sink, int leaf_streak_min = 0) {
+    if (leaf_streak_min <= 0) leaf_streak_min = node_streak_min;
     const unsigned lane = lane_id();
     int overflow[kStackSize - SMEM_DEPTH];
     Bvh2Walker<ANY, SMEM_DEPTH, BLOCK> w;
@@ -147,7 +148,7 @@ __device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict_
             do {
                 if (go) w.leaf_step(tris);
                 go = has && w.wants_leaf();
-            } while (__popc(__ballot_sync(0xffffffffu, go)) >= node_streak_min);
+            } while (__popc(__ballot_sync(0xffffffffu, go)) >= leaf_streak_min);
         }
     }
 }
