@@ -372,6 +372,30 @@ void   render(const Settings* settings, int32_t iter);
 
 
 /* ======================================================================== *
+ * The reference's data containers (src/driver/buffer.h, data/bvh.bin)
+ * ======================================================================== */
+
+/* The LZ4 block format, both directions (the reference calls LZ4_compress_default / LZ4_decompress_safe of liblz4,
+ * src/driver/buffer.h:17-20,39-44).  decompress: bytes written, or -1 on malformed input or too small a destination;
+ * compress: bytes written, or -1 unless dst_capacity >= rodent_b200_lz4_compress_bound(n). */
+int64_t rodent_b200_lz4_decompress(const void* src, int64_t src_size, void* dst, int64_t dst_capacity);
+int64_t rodent_b200_lz4_compress_bound(int64_t n);
+int64_t rodent_b200_lz4_compress(const void* src, int64_t n, void* dst, int64_t dst_capacity);
+/* One buffer file of the converter's data directory, [u32 raw size][u32 compressed size][LZ4 block] (read_buffer /
+ * write_buffer, buffer.h:22-61; the role of rodent_load_buffer, interface.cpp:598-601, without the per-device cache).
+ * load: a malloc'ed copy of the raw bytes (free it with rodent_b200_free_buffer) or NULL; write: 1 on success. */
+void*   rodent_b200_load_buffer(const char* file, int64_t* size);
+void    rodent_b200_free_buffer(void* p);
+int32_t rodent_b200_write_buffer(const char* file, const void* data, int64_t bytes);
+/* data/bvh.bin: repeated { u32 sizeof(Node), u32 sizeof(Tri), buffer(nodes), buffer(tris) } (write_bvh, converter.cpp:428-438;
+ * load_bvh<Node, Tri>, interface.cpp:432-454).  load returns the first entry with these record sizes (256 / 224: BVH8 / Tri4,
+ * 128 / 224: BVH4 / Tri4, 64 / 48: BVH2 / Tri1) as malloc'ed arrays, 0 if there is none; append adds an entry. */
+int32_t rodent_b200_load_bvh_bin(const char* file, int32_t node_size, int32_t tri_size,
+                                 void** nodes, int64_t* num_nodes, void** tris, int64_t* num_tris);
+int32_t rodent_b200_append_bvh_bin(const char* file, int32_t node_size, int32_t tri_size,
+                                   const void* nodes, int64_t num_nodes, const void* tris, int64_t num_tris);
+
+/* ======================================================================== *
  * Shading-interface micro-benchmark (tools/bench_interface)
  * ======================================================================== */
 

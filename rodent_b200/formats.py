@@ -124,3 +124,78 @@ def unpack_hits(hits: np.ndarray) -> np.ndarray:
     for name in ("tri_id", "t", "u", "v"):
         out[name] = hits[name].reshape(-1)
     return out
+
+
+# ---- the reference's data containers (src/driver/buffer.h, data/bvh.bin) --------------------------------------
+def lz4_compress(data: bytes) -> bytes:
+    """One LZ4 block (what LZ4_compress_default writes)."""
+    import ctypes
+    from . import lib
+    L = lib.load()
+    cap = L.rodent_b200_lz4_compress_bound(len(data))
+    out = ctypes.create_string_buffer(cap)
+    n = L.rodent_b200_lz4_compress(data, len(data), out, cap)
+    if n < 0:
+        raise ValueError("LZ4 compression failed")
+    return out.raw[:n]
+
+
+def lz4_decompress(block: bytes, raw_size: int) -> bytes:
+    """LZ4_decompress_safe: raises on malformed input or when the block does not decode to exactly raw_size bytes."""
+    import ctypes
+    from . import lib
+    out = ctypes.create_string_buffer(max(raw_size, 1))
+    n = lib.load().rodent_b200_lz4_decompress(block, len(block), out, raw_size)
+    if n != raw_size:
+        raise ValueError("malformed LZ4 block")
+    return out.raw[:raw_size]
+
+
+def load_buffer(path, dtype=np.uint8) -> np.ndarray:
+    """A `data/*.bin` buffer of the reference's converter (read_buffer, buffer.h:22-37)."""
+    import ctypes
+    from . import lib
+    L = lib.load()
+    size = ctypes.c_int64()
+    p = L.rodent_b200_load_buffer(str(path).encode(), ctypes.byref(size))
+    if not p:
+        raise ValueError(f"{path}: not a buffer file")
+    try:
+        return np.frombuffer(ctypes.string_at(p, size.value), dtype).copy()
+    finally:
+        L.rodent_b200_free_buffer(p)
+
+
+def write_buffer(path, array: np.ndarray) -> None:
+    """write_buffer, buffer.h:46-61."""
+    from . import lib
+    a = np.ascontiguousarray(array)
+    if not lib.load().rodent_b200_write_buffer(str(path).encode(), a.ctypes.data, a.nbytes):
+        raise OSError(f"cannot write {path}")
+
+
+def load_bvh_bin(path, bvh_type: int = BVH8_TRI4):
+    """(nodes, tris) of the entry of `data/bvh.bin` with this layout (load_bvh<Node, Tri>, interface.cpp:432-454)."""
+    import ctypes
+    from . import lib
+    L = lib.load()
+    node_dt, tri_dt = _BLOCK_TYPES[bvh_type]
+    nodes, tris, nn, nt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64()
+    if not L.rodent_b200_load_bvh_bin(str(path).encode(), node_dt.itemsize, tri_dt.itemsize, ctypes.byref(nodes), ctypes.byref(nn),
+                                      ctypes.byref(tris), ctypes.byref(nt)):
+        raise ValueError(f"{path}: no BVH entry of type {bvh_type}")
+    try:
+        return (np.frombuffer(ctypes.string_at(nodes.value, nn.value * node_dt.itemsize), node_dt).copy(),
+                np.frombuffer(ctypes.string_at(tris.value, nt.value * tri_dt.itemsize), tri_dt).copy())
+    finally:
+        L.rodent_b200_free_buffer(nodes)
+        L.rodent_b200_free_buffer(tris)
+
+
+def append_bvh_bin(path, nodes: np.ndarray, tris: np.ndarray) -> None:
+    """write_bvh, converter.cpp:428-438 (the file is opened for appending there too)."""
+    from . import lib
+    nodes, tris = np.ascontiguousarray(nodes), np.ascontiguousarray(tris)
+    if not lib.load().rodent_b200_append_bvh_bin(str(path).encode(), nodes.dtype.itemsize, tris.dtype.itemsize, nodes.ctypes.data, len(nodes),
+                                                 tris.ctypes.data, len(tris)):
+        raise OSError(f"cannot write {path}")

@@ -29,6 +29,15 @@ SIGNATURES = {
     "b200_intersect_single_ray1_bvh8_tri4": (None, _TRAVERSE_HOST),
     "b200_occluded_single_ray1_bvh8_tri4": (None, _TRAVERSE_HOST),
     "rodent_b200_forget_bvh": (None, [c_void_p, c_void_p]),
+    "rodent_b200_lz4_decompress": (ctypes.c_int64, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
+    "rodent_b200_lz4_compress_bound": (ctypes.c_int64, [ctypes.c_int64]),
+    "rodent_b200_lz4_compress": (ctypes.c_int64, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
+    "rodent_b200_load_buffer": (c_void_p, [c_char_p, ctypes.POINTER(ctypes.c_int64)]),
+    "rodent_b200_free_buffer": (None, [c_void_p]),
+    "rodent_b200_write_buffer": (c_int32, [c_char_p, c_void_p, ctypes.c_int64]),
+    "rodent_b200_load_bvh_bin": (c_int32, [c_char_p, c_int32, c_int32, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_int64)]),
+    "rodent_b200_append_bvh_bin": (c_int32, [c_char_p, c_int32, c_int32, c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
     "rodent_b200_device_count": (c_int32, []),
     "rodent_b200_set_device": (None, [c_int32]),
     "rodent_b200_alloc_device": (c_void_p, [c_int32, c_size_t]),
