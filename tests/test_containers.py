@@ -86,3 +86,25 @@ def test_bvh_bin_with_several_layouts(tmp_path, sponza):
     with pytest.raises(ValueError):
         formats.load_bvh_bin(path, formats.BVH4_TRI4)
     assert path.stat().st_size < 0.8 * (nodes8.nbytes + tris4.nbytes + nodes2.nbytes + tris1.nbytes)     # it does compress
+
+
+def test_lz4_round_trip_property():
+    """Any byte string survives compress -> decompress; a flipped bit in the block is either rejected or decodes to exactly
+    raw_size bytes (never past the destination)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.binary(max_size=4000), st.integers(0, 7), st.integers(0, 1 << 30))
+    def check(raw, bit, where):
+        # make part of the input repetitive so that matches occur
+        raw = raw + raw[: len(raw) // 2] * 3
+        block = formats.lz4_compress(raw)
+        assert formats.lz4_decompress(block, len(raw)) == raw
+        damaged = bytearray(block)
+        damaged[where % len(damaged)] ^= 1 << bit
+        try:
+            out = formats.lz4_decompress(bytes(damaged), len(raw))
+            assert len(out) == len(raw)
+        except ValueError:
+            pass
+    check()
