@@ -315,6 +315,10 @@ int32_t rodent_b200_scene_add_png(RodentScene* scene, const char* png_file);
 /* The same for a JPEG file, as load_jpg leaves it (image.cpp:186-238: libjpeg defaults, (r, g, b, 0) or (grey, 0, 0, 0),
  * rows flipped, gamma 2.2).  Sequential and progressive Huffman files; arithmetic-coded ones are reported as unsupported. */
 int32_t rodent_b200_scene_add_jpg(RodentScene* scene, const char* jpg_file);
+/* The same for a TGA file (types 1, 2, 3 and their run-length forms, 8 / 15 / 16 / 24 / 32 bit).  The reference's converter
+ * emits device.load_tga for such images (converter.cpp:759-762) but no device provides it; the layout is that of the PNG
+ * loader (bottom row first, gamma 2.2, alpha kept). */
+int32_t rodent_b200_scene_add_tga(RodentScene* scene, const char* tga_file);
 void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out);
 void rodent_b200_scene_free(RodentScene* scene);
 /* The scene's triangles under a BVH4 as well (built on first use, owned by the scene), for writing .bvh files with both

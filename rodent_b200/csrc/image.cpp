@@ -109,6 +109,7 @@ static bool decode_png(const std::string& path, int& width, int& height, std::ve
         if (int(w) <= passes[p].x0 || int(h) <= passes[p].y0) continue;
         raw_size += ph * (1 + (pw * bits_pp + 7) / 8);
     }
+    if (raw_size / 1100 > idat.size() + 16) { why = "image data too short for the stated size"; return false; }   // deflate expands at most ~1032 : 1
     std::vector<uint8_t> raw(raw_size);
     uLongf got = uLongf(raw_size);
     const int zr = uncompress(raw.data(), &got, idat.data(), uLong(idat.size()));

@@ -191,6 +191,11 @@ static bool decode_jpg(const std::string& path, int& width, int& height, std::ve
             } else comps[0].h = comps[0].v = 1;                              // a single component is never interleaved
             for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
             mcus_x = (w + 8 * hmax - 1) / (8 * hmax); mcus_y = (h + 8 * vmax - 1) / (8 * vmax);
+            {   // every block costs at least one bit of entropy-coded data: refuse sizes the file cannot hold
+                uint64_t blocks = 0;
+                for (auto& c : comps) blocks += uint64_t(mcus_x) * c.h * uint64_t(mcus_y) * c.v;
+                if (blocks > uint64_t(file.size()) * 8) { why = "image data too short for the stated size"; return false; }
+            }
             for (auto& c : comps) {                                          // planes and coefficients padded to whole MCUs
                 c.blocks_w = mcus_x * c.h; c.blocks_h = mcus_y * c.v;
                 c.stride = c.blocks_w * 8; c.rows = c.blocks_h * 8;

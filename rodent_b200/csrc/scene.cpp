@@ -490,7 +490,7 @@ Scene* load_obj_scene(const std::string& path) {
 
     auto scene = new Scene();
     // Images, converter.cpp:595-602, 748-768: one per distinct file name, relative to the OBJ's directory, '\\' -> '/';
-    // .png and .jpg / .jpeg are decoded, an unknown extension gives the reference's 1x1 black dummy image.  (The reference registers map_Ks
+    // .png, .jpg / .jpeg and .tga are decoded, an unknown extension gives the reference's 1x1 black dummy image.  (The reference registers map_Ks
     // under map_Kd's name, :600, so a specular map silently samples image 0 there; here it samples its own file.)
     std::unordered_map<std::string, int> images;
     bool failed = false;
@@ -510,7 +510,12 @@ Scene* load_obj_scene(const std::string& path) {
             if (load_jpg(dir + "/" + name, w, h, px, why)) id = scene->add_texture(px.data(), w, h);
             else if (why == "cannot open file") { fail("cannot load JPG file '" + dir + "/" + name + "': " + why); failed = true; }
             else warn("'" + name + "' (material '" + material + "'): " + why + "; the material's constant colour is used instead");
-        } else if (ends_with(".tga") || ends_with(".tiff")) {
+        } else if (ends_with(".tga")) {
+            int w = 0, h = 0; std::vector<uint32_t> px; std::string why;
+            if (load_tga(dir + "/" + name, w, h, px, why)) id = scene->add_texture(px.data(), w, h);
+            else if (why == "cannot open file") { fail("cannot load TGA file '" + dir + "/" + name + "': " + why); failed = true; }
+            else warn("'" + name + "' (material '" + material + "'): " + why + "; the material's constant colour is used instead");
+        } else if (ends_with(".tiff")) {
             warn("no decoder for '" + name + "' (material '" + material + "'): the material's constant colour is used instead");
         } else {
             const uint32_t black = 0xFF000000u;
@@ -723,6 +728,14 @@ int32_t rodent_b200_scene_add_png(RodentScene* scene, const char* png_file) {
     int w = 0, h = 0; std::vector<uint32_t> px; std::string why;
     if (!scene || !rb200::load_png(png_file, w, h, px, why)) {
         std::fprintf(stderr, "rodent_b200: cannot load PNG file '%s': %s\n", png_file, why.c_str());
+        return 0;
+    }
+    return reinterpret_cast<Scene*>(scene)->add_texture(px.data(), w, h);
+}
+int32_t rodent_b200_scene_add_tga(RodentScene* scene, const char* tga_file) {
+    int w = 0, h = 0; std::vector<uint32_t> px; std::string why;
+    if (!scene || !rb200::load_tga(tga_file, w, h, px, why)) {
+        std::fprintf(stderr, "rodent_b200: cannot load TGA file '%s': %s\n", tga_file, why.c_str());
         return 0;
     }
     return reinterpret_cast<Scene*>(scene)->add_texture(px.data(), w, h);

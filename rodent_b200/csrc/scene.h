@@ -32,6 +32,8 @@ struct Scene {
 bool load_png(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 // src/driver/image.cpp:186-238 (jpeg.cpp of this directory)
 bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
+// tga.cpp of this directory (the reference names a load_tga, converter.cpp:759-762, that no device provides)
+bool load_tga(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 
 Scene* load_obj_scene(const std::string& path);
 void build_bvh4(Scene& scene);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "rodent_b200_scene_add_texture": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
     "rodent_b200_scene_add_png": (c_int32, [c_void_p, ctypes.c_char_p]),
     "rodent_b200_scene_add_jpg": (c_int32, [c_void_p, ctypes.c_char_p]),
+    "rodent_b200_scene_add_tga": (c_int32, [c_void_p, ctypes.c_char_p]),
     "rodent_b200_scene_build_bvh2": (None, [c_void_p]),
     "rodent_b200_scene_set_bvh2": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
@@ -141,10 +142,12 @@ class Scene:
         return tid
 
     def add_png(self, path) -> int:
-        """Decodes a .png (or .jpg / .jpeg) file the way the reference's loaders do and appends it."""
+        """Decodes a .png (or .jpg / .jpeg / .tga) file the way the reference's loaders do and appends it."""
         L = _bind(lib.load())
-        jpg = str(path).lower().endswith((".jpg", ".jpeg"))
-        tid = (L.rodent_b200_scene_add_jpg if jpg else L.rodent_b200_scene_add_png)(self.handle, str(path).encode())
+        name = str(path).lower()
+        fn = L.rodent_b200_scene_add_jpg if name.endswith((".jpg", ".jpeg")) else L.rodent_b200_scene_add_tga if name.endswith(".tga") \
+            else L.rodent_b200_scene_add_png
+        tid = fn(self.handle, str(path).encode())
         if not tid:
             raise RuntimeError(f"cannot load {path} (see stderr)")
         L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))

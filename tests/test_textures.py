@@ -232,6 +232,44 @@ def test_jpg_grey_and_errors(tmp_path, capfd):
         R.Scene.load_obj(write_scene(tmp_path, "floor.jpg", "nowhere.jpeg"))
 
 
+# ---- the TGA loader --------------------------------------------------------------------------------------------
+def test_tga_loader(tmp_path, capfd):
+    """Types 1 / 2 / 3 and their run-length forms, both row orders, against PIL's reading of the same files; 5-5-5 pixels by
+    hand.  (The reference names a load_tga, converter.cpp:759-762, but no device defines it.)"""
+    import struct
+    scene = R.Scene.load_obj(write_scene(tmp_path, "none.xyz", "none.xyz"))
+    rng = np.random.default_rng(0)
+    h, w = 19, 27
+    img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    img[:, :9] = img[:, :1]                                                # runs, so that the RLE packets are of both kinds
+    for mode in ("RGBA", "RGB", "L", "P"):
+        for kw in (dict(), dict(compression="tga_rle"), dict(orientation=-1), dict(compression="tga_rle", orientation=-1)):
+            im = Image.fromarray(img) if mode == "RGBA" else Image.fromarray(img[..., 0]) if mode == "L" else \
+                Image.fromarray(img[..., :3]).convert(mode)
+            path = tmp_path / "t.tga"
+            im.save(path, **kw)
+            tid = scene.add_png(path)
+            tex = scene.array("textures")[tid - 1]
+            got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + w * h].reshape(h, w)
+            assert np.array_equal(got, expected_pixels(np.array(Image.open(path).convert("RGBA")))), (mode, kw)
+    # 16-bit true colour, bottom row first: 5 bits per channel widened by bit replication
+    vals = np.array([[0x7C00, 0x03E0], [0x001F, 0x4210]], np.uint16)        # red, green / blue, mid grey (16, 16, 16)
+    (tmp_path / "w.tga").write_bytes(struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, 2, 2, 16, 0) + vals.tobytes())
+    tid = scene.add_png(tmp_path / "w.tga")
+    tex = scene.array("textures")[tid - 1]
+    got = scene.array("texture_pixels")[tex["offset"]:tex["offset"] + 4].reshape(2, 2)
+    lut = gamma_lut().astype(np.uint32)
+    g = lut[132]
+    assert got.tolist() == [[0xFF000000 | 255, 0xFF000000 | 255 << 8], [0xFF000000 | 255 << 16, 0xFF000000 | g | g << 8 | g << 16]]
+    blob = (tmp_path / "t.tga").read_bytes()
+    (tmp_path / "cut.tga").write_bytes(blob[:40])
+    (tmp_path / "odd.tga").write_bytes(blob[:2] + bytes([32]) + blob[3:])
+    for name in ("cut.tga", "odd.tga", "missing.tga"):
+        with pytest.raises(RuntimeError):
+            scene.add_png(tmp_path / name)
+    assert capfd.readouterr().err.count("cannot load TGA file") == 3
+
+
 # ---- binding images to materials --------------------------------------------------------------------------------
 def test_obj_binds_images_to_materials(tmp_path, capfd):
     Image.fromarray(checker()).save(tmp_path / "floor.png")
@@ -254,9 +292,9 @@ def test_obj_binds_images_to_materials(tmp_path, capfd):
     scene = R.Scene.load_obj(write_scene(tmp_path, "floor.png", "floor.png"))
     assert scene.array("materials")["map_kd"].tolist()[0] == 1 and scene.array("materials")["map_ks"].tolist()[1] == 1
     assert scene.view.num_textures == 1
-    scene = R.Scene.load_obj(write_scene(tmp_path, "floor.bmp", "wall.tga"))
+    scene = R.Scene.load_obj(write_scene(tmp_path, "floor.bmp", "wall.tiff"))
     err = capfd.readouterr().err
-    assert "no decoder for 'wall.tga'" in err
+    assert "no decoder for 'wall.tiff'" in err
     assert scene.array("materials")["map_kd"].tolist()[0] == 1 and scene.array("materials")["map_ks"].tolist()[1] == 0
     assert scene.array("texture_pixels").tolist() == [0xFF000000]
     # a PNG that cannot be read fails the load, as the reference's load_png does at start-up (interface.cpp:476-477)
@@ -336,7 +374,7 @@ def test_textured_film_matches_oracle(tmp_path, size, spp, depth):
     assert abs(got.mean() - want.mean()) / want.mean() < 2e-3
     assert abs(stats["primary_rays"] - st.primary_rays) <= 0.001 * st.primary_rays + 4
     # and the texture matters: the same scene without its images renders something else
-    flat = R.Scene.load_obj(write_scene(tmp_path, "floor.tga", "wall.tga"))
+    flat = R.Scene.load_obj(write_scene(tmp_path, "floor.tiff", "wall.tiff"))
     r = R.Renderer(flat, 0, W, H, spp, depth)
     for it in range(2):
         r.render(cam, it)
