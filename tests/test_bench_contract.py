@@ -28,3 +28,28 @@ def test_reference_arm_runs_on_rank_0_only():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "3", "--warmup", "3", "--no-path-trace", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "per_set", "variants"):
+        assert key in line, key
+    assert "impl" not in line and line["metric"] == "Mrays/sec on Sponza primary+random" and line["dtype"] == "f32"
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["gpu_launches"] == 2 * line["steps"]                       # two traversal launches per step, nothing else of ours
+    assert abs(line["value"] - 2 * 1048576 / line["ms_per_step"] / 1e3) / line["value"] < 0.01
+    assert line["value"] > 500 and 0 < line["e2e"]["value"] < line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 2 * 1048576 * 32 and line["e2e"]["d2h_bytes_per_step"] == 2 * 1048576 * 16
+    assert line["e2e"]["results_match_device_path"] is True
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3 and rf["traffic"] > 0
+    assert line["per_set"]["primary"]["hits"] == 1026430 and line["per_set"]["random"]["hits"] == 959359
+    assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
