@@ -10,7 +10,8 @@
  * definition (see DESIGN.md "Parity contract").
  *
  * Arithmetic contract: IEEE-754 binary32, round-to-nearest, no FMA contraction
- * (build with -ffp-contract=off, no -ffast-math), operations in the source order
+ * (build with -ffp-contract=off, no -ffast-math; the AVX2 forms of the node and triangle tests use separate
+ * multiply and add intrinsics and give the same bits as the scalar code, which stays as the fallback), operations in the source order
  * of the reference, integer compares of float bits where the reference uses them
  * (enable_cpu_int_min_max = true, tools/bench_traversal/bench_traversal.impala:11).
  * The reference binary itself is built -ffast-math (CMakeLists.txt:12), so its own
@@ -23,6 +24,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#if defined(__AVX2__)
+#include <immintrin.h>    /* the 8-lane node test and the 4-lane triangle test below, as the reference's vectorised build has them */
+#endif
 
 #include "../include/rodent_b200.h"
 
@@ -175,6 +179,44 @@ static inline int intersect_ray_tri_lane(const Tri4* tp, int i,
     return 1;
 }
 
+#if defined(__AVX2__)
+/* The four lanes of a Tri4 at once: the same operations in the same order as intersect_ray_tri_lane (so the same bits),
+ * lanes that miss or are invalid report (FLT_MAX, 0, 0).  Returns the hit mask. */
+static inline int intersect_ray_tri4(const Tri4* tp, const float org[3], const float dir[3], float tmin, float tmax,
+                                     float lt[4], float lu[4], float lv[4]) {
+    const __m128 ox = _mm_set1_ps(org[0]), oy = _mm_set1_ps(org[1]), oz = _mm_set1_ps(org[2]);
+    const __m128 dx = _mm_set1_ps(dir[0]), dy = _mm_set1_ps(dir[1]), dz = _mm_set1_ps(dir[2]);
+    const __m128 e1x = _mm_loadu_ps(tp->e1[0]), e1y = _mm_loadu_ps(tp->e1[1]), e1z = _mm_loadu_ps(tp->e1[2]);
+    const __m128 e2x = _mm_loadu_ps(tp->e2[0]), e2y = _mm_loadu_ps(tp->e2[1]), e2z = _mm_loadu_ps(tp->e2[2]);
+    const __m128 nx = _mm_loadu_ps(tp->n[0]), ny = _mm_loadu_ps(tp->n[1]), nz = _mm_loadu_ps(tp->n[2]);
+    const __m128 cx = _mm_sub_ps(_mm_loadu_ps(tp->v0[0]), ox), cy = _mm_sub_ps(_mm_loadu_ps(tp->v0[1]), oy), cz = _mm_sub_ps(_mm_loadu_ps(tp->v0[2]), oz);
+    const __m128 rx = _mm_sub_ps(_mm_mul_ps(dy, cz), _mm_mul_ps(dz, cy));
+    const __m128 ry = _mm_sub_ps(_mm_mul_ps(dz, cx), _mm_mul_ps(dx, cz));
+    const __m128 rz = _mm_sub_ps(_mm_mul_ps(dx, cy), _mm_mul_ps(dy, cx));
+#define DOT3(ax, ay, az, bx, by, bz) _mm_add_ps(_mm_add_ps(_mm_mul_ps(ax, bx), _mm_mul_ps(ay, by)), _mm_mul_ps(az, bz))
+    const __m128 det = DOT3(nx, ny, nz, dx, dy, dz);
+    const __m128 sign = _mm_and_ps(det, _mm_castsi128_ps(_mm_set1_epi32((int32_t)0x80000000u)));
+    const __m128 abs_det = _mm_and_ps(det, _mm_castsi128_ps(_mm_set1_epi32(0x7FFFFFFF)));
+    const __m128 u = _mm_xor_ps(DOT3(rx, ry, rz, e2x, e2y, e2z), sign);
+    const __m128 v = _mm_xor_ps(DOT3(rx, ry, rz, e1x, e1y, e1z), sign);
+    const __m128 zero = _mm_setzero_ps();
+    __m128 m = _mm_and_ps(_mm_and_ps(_mm_cmpge_ps(u, zero), _mm_cmpge_ps(v, zero)), _mm_cmple_ps(_mm_add_ps(u, v), abs_det));
+    m = _mm_and_ps(m, _mm_castsi128_ps(_mm_xor_si128(_mm_cmpeq_epi32(_mm_loadu_si128((const __m128i*)tp->prim_id), _mm_set1_epi32(-1)), _mm_set1_epi32(-1))));
+    const __m128 t = _mm_xor_ps(DOT3(cx, cy, cz, nx, ny, nz), sign);
+#undef DOT3
+    m = _mm_and_ps(m, _mm_cmpneq_ps(abs_det, zero));
+    m = _mm_and_ps(m, _mm_cmpge_ps(t, _mm_mul_ps(abs_det, _mm_set1_ps(tmin))));
+    m = _mm_and_ps(m, _mm_cmple_ps(t, _mm_mul_ps(abs_det, _mm_set1_ps(tmax))));
+    const int hm = _mm_movemask_ps(m);
+    if (!hm) { for (int j = 0; j < 4; j++) { lt[j] = FLT_MAX_; lu[j] = 0.0f; lv[j] = 0.0f; } return 0; }
+    const __m128 inv_det = _mm_div_ps(_mm_set1_ps(1.0f), abs_det);
+    _mm_storeu_ps(lt, _mm_blendv_ps(_mm_set1_ps(FLT_MAX_), _mm_mul_ps(t, inv_det), m));
+    _mm_storeu_ps(lu, _mm_and_ps(_mm_mul_ps(u, inv_det), m));
+    _mm_storeu_ps(lv, _mm_and_ps(_mm_mul_ps(v, inv_det), m));
+    return hm;
+}
+#endif
+
 /* ---- the traversal kernel, src/traversal/mapping_cpu.impala:138-256 ------
  * N = arity (4 or 8); `nodes` is Node4* or Node8* (same field order, bounds[6][N],
  * child[N], pad[N]).  Stack discipline of src/traversal/stack.impala:52-123: the
@@ -227,6 +269,27 @@ void traverse_single(const int N, const int any_hit,
 
             /* intersect_ray_box ordered, intersection.impala:194-208, integer min/max */
             float tentry[8]; int mask = 0;
+#if defined(__AVX2__)
+            if (N == 8) {
+                /* The same operations on eight children at once (what the reference's RV-vectorised CPU build does): one
+                 * multiply and one add per plane, never fused (-ffp-contract=off), integer min / max in the scalar nesting.
+                 * Bit-identical to the loop below, NaNs included (same SSE default NaN). */
+                const __m256 vix = _mm256_set1_ps(idx), viy = _mm256_set1_ps(idy), viz = _mm256_set1_ps(idz);
+                const __m256 vox = _mm256_set1_ps(iox), voy = _mm256_set1_ps(ioy), voz = _mm256_set1_ps(ioz);
+                const __m256 t0x = _mm256_add_ps(_mm256_mul_ps(vix, _mm256_loadu_ps(nb + near_x)), vox);
+                const __m256 t0y = _mm256_add_ps(_mm256_mul_ps(viy, _mm256_loadu_ps(nb + near_y)), voy);
+                const __m256 t0z = _mm256_add_ps(_mm256_mul_ps(viz, _mm256_loadu_ps(nb + near_z)), voz);
+                const __m256 t1x = _mm256_add_ps(_mm256_mul_ps(vix, _mm256_loadu_ps(nb + far_x)), vox);
+                const __m256 t1y = _mm256_add_ps(_mm256_mul_ps(viy, _mm256_loadu_ps(nb + far_y)), voy);
+                const __m256 t1z = _mm256_add_ps(_mm256_mul_ps(viz, _mm256_loadu_ps(nb + far_z)), voz);
+#define CI(x) _mm256_castps_si256(x)
+                const __m256i te = _mm256_max_epi32(_mm256_max_epi32(CI(t0x), CI(t0y)), _mm256_max_epi32(CI(t0z), CI(_mm256_set1_ps(tmin))));
+                const __m256i tx = _mm256_min_epi32(_mm256_min_epi32(CI(t1x), CI(t1y)), _mm256_min_epi32(CI(t1z), CI(_mm256_set1_ps(tmax))));
+#undef CI
+                _mm256_storeu_ps(tentry, _mm256_castsi256_ps(te));
+                mask = ~_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpgt_epi32(te, tx))) & 0xFF;      /* :184 */
+            } else
+#endif
             for (int i = 0; i < N; i++) {
                 const float t0x = idx * nb[near_x + i] + iox;
                 const float t0y = idy * nb[near_y + i] + ioy;
@@ -279,6 +342,9 @@ void traverse_single(const int N, const int any_hit,
             n_tri4++;
             ORACLE_TRACE('L');
             float lt[4], lu[4], lv[4]; int hm = 0;
+#if defined(__AVX2__)
+            hm = intersect_ray_tri4(tp, org, dir, tmin, tmax, lt, lu, lv);
+#else
             for (int j = 0; j < 4; j++) {
                 lt[j] = FLT_MAX_; lu[j] = 0.0f; lv[j] = 0.0f;
                 if (tp->prim_id[j] == -1) continue;                      /* is_valid, mapping_cpu.impala:39 */
@@ -287,6 +353,7 @@ void traverse_single(const int N, const int any_hit,
                 else
                     lt[j] = FLT_MAX_;
             }
+#endif
             if (hm) {
                 int lane;
                 if (any_hit) {

@@ -149,3 +149,40 @@ def test_bvh4_hit_distance_matches_golden_png(ray_sets):
         h4 = oracle.traverse(nodes4, tris4, ray_sets[name])
         ref = np.array(Image.open(GOLDEN / f"ref-{name}.png"))[..., 0]
         assert int((ref != formats.fbuf_to_gray(h4["t"]).reshape(1024, 1024)).sum()) <= 2
+
+
+def test_vector_and_scalar_builds_agree(tmp_path, sponza, ray_sets):
+    """The oracle's AVX2 node test / 4-lane triangle test (what the shipped liboracle.so runs, and what the reference's
+    vectorised CPU build does) against the scalar code of the same file, compiled without AVX2: same bits, degenerate rays
+    included."""
+    import ctypes
+    import subprocess
+    src = Path(oracle.__file__).resolve().parent
+    so = tmp_path / "liboracle_scalar.so"
+    subprocess.run(["gcc", "-O2", "-march=x86-64", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-D_GNU_SOURCE", "-shared",
+                    "-o", str(so), str(src / "render_oracle.c"), str(src / "shading_bench_oracle.c"), str(src / "traversal_bvh2_oracle.c"),
+                    "-lpthread", "-lm"], check=True)
+    scalar = ctypes.CDLL(str(so))
+    scalar.oracle_traverse.argtypes = oracle.lib().oracle_traverse.argtypes
+    scalar.oracle_traverse.restype = None
+    nodes, tris = sponza
+    nodes4, tris4 = formats.load_bvh(testdata.sponza_bvh4(), formats.BVH4_TRI4)
+    rng = np.random.default_rng(5)
+    n = 40000
+    d = rng.normal(size=(n, 3))
+    d[np.arange(n), rng.integers(0, 3, n)] = 0.0
+    d[n // 2:][np.abs(d[n // 2:]) < 0.3] = 1e-9
+    d[(d == 0).all(axis=1), 0] = 1.0
+    od = np.concatenate([rng.uniform([-1900, -100, -1100], [1800, 1400, 1100], (n, 3)), d], axis=1).astype(np.float32)
+    sets = [formats.make_rays(od, 0.0, 1e30), np.ascontiguousarray(ray_sets["primary"][::16]), np.ascontiguousarray(ray_sets["random"][::16])]
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for rays in sets:
+        for arity, (nn, tt) in ((8, (nodes, tris)), (4, (nodes4, tris4))):
+            for any_hit in (False, True):
+                want = np.zeros(len(rays), formats.HIT1)
+                scalar.oracle_traverse(arity, int(any_hit), ptr(nn), ptr(tt), ptr(rays), ptr(want), len(rays), 4, None)
+                got = oracle.traverse(nn, tt, rays, any_hit=any_hit)
+                if any_hit:
+                    assert np.array_equal(got["tri_id"] >= 0, want["tri_id"] >= 0)
+                else:
+                    assert got.tobytes() == want.tobytes()
