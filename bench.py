@@ -257,7 +257,7 @@ def run_reference(args):
         "config": config_dict(args.gpus),
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "oracle/traversal_oracle.c: restated reference single-ray BVH8 algorithm (the AnyDSL build "
-                                 "cannot be produced here), gcc -O3 -march=x86-64-v3 -ffp-contract=off"},
+                                 "cannot be produced here), gcc -O3 -march=x86-64-v3 -ffp-contract=off, AVX2 node test and 4-lane triangle test"},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "path_trace": {"cornell_cpu_sample": cpu_path_trace_sample(threads)},
