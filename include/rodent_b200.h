@@ -135,18 +135,25 @@ void cuda_occluded_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, 
  * Drop-ins for the call sites of
  *   cpu_{intersect,occluded}_single_ray1_bvh8_tri4(nodes, tris, rays, hits, num_packets)
  *   (tools/bench_traversal/bench_traversal.cpp:76-82): identical signature, HOST
- * buffers.  The BVH is uploaded to the current device on first use and cached by
- * (nodes, tris) address; its extent is found by walking it from the root (node 1),
- * because the reference signature carries no sizes.  Rays are copied in and hits
- * copied out on every call.  Like the cpu_* functions they replace, the calls are reentrant: each takes its own device
+ * buffers.  The BVH is uploaded to the current device on first use; its extent is found by walking it from the root
+ * (node 1), because the reference signature carries no sizes (a malformed BVH -- ids out of range, cycles, a leaf
+ * without its end marker -- aborts with a message).  The cpu_* functions are pure, so the cached copy is keyed on
+ * CONTENT: every call re-hashes samples of both arrays (first and last KB plus 64 lines spread over each) and uploads
+ * again when they changed under a known address; at most 8 copies per device are kept (least recently used goes first).
+ * A caller that patches a BVH in place in bytes the samples may miss calls rodent_b200_forget_bvh.
+ * Rays are copied in and hits copied out on every call.  Pinned (cudaMallocHost / rodent_b200_alloc_host) buffers are
+ * copied by DMA directly; pageable ones (malloc, std::vector, anydsl::Array host memory) go through the library's own
+ * pinned staging buffers, filled and drained by a few helper threads while the device works on the previous piece.
+ * Like the cpu_* functions they replace, the calls are reentrant: each takes its own device
  * staging buffers and streams, so calls from several host threads overlap on the device (one set's transfers under
- * another set's traversal).  rodent_b200_forget_bvh drops a cached copy (call it
- * before freeing or rewriting a BVH that was passed here). */
+ * another set's traversal). */
 void b200_intersect_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris,
                                           const Ray1* rays, Hit1* hits, int32_t num_packets);
 void b200_occluded_single_ray1_bvh8_tri4(const Node8* nodes, const Tri4* tris,
                                          const Ray1* rays, Hit1* hits, int32_t num_packets);
 void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris);
+/* uploads, re-uploads after a content change, live copies -- of the cache above (current device) */
+void rodent_b200_bvh_cache_stats(int64_t out[3]);
 
 /* ---- The same four over a BVH4 -------------------------------------------- *
  * cpu_{intersect,occluded}_single_ray1_bvh4_tri4 (tools/bench_traversal/bench_traversal.impala:279-305) is what

@@ -111,6 +111,11 @@ def render(scene_view, settings, width: int, height: int, spp: int, max_path_len
     return film, stats
 
 
+def set_poly_trig(on: bool) -> None:
+    """sin / cos of the path tracer from rodent_b200/csrc/poly_trig.h (the device has the same switch) instead of libm."""
+    lib().oracle_set_poly_trig(int(on))
+
+
 def bench_interface(mesh, tri_hits: np.ndarray, in_dirs: np.ndarray, out_dirs: np.ndarray) -> np.ndarray:
     """oracle_bench_interface: `mesh` is a rodent_b200.shading_bench.ShadedMesh whose pointers are HOST pointers."""
     L = lib()

@@ -113,8 +113,16 @@ static inline float cosine_power_hemisphere_pdf(float c, float k) {             
 }
 
 typedef struct { V3 dir; float pdf; } DirSample;
+/* Test switch: sin / cos from the polynomial both sides share (rodent_b200/csrc/poly_trig.h) instead of libm's; with it
+ * the device's films agree with this oracle's up to the order of the atomic adds (tests/test_gpu_render.py). */
+#include "../rodent_b200/csrc/poly_trig.h"
+static int g_poly_trig = 0;
+void oracle_set_poly_trig(int on) { g_poly_trig = on; }
 static inline DirSample make_dir_sample(float c, float s, float phi, float pdf) {                          /* random.impala:39-48 */
-    DirSample d; d.dir = v3(s * cosf(phi), s * sinf(phi), c); d.pdf = pdf; return d;
+    float sn, cs;
+    if (g_poly_trig) rb_poly_sincos(phi, &sn, &cs);
+    else { sn = sinf(phi); cs = cosf(phi); }
+    DirSample d; d.dir = v3(s * cs, s * sn, c); d.pdf = pdf; return d;
 }
 static inline DirSample sample_cosine_hemisphere(float u, float v) {                                       /* random.impala:72-77 */
     const float c = sqrtf(1.0f - v), s = sqrtf(v), phi = 2.0f * kPi * u;
@@ -258,14 +266,19 @@ typedef struct {
     OracleRenderStats stats;
 } RenderJob;
 
-void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom);   /* traversal_bvh2_oracle.c */
+void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom, uint64_t* counters);   /* traversal_bvh2_oracle.c */
 
 /* Through the scene's BVH2 / Tri1 when it carries one -- the reference GPU device's layout and traversal
  * (gpu_traverse_primary / gpu_traverse_secondary, mapping_gpu.impala:18-80) -- otherwise the BVH8 single-ray kernel: the
  * same choice as the CUDA render loop (rodent_b200/csrc/render.cu). */
 static inline void trace(const RodentSceneView* sc, int any, V3 org, V3 dir, float tmin, float tmax, Hit1* hit, int32_t* geom, OracleStats* st) {
     Ray1 r = {{org.x, org.y, org.z}, tmin, {dir.x, dir.y, dir.z}, tmax};
-    if (sc->nodes2) { oracle_bvh2_trace_one(any, sc->nodes2, sc->tris1, &r, hit, geom); return; }
+    if (sc->nodes2) {                     /* the work counters then count Node2 visits and Tri1 tests */
+        uint64_t c[2] = {0, 0};
+        oracle_bvh2_trace_one(any, sc->nodes2, sc->tris1, &r, hit, geom, st ? c : NULL);
+        if (st) { st->nodes += c[0]; st->tri4 += c[1]; }
+        return;
+    }
     if (any) traverse_single(8, 1, sc->nodes, sc->tris, &r, hit, st, geom);
     else     traverse_single(8, 0, sc->nodes, sc->tris, &r, hit, st, geom);
 }

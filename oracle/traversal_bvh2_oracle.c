@@ -126,8 +126,8 @@ static void traverse_bvh2(int any_hit, const Node2* nodes, const Tri1* tris, con
 }
 
 /* One ray, with the geometry id of the hit (make_hit(geom_id, ...), mapping_gpu.impala:60): for the path-tracing oracle. */
-void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom) {
-    traverse_bvh2(any_hit, nodes, tris, ray, hit, NULL, geom);
+void oracle_bvh2_trace_one(int any_hit, const Node2* nodes, const Tri1* tris, const Ray1* ray, Hit1* hit, int32_t* geom, uint64_t* counters) {
+    traverse_bvh2(any_hit, nodes, tris, ray, hit, counters, geom);      /* counters (optional): [0] += Node2 visited, [1] += Tri1 tested */
 }
 
 typedef struct { int any_hit; const Node2* nodes; const Tri1* tris; const Ray1* rays; Hit1* hits; int32_t begin, end; uint64_t counters[2]; } Job;

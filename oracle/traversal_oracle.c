@@ -40,6 +40,11 @@ typedef struct { int32_t node; float tmin; } NodeRef;
 #ifndef ORACLE_TRACE
 #define ORACLE_TRACE(kind) ((void)0)
 #endif
+/* ... and per inner-node visit the hit mask and which of the hit children became the new top (bit set)
+ * rather than going below it: the push blocks a SIMT lane would execute (scripts/sim_sched2.c). */
+#ifndef ORACLE_TRACE_PUSHES
+#define ORACLE_TRACE_PUSHES(mask, tops) ((void)0)
+#endif
 
 /* Work counters, for the roofline's algorithmic bytes. */
 typedef struct OracleStats {
@@ -308,15 +313,16 @@ void traverse_single(const int N, const int any_hit,
                 restart = 1; break;
             }
 
-            int num_intrs = 0;                                           /* :195-208 */
+            int num_intrs = 0, tops = 0;                                 /* :195-208 */
             for (int m = mask; m != 0; m &= m - 1) {
                 const int lane = __builtin_ctz((unsigned)m);
                 const int32_t child_id = child[lane];
                 const float t = tentry[lane];
                 num_intrs++;
-                if (any_hit || t < top_t) PUSH(child_id, t);
+                if (any_hit || t < top_t) { PUSH(child_id, t); tops |= 1 << lane; }
                 else                      PUSH_AFTER(child_id, t);
             }
+            ORACLE_TRACE_PUSHES(mask, tops); (void)tops;
             if (ptr > max_ptr) max_ptr = ptr;
             ORACLE_TRACE('0' + num_intrs);
 

@@ -36,6 +36,17 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
     return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
 }
 
+// The same expressions with the contraction switched on by a template flag.  FMA = true is used by the renderer's stream
+// kernels only (rodent_b200_tune "render_fma"): their films are held to statistical parity, and half of a slab test's
+// instructions go away; the bench_traversal entry points, whose records are compared bit for bit, never set it.
+template <bool FMA> __device__ __forceinline__ float madd(float a, float b, float c) { return FMA ? __fmaf_rn(a, b, c) : add(mul(a, b), c); }
+template <bool FMA> __device__ __forceinline__ float msub(float a, float b, float c, float d) {          // a*b - c*d
+    return FMA ? __fmaf_rn(a, b, -mul(c, d)) : sub(mul(a, b), mul(c, d));
+}
+template <bool FMA> __device__ __forceinline__ float dot3f(float ax, float ay, float az, float bx, float by, float bz) {
+    return FMA ? __fmaf_rn(az, bz, __fmaf_rn(ay, by, mul(ax, bx))) : dot3(ax, ay, az, bx, by, bz);
+}
+
 // src/core/common.impala:78-80
 __device__ __forceinline__ float prodsign(float x, float y) {
     return __int_as_float(__float_as_int(x) ^ (__float_as_int(y) & int(0x80000000u)));

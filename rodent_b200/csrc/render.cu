@@ -1,10 +1,13 @@
 // Wavefront path tracer for sm_100a: the B200 counterpart of gpu_streaming_trace
 // (src/render/mapping_gpu.impala:308-369) behind render() / the rodent_b200_render* C ABI.
 //
-// One wavefront = up to 1 Mi rays (the reference's stream capacity, :319) and six launches,
-// all fed from device-side counters; the host reads back two integers per wavefront (the
-// reference blocks on four copies, :201,208,279,298):
+// One wavefront = up to 1 Mi rays (the reference's stream capacity, :319) and seven launches, all
+// fed from device-side state: the host never waits for a wavefront (the reference blocks on four
+// copies per wavefront, :201,208,279,298).  It enqueues wavefronts a few ahead and learns from a
+// small asynchronous copy, some wavefronts later, that the loop has ended:
 //
+//   plan              one thread: survivors of the last wavefront -> size of this one, how many
+//                     camera rays fill the stream's free tail, end of the loop         (host code of :321-366)
 //   generate          refill the free tail of the primary stream with camera rays      (:223-265)
 //   traverse_primary  persistent closest-hit traversal; writes the hit record and
 //                     counts rays per material in shared memory                       (:18-30 + count pass of :191-199)
@@ -33,7 +36,7 @@ extern "C" void rodent_b200_count_launches(int64_t n);   // traverse.cu: the lib
 
 namespace rb200 {
 
-static int kCapacity = 1 << 20;              // rays per stream: mapping_gpu.impala:319 (rodent_b200_tune "render_capacity", before a renderer is created)
+static int g_capacity = 1 << 20;             // rays per stream of renderers created from now on: mapping_gpu.impala:319 (rodent_b200_tune "render_capacity")
 constexpr int kRBlock = 128;
 constexpr int kRSmemStack = 24;
 constexpr int kRefillMin = 16;                // idle lanes that trigger a refill of the warp (traverse_sched.cuh)
@@ -54,7 +57,19 @@ struct ShadowStream {                         // src/render/driver.impala:54-61
     float4* ray_d;
     float4* color;                            // rgb, unused
 };
+
 enum Counter { kWorkPrimary = 0, kWorkShadow, kHitCount, kSurvivors, kShadows, kNumCounters = 8 };
+
+// Device-resident state of one pipeline's wavefront loop (the host variables `id` and `size` of
+// gpu_streaming_trace, mapping_gpu.impala:321-323, plus the statistics).
+struct LoopState {
+    long long next_id, total;                 // next camera sample to generate / samples of this render call
+    long long gen_first_id;                   // generate: first sample id,
+    int gen_first_dst, gen_n;                 //           where it goes in the stream, how many
+    int size;                                 // rays in the primary stream of the current wavefront
+    int done;                                 // nothing left: every later wavefront is empty
+    long long n_primary, n_shadow, n_waves;
+};
 
 struct SceneDev {
     const Node8* nodes; const Tri4* tris;
@@ -67,14 +82,32 @@ struct SceneDev {
 struct CameraDev { shade::V3 eye, dir, up, right; float w, h; };
 
 // ---- generate (gpu_generate_rays + make_camera_emitter, renderer.impala:26-40, camera.impala:35-44) ----
+// ---- plan: the host part of the loop body (mapping_gpu.impala:325-366), one thread on the device ----
+// `prev`: the counters the previous wavefront's shade kernel left (null for the first wavefront of a render call);
+// `cur`: this wavefront's counters, reset here.
+__global__ void plan_wavefront(LoopState* __restrict__ st, const int* __restrict__ prev, int* __restrict__ cur, int capacity) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int size = st->size;
+    if (prev) { size = prev[kSurvivors]; st->n_shadow += prev[kShadows]; }
+    const long long left = st->total - st->next_id;
+    const int n = int(left < (long long)(capacity - size) ? left : (long long)(capacity - size));     // :326-333
+    st->gen_first_id = st->next_id; st->gen_first_dst = size; st->gen_n = n;
+    st->next_id += n;
+    size += n;
+    st->size = size;
+    st->done = size == 0;                                                                              // :323
+    if (size > 0) { st->n_primary += size; st->n_waves += 1; }
+    for (int k = 0; k < kNumCounters; k++) cur[k] = 0;
+}
+
 __global__ void __launch_bounds__(256)
-generate_rays(PrimaryStream s, long long first_ray_id, int first_dst, int n, CameraDev cam, int width, int height, int spp, int iter,
+generate_rays(PrimaryStream s, const LoopState* __restrict__ st, CameraDev cam, int width, int height, int spp, int iter,
               const int* __restrict__ rows) {
     using namespace shade;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n) return;
-    const long long ray_id = first_ray_id + gid;
-    const int dst = first_dst + gid;
+    if (gid >= st->gen_n) return;
+    const long long ray_id = st->gen_first_id + gid;
+    const int dst = st->gen_first_dst + gid;
     const int sample = int(ray_id % spp), local_pixel = int(ray_id / spp);
     const int ly = local_pixel / width, x = local_pixel - ly * width;
     const int y = __ldg(rows + ly);
@@ -92,7 +125,7 @@ generate_rays(PrimaryStream s, long long first_ray_id, int first_dst, int n, Cam
 // ---- persistent traversal over a stream -----------------------------------------------------
 // SHADOW = false: closest hit, hit record + geometry id + per-material count.
 // SHADOW = true : any hit; unoccluded rays add their colour to the film.
-template <bool SHADOW, bool WIDE = false>
+template <bool SHADOW, bool WIDE = false, bool FMA = false>
 __global__ void __launch_bounds__(kRBlock, 5)
 traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
                 const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
@@ -108,7 +141,7 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
     }
     int* const hist_bins = hist;
     // the vote-scheduled persistent loop of traverse_sched.cuh, fed from / draining into the SoA streams
-    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock, 8, WIDE>(      // WIDE: 256-bit record loads (the scene arrays are cudaMalloc'ed)
+    traverse_vote_scheduled<SHADOW, !SHADOW, kRSmemStack, kRBlock, 8, WIDE, FMA>(      // WIDE: 256-bit record loads (the scene arrays are cudaMalloc'ed)
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
@@ -141,7 +174,7 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
 // STACK: levels of the id stack kept in shared memory (deeper ones go to a thread-local array).  The per-material counts
 // live in dynamic shared memory, (num_geoms + 1) ints for the closest-hit form: what a CTA does not take as shared memory
 // the SM keeps as L1, which serves two thirds of this kernel's record reads.
-template <bool SHADOW, int STACK>
+template <bool SHADOW, int STACK, bool FMA = false>
 __global__ void __launch_bounds__(kRBlock, 8)
 traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
@@ -156,7 +189,7 @@ traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ t
         __syncthreads();
     }
     int* const hist_bins = hist;
-    traverse_bvh2_scheduled<SHADOW, STACK, kRBlock>(
+    traverse_bvh2_scheduled<SHADOW, STACK, kRBlock, FMA>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, streak_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
@@ -199,8 +232,10 @@ __global__ void scan_bins(int* __restrict__ histogram, int* __restrict__ cursor,
 // ray's INDEX is moved: order[d] = i, 8 bytes of traffic per ray instead of 164, and the shade kernel gathers its
 // inputs through `order` (rays of one material keep their stream order, so the gather stays sector-friendly).
 __global__ void __launch_bounds__(256)
-scatter_by_material(PrimaryStream src, int* __restrict__ order, int size, int num_geoms, int* __restrict__ cursor) {
+scatter_by_material(PrimaryStream src, int* __restrict__ order, const LoopState* __restrict__ st, int num_geoms, int* __restrict__ cursor) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int size = st->size;
+    if ((i & ~31) >= size) return;                             // whole warp beyond the stream
     const int g = i < size ? src.geom[i] : num_geoms;
     const bool live = g < num_geoms;
     // one atomicAdd per (warp, material): peers with the same material take consecutive slots
@@ -322,23 +357,32 @@ shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, S
 }
 
 // ---- host side --------------------------------------------------------------------------------
+constexpr int kLookahead = 3;                   // wavefronts enqueued before the host looks at the loop state again
+
 struct Renderer {
     int dev = 0, width = 0, height = 0, spp = 1, max_path_len = 64;
+    int capacity = 1 << 20;                     // rays per stream, fixed at creation
     std::vector<int> rows;                      // image rows owned by this renderer
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_shaded = nullptr, ev_shadow_done = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_shaded = nullptr, ev_shadow_done = nullptr, ev_done = nullptr;
     PrimaryStream prim[2]{};
     ShadowStream shadow{};
     SceneDev scene{};
     std::vector<void*> allocations;
     int* counters = nullptr; int* histogram = nullptr; int* cursor = nullptr; int* d_rows = nullptr; int* order = nullptr;
-    int* h_counters = nullptr;                  // pinned
+    LoopState* state = nullptr;                 // device
+    LoopState* h_state = nullptr;               // pinned: kLookahead snapshots + the final one
+    cudaEvent_t ev_state[kLookahead] = {};
     float* film = nullptr; float* own_film = nullptr; float* h_film = nullptr;
     int sm_count = 0, occ_primary = 0, occ_shadow = 0, occ_primary2 = 0, occ_shadow2 = 0;
     int64_t stats[5] = {0, 0, 0, 0, 0};
     double last_ms = 0.0;
+    // per render call
+    int64_t head = 0, tail = 0, n_kernels = 0;  // wavefronts enqueued / whose state snapshot was read
+    bool finished = false, generation_over = false;
+    int bound = 0;                              // no wavefront from now on holds more rays than this
     // A renderer with several LANES drives that many independent wavefront pipelines (own streams, ray streams and
-    // counters, interleaved row bands, one host thread each) into the same film: see render_device.
+    // counters, interleaved row bands) into the same film: see render_device.
     std::vector<Renderer*> lanes;
     Renderer* parent = nullptr;
 
@@ -358,18 +402,21 @@ struct Renderer {
 };
 
 static void alloc_stream(Renderer& r, PrimaryStream& s) {
-    s.pixel = r.alloc<int>(kCapacity); s.ray_o = r.alloc<float4>(kCapacity); s.ray_d = r.alloc<float4>(kCapacity);
-    s.hit = r.alloc<float4>(kCapacity); s.geom = r.alloc<int>(kCapacity); s.contrib_mis = r.alloc<float4>(kCapacity);
-    s.rnd_depth = r.alloc<uint2>(kCapacity);
+    const size_t n = size_t(r.capacity);
+    s.pixel = r.alloc<int>(n); s.ray_o = r.alloc<float4>(n); s.ray_d = r.alloc<float4>(n);
+    s.hit = r.alloc<float4>(n); s.geom = r.alloc<int>(n); s.contrib_mis = r.alloc<float4>(n);
+    s.rnd_depth = r.alloc<uint2>(n);
 }
 
 static int g_render_leaf_streak_min = 2;                        // triangle steps follow each other while this many lanes want one (0: as for node steps)
 static int g_render_refill_min = 20, g_render_streak_min = 8;   // BVH2 stream kernels: refill threshold, step-streak threshold (swept: profiles/r01_experiments.md)
-static int g_render_bvh2_stack = 16;   // BVH2 stream kernels: stack levels in shared memory (8, 16, 24, 32; measured 518 / 518 / 518 / 513 Msamples/s)
 static int g_render_wide = 0;          // 256-bit record loads in the BVH8 stream kernels (rodent_b200_tune "render_wide")
 static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
+static int g_render_fma = 1;       // contracted slab / triangle arithmetic in the stream kernels (rodent_b200_tune "render_fma")
+static int g_render_poly_trig = 0; // test switch: sin / cos from poly_trig.h (rodent_b200_tune "render_poly_trig")
+constexpr int kBvh2Stack = 16;     // BVH2 stream kernels: stack levels in shared memory (8 / 16 / 24 / 32 measured 518 / 518 / 518 / 513 Msamples/s)
 
 // Streams, events, ray streams and counters of one wavefront pipeline; `r->rows` must be set.
 static void alloc_pipeline(Renderer* r) {
@@ -377,17 +424,20 @@ static void alloc_pipeline(Renderer* r) {
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking));
     RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_shaded, cudaEventDisableTiming));
     RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_shadow_done, cudaEventDisableTiming));
-    RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
-    RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
+    RB_CUDA_CHECK(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+    for (auto& e : r->ev_state) RB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!r->ev0) { RB_CUDA_CHECK(cudaEventCreate(&r->ev0)); RB_CUDA_CHECK(cudaEventCreate(&r->ev1)); }
     alloc_stream(*r, r->prim[0]);
     alloc_stream(*r, r->prim[1]);
-    r->shadow.pixel = r->alloc<int>(kCapacity); r->shadow.ray_o = r->alloc<float4>(kCapacity);
-    r->shadow.ray_d = r->alloc<float4>(kCapacity); r->shadow.color = r->alloc<float4>(kCapacity);
+    const size_t n = size_t(r->capacity);
+    r->shadow.pixel = r->alloc<int>(n); r->shadow.ray_o = r->alloc<float4>(n);
+    r->shadow.ray_d = r->alloc<float4>(n); r->shadow.color = r->alloc<float4>(n);
     r->counters = r->alloc<int>(2 * kNumCounters); r->histogram = r->alloc<int>(kMaxBins); r->cursor = r->alloc<int>(kMaxBins);
-    r->order = r->alloc<int>(kCapacity);
+    r->order = r->alloc<int>(n);
+    r->state = r->alloc<LoopState>(1);
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
-    RB_CUDA_CHECK(cudaMallocHost(&r->h_counters, 2 * kNumCounters * sizeof(int)));
+    RB_CUDA_CHECK(cudaMallocHost(&r->h_state, (kLookahead + 1) * sizeof(LoopState)));
 }
 
 static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
@@ -401,9 +451,24 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         }
         textured |= (m.map_kd | m.map_ks) != 0;
     }
+    // the stream kernels index per-material tables and shared-memory bins with the ids stored in the BVHs
+    const int num_materials = int(sc.materials.size());
+    for (const Tri4& t : sc.tris)
+        for (int j = 0; j < 4; j++)
+            if (t.prim_id[j] != -1 && (t.geom_id[j] < 0 || t.geom_id[j] >= num_materials)) {
+                std::fprintf(stderr, "rodent_b200: the scene's BVH8 holds geometry id %d, it has %d materials\n", t.geom_id[j], num_materials);
+                return nullptr;
+            }
+    for (const Tri1& t : sc.tris1)
+        if (t.geom_id < 0 || t.geom_id >= num_materials) {
+            std::fprintf(stderr, "rodent_b200: the scene's BVH2 holds geometry id %d, it has %d materials\n", t.geom_id, num_materials);
+            return nullptr;
+        }
     RB_CUDA_CHECK(cudaSetDevice(dev));
+    RB_CUDA_CHECK(cudaMemcpyToSymbol(shade::g_poly_trig, &g_render_poly_trig, sizeof(int)));
     auto r = new Renderer();
     r->dev = dev; r->width = width; r->height = height; r->spp = spp; r->max_path_len = max_path_len;
+    r->capacity = g_capacity;
     for (int y = 0; y < height; y++)
         if ((y / band) % num_parts == part) r->rows.push_back(y);
     cudaDeviceProp prop;
@@ -427,28 +492,38 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
         d.textures = r->upload(sc.textures.data(), sc.textures.size());
         d.texture_pixels = r->upload(sc.texture_pixels.data(), sc.texture_pixels.size());
     }
-    d.num_materials = int(sc.materials.size()); d.num_lights = int(sc.lights.size());
+    d.num_materials = num_materials; d.num_lights = int(sc.lights.size());
     if (!sc.nodes2.empty() && g_render_bvh2) {
         d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
         d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
     }
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, 16>, kRBlock, (sc.materials.size() + 1) * sizeof(int)));
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, 16>, kRBlock, sizeof(int)));
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false>, kRBlock, 0));
-    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true>, kRBlock, 0));
+    // persistent grids are sized from the occupancy of the instantiations that are launched
+    const size_t bins = (sc.materials.size() + 1) * sizeof(int);
+    if (g_render_fma) {
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, kBvh2Stack, true>, kRBlock, bins));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, kBvh2Stack, true>, kRBlock, sizeof(int)));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false, false, true>, kRBlock, 0));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true, false, true>, kRBlock, 0));
+    } else {
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, kBvh2Stack, false>, kRBlock, bins));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, kBvh2Stack, false>, kRBlock, sizeof(int)));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false, false, false>, kRBlock, 0));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true, false, false>, kRBlock, 0));
+    }
     // lanes: the rows of this renderer dealt out in bands of eight; small images keep a single pipeline
     const int bands = int((r->rows.size() + 7) / 8);
     const int num_lanes = std::max(1, std::min(g_render_lanes, bands / 4));
+    RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
+    RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
     if (num_lanes == 1) {
         alloc_pipeline(r);
     } else {
         RB_CUDA_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));      // film copies, timing events
-        RB_CUDA_CHECK(cudaEventCreate(&r->ev0));
-        RB_CUDA_CHECK(cudaEventCreate(&r->ev1));
         for (int j = 0; j < num_lanes; j++) {
             auto lane = new Renderer();
             lane->parent = r;
             lane->dev = dev; lane->width = width; lane->height = height; lane->spp = spp; lane->max_path_len = max_path_len;
+            lane->capacity = r->capacity;
             lane->sm_count = r->sm_count; lane->occ_primary = r->occ_primary; lane->occ_primary2 = r->occ_primary2; lane->occ_shadow2 = r->occ_shadow2; lane->occ_shadow = r->occ_shadow;
             lane->scene = r->scene;
             for (size_t k = 0; k < r->rows.size(); k++)
@@ -468,120 +543,163 @@ static void destroy_renderer(Renderer* r) {
     if (r->stream2) RB_CUDA_CHECK(cudaStreamSynchronize(r->stream2));
     for (void* p : r->allocations) RB_CUDA_CHECK(cudaFree(p));
     if (r->h_film) RB_CUDA_CHECK(cudaFreeHost(r->h_film));
-    if (r->h_counters) RB_CUDA_CHECK(cudaFreeHost(r->h_counters));
-    if (r->ev0) RB_CUDA_CHECK(cudaEventDestroy(r->ev0));
-    if (r->ev1) RB_CUDA_CHECK(cudaEventDestroy(r->ev1));
-    if (r->ev_shaded) RB_CUDA_CHECK(cudaEventDestroy(r->ev_shaded));
-    if (r->ev_shadow_done) RB_CUDA_CHECK(cudaEventDestroy(r->ev_shadow_done));
+    if (r->h_state) RB_CUDA_CHECK(cudaFreeHost(r->h_state));
+    for (cudaEvent_t e : {r->ev0, r->ev1, r->ev_shaded, r->ev_shadow_done, r->ev_done}) if (e) RB_CUDA_CHECK(cudaEventDestroy(e));
+    for (cudaEvent_t e : r->ev_state) if (e) RB_CUDA_CHECK(cudaEventDestroy(e));
     if (r->stream) RB_CUDA_CHECK(cudaStreamDestroy(r->stream));
     if (r->stream2) RB_CUDA_CHECK(cudaStreamDestroy(r->stream2));
     delete r;
 }
 
-// gpu_streaming_trace, mapping_gpu.impala:308-369
-static void render_pipeline(Renderer& r, float* film, const Settings& st, int iter);
+// ---- gpu_streaming_trace, mapping_gpu.impala:308-369, driven without waiting for the device ----
+// The reference's loop needs `size` (the survivors) on the host before it can launch the next wavefront.  Here the
+// loop variables live on the device (LoopState, plan_wavefront) and every kernel reads its counts from there, so the
+// host can enqueue wavefront k + 1 while wavefront k is still running.  What the host cannot know is when the loop ends:
+// each wavefront copies the loop state to pinned memory right after its plan step, and the host reads the snapshot of
+// wavefront k - kLookahead before it enqueues wavefront k.  Once a snapshot says `done`, the wavefronts already in the
+// queue find an empty stream and fall through.  Grids: the persistent traversal kernels have theirs; generate / scatter /
+// shade get a grid for `bound` rays, the full stream until a snapshot shows that all camera rays are out, after which
+// the stream can only shrink and the last seen size bounds it.
 
-// One render(settings, iter) call.  With lanes, every lane runs its own wavefront loop on its own host thread and
-// streams; their kernels interleave on the device, so the stragglers at the end of one pipeline's traversal kernels
-// and the host round trip per wavefront are covered by the other pipelines' work.
+static void begin_pipeline(Renderer& r, cudaEvent_t start, int64_t total) {
+    r.head = r.tail = 0; r.n_kernels = 0; r.finished = false; r.generation_over = false; r.bound = r.capacity;
+    LoopState init{};
+    init.total = total;
+    r.h_state[kLookahead] = init;                         // (pinned scratch for the upload)
+    RB_CUDA_CHECK(cudaStreamWaitEvent(r.stream, start, 0));
+    RB_CUDA_CHECK(cudaMemcpyAsync(r.state, &r.h_state[kLookahead], sizeof(LoopState), cudaMemcpyHostToDevice, r.stream));
+}
+
+template <bool FMA>
+static void enqueue_wavefront(Renderer& r, float* film, const CameraDev& cam, int iter) {
+    const int parity = int(r.head & 1);
+    int* counters = r.counters + parity * kNumCounters;
+    const int* prev = r.head ? r.counters + (parity ^ 1) * kNumCounters : nullptr;
+    const float inv_spp = 1.0f / float(r.spp);
+    const int num_geoms = r.scene.num_materials;
+    PrimaryStream& P = r.prim[0];
+    PrimaryStream& Q = r.prim[1];
+    const int cap = r.capacity, bound = r.bound;
+    // Two streams: everything up to the shade kernel runs on `s`; the shadow-ray traversal of a wavefront runs on
+    // `s2` and overlaps the generation and closest-hit traversal of the NEXT wavefront.  Both traversals are
+    // persistent kernels whose last rays straggle: the CTAs that drain early make room for the other kernel.  The two
+    // kernels only share the film (atomics); counters alternate between two sets, and the shade kernel of wavefront
+    // k waits for the shadow pass of wavefront k - 1, so a set is never reset under a pass that still reads it.
+    cudaStream_t s = r.stream, s2 = r.stream2;
+    plan_wavefront<<<1, 32, 0, s>>>(r.state, prev, counters, cap);
+    const int slot = int(r.head % kLookahead);
+    RB_CUDA_CHECK(cudaMemcpyAsync(&r.h_state[slot], r.state, sizeof(LoopState), cudaMemcpyDeviceToHost, s));
+    RB_CUDA_CHECK(cudaEventRecord(r.ev_state[slot], s));
+    if (!r.generation_over)
+        generate_rays<<<(cap + 255) / 256, 256, 0, s>>>(P, r.state, cam, r.width, r.height, r.spp, iter, r.d_rows);
+    if (r.scene.nodes2) {
+        const int grid_p = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
+        traverse_stream_bvh2<false, kBvh2Stack, FMA><<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(
+            r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, &r.state->size, cap, P.hit, P.geom, num_geoms,
+            r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
+    } else {
+        const int grid_p = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
+        auto kernel = g_render_wide ? traverse_stream<false, true, FMA> : traverse_stream<false, false, FMA>;
+        kernel<<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, &r.state->size, cap, P.hit, P.geom, num_geoms,
+                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
+    }
+    scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
+    scatter_by_material<<<(bound + 255) / 256, 256, 0, s>>>(P, r.order, r.state, num_geoms, r.cursor);
+    RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
+    shade_rays<<<(bound + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
+    RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));
+    std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
+    RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
+    if (r.scene.nodes2 && g_render_shadow_bvh2) {
+        const int grid_s = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
+        traverse_stream_bvh2<true, kBvh2Stack, FMA><<<grid_s, kRBlock, sizeof(int), s2>>>(
+            r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, cap,
+            nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+            counters + kWorkShadow, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
+    } else {
+        const int grid_s = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
+        auto kernel = g_render_wide ? traverse_stream<true, true, FMA> : traverse_stream<true, false, FMA>;
+        kernel<<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, cap,
+                                           nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
+                                           counters + kWorkShadow, kRefillMin);
+    }
+    RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
+    RB_CUDA_CHECK(cudaGetLastError());
+    r.n_kernels += r.generation_over ? 6 : 7;
+    r.head++;
+}
+
+// Reads the snapshots that have arrived (all of them up to `upto` when `wait`); returns true when one was read.
+static bool retire_snapshots(Renderer& r, bool wait) {
+    bool any = false;
+    while (r.tail < r.head) {
+        const int slot = int(r.tail % kLookahead);
+        if (wait) RB_CUDA_CHECK(cudaEventSynchronize(r.ev_state[slot]));
+        else {
+            const cudaError_t q = cudaEventQuery(r.ev_state[slot]);
+            if (q == cudaErrorNotReady) break;
+            RB_CUDA_CHECK(q);
+        }
+        const LoopState& st = r.h_state[slot];
+        if (st.done) { r.finished = true; r.h_state[kLookahead] = st; }
+        if (st.next_id >= st.total) { r.generation_over = true; r.bound = std::max(st.size, 1); }
+        r.tail++;
+        any = true;
+        wait = false;                                           // one blocking wait per call is enough
+    }
+    return any;
+}
+
+// One render(settings, iter) call.  With lanes, the pipelines' kernels interleave on the device, so the stragglers at
+// the end of one pipeline's traversal kernels are covered by the other pipelines' work; one host thread feeds them all.
 static void render_device(Renderer& r, const Settings& st, int iter) {
     RB_CUDA_CHECK(cudaSetDevice(r.dev));
-    if (r.lanes.empty()) { render_pipeline(r, r.film, st, iter); return; }
+    const CameraDev cam{{st.eye.x, st.eye.y, st.eye.z}, {st.dir.x, st.dir.y, st.dir.z}, {st.up.x, st.up.y, st.up.z},
+                        {st.right.x, st.right.y, st.right.z}, st.width, st.height};
+    std::vector<Renderer*> pipes = r.lanes.empty() ? std::vector<Renderer*>{&r} : r.lanes;
     RB_CUDA_CHECK(cudaEventRecord(r.ev0, r.stream));
-    std::vector<std::thread> threads;
-    for (Renderer* lane : r.lanes)
-        threads.emplace_back([lane, &r, &st, iter] { render_pipeline(*lane, r.film, st, iter); });
-    for (auto& t : threads) t.join();
+    for (Renderer* p : pipes) begin_pipeline(*p, r.ev0, int64_t(p->spp) * p->width * int64_t(p->rows.size()));
+    for (;;) {
+        bool all_finished = true, progressed = false;
+        for (Renderer* p : pipes) {
+            if (p->finished) continue;
+            progressed |= retire_snapshots(*p, false);
+            if (p->finished) continue;
+            all_finished = false;
+            if (p->head - p->tail < kLookahead) {
+                if (g_render_fma) enqueue_wavefront<true>(*p, r.film, cam, iter); else enqueue_wavefront<false>(*p, r.film, cam, iter);
+                progressed = true;
+            }
+        }
+        if (all_finished) break;
+        if (!progressed) {                                      // every queue is full: wait for the oldest snapshot of one of them
+            Renderer* oldest = nullptr;
+            for (Renderer* p : pipes) if (!p->finished && (!oldest || p->tail < oldest->tail)) oldest = p;
+            retire_snapshots(*oldest, true);
+        }
+    }
+    // the wavefronts still in the queues are empty; the render ends when the last shadow pass has added its light
+    for (Renderer* p : pipes) {
+        RB_CUDA_CHECK(cudaStreamWaitEvent(p->stream, p->ev_shadow_done, 0));
+        if (p != &r) {
+            RB_CUDA_CHECK(cudaEventRecord(p->ev_done, p->stream));
+            RB_CUDA_CHECK(cudaStreamWaitEvent(r.stream, p->ev_done, 0));
+        }
+    }
     RB_CUDA_CHECK(cudaEventRecord(r.ev1, r.stream));
     RB_CUDA_CHECK(cudaEventSynchronize(r.ev1));
     float ms = 0.0f;
     RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
     r.last_ms = ms;
     for (int k = 0; k < 5; k++) r.stats[k] = 0;
-    for (Renderer* lane : r.lanes) {
-        for (int k = 0; k < 5; k++) r.stats[k] += lane->stats[k];
+    for (Renderer* p : pipes) {
+        const LoopState& fin = p->h_state[kLookahead];
+        r.stats[0] += fin.total; r.stats[1] += fin.n_primary; r.stats[2] += fin.n_shadow;
+        r.stats[3] = std::max<int64_t>(r.stats[3], fin.n_waves);           // wavefronts: the longest pipeline
+        r.stats[4] += p->n_kernels;
+        p->tail = p->head;                                                 // (snapshots of the empty wavefronts are not read)
     }
-    r.stats[3] = 0;
-    for (Renderer* lane : r.lanes) r.stats[3] = std::max(r.stats[3], lane->stats[3]);     // wavefronts: the longest pipeline
-}
-
-static void render_pipeline(Renderer& r, float* film, const Settings& st, int iter) {
-    RB_CUDA_CHECK(cudaSetDevice(r.dev));
-    const CameraDev cam{{st.eye.x, st.eye.y, st.eye.z}, {st.dir.x, st.dir.y, st.dir.z}, {st.up.x, st.up.y, st.up.z},
-                        {st.right.x, st.right.y, st.right.z}, st.width, st.height};
-    const int64_t total = int64_t(r.spp) * r.width * int64_t(r.rows.size());
-    const float inv_spp = 1.0f / float(r.spp);
-    const int num_geoms = r.scene.num_materials;
-    PrimaryStream& P = r.prim[0];
-    PrimaryStream& Q = r.prim[1];
-    int64_t id = 0; int size = 0;
-    int64_t n_primary = 0, n_shadow = 0, n_waves = 0, n_kernels = 0;
-    // Two streams: everything up to the shade kernel runs on `s`; the shadow-ray traversal of a wavefront runs on
-    // `s2` and overlaps the generation and closest-hit traversal of the NEXT wavefront.  Both traversals are
-    // persistent kernels whose last rays straggle (a few rays take ten times the median number of steps): the CTAs
-    // that drain early make room for the other kernel, so the tails are filled instead of waited for.  The two
-    // kernels only share the film (atomics); counters alternate between two sets so that a shadow pass still
-    // reading its set is never reset under it.
-    cudaStream_t s = r.stream, s2 = r.stream2;
-    RB_CUDA_CHECK(cudaEventRecord(r.ev0, s));
-    while (id < total || size > 0) {
-        const int parity = int(n_waves & 1);
-        int* counters = r.counters + parity * kNumCounters;
-        int* h_counters = r.h_counters + parity * kNumCounters;
-        if (size < kCapacity && id < total) {
-            const int n = int(std::min<int64_t>(total - id, kCapacity - size));
-            generate_rays<<<(n + 255) / 256, 256, 0, s>>>(P, (long long)id, size, n, cam, r.width, r.height, r.spp, iter, r.d_rows);
-            id += n; size += n; n_kernels++;
-        }
-        RB_CUDA_CHECK(cudaMemsetAsync(counters, 0, kNumCounters * sizeof(int), s));
-        if (r.scene.nodes2) {
-            const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
-            auto kernel = g_render_bvh2_stack <= 8 ? traverse_stream_bvh2<false, 8> : g_render_bvh2_stack <= 16 ? traverse_stream_bvh2<false, 16> :
-                          g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<false, 24> : traverse_stream_bvh2<false, 32>;
-            kernel<<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                                                          r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
-        } else {
-            const int grid_p = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
-            auto kernel = g_render_wide ? traverse_stream<false, true> : traverse_stream<false, false>;
-            kernel<<<grid_p, kRBlock, 0, s>>>(r.scene.nodes, r.scene.tris, P.ray_o, P.ray_d, nullptr, size, P.hit, P.geom, num_geoms,
-                                              r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
-        }
-        scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
-        scatter_by_material<<<(size + 255) / 256, 256, 0, s>>>(P, r.order, size, num_geoms, r.cursor);
-        RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
-        shade_rays<<<(size + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
-        RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));
-        RB_CUDA_CHECK(cudaMemcpyAsync(h_counters, counters, kNumCounters * sizeof(int), cudaMemcpyDeviceToHost, s));
-        std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
-        RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
-        if (r.scene.nodes2 && g_render_shadow_bvh2) {
-            const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
-            auto kernel = g_render_bvh2_stack <= 8 ? traverse_stream_bvh2<true, 8> : g_render_bvh2_stack <= 16 ? traverse_stream_bvh2<true, 16> :
-                          g_render_bvh2_stack <= 24 ? traverse_stream_bvh2<true, 24> : traverse_stream_bvh2<true, 32>;
-            kernel<<<grid_s, kRBlock, sizeof(int), s2>>>(r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                                         nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                                         counters + kWorkShadow, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
-        } else {
-            const int grid_s = std::min((size + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow);
-            auto kernel = g_render_wide ? traverse_stream<true, true> : traverse_stream<true, false>;
-            kernel<<<grid_s, kRBlock, 0, s2>>>(r.scene.nodes, r.scene.tris, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, size,
-                                               nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
-                                               counters + kWorkShadow, kRefillMin);
-        }
-        RB_CUDA_CHECK(cudaEventRecord(r.ev_shadow_done, s2));
-        RB_CUDA_CHECK(cudaGetLastError());
-        RB_CUDA_CHECK(cudaStreamSynchronize(s));                // survivors and shadow-ray count of this wavefront (the shadow pass runs on)
-        n_primary += size; n_shadow += h_counters[kShadows]; n_waves++; n_kernels += 5;
-        size = h_counters[kSurvivors];
-    }
-    RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));
-    RB_CUDA_CHECK(cudaEventRecord(r.ev1, s));
-    RB_CUDA_CHECK(cudaEventSynchronize(r.ev1));
-    float ms = 0.0f;
-    RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
-    r.last_ms = ms;
-    rodent_b200_count_launches(n_kernels);
-    r.stats[0] = total; r.stats[1] = n_primary; r.stats[2] = n_shadow; r.stats[3] = n_waves; r.stats[4] = n_kernels;
+    rodent_b200_count_launches(r.stats[4]);
 }
 
 static void present(Renderer& r) {
@@ -630,16 +748,22 @@ void rodent_b200_clear(RodentRenderer* rr) {
 void rodent_b200_render_stats(const RodentRenderer* r, int64_t out[5]) { std::memcpy(out, reinterpret_cast<const Renderer*>(r)->stats, 5 * sizeof(int64_t)); }
 double rodent_b200_render_last_ms(const RodentRenderer* r) { return reinterpret_cast<const Renderer*>(r)->last_ms; }
 
+// Thresholds are clamped to [1, 33] (below 1 a streak loop would never end, and the refill leader would be lane -1);
+// the stream capacity is read when a renderer is created and kept by it, so changing it later cannot outgrow buffers.
 void rodent_b200_render_tune(const char* key, int32_t value) {
-    if (!std::strcmp(key, "render_lanes")) g_render_lanes = std::max(1, int(value));
-    if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value;
-    if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value;
-    if (!std::strcmp(key, "render_wide")) g_render_wide = value;
-    if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = value;
-    if (!std::strcmp(key, "render_bvh2_stack")) g_render_bvh2_stack = value;
-    if (!std::strcmp(key, "render_capacity") && value >= 1024) kCapacity = value;
-    if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = value;
-    if (!std::strcmp(key, "render_leaf_streak_min")) g_render_leaf_streak_min = value;
+    auto clamp = [](int v, int lo, int hi) { return std::max(lo, std::min(v, hi)); };
+    if (!std::strcmp(key, "render_lanes")) g_render_lanes = clamp(value, 1, 16);
+    else if (!std::strcmp(key, "render_bvh2")) g_render_bvh2 = value != 0;
+    else if (!std::strcmp(key, "render_shadow_bvh2")) g_render_shadow_bvh2 = value != 0;
+    else if (!std::strcmp(key, "render_wide")) g_render_wide = value != 0;
+    else if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = clamp(value, 1, 32);
+    else if (!std::strcmp(key, "render_bvh2_stack")) {}        // fixed at 16 since round 2 (8 .. 32 measured the same)
+    else if (!std::strcmp(key, "render_fma")) g_render_fma = value != 0;
+    else if (!std::strcmp(key, "render_poly_trig")) g_render_poly_trig = value != 0;
+    else if (!std::strcmp(key, "render_capacity")) g_capacity = clamp(value, 1024, 1 << 24);
+    else if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = clamp(value, 1, 33);
+    else if (!std::strcmp(key, "render_leaf_streak_min")) g_render_leaf_streak_min = clamp(value, 0, 33);
+    else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;

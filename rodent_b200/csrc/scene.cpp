@@ -463,6 +463,9 @@ void collect_lights(Scene& s, const std::vector<F3>& verts) {
         if (!s.materials[m].is_emissive) continue;
         const F3 a = verts[s.indices[4 * i]], b = verts[s.indices[4 * i + 1]], c = verts[s.indices[4 * i + 2]];
         F3 n = cross(b - a, c - a);
+        // a triangle without area (or one no Tri4 ever described: its vertices are zero) cannot be sampled: it would
+        // carry inv_area = inf and a NaN normal into every next-event estimate that picks it
+        if (!(length(n) > 0.0f)) continue;
         RodentLight l{};
         l.inv_area = 1.0f / (0.5f * length(n));
         n = normalize(n);
@@ -639,6 +642,7 @@ bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris,
         const int p = tri.prim_id & 0x7FFFFFFF;
         if (p >= num_prims) return fail("prim_id out of range in BVH2");
         tri.geom_id = scene.indices[4 * p + 3];
+        if (tri.geom_id < 0 || tri.geom_id >= int(scene.materials.size())) return fail("geometry id out of range in BVH2");
     }
     scene.nodes2.assign(nodes, nodes + num_nodes);
     scene.tris1 = std::move(t);
@@ -647,6 +651,16 @@ bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris,
 
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
                        const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims) {
+    if (num_nodes <= 0 || num_tri4 < 0 || num_materials <= 0 || num_prims < 0 || !nodes || !tris || !materials || !material_of_prim) {
+        fail("scene_from_bvh8: empty or null input");
+        return nullptr;
+    }
+    // the ids index the materials table, the per-material bins of the sort and the light table on the device
+    for (int p = 0; p < num_prims; p++)
+        if (material_of_prim[p] < 0 || material_of_prim[p] >= num_materials) {
+            std::fprintf(stderr, "rodent_b200: material_of_prim[%d] = %d, the scene has %d materials\n", p, material_of_prim[p], num_materials);
+            return nullptr;
+        }
     auto scene = new Scene();
     scene->nodes.assign(nodes, nodes + num_nodes);
     scene->tris.assign(tris, tris + num_tri4);

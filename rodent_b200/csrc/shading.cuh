@@ -7,6 +7,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "poly_trig.h"
 
 namespace rb200 {
 namespace shade {
@@ -89,8 +90,13 @@ __device__ __forceinline__ float cosine_hemisphere_pdf(float c) { return c * (1.
 __device__ __forceinline__ float cosine_power_hemisphere_pdf(float c, float k) { return fastpow(c, k) * (k + 1.0f) * (1.0f / (2.0f * kPi)); }
 
 struct DirSample { V3 dir; float pdf; };
+// Test switch (rodent_b200_tune "render_poly_trig"): sin / cos from poly_trig.h instead of CUDA's sinf / cosf.
+static __device__ int g_poly_trig = 0;                  // one per translation unit; render.cu sets its own
 __device__ __forceinline__ DirSample make_dir_sample(float c, float s, float phi, float pdf) {          // random.impala:39-48
-    return DirSample{v3(s * cosf(phi), s * sinf(phi), c), pdf};
+    float sn, cs;
+    if (g_poly_trig) rb_poly_sincos(phi, &sn, &cs);
+    else { sn = sinf(phi); cs = cosf(phi); }
+    return DirSample{v3(s * cs, s * sn, c), pdf};
 }
 __device__ __forceinline__ DirSample sample_cosine_hemisphere(float u, float v) {                       // random.impala:72-77
     const float c = sqrtf(1.0f - v), s = sqrtf(v);

@@ -13,6 +13,8 @@
 // Measurements and what each experiment showed: profiles/r01_experiments.md.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <thread>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -46,6 +48,7 @@ struct Tuning {
     int pool_prefetch = 0;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
+    int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_chunks = 3;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 3..4)
 };
 static Tuning g_tuning;
@@ -282,6 +285,12 @@ traverse_bvh8_quad(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
 }
 
 // ---- per-device state ---------------------------------------------------------
+// A BVH uploaded on behalf of a host-pointer call (cached_bvh below).
+struct BvhCopy {
+    void* d_nodes = nullptr; Tri4* d_tris = nullptr;
+    size_t num_nodes = 0, num_tri4 = 0, node_size = 0;
+    uint64_t fingerprint = 0, last_use = 0;
+};
 struct DeviceState {
     std::atomic<bool> init{false};
     int sm_count = 0;
@@ -294,10 +303,11 @@ struct DeviceState {
     int occ_bvh4[2] = {0, 0};
     int occ_bvh2[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 8, 10, 12][closest, any]
     StackEntry* pool_overflow = nullptr; size_t pool_overflow_warps = 0;   // global backing of the pools' deep stack levels
-    int occ_vote[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [min blocks 4, 5, 6][closest, any]
     // host-pointer path: staging contexts (one per call in flight, reused) and the uploaded BVHs
     std::vector<struct HostContext*> idle_contexts;
-    std::map<std::pair<const void*, const void*>, std::pair<void*, Tri4*>> bvh_cache;
+    std::map<std::pair<const void*, const void*>, struct BvhCopy> bvh_cache;
+    uint64_t bvh_clock = 0; int64_t bvh_uploads = 0, bvh_reuploads = 0;
+    std::map<const void*, int> occupancy;      // kernel -> resident CTAs per SM
 };
 // What one host-pointer call needs on the device.  The reference's cpu_* functions are reentrant, so their drop-ins are
 // too: every call takes a context of its own, and concurrent calls (from several host threads) overlap on the device.
@@ -305,6 +315,9 @@ struct HostContext {
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     Ray1* d_rays = nullptr; Hit1* d_hits = nullptr; size_t ray_capacity = 0;
     int* counters = nullptr;   // 3 x 8 ints: one work counter per stream
+    // pinned staging for callers whose buffers are pageable (grown on demand, kept)
+    Ray1* h_rays = nullptr; Hit1* h_hits = nullptr; size_t stage_capacity = 0;
+    cudaEvent_t piece_done[16] = {};
 };
 static DeviceState g_dev[64];
 static std::mutex g_mutex;
@@ -332,12 +345,6 @@ static DeviceState& device_state(int dev) {
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ[1], traverse_bvh8_persistent<true>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[0], traverse_bvh8_quad<false>, kQuadBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_quad[1], traverse_bvh8_quad<true>, kQuadBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[0][0], traverse_bvh8_vote<false, 4>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[0][1], traverse_bvh8_vote<true, 4>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][0], traverse_bvh8_vote<false, 5>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[1][1], traverse_bvh8_vote<true, 5>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][0], traverse_bvh8_vote<false, 6>, kBlock, 0));
-            RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_vote[2][1], traverse_bvh8_vote<true, 6>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[0], traverse_bvh4_vote<false>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh4[1], traverse_bvh4_vote<true>, kBlock, 0));
             RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_bvh2[0][0], traverse_bvh2_vote<false, 8, 32>, kBlock, 0));
@@ -352,6 +359,17 @@ static DeviceState& device_state(int dev) {
         }
     }
     return s;
+}
+
+// Resident CTAs per SM of `kernel` at `block` threads (static shared memory only), looked up once per device and kernel.
+static int occupancy(DeviceState& s, const void* kernel, int block) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = s.occupancy.find(kernel);
+    if (it != s.occupancy.end()) return it->second;
+    int n = 0;
+    RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block, 0));
+    s.occupancy[kernel] = std::max(n, 1);
+    return std::max(n, 1);
 }
 
 template <bool ANY>
@@ -378,17 +396,18 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
     } else if (g_tuning.mapping == 2) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-        const int v = std::min(std::max(g_tuning.vote_min_blocks, 4), 6) - 4;
-        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ_vote[v][ANY ? 1 : 0];
+        const int v = std::min(std::max(g_tuning.vote_min_blocks, 4), 6);
+        const bool wide = g_tuning.wide_loads && ((reinterpret_cast<uintptr_t>(nodes) | reinterpret_cast<uintptr_t>(tris)) & 31) == 0;
+        using Kernel = void (*)(const Node8*, const Tri4*, const Ray1*, Hit1*, int, int*, int, int);
+        Kernel kernel = v == 4 ? traverse_bvh8_vote<ANY, 4> : v == 6 ? traverse_bvh8_vote<ANY, 6> :
+                        !wide ? traverse_bvh8_vote<ANY, 5> :
+                        g_tuning.vote_smem_depth >= 24 ? traverse_bvh8_vote<ANY, 5, true> :
+                        g_tuning.vote_smem_depth >= 16 ? traverse_bvh8_vote<ANY, 5, true, 16> : traverse_bvh8_vote<ANY, 5, true, 12>;
+        // the persistent grid is sized from the occupancy of the very instantiation that is launched
+        const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(kernel), kBlock);
         const int needed = (num_rays + kBlock - 1) / kBlock;
         const int grid = std::min(needed, s.sm_count * per_sm);
-        if (v == 0) traverse_bvh8_vote<ANY, 4><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        const bool wide = g_tuning.wide_loads && ((reinterpret_cast<uintptr_t>(nodes) | reinterpret_cast<uintptr_t>(tris)) & 31) == 0;
-        if (v == 1 && wide && g_tuning.vote_smem_depth >= 24) traverse_bvh8_vote<ANY, 5, true><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        if (v == 1 && wide && g_tuning.vote_smem_depth < 24 && g_tuning.vote_smem_depth >= 16) traverse_bvh8_vote<ANY, 5, true, 16><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        if (v == 1 && wide && g_tuning.vote_smem_depth < 16) traverse_bvh8_vote<ANY, 5, true, 12><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        if (v == 1 && !wide) traverse_bvh8_vote<ANY, 5><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
-        if (v == 2) traverse_bvh8_vote<ANY, 6><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
+        kernel<<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_min, g_tuning.node_streak_min);
     } else if (g_tuning.mapping == 4) {
         if (!counter) counter = s.counter;
         RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -446,9 +465,14 @@ static void launch(DeviceState& s, const Node2* nodes, const Tri1* tris, const R
     g_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
+// The synchronous device-pointer calls share the device's default work counter, its timing events and last_ms, so they
+// are serialised per device (the reference's nvvm_* exports are called from one thread); callers that want
+// concurrent launches use the _async forms with their own counters.
+static std::mutex g_sync_mutex[64];
 template <bool ANY, typename NodeT, typename TriT>
 static void run_sync(int dev, const NodeT* nodes, const TriT* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     DeviceState& s = device_state(dev);
+    std::lock_guard<std::mutex> lock(g_sync_mutex[dev]);
     RB_CUDA_CHECK(cudaEventRecord(s.ev0, 0));
     launch<ANY>(s, nodes, tris, rays, hits, num_rays, 0, nullptr);
     RB_CUDA_CHECK(cudaEventRecord(s.ev1, 0));
@@ -459,13 +483,23 @@ static void run_sync(int dev, const NodeT* nodes, const TriT* tris, const Ray1* 
 }
 
 // ---- host-pointer path ----------------------------------------------------------
-// Extent of a BVH given only its arrays: walk from the root (node 1).
+// Extent of a BVH given only its arrays: walk from the root (node 1).  The arrays come from the caller and are not
+// trusted: ids are bounded, every node is visited once, a leaf's packet run is bounded.
+constexpr size_t kMaxBvhNodes = size_t(1) << 26, kMaxBvhTri4 = size_t(1) << 28;
 template <typename NodeT>
 static void bvh_extent(const NodeT* nodes, const Tri4* tris, size_t& num_nodes, size_t& num_tri4) {
     std::vector<int> todo{1};
+    std::vector<bool> seen;
     num_nodes = 0; num_tri4 = 0;
+    size_t visited = 0;
+    auto bad = [](const char* why) { std::fprintf(stderr, "rodent_b200: malformed BVH passed to a host-pointer entry point (%s)\n", why); std::abort(); };
     while (!todo.empty()) {
         const int id = todo.back(); todo.pop_back();
+        if (size_t(id) > kMaxBvhNodes) bad("node id out of range");
+        if (seen.size() < size_t(id)) seen.resize(std::max(size_t(id), seen.size() * 2), false);
+        if (seen[id - 1]) bad("a node is reachable twice");
+        seen[id - 1] = true;
+        if (++visited > kMaxBvhNodes) bad("too many nodes");
         num_nodes = std::max(num_nodes, size_t(id));
         const NodeT& n = nodes[id - 1];
         for (int i = 0; i < int(sizeof(n.child) / sizeof(n.child[0])); i++) {
@@ -473,11 +507,37 @@ static void bvh_extent(const NodeT* nodes, const Tri4* tris, size_t& num_nodes, 
             if (c > 0) todo.push_back(c);
             else if (c < 0) {
                 size_t k = size_t(~c);
-                while (tris[k].prim_id[3] >= 0) k++;     // is_last sentinel, mapping_cpu.impala:40
+                if (k >= kMaxBvhTri4) bad("leaf index out of range");
+                while (tris[k].prim_id[3] >= 0) {        // is_last sentinel, mapping_cpu.impala:40
+                    if (++k >= kMaxBvhTri4) bad("leaf without an end marker");
+                }
                 num_tri4 = std::max(num_tri4, k + 1);
             }
         }
     }
+}
+
+// The cpu_* functions these entry points replace are pure: they read whatever the arrays hold at the time of the call.
+// The uploaded copy is therefore keyed on CONTENT, not on the addresses alone: every call hashes the first and last KB of
+// both arrays and 64 cache lines spread over each (about 12 KB, ~1 us) and compares with what was uploaded; a caller
+// that rebuilt a BVH in place or reused an allocation gets a fresh upload.  (A change confined to bytes the samples miss
+// is not seen: callers that patch a BVH in place call rodent_b200_forget_bvh.)  At most kBvhCacheEntries copies are kept
+// per device, least recently used first out.
+constexpr size_t kBvhCacheEntries = 8;
+static uint64_t sample_hash(const void* base, size_t bytes, uint64_t h) {
+    const unsigned char* p = static_cast<const unsigned char*>(base);
+    auto mix = [&h](const unsigned char* q, size_t n) {
+        for (size_t i = 0; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, q + i, 8); h = (h ^ w) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; }
+    };
+    const size_t edge = std::min<size_t>(bytes, 1024);
+    mix(p, edge);
+    mix(p + bytes - edge, edge);
+    if (bytes > 2048)
+        for (int k = 1; k <= 64; k++) mix(p + ((bytes - 64) * size_t(k) / 65 & ~size_t(7)), 64);
+    return h ^ bytes;
+}
+static uint64_t bvh_fingerprint(const void* nodes, size_t node_bytes, const void* tris, size_t tri_bytes) {
+    return sample_hash(tris, tri_bytes, sample_hash(nodes, node_bytes, 0xCBF29CE484222325ull));
 }
 
 template <typename NodeT>
@@ -485,15 +545,36 @@ static std::pair<NodeT*, Tri4*> cached_bvh(DeviceState& s, const NodeT* nodes, c
     std::lock_guard<std::mutex> lock(g_mutex);
     auto key = std::make_pair((const void*)nodes, (const void*)tris);
     auto it = s.bvh_cache.find(key);
-    if (it != s.bvh_cache.end()) return std::make_pair(static_cast<NodeT*>(it->second.first), it->second.second);
-    size_t nn, nt;
-    bvh_extent(nodes, tris, nn, nt);
+    if (it != s.bvh_cache.end()) {
+        BvhCopy& c = it->second;
+        if (c.node_size == sizeof(NodeT) && c.fingerprint == bvh_fingerprint(nodes, c.num_nodes * sizeof(NodeT), tris, c.num_tri4 * sizeof(Tri4))) {
+            c.last_use = ++s.bvh_clock;
+            return std::make_pair(static_cast<NodeT*>(c.d_nodes), c.d_tris);
+        }
+        RB_CUDA_CHECK(cudaDeviceSynchronize());          // another call may still trace the stale copy
+        RB_CUDA_CHECK(cudaFree(c.d_nodes)); RB_CUDA_CHECK(cudaFree(c.d_tris));
+        s.bvh_cache.erase(it);
+        s.bvh_reuploads++;
+    }
+    if (s.bvh_cache.size() >= kBvhCacheEntries) {
+        auto lru = s.bvh_cache.begin();
+        for (auto i = s.bvh_cache.begin(); i != s.bvh_cache.end(); ++i) if (i->second.last_use < lru->second.last_use) lru = i;
+        RB_CUDA_CHECK(cudaDeviceSynchronize());
+        RB_CUDA_CHECK(cudaFree(lru->second.d_nodes)); RB_CUDA_CHECK(cudaFree(lru->second.d_tris));
+        s.bvh_cache.erase(lru);
+    }
+    BvhCopy c;
+    bvh_extent(nodes, tris, c.num_nodes, c.num_tri4);
+    c.node_size = sizeof(NodeT);
+    c.fingerprint = bvh_fingerprint(nodes, c.num_nodes * sizeof(NodeT), tris, c.num_tri4 * sizeof(Tri4));
     NodeT* dn; Tri4* dt;
-    RB_CUDA_CHECK(cudaMalloc(&dn, nn * sizeof(NodeT)));
-    RB_CUDA_CHECK(cudaMalloc(&dt, std::max<size_t>(nt, 1) * sizeof(Tri4)));
-    RB_CUDA_CHECK(cudaMemcpy(dn, nodes, nn * sizeof(NodeT), cudaMemcpyHostToDevice));
-    RB_CUDA_CHECK(cudaMemcpy(dt, tris, nt * sizeof(Tri4), cudaMemcpyHostToDevice));
-    s.bvh_cache[key] = std::make_pair(static_cast<void*>(dn), dt);
+    RB_CUDA_CHECK(cudaMalloc(&dn, c.num_nodes * sizeof(NodeT)));
+    RB_CUDA_CHECK(cudaMalloc(&dt, std::max<size_t>(c.num_tri4, 1) * sizeof(Tri4)));
+    RB_CUDA_CHECK(cudaMemcpy(dn, nodes, c.num_nodes * sizeof(NodeT), cudaMemcpyHostToDevice));
+    RB_CUDA_CHECK(cudaMemcpy(dt, tris, c.num_tri4 * sizeof(Tri4), cudaMemcpyHostToDevice));
+    c.d_nodes = dn; c.d_tris = dt; c.last_use = ++s.bvh_clock;
+    s.bvh_cache[key] = c;
+    s.bvh_uploads++;
     return std::make_pair(dn, dt);
 }
 
@@ -526,6 +607,53 @@ static void release_host_context(DeviceState& s, HostContext* c) {
 // The ray-pool variant (mapping 3) indexes one per-device overflow buffer by warp: its launches must not overlap.
 static std::mutex g_pool_serial;
 
+// A few helper threads that copy between the caller's pageable buffers and pinned staging memory (one memcpy runs at
+// ~10 GB/s on one core; the PCIe link takes five times that).  Jobs are byte ranges; parallel_copy returns when all are done.
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    void parallel_copy(void* dst, const void* src, size_t bytes) {
+        const size_t kMin = size_t(1) << 20;
+        const int parts = int(std::min<size_t>(kThreads + 1, std::max<size_t>(1, bytes / kMin)));
+        if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
+        const size_t each = ((bytes / parts) + 4095) & ~size_t(4095);
+        std::atomic<int> pending{parts - 1};
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (int k = 1; k < parts; k++) {
+                const size_t b = std::min(bytes, each * k), e = std::min(bytes, each * (k + 1));
+                jobs_.push_back(Job{static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, e - b, &pending});
+            }
+        }
+        cv_.notify_all();
+        std::memcpy(dst, src, std::min(bytes, each));            // the caller's thread takes the first part
+        while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
+private:
+    struct Job { char* dst; const char* src; size_t bytes; std::atomic<int>* pending; };
+    static constexpr int kThreads = 3;
+    CopyPool() { for (int i = 0; i < kThreads; i++) std::thread([this] { work(); }).detach(); }
+    void work() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [this] { return !jobs_.empty(); });
+                j = jobs_.back(); jobs_.pop_back();
+            }
+            std::memcpy(j.dst, j.src, j.bytes);
+            j.pending->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::mutex m_; std::condition_variable cv_; std::vector<Job> jobs_;
+};
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 // Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
 // transfers of one chunk overlap the traversal of another.
 template <bool ANY, typename NodeT>
@@ -536,6 +664,17 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     std::unique_lock<std::mutex> serial(g_pool_serial, std::defer_lock);
     if (g_tuning.mapping == 3) serial.lock();
     HostContext* c = acquire_host_context(s, size_t(num_rays));
+    // pageable buffers are staged through pinned memory of this context (cudaMemcpyAsync on pageable memory is
+    // synchronous and slow); g_tuning.host_staging = 0 hands them to the driver as they are
+    const bool stage_in = g_tuning.host_staging && !is_pinned(rays), stage_out = g_tuning.host_staging && !is_pinned(hits);
+    if ((stage_in || stage_out) && c->stage_capacity < size_t(num_rays)) {
+        if (c->h_rays) { RB_CUDA_CHECK(cudaFreeHost(c->h_rays)); RB_CUDA_CHECK(cudaFreeHost(c->h_hits)); }
+        RB_CUDA_CHECK(cudaMallocHost(&c->h_rays, size_t(num_rays) * sizeof(Ray1)));
+        RB_CUDA_CHECK(cudaMallocHost(&c->h_hits, size_t(num_rays) * sizeof(Hit1)));
+        c->stage_capacity = size_t(num_rays);
+    }
+    const Ray1* src = stage_in ? c->h_rays : rays;
+    Hit1* dst = stage_out ? c->h_hits : hits;
     if (ANY) {  // occluded leaves t/u/v untouched: round-trip the caller's records
         RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, c->streams[0]));
         RB_CUDA_CHECK(cudaStreamSynchronize(c->streams[0]));
@@ -546,16 +685,29 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
     const int64_t parts = int64_t(pieces) * (pieces + 1) / 2;
     int k = 0;
+    int piece_first[17], piece_n[17];
     for (int first = 0; first < num_rays; k++) {
         const int weight = std::max(1, pieces - k);
         int n = int((int64_t(num_rays) * weight / parts + 3) & ~int64_t(3));
         n = std::max(n, 1 << 14);
         if (k >= pieces - 1 || n > num_rays - first) n = num_rays - first;
         cudaStream_t st = c->streams[k % 3];
-        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays + first, rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
+        if (stage_in) CopyPool::get().parallel_copy(c->h_rays + first, rays + first, size_t(n) * sizeof(Ray1));
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays + first, src + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
         launch<ANY>(s, bvh.first, bvh.second, c->d_rays + first, c->d_hits + first, n, st, c->counters + 8 * (k % 3));
-        RB_CUDA_CHECK(cudaMemcpyAsync(hits + first, c->d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_CHECK(cudaMemcpyAsync(dst + first, c->d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+        if (stage_out) {
+            if (!c->piece_done[k]) RB_CUDA_CHECK(cudaEventCreateWithFlags(&c->piece_done[k], cudaEventDisableTiming));
+            RB_CUDA_CHECK(cudaEventRecord(c->piece_done[k], st));
+        }
+        piece_first[k] = first; piece_n[k] = n;
         first += n;
+    }
+    if (stage_out) {
+        for (int j = 0; j < k; j++) {            // drain piece by piece while the later ones are still in flight
+            RB_CUDA_CHECK(cudaEventSynchronize(c->piece_done[j]));
+            CopyPool::get().parallel_copy(hits + piece_first[j], c->h_hits + piece_first[j], size_t(piece_n[j]) * sizeof(Hit1));
+        }
     }
     for (auto& st : c->streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
     release_host_context(s, c);
@@ -575,7 +727,8 @@ static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* r
     RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));     // a packet is W * 32 bytes
     if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st)); // t/u/v stay the caller's
     RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * s.occ_vote[1][ANY ? 1 : 0]);
+    const int grid = std::min((num_rays + kBlock - 1) / kBlock,
+                              s.sm_count * occupancy(s, reinterpret_cast<const void*>(traverse_packets_vote<ANY, ARITY, W>), kBlock));
     traverse_packets_vote<ANY, ARITY, W><<<grid, kBlock, 0, st>>>(bvh.first, bvh.second, reinterpret_cast<const float*>(c->d_rays),
                                                                   reinterpret_cast<float*>(c->d_hits), num_rays, counter,
                                                                   g_tuning.refill_min, g_tuning.node_streak_min);
@@ -647,9 +800,16 @@ void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris) {
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = s.bvh_cache.find(std::make_pair((const void*)nodes, (const void*)tris));
     if (it == s.bvh_cache.end()) return;
-    RB_CUDA_CHECK(cudaFree(it->second.first));
-    RB_CUDA_CHECK(cudaFree(it->second.second));
+    RB_CUDA_CHECK(cudaDeviceSynchronize());
+    RB_CUDA_CHECK(cudaFree(it->second.d_nodes));
+    RB_CUDA_CHECK(cudaFree(it->second.d_tris));
     s.bvh_cache.erase(it);
+}
+// uploads / re-uploads (content changed under a known address) / live copies of the host-pointer BVH cache
+void rodent_b200_bvh_cache_stats(int64_t out[3]) {
+    DeviceState& s = device_state(g_host_dev);
+    std::lock_guard<std::mutex> lock(g_mutex);
+    out[0] = s.bvh_uploads; out[1] = s.bvh_reuploads; out[2] = int64_t(s.bvh_cache.size());
 }
 
 int32_t rodent_b200_device_count(void) {
@@ -686,26 +846,28 @@ const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }
 
 void rodent_b200_render_tune(const char* key, int32_t value);   // render.cu
 
-// Tuning knobs for experiments (not part of the drop-in surface).
+// Tuning knobs for experiments (not part of the drop-in surface).  Values are clamped to what the kernels can take: a
+// streak or refill threshold below 1 would never leave its loop (or elect lane -1), so thresholds live in [1, 33]
+// (33 = never), block counts and variants in their implemented ranges.
 void rodent_b200_tune(const char* key, int32_t value) {
-    if (!std::strcmp(key, "persistent")) g_tuning.persistent = value;
-    else if (!std::strcmp(key, "mapping")) g_tuning.mapping = value;
-    else if (!std::strcmp(key, "quad_refill_below")) g_tuning.quad_refill_below = value;
-    else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = value;
-    else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = value;
-    else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = value;
-    else if (!std::strcmp(key, "node_streak_min")) g_tuning.node_streak_min = value;
-    else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = value;
-    else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = value;
-    else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value;
-    else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = value;
-    else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = value;
-    else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value;
-    else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = value;
-    else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = value;
-    else if (!std::strcmp(key, "render_lanes") || !std::strcmp(key, "render_bvh2") || !std::strcmp(key, "render_shadow_bvh2") || !std::strcmp(key, "render_wide") ||
-             !std::strcmp(key, "render_refill_min") || !std::strcmp(key, "render_streak_min") || !std::strcmp(key, "render_leaf_streak_min") || !std::strcmp(key, "render_bvh2_stack") ||
-             !std::strcmp(key, "render_capacity")) rodent_b200_render_tune(key, value);
+    auto clamp = [](int v, int lo, int hi) { return std::max(lo, std::min(v, hi)); };
+    if (!std::strcmp(key, "persistent")) g_tuning.persistent = value != 0;
+    else if (!std::strcmp(key, "mapping")) g_tuning.mapping = clamp(value, 0, 4);
+    else if (!std::strcmp(key, "quad_refill_below")) g_tuning.quad_refill_below = clamp(value, 1, 9);
+    else if (!std::strcmp(key, "refill_below")) g_tuning.refill_below = clamp(value, 1, 33);
+    else if (!std::strcmp(key, "refill_min")) g_tuning.refill_min = clamp(value, 1, 32);
+    else if (!std::strcmp(key, "vote_min_blocks")) g_tuning.vote_min_blocks = clamp(value, 4, 6);
+    else if (!std::strcmp(key, "node_streak_min")) g_tuning.node_streak_min = clamp(value, 1, 33);
+    else if (!std::strcmp(key, "blocks_per_sm")) g_tuning.blocks_per_sm = clamp(value, 0, 32);
+    else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = clamp(value, 1, 64);
+    else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value != 0;
+    else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = clamp(value, 1, 16);
+    else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
+    else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = clamp(value, 8, 12);
+    else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value != 0;
+    else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = clamp(value, 12, 24);
+    else if (!std::strcmp(key, "bvh2_streak_min")) g_tuning.bvh2_streak_min = clamp(value, 1, 33);
+    else if (!std::strncmp(key, "render_", 7)) rodent_b200_render_tune(key, value);
     else { std::fprintf(stderr, "rodent_b200_tune: unknown key '%s'\n", key); std::abort(); }
 }
 

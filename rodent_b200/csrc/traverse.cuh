@@ -54,14 +54,15 @@ struct RaySetup {
 struct HitRecord { int prim; int geom; float t, u, v; };
 
 // inv_dir * plane + inv_org (intersection.impala:195-196); X86_NAN: see RaySetup::degenerate.
-template <bool X86_NAN>
+template <bool X86_NAN, bool FMA = false>
 __device__ __forceinline__ float slab(float inv_dir, float plane, float inv_org) {
-    const float r = add(mul(inv_dir, plane), inv_org);
+    const float r = madd<FMA>(inv_dir, plane, inv_org);
     if (X86_NAN) return r != r ? __int_as_float(int(0xFFC00000u)) : r;
     return r;
 }
 
 // One lane of a Tri4 (mapping_cpu.impala:24-42 + intersection.impala:164-192).
+template <bool FMA = false>
 __device__ __forceinline__ bool intersect_tri_lane(const RaySetup& r, float tmax,
                                                    float v0x, float v0y, float v0z,
                                                    float e1x, float e1y, float e1z,
@@ -69,15 +70,15 @@ __device__ __forceinline__ bool intersect_tri_lane(const RaySetup& r, float tmax
                                                    float nx, float ny, float nz,
                                                    float& t_out, float& u_out, float& v_out) {
     const float cx = sub(v0x, r.ox), cy = sub(v0y, r.oy), cz = sub(v0z, r.oz);
-    const float rx = sub(mul(r.dy, cz), mul(r.dz, cy));
-    const float ry = sub(mul(r.dz, cx), mul(r.dx, cz));
-    const float rz = sub(mul(r.dx, cy), mul(r.dy, cx));
-    const float det = dot3(nx, ny, nz, r.dx, r.dy, r.dz);
+    const float rx = msub<FMA>(r.dy, cz, r.dz, cy);
+    const float ry = msub<FMA>(r.dz, cx, r.dx, cz);
+    const float rz = msub<FMA>(r.dx, cy, r.dy, cx);
+    const float det = dot3f<FMA>(nx, ny, nz, r.dx, r.dy, r.dz);
     const float abs_det = fabsf(det);
-    const float u = prodsign(dot3(rx, ry, rz, e2x, e2y, e2z), det);
-    const float v = prodsign(dot3(rx, ry, rz, e1x, e1y, e1z), det);
+    const float u = prodsign(dot3f<FMA>(rx, ry, rz, e2x, e2y, e2z), det);
+    const float v = prodsign(dot3f<FMA>(rx, ry, rz, e1x, e1y, e1z), det);
     if (!(u >= 0.0f && v >= 0.0f && add(u, v) <= abs_det)) return false;
-    const float t = prodsign(dot3(cx, cy, cz, nx, ny, nz), det);
+    const float t = prodsign(dot3f<FMA>(cx, cy, cz, nx, ny, nz), det);
     if (!(abs_det != 0.0f && t >= mul(abs_det, r.tmin) && t <= mul(abs_det, tmax))) return false;
     const float inv_det = __fdiv_rn(1.0f, abs_det);
     t_out = mul(t, inv_det); u_out = mul(u, inv_det); v_out = mul(v, inv_det);

@@ -27,7 +27,7 @@ struct IdStack {
     }
 };
 
-template <bool ANY, int SMEM_DEPTH, int BLOCK>
+template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false>
 struct Bvh2Walker {
     RaySetup ray;
     float tmax;
@@ -50,9 +50,9 @@ struct Bvh2Walker {
 
     // intersect_ray_box(min_max, ordered = false, ...), intersection.impala:194-208
     __device__ __forceinline__ bool hit_box(float lx, float hx, float ly, float hy, float lz, float hz, float& tentry) const {
-        const float t0x = add(mul(ray.idx, lx), ray.iox), t1x = add(mul(ray.idx, hx), ray.iox);
-        const float t0y = add(mul(ray.idy, ly), ray.ioy), t1y = add(mul(ray.idy, hy), ray.ioy);
-        const float t0z = add(mul(ray.idz, lz), ray.ioz), t1z = add(mul(ray.idz, hz), ray.ioz);
+        const float t0x = madd<FMA>(ray.idx, lx, ray.iox), t1x = madd<FMA>(ray.idx, hx, ray.iox);
+        const float t0y = madd<FMA>(ray.idy, ly, ray.ioy), t1y = madd<FMA>(ray.idy, hy, ray.ioy);
+        const float t0z = madd<FMA>(ray.idz, lz, ray.ioz), t1z = madd<FMA>(ray.idz, hz, ray.ioz);
         const int zmin = max(min(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(ray.tmin));      // fminmaxf
         const int zmax = min(max(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(tmax));          // fmaxminf
         tentry = __int_as_float(__vimax3_s32(__float_as_int(fminf(t0x, t1x)), __float_as_int(fminf(t0y, t1y)), zmin));
@@ -86,11 +86,11 @@ struct Bvh2Walker {
         const float4* p = reinterpret_cast<const float4*>(tris + leaf);
         const float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);       // v0 | e1, geom | e2, prim
         const int prim = __float_as_int(c.w);
-        const float nx = sub(mul(b.y, c.z), mul(b.z, c.y));                // cross(e1, e2), vector.impala:62-66
-        const float ny = sub(mul(b.z, c.x), mul(b.x, c.z));
-        const float nz = sub(mul(b.x, c.y), mul(b.y, c.x));
+        const float nx = msub<FMA>(b.y, c.z, b.z, c.y);                    // cross(e1, e2), vector.impala:62-66
+        const float ny = msub<FMA>(b.z, c.x, b.x, c.z);
+        const float nz = msub<FMA>(b.x, c.y, b.y, c.x);
         float t, u, v;
-        if (intersect_tri_lane(ray, tmax, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, nx, ny, nz, t, u, v)) {
+        if (intersect_tri_lane<FMA>(ray, tmax, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, nx, ny, nz, t, u, v)) {
             hit.prim = prim & 0x7FFFFFFF; hit.geom = __float_as_int(b.w); hit.t = t; hit.u = u; hit.v = v;
             tmax = t;
             if (ANY) { top = 0; leaf = -1; return; }                       // early_exit, :168
@@ -100,14 +100,14 @@ struct Bvh2Walker {
 };
 
 // The scheduler of traverse_vote_scheduled (traverse_sched.cuh) for this walker.
-template <bool ANY, int SMEM_DEPTH, int BLOCK, typename Fetch, typename Sink>
+template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false, typename Fetch, typename Sink>
 __device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris, int* smem_column,
                                                         int num_rays, int* __restrict__ work_counter, int refill_min, int node_streak_min,
                                                         Fetch fetch, Sink sink, int leaf_streak_min = 0) {
     if (leaf_streak_min <= 0) leaf_streak_min = node_streak_min;
     const unsigned lane = lane_id();
     int overflow[kStackSize - SMEM_DEPTH];
-    Bvh2Walker<ANY, SMEM_DEPTH, BLOCK> w;
+    Bvh2Walker<ANY, SMEM_DEPTH, BLOCK, FMA> w;
     w.st.smem = smem_column;
     w.st.overflow = overflow;
     w.leaf = -1; w.top = 0;

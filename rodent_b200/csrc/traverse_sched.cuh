@@ -42,7 +42,8 @@ struct SplitStack {
 // ARITY: 8 for Node8 (BVH8), 4 for Node4 (BVH4); the leaves are Tri4 in both.
 // WIDE: fetch records with 256-bit loads (7 per Node8 instead of 14 x 128 bit, 7 per Tri4 instead of 13);
 // needs 32-byte aligned arrays.
-template <bool ANY, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false>
+// FMA: contract the slab and triangle arithmetic (renderer only, see common.cuh).
+template <bool ANY, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, bool FMA = false>
 struct RayWalker {
     RaySetup ray;
     float tmax;
@@ -115,12 +116,12 @@ struct RayWalker {
         unsigned mask = 0;
 #pragma unroll
         for (int i = 0; i < ARITY; i++) {
-            const float t0x = slab<X86_NAN>(ray.idx, nx[i], ray.iox);
-            const float t0y = slab<X86_NAN>(ray.idy, ny[i], ray.ioy);
-            const float t0z = slab<X86_NAN>(ray.idz, nz[i], ray.ioz);
-            const float t1x = slab<X86_NAN>(ray.idx, fx[i], ray.iox);
-            const float t1y = slab<X86_NAN>(ray.idy, fy[i], ray.ioy);
-            const float t1z = slab<X86_NAN>(ray.idz, fz[i], ray.ioz);
+            const float t0x = slab<X86_NAN, FMA>(ray.idx, nx[i], ray.iox);
+            const float t0y = slab<X86_NAN, FMA>(ray.idy, ny[i], ray.ioy);
+            const float t0z = slab<X86_NAN, FMA>(ray.idz, nz[i], ray.ioz);
+            const float t1x = slab<X86_NAN, FMA>(ray.idx, fx[i], ray.iox);
+            const float t1y = slab<X86_NAN, FMA>(ray.idy, fy[i], ray.ioy);
+            const float t1z = slab<X86_NAN, FMA>(ray.idz, fz[i], ray.ioz);
             const float te = imax2(imax3(t0x, t0y, t0z), ray.tmin);
             const float tx = imin2(imin3(t1x, t1y, t1z), tmax);
             tentry[i] = te;
@@ -178,7 +179,7 @@ struct RayWalker {
 #define RB_LANE(j, c)                                                                               \
         lt[j] = kFltMax; lu[j] = 0.0f; lv[j] = 0.0f;                                                \
         if (pid.c != -1 &&                                                                          \
-            intersect_tri_lane(ray, tmax, v0x.c, v0y.c, v0z.c, e1x.c, e1y.c, e1z.c,                 \
+            intersect_tri_lane<FMA>(ray, tmax, v0x.c, v0y.c, v0z.c, e1x.c, e1y.c, e1z.c,                 \
                                e2x.c, e2y.c, e2z.c, nnx.c, nny.c, nnz.c, lt[j], lu[j], lv[j]))      \
             hm |= 1u << j;
         RB_LANE(0, x) RB_LANE(1, y) RB_LANE(2, z) RB_LANE(3, w)
@@ -219,13 +220,13 @@ struct RayWalker {
 //   sink(i, hit)      consumes the finished ray's record
 // `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
 // `node_streak_min`: see the node branch at the end of the loop (33: one step per vote).
-template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, typename Fetch, typename Sink>
+template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, bool FMA = false, typename Fetch, typename Sink>
 __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
                                                         StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
                                                         int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8) {
     const unsigned lane = lane_id();
     StackEntry overflow[kStackSize - SMEM_DEPTH];
-    RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY, WIDE> w;
+    RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY, WIDE, FMA> w;
     w.st.smem = smem_column;
     w.st.overflow = overflow;
     w.leaf = -1; w.top_node = 0;

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200_intersect_single_ray1_bvh8_tri4": (None, _TRAVERSE_HOST),
     "b200_occluded_single_ray1_bvh8_tri4": (None, _TRAVERSE_HOST),
     "rodent_b200_forget_bvh": (None, [c_void_p, c_void_p]),
+    "rodent_b200_bvh_cache_stats": (None, [ctypes.POINTER(c_int64)]),
     "rodent_b200_lz4_decompress": (ctypes.c_int64, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),
     "rodent_b200_lz4_compress_bound": (ctypes.c_int64, [ctypes.c_int64]),
     "rodent_b200_lz4_compress": (ctypes.c_int64, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int64]),

@@ -63,3 +63,38 @@ def reduce_film(film, dst: int = 0):
     import torch.distributed as dist
     dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM)
     return film
+
+
+def pin_to_gpu_numa_node(device_index: int) -> dict:
+    """Binds the calling process to the CPUs of the NUMA node the GPU hangs off (Linux sysfs; best effort), so that the
+    host threads that feed the GPU run next to it and the pinned staging memory they allocate afterwards is local to it
+    (first touch).  With eight ranks on one box, leaving everything on node 0 sends every PCIe transfer through one
+    socket's memory controllers (round 1: 8 ranks x 96 MB per step topped out at 157 GB/s).  Returns what was done."""
+    import os
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"], info["bound"] = len(allowed), True
+    except Exception as exc:                      # no sysfs entry, container without the node files, ...
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
+def gather_hits_device(local_hits, out_list, dst: int = 0, async_op: bool = False):
+    """The same gather on device tensors (NCCL): `local_hits` an (n, 4) int32 tensor holding this rank's Hit1 records,
+    `out_list` on rank `dst` a list of world tensors of that shape (None elsewhere).  Every rank passes the same n."""
+    import torch.distributed as dist
+    return dist.gather(local_hits, out_list, dst=dst, async_op=async_op)

@@ -44,6 +44,8 @@ def assert_records_equal(got, want):
 VARIANTS = {"vote": {"mapping": 2}, "vote-refill1": {"mapping": 2, "refill_min": 1}, "vote-no-streaks": {"mapping": 2, "node_streak_min": 33},
             "vote-long-streaks": {"mapping": 2, "node_streak_min": 1}, "pool": {"mapping": 3}, "pool-refill1": {"mapping": 3, "pool_refill_min": 1},
             "quad": {"mapping": 4},
+            # out-of-range knobs are clamped by rodent_b200_tune (0 would never leave the streak loop / elect lane -1)
+            "vote-clamped-knobs": {"mapping": 2, "node_streak_min": 0, "refill_min": 0},
             "thread-persistent": {"mapping": 1, "persistent": 1}, "thread-grid": {"mapping": 1, "persistent": 0}}
 DEFAULTS = {"mapping": 2, "persistent": 1, "refill_min": 24, "pool_refill_min": 24, "node_streak_min": 8}
 
@@ -143,6 +145,67 @@ def test_host_pointer_entry_points(sponza, ray_sets, oracle_hits):
     occl = traversal.intersect_host(nodes, tris, np.ascontiguousarray(ray_sets["random"][:5000]), hits=pre, any_hit=True)
     assert ((occl["tri_id"] >= 0) == (oracle_hits["random"][:5000]["tri_id"] >= 0)).all()
     assert (occl["t"] == 3.0).all()
+
+
+def test_host_bvh_cache_follows_the_content(sponza, ray_sets, oracle_hits):
+    """The cpu_* functions read whatever the arrays hold at call time.  One allocation that first holds the Sponza BVH8 and
+    is then overwritten in place -- by a BVH over other triangles, then by the original again -- must be traced as it
+    is at each call (the upload is keyed on sampled content, not on the address)."""
+    import ctypes
+    from oracle import oracle
+    from rodent_b200 import lib, render, traversal
+    L = lib.load()
+    nodes, tris = sponza
+    rays = np.ascontiguousarray(ray_sets["random"][:20000])
+    buf_n, buf_t = nodes.copy(), tris.copy()
+    stats = (ctypes.c_int64 * 3)()
+    L.rodent_b200_bvh_cache_stats(stats)
+    uploads0, reuploads0 = stats[0], stats[1]
+    assert_records_equal(traversal.intersect_host(buf_n, buf_t, rays), oracle_hits["random"][:20000])
+    assert_records_equal(traversal.intersect_host(buf_n, buf_t, rays), oracle_hits["random"][:20000])
+    L.rodent_b200_bvh_cache_stats(stats)
+    assert stats[0] == uploads0 + 1 and stats[1] == reuploads0, "the second call must reuse the upload"
+    # another BVH8 in the same allocation: the Cornell box (36 triangles, scaled into the ray set's neighbourhood)
+    cornell = render.Scene.load_obj(GOLDEN / "cornell_box.obj")
+    cn, ct = cornell.array("nodes").copy(), cornell.array("tris").copy()
+    buf_n[:len(cn)] = cn
+    buf_t[:len(ct)] = ct
+    crays = formats.make_rays(np.random.default_rng(5).uniform(-1, 1, (5000, 6)).astype(np.float32) + np.array([0, 1, 0, 0, 0, 0], np.float32), 0.0, 10.0)
+    want = oracle.traverse(cn, ct, crays)
+    assert (want["tri_id"] >= 0).sum() > 1000
+    assert_records_equal(traversal.intersect_host(buf_n, buf_t, crays), want)
+    buf_n[:], buf_t[:] = nodes, tris
+    assert_records_equal(traversal.intersect_host(buf_n, buf_t, rays), oracle_hits["random"][:20000])
+    L.rodent_b200_bvh_cache_stats(stats)
+    assert stats[1] == reuploads0 + 2
+    L.rodent_b200_forget_bvh(buf_n.ctypes.data, buf_t.ctypes.data)
+    cornell.free()
+
+
+def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
+    """Pinned caller buffers are copied by DMA as they are, pageable ones through the library's staging memory (or, with
+    the staging switched off, by the driver): same records every way, closest and any hit."""
+    from rodent_b200 import lib, traversal
+    nodes, tris = sponza
+    n = 300001
+    rays = np.ascontiguousarray(ray_sets["random"][:n])
+    want = oracle_hits["random"][:n]
+    assert_records_equal(traversal.intersect_host(nodes, tris, rays), want)                      # pageable, staged
+    lib.tune("host_staging", 0)
+    try:
+        assert_records_equal(traversal.intersect_host(nodes, tris, rays), want)                  # pageable, driver-staged
+    finally:
+        lib.tune("host_staging", 1)
+    pin_r, pin_h = traversal.PinnedArray(formats.RAY1, n), traversal.PinnedArray(formats.HIT1, n)
+    pin_r.array[:] = rays
+    assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array, pin_h.array).copy(), want)     # pinned
+    mixed = traversal.intersect_host(nodes, tris, pin_r.array)                                    # pinned in, pageable out
+    assert_records_equal(mixed, want)
+    pre = np.zeros(n, formats.HIT1)
+    pre["t"] = 7.0
+    occl = traversal.intersect_host(nodes, tris, rays, hits=pre, any_hit=True)
+    assert ((occl["tri_id"] >= 0) == (want["tri_id"] >= 0)).all() and (occl["t"] == 7.0).all()
+    pin_r.free(); pin_h.free()
 
 
 def test_host_entry_points_are_reentrant(sponza, ray_sets, oracle_hits):

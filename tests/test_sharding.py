@@ -54,6 +54,15 @@ def _worker(rank, world, port, out_dir):
         b, e = sharding.ray_range(rank, world, len(rays))
         local = oracle.traverse(nodes, tris, np.ascontiguousarray(rays[b:e]), threads=2)
         hits = sharding.gather_hits(local, rank, world, len(rays))
+        # the tensor form bench.py uses on the GPUs (equal shares): every rank sends (n, 4) int32 records
+        even = torch.from_numpy(np.ascontiguousarray(local[:5000]).view(np.int32).reshape(-1, 4).copy())
+        parts = [torch.empty_like(even) for _ in range(world)] if rank == 0 else None
+        sharding.gather_hits_device(even, parts)
+        if rank == 0:
+            assert torch.equal(parts[0], even) and parts[1].shape == even.shape
+            b1, _ = sharding.ray_range(1, world, len(rays))
+            want1 = oracle.traverse(nodes, tris, np.ascontiguousarray(rays[b1:b1 + 5000]), threads=2)
+            assert parts[1].numpy().tobytes() == want1.tobytes()
         # rendering: each rank keeps only the rows it owns, one reduce puts the film together
         scene = R.Scene.load_obj(ROOT / "tests" / "golden" / "cornell_box.obj")
         W, H = 48, 40
@@ -77,3 +86,24 @@ def test_two_ranks_reassemble_hits_and_film(tmp_path):
     z = np.load(tmp_path / "rank0.npz")
     assert z["hits"].tobytes() == z["want"].tobytes(), "gathered hit records differ from the single-process run"
     assert np.array_equal(z["film"], z["full"]), "reduced film differs from the single-process film"
+
+
+def test_numa_binding_is_best_effort_without_a_gpu():
+    info = sharding.pin_to_gpu_numa_node(0)
+    assert set(info) >= {"numa_node", "cpus", "bound"} and (info["bound"] or "error" in info or info["numa_node"] in (None, -1))
+
+
+def test_bench_shards_are_generated_by_the_ray_gen_rules():
+    """bench.py --gpus N: rank r > 0 traces shard r of the job -- the reference's generator with the camera turned by
+    3 r degrees / the random seed 42 + r; shard 0 is the pair of reference files."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    a, b = bench.load_rays(0), bench.load_rays(1)
+    for name in ("primary", "random"):
+        assert len(a[name]) == len(b[name]) == 1 << 20
+        assert a[name]["tmax"][0] == b[name]["tmax"][0]
+        assert not np.array_equal(a[name]["dir"], b[name]["dir"])
+    assert np.array_equal(a["primary"]["org"], b["primary"]["org"])                 # same eye, turned camera
+    lo, hi = a["random"]["org"].min(0), a["random"]["org"].max(0)
+    assert ((b["random"]["org"] >= lo - 1) & (b["random"]["org"] <= hi + 1)).all()   # same bounding box
+    assert bench.load_rays(1)["random"].tobytes() == b["random"].tobytes()

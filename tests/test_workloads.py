@@ -47,3 +47,18 @@ def test_camera_of_the_sponza_config_is_the_primary_ray_camera():
     assert (round(cam.eye.x, 3), round(cam.eye.y, 3), round(cam.eye.z, 4)) == (-928.012, 483.962, -31.5451)
     assert (cam.dir.x, cam.dir.y, cam.dir.z) == (1.0, 0.0, 0.0) and (cam.up.x, cam.up.y, cam.up.z) == (0.0, 1.0, 0.0)
     assert abs(cam.width - np.tan(np.pi / 6)) < 1e-6 and abs(cam.height - cam.width * 1080 / 1920) < 1e-6
+
+
+def test_scene_from_bvh8_rejects_material_ids_outside_the_table(capfd):
+    """The ids index device tables and shared-memory bins: one bad id must be an error, not an out-of-bounds write."""
+    import pytest
+    from rodent_b200 import formats, render, testdata, workloads
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8(), formats.BVH8_TRI4)
+    mats = workloads.sponza_materials()
+    good = workloads.sponza_material_of_prim(tris)
+    for bad_value in (len(mats), -1, 1 << 20):
+        bad = good.copy()
+        bad[12345] = bad_value
+        with pytest.raises(RuntimeError):
+            render.Scene.from_bvh8(nodes, tris, mats, bad)
+    assert "material_of_prim[12345]" in capfd.readouterr().err
