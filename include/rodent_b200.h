@@ -203,6 +203,9 @@ void b200_occluded_hybrid_ray8_bvh8_tri4(const Node8* nodes, const Tri4* tris, c
  * tools/common/load_bvh.h:58-68, load_rays.h:85-88) ------------------------ */
 int32_t rodent_b200_device_count(void);
 void    rodent_b200_set_device(int32_t dev);          /* device used by the host-pointer entry points */
+/* ... or several: every host-pointer call is then cut into contiguous ray ranges, one per device, BVH replicated, each
+ * range copied back into its slice of the caller's array (no collective on this path). */
+void    rodent_b200_set_devices(const int32_t* devs, int32_t num_devs);
 void*   rodent_b200_alloc_device(int32_t dev, size_t bytes);
 void    rodent_b200_free_device(int32_t dev, void* ptr);
 void*   rodent_b200_alloc_host(size_t bytes);         /* page-locked */
@@ -348,6 +351,12 @@ typedef struct RodentRenderer RodentRenderer;
  * (y / band) % num_parts == part; pass part 0 of 1 for the whole film. */
 RodentRenderer* rodent_b200_renderer_create(const RodentScene* scene, int32_t dev, int32_t width, int32_t height,
                                             int32_t spp, int32_t max_path_len, int32_t part, int32_t num_parts, int32_t band);
+/* The same renderer spread over several devices of this process: device devs[k] owns the row bands with
+ * (y / band) % num_devs == k, the scene is replicated, and every render call ends with one ncclReduce that sums the
+ * films onto devs[0] (NCCL is bound at run time: csrc/nccl_dyn.h).  The handle is used like a single-device one --
+ * render, present, film, clear, stats, free.  The reference has no counterpart (one device per process). */
+RodentRenderer* rodent_b200_renderer_create_multi(const RodentScene* scene, const int32_t* devs, int32_t num_devs,
+                                                  int32_t width, int32_t height, int32_t spp, int32_t max_path_len, int32_t band);
 void  rodent_b200_renderer_free(RodentRenderer* r);
 /* render(settings, iter) of the generated main (converter.cpp:628-967): adds
  * (sum over spp samples) / spp of iteration `iter` to the device film and copies the
@@ -373,6 +382,8 @@ double rodent_b200_render_last_ms(const RodentRenderer* r);   /* CUDA-event time
  * renderer made current by rodent_b200_bind(), which stands for what the reference
  * bakes in at build time (SCENE_FILE, SPP, MAX_PATH_LEN, TARGET_DEVICE). */
 void   rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len);
+/* ... spread over several devices (setup_interface then builds a rodent_b200_renderer_create_multi renderer). */
+void   rodent_b200_bind_multi(const RodentScene* scene, const int32_t* devs, int32_t num_devs, int32_t spp, int32_t max_path_len);
 void   setup_interface(size_t width, size_t height);
 void   cleanup_interface(void);
 float* get_pixels(void);

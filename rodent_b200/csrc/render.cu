@@ -24,6 +24,7 @@
 // primary ray and 52 per shadow ray, as in the reference (src/render/driver.impala:24-61).
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -31,6 +32,7 @@
 #include "shading.cuh"
 #include "traverse_sched.cuh"
 #include "traverse_bvh2.cuh"
+#include "nccl_dyn.h"
 
 extern "C" void rodent_b200_count_launches(int64_t n);   // traverse.cu: the library-wide launch counter
 
@@ -385,6 +387,10 @@ struct Renderer {
     // counters, interleaved row bands) into the same film: see render_device.
     std::vector<Renderer*> lanes;
     Renderer* parent = nullptr;
+    // Multi-device (rodent_b200_renderer_create_multi): this renderer is the one of devs[0] and owns part 0 of the row
+    // bands; `peers` are the renderers of the other devices, `comms` one NCCL communicator per device (this one first).
+    std::vector<Renderer*> peers;
+    std::vector<ncclComm_t> comms;
 
     template <typename T>
     T* alloc(size_t n) {
@@ -537,6 +543,8 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
 
 static void destroy_renderer(Renderer* r) {
     if (!r) return;
+    for (ncclComm_t c : r->comms) RB_NCCL_CHECK(Nccl::get().CommDestroy(c));
+    for (Renderer* peer : r->peers) destroy_renderer(peer);
     RB_CUDA_CHECK(cudaSetDevice(r->dev));
     for (Renderer* lane : r->lanes) destroy_renderer(lane);
     if (r->stream) RB_CUDA_CHECK(cudaStreamSynchronize(r->stream));
@@ -702,6 +710,43 @@ static void render_device(Renderer& r, const Settings& st, int iter) {
     rodent_b200_count_launches(r.stats[4]);
 }
 
+// One render call on several devices of this process: every device renders its row bands (own host thread, own wavefront
+// loops), then ONE ncclReduce sums the films onto the first device -- the only communication, as in the one-process-per-GPU
+// form (rodent_b200/sharding.py).  The peers' films are cleared after the reduce: what they held is now part of the
+// first device's film, which keeps accumulating over iterations like a single renderer's.
+static void render_multi(Renderer& r, const Settings& st, int iter) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (Renderer* p : r.peers) threads.emplace_back([p, &st, iter] { render_device(*p, st, iter); });
+    render_device(r, st, iter);
+    for (auto& t : threads) t.join();
+    const size_t count = size_t(r.width) * r.height * 3;
+    Nccl& nccl = Nccl::get();
+    RB_NCCL_CHECK(nccl.GroupStart());
+    for (size_t k = 0; k < r.comms.size(); k++) {
+        Renderer& p = k == 0 ? r : *r.peers[k - 1];
+        RB_CUDA_CHECK(cudaSetDevice(p.dev));
+        RB_NCCL_CHECK(nccl.Reduce(p.film, p.film, count, ncclFloat, ncclSum, 0, r.comms[k], p.stream));
+    }
+    RB_NCCL_CHECK(nccl.GroupEnd());
+    for (Renderer* p : r.peers) {
+        RB_CUDA_CHECK(cudaSetDevice(p->dev));
+        RB_CUDA_CHECK(cudaMemsetAsync(p->film, 0, count * sizeof(float), p->stream));
+        RB_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    }
+    RB_CUDA_CHECK(cudaSetDevice(r.dev));
+    RB_CUDA_CHECK(cudaStreamSynchronize(r.stream));
+    r.last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (Renderer* p : r.peers) {
+        for (int k : {0, 1, 2, 4}) r.stats[k] += p->stats[k];
+        r.stats[3] = std::max(r.stats[3], p->stats[3]);
+    }
+}
+
+static void render_any(Renderer& r, const Settings& st, int iter) {
+    if (r.peers.empty()) render_device(r, st, iter); else render_multi(r, st, iter);
+}
+
 static void present(Renderer& r) {
     RB_CUDA_CHECK(cudaSetDevice(r.dev));
     RB_CUDA_CHECK(cudaMemcpyAsync(r.h_film, r.film, size_t(r.width) * r.height * 3 * sizeof(float), cudaMemcpyDeviceToHost, r.stream));
@@ -711,6 +756,7 @@ static void present(Renderer& r) {
 // state behind the reference driver's global entry points
 static const Scene* g_bound_scene = nullptr;
 static int g_bound_dev = 0, g_bound_spp = 4, g_bound_max_path_len = 64;
+static std::vector<int> g_bound_devs;          // rodent_b200_bind_multi: setup_interface then spreads the film over these devices
 static Renderer* g_current = nullptr;
 
 }  // namespace rb200
@@ -724,11 +770,28 @@ RodentRenderer* rodent_b200_renderer_create(const RodentScene* scene, int32_t de
     return reinterpret_cast<RodentRenderer*>(create_renderer(*reinterpret_cast<const Scene*>(scene), dev, width, height, spp, max_path_len, part, num_parts, band));
 }
 void rodent_b200_renderer_free(RodentRenderer* r) { destroy_renderer(reinterpret_cast<Renderer*>(r)); }
+RodentRenderer* rodent_b200_renderer_create_multi(const RodentScene* scene, const int32_t* devs, int32_t num_devs, int32_t width, int32_t height,
+                                                  int32_t spp, int32_t max_path_len, int32_t band) {
+    if (!devs || num_devs <= 0) return nullptr;
+    const Scene& sc = *reinterpret_cast<const Scene*>(scene);
+    Renderer* root = create_renderer(sc, devs[0], width, height, spp, max_path_len, 0, num_devs, band);
+    if (!root || num_devs == 1) return reinterpret_cast<RodentRenderer*>(root);
+    for (int k = 1; k < num_devs; k++) {
+        Renderer* p = create_renderer(sc, devs[k], width, height, spp, max_path_len, k, num_devs, band);
+        if (!p) { destroy_renderer(root); return nullptr; }
+        root->peers.push_back(p);
+    }
+    root->comms.resize(num_devs);
+    std::vector<int> d(devs, devs + num_devs);
+    RB_NCCL_CHECK(Nccl::get().CommInitAll(root->comms.data(), num_devs, d.data()));
+    RB_CUDA_CHECK(cudaSetDevice(devs[0]));
+    return reinterpret_cast<RodentRenderer*>(root);
+}
 void rodent_b200_render(RodentRenderer* r, const Settings* settings, int32_t iter) {
-    render_device(*reinterpret_cast<Renderer*>(r), *settings, iter);
+    render_any(*reinterpret_cast<Renderer*>(r), *settings, iter);
     present(*reinterpret_cast<Renderer*>(r));
 }
-void rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int32_t iter) { render_device(*reinterpret_cast<Renderer*>(r), *settings, iter); }
+void rodent_b200_render_device(RodentRenderer* r, const Settings* settings, int32_t iter) { render_any(*reinterpret_cast<Renderer*>(r), *settings, iter); }
 void rodent_b200_present(RodentRenderer* r) { present(*reinterpret_cast<Renderer*>(r)); }
 float* rodent_b200_film(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->h_film; }
 void* rodent_b200_film_device(RodentRenderer* r) { return reinterpret_cast<Renderer*>(r)->film; }
@@ -740,6 +803,11 @@ void rodent_b200_renderer_bind_film(RodentRenderer* rr, float* device_film) {
 }
 void rodent_b200_clear(RodentRenderer* rr) {
     Renderer& r = *reinterpret_cast<Renderer*>(rr);
+    for (Renderer* p : r.peers) {
+        RB_CUDA_CHECK(cudaSetDevice(p->dev));
+        RB_CUDA_CHECK(cudaMemsetAsync(p->film, 0, size_t(p->width) * p->height * 3 * sizeof(float), p->stream));
+        RB_CUDA_CHECK(cudaStreamSynchronize(p->stream));
+    }
     RB_CUDA_CHECK(cudaSetDevice(r.dev));
     RB_CUDA_CHECK(cudaMemsetAsync(r.film, 0, size_t(r.width) * r.height * 3 * sizeof(float), r.stream));
     RB_CUDA_CHECK(cudaStreamSynchronize(r.stream));
@@ -767,11 +835,21 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
 }
 void rodent_b200_bind(const RodentScene* scene, int32_t dev, int32_t spp, int32_t max_path_len) {
     g_bound_scene = reinterpret_cast<const Scene*>(scene); g_bound_dev = dev; g_bound_spp = spp; g_bound_max_path_len = max_path_len;
+    g_bound_devs.clear();
+}
+void rodent_b200_bind_multi(const RodentScene* scene, const int32_t* devs, int32_t num_devs, int32_t spp, int32_t max_path_len) {
+    rodent_b200_bind(scene, num_devs > 0 ? devs[0] : 0, spp, max_path_len);
+    g_bound_devs.assign(devs, devs + std::max(num_devs, 0));
 }
 void setup_interface(size_t width, size_t height) {
     if (!g_bound_scene) { std::fprintf(stderr, "rodent_b200: setup_interface() without rodent_b200_bind()\n"); std::abort(); }
     destroy_renderer(g_current);
-    g_current = create_renderer(*g_bound_scene, g_bound_dev, int(width), int(height), g_bound_spp, g_bound_max_path_len, 0, 1, 1);
+    if (g_bound_devs.size() > 1)
+        g_current = reinterpret_cast<Renderer*>(rodent_b200_renderer_create_multi(reinterpret_cast<const RodentScene*>(g_bound_scene), g_bound_devs.data(),
+                                                                                   int32_t(g_bound_devs.size()), int32_t(width), int32_t(height),
+                                                                                   g_bound_spp, g_bound_max_path_len, 8));
+    else
+        g_current = create_renderer(*g_bound_scene, g_bound_dev, int(width), int(height), g_bound_spp, g_bound_max_path_len, 0, 1, 1);
     if (!g_current) std::abort();
 }
 void cleanup_interface(void) { destroy_renderer(g_current); g_current = nullptr; }

@@ -323,6 +323,7 @@ static DeviceState g_dev[64];
 static std::mutex g_mutex;
 static std::atomic<int64_t> g_launches{0};
 static int g_host_dev = 0;
+static std::vector<int> g_host_devs;      // rodent_b200_set_devices: the host-pointer entry points then cut every call over these
 
 static DeviceState& device_state(int dev) {
     if (dev < 0 || dev >= 64) { std::fprintf(stderr, "rodent_b200: bad device %d\n", dev); std::abort(); }
@@ -657,9 +658,29 @@ static bool is_pinned(const void* p) {
 // Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
 // transfers of one chunk overlap the traversal of another.
 template <bool ANY, typename NodeT>
+static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays);
+
+// With several devices (rodent_b200_set_devices) a call is cut into contiguous ray ranges, one per device, BVH replicated
+// (uploaded to each on first use); every range is traced and copied straight back into its slice of the caller's array,
+// so the path needs no collective.
+template <bool ANY, typename NodeT>
 static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     if (num_rays <= 0) return;
-    DeviceState& s = device_state(g_host_dev);
+    const std::vector<int> devs = g_host_devs;
+    if (devs.size() <= 1 || num_rays < int(devs.size()) * 4096) return run_host_on<ANY>(devs.empty() ? g_host_dev : devs[0], nodes, tris, rays, hits, num_rays);
+    std::vector<std::thread> threads;
+    const int64_t n = int64_t(devs.size());
+    for (int64_t k = 0; k < n; k++) {
+        const int b = int(num_rays * k / n), e = int(num_rays * (k + 1) / n);
+        threads.emplace_back([=] { run_host_on<ANY>(devs[size_t(k)], nodes, tris, rays + b, hits + b, e - b); });
+    }
+    for (auto& t : threads) t.join();
+}
+
+template <bool ANY, typename NodeT>
+static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
+    if (num_rays <= 0) return;
+    DeviceState& s = device_state(dev);
     auto bvh = cached_bvh(s, nodes, tris);
     std::unique_lock<std::mutex> serial(g_pool_serial, std::defer_lock);
     if (g_tuning.mapping == 3) serial.lock();
@@ -816,7 +837,12 @@ int32_t rodent_b200_device_count(void) {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
-void rodent_b200_set_device(int32_t dev) { device_state(dev); g_host_dev = dev; }
+void rodent_b200_set_device(int32_t dev) { device_state(dev); g_host_dev = dev; g_host_devs.clear(); }
+void rodent_b200_set_devices(const int32_t* devs, int32_t num_devs) {
+    g_host_devs.assign(devs, devs + std::max(num_devs, 0));
+    for (int d : g_host_devs) device_state(d);
+    if (!g_host_devs.empty()) { g_host_dev = g_host_devs[0]; device_state(g_host_dev); }
+}
 void* rodent_b200_alloc_device(int32_t dev, size_t bytes) {
     device_state(dev);
     void* p = nullptr;

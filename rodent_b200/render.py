@@ -51,6 +51,8 @@ SIGNATURES = {
     "rodent_b200_scene_set_bvh2": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
     "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
+    "rodent_b200_renderer_create_multi": (c_void_p, [c_void_p, POINTER(c_int32), c_int32] + [c_int32] * 5),
+    "rodent_b200_bind_multi": (None, [c_void_p, POINTER(c_int32), c_int32, c_int32, c_int32]),
     "rodent_b200_renderer_free": (None, [c_void_p]),
     "rodent_b200_render": (None, [c_void_p, POINTER(Settings), c_int32]),
     "rodent_b200_render_device": (None, [c_void_p, POINTER(Settings), c_int32]),
@@ -191,11 +193,17 @@ class Scene:
 class Renderer:
     """Wavefront path tracer on one device (rodent_b200_renderer_*)."""
 
-    def __init__(self, scene: Scene, dev: int, width: int, height: int, spp: int, max_path_len: int,
+    def __init__(self, scene: Scene, dev, width: int, height: int, spp: int, max_path_len: int,
                  part: int = 0, num_parts: int = 1, band: int = 8):
+        """`dev`: a device index, or a list of them (one process driving several devices: row bands dealt out over them,
+        one ncclReduce per render call, rodent_b200_renderer_create_multi)."""
         self.L = _bind(lib.load())
         self.scene, self.width, self.height, self.spp = scene, width, height, spp
-        self.handle = c_void_p(self.L.rodent_b200_renderer_create(scene.handle, dev, width, height, spp, max_path_len, part, num_parts, band))
+        if isinstance(dev, (list, tuple)):
+            devs = (c_int32 * len(dev))(*dev)
+            self.handle = c_void_p(self.L.rodent_b200_renderer_create_multi(scene.handle, devs, len(dev), width, height, spp, max_path_len, band))
+        else:
+            self.handle = c_void_p(self.L.rodent_b200_renderer_create(scene.handle, dev, width, height, spp, max_path_len, part, num_parts, band))
         if not self.handle:
             raise RuntimeError("renderer could not be created")
 

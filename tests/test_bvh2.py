@@ -169,3 +169,33 @@ def test_cuda_tuning_does_not_change_results(gpu2, ray_sets, oracle2_hits):
         lib.tune("refill_min", 24)
         lib.tune("bvh2_streak_min", 4)
         lib.tune("bvh2_min_blocks", 8)
+
+
+@pytest.mark.gpu
+def test_aila_comparator_agrees_with_the_bvh2_kernel(tmp_path):
+    """The reference's Aila-Laine kernel (baseline/aila, built from /root/reference for CUDA 12) on the same BVH2 block:
+    another traversal order and triangle test, so records agree in hit / miss and in t up to rounding."""
+    import subprocess
+    from pathlib import Path
+    from rodent_b200 import formats, testdata, traversal
+    exe = Path(__file__).resolve().parent.parent / "baseline" / "_ref" / "aila" / "bench_aila"
+    if not exe.exists():
+        pytest.skip("baseline/_ref/aila/bench_aila is not built")
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
+    bvh = traversal.Bvh8(0, nodes, tris)
+    for name, (tmin, tmax) in testdata.RAY_SETS.items():
+        out = tmp_path / f"{name}.fbuf"
+        r = subprocess.run([str(exe), "-bvh", str(testdata.sponza_bvh2()), "-ray", str(testdata.rays(name)), "--tmin", str(tmin),
+                            "--tmax", str(tmax), "-o", str(out)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        t_aila = np.fromfile(out, "<f4")
+        rays = formats.load_rays(testdata.rays(name), tmin, tmax)
+        d_rays = traversal.DeviceArray.from_host(0, rays)
+        d_hits = traversal.DeviceArray.from_host(0, np.zeros(len(rays), formats.HIT1))
+        traversal.intersect(bvh, d_rays, d_hits)
+        mine = d_hits.to_host()
+        hit_mine, hit_aila = mine["tri_id"] >= 0, t_aila < np.float32(tmax)
+        assert (hit_mine != hit_aila).sum() <= 20, (hit_mine != hit_aila).sum()
+        both = hit_mine & hit_aila
+        rel = np.abs(t_aila[both] - mine["t"][both]) / np.maximum(np.abs(mine["t"][both]), 1e-6)
+        assert np.quantile(rel, 0.9999) < 1e-4, np.quantile(rel, 0.9999)

@@ -30,7 +30,7 @@ namespace {
 struct Options {
     std::string bvh_file, ray_file, out_file, gpu;
     float tmin = 0.0f, tmax = 1e9f;
-    int iters = 1, warmup = 0, dev = 0, bvh_width = 4, ray_width = 8;
+    int iters = 1, warmup = 0, dev = 0, bvh_width = 4, ray_width = 8, gpus = 1;
     bool any_hit = false, single = false, packet = false, bvh_width_given = false;
 };
 
@@ -44,6 +44,7 @@ void usage() {
                  "        --bench / --warmup  timed / untimed iterations (default 1 / 0)\n"
                  "  -gpu  cuda         device-resident arrays on a B200\n"
                  "  -dev  k            CUDA device index\n"
+                 "        --gpus n     with -s: cut every call into n contiguous ray ranges over devices dev .. dev+n-1 (BVH replicated)\n"
                  "  -any               exit at the first intersection\n"
                  "  -s    --single     host-buffer single-ray entry point\n"
                  "        --bvh-width  4 or 8 (default 4; 2 with -gpu: the reference GPU path's BVH2 block) ; --ray-width 4 or 8 (default 8)\n"
@@ -67,6 +68,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--warmup" || a == "--warmup-iters") o.warmup = int(std::strtol(value(), nullptr, 10));
         else if (a == "-gpu" || a == "--gpu-platform") o.gpu = value();
         else if (a == "-dev" || a == "--gpu-device") o.dev = int(std::strtol(value(), nullptr, 10));
+        else if (a == "--gpus") o.gpus = int(std::strtol(value(), nullptr, 10));
         else if (a == "-any") o.any_hit = true;
         else if (a == "-s" || a == "--single") o.single = true;
         else if (a == "-p" || a == "--packet") o.packet = true;
@@ -83,6 +85,7 @@ Options parse(int argc, char** argv) {
     if (o.single && o.packet) fail("Options '--packet' and '--single' are incompatible");
     if (o.bvh_width != 4 && o.bvh_width != 8 && !(o.bvh_width == 2 && !o.gpu.empty())) fail("Invalid BVH width");
     if (o.ray_width != 4 && o.ray_width != 8) fail("Invalid ray width");
+    if (o.gpus < 1 || (o.gpus > 1 && !o.single)) fail("Option '--gpus' needs '--single' (the host-pointer entry points shard a call over the devices)");
     return o;
 }
 
@@ -118,7 +121,14 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
             return rodent_b200_last_kernel_ms(o.dev);
         };
     } else {
-        rodent_b200_set_device(o.dev);
+        if (o.dev < 0 || o.dev + o.gpus > rodent_b200_device_count()) fail("Invalid GPU device");
+        if (o.gpus > 1) {
+            std::vector<int32_t> devs(o.gpus);
+            std::iota(devs.begin(), devs.end(), o.dev);
+            rodent_b200_set_devices(devs.data(), o.gpus);
+        } else {
+            rodent_b200_set_device(o.dev);
+        }
         bench = [&] {
             const auto t0 = std::chrono::steady_clock::now();
             (o.any_hit ? host_occluded : host_intersect)(nodes.data(), tris.data(), rays.data(), hits.data(), int32_t(ray_count));

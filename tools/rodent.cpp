@@ -7,7 +7,7 @@
 //
 // What the reference bakes in at build time is given at run time here:
 //   --scene file.obj  (SCENE_FILE)   --spp n (SPP, default 4)   --max-path-len n (MAX_PATH_LEN, default 64)
-//   --dev k           (TARGET_DEVICE)
+//   --dev k           (TARGET_DEVICE)      --gpus n  (this repository's addition: the film spread over n devices)
 #include <zlib.h>
 
 #include <algorithm>
@@ -42,6 +42,7 @@ void usage() {
               << "   --spp    n          Samples per pixel and iteration (the reference's SPP, default 4)\n"
               << "   --max-path-len n    Maximum path length (the reference's MAX_PATH_LEN, default 64)\n"
               << "   --dev    k          CUDA device index\n"
+              << "   --gpus   n          Spread the film over devices k .. k+n-1 (row bands of 8, one ncclReduce per frame)\n"
               << "   --width  pixels     Sets the viewport horizontal dimension (in pixels)\n"
               << "   --height pixels     Sets the viewport vertical dimension (in pixels)\n"
               << "   --eye    x y z      Sets the position of the camera\n"
@@ -72,7 +73,7 @@ void save_image(const std::string& out_file, size_t width, size_t height, uint32
 int main(int argc, char** argv) {
     std::string out_file, scene_file;
     size_t bench_iter = 0, width = 1080, height = 720;
-    int spp = 4, max_path_len = 64, dev = 0;
+    int spp = 4, max_path_len = 64, dev = 0, gpus = 1;
     float fov = 60.0f;
     F3 eye{0, 0, 0}, dir{0, 0, 1}, up{0, 1, 0};
     for (int i = 1; i < argc; ++i) {
@@ -90,6 +91,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--spp")) { check_arg(argc, argv, i, 1); spp = int(strtol(argv[++i], nullptr, 10)); }
         else if (!strcmp(argv[i], "--max-path-len")) { check_arg(argc, argv, i, 1); max_path_len = int(strtol(argv[++i], nullptr, 10)); }
         else if (!strcmp(argv[i], "--dev")) { check_arg(argc, argv, i, 1); dev = int(strtol(argv[++i], nullptr, 10)); }
+        else if (!strcmp(argv[i], "--gpus")) { check_arg(argc, argv, i, 1); gpus = int(strtol(argv[++i], nullptr, 10)); }
         else if (!strcmp(argv[i], "--help")) { usage(); return 0; }
         else error(std::string("Unknown option '") + argv[i] + "'");
     }
@@ -104,8 +106,14 @@ int main(int argc, char** argv) {
 
     RodentScene* scene = rodent_b200_scene_load_obj(scene_file.c_str());
     if (!scene) return 1;
-    if (rodent_b200_device_count() <= dev) error("No such CUDA device");
-    rodent_b200_bind(scene, dev, spp, max_path_len);
+    if (gpus < 1 || dev < 0 || rodent_b200_device_count() < dev + gpus) error("No such CUDA device");
+    if (gpus > 1) {
+        std::vector<int32_t> devs(gpus);
+        for (int k = 0; k < gpus; k++) devs[k] = dev + k;
+        rodent_b200_bind_multi(scene, devs.data(), gpus, spp, max_path_len);
+    } else {
+        rodent_b200_bind(scene, dev, spp, max_path_len);
+    }
     setup_interface(width, height);
 
     std::vector<double> samples_sec;
