@@ -270,47 +270,196 @@ struct Builder {
     std::vector<Box> boxes; std::vector<F3> centers; std::vector<int> order;
     std::vector<Bvh2Node> n2;
     std::vector<NodeT>& nodes; std::vector<Tri4>& tris;
-    static constexpr int kBins = 16, kLeaf = 4;
     static constexpr int kArity = int(sizeof(NodeT::child) / sizeof(int32_t));
 
-    int build2(int first, int count) {
-        Bvh2Node node; node.first = first; node.count = count;
-        Box cb;
-        for (int i = first; i < first + count; i++) { node.box.grow(boxes[order[i]]); cb.grow(centers[order[i]]); }
-        const int id = int(n2.size());
-        n2.push_back(node);
-        if (count <= kLeaf) return id;
-        // binned SAH over the three axes; leaves hold at most one Tri4
-        float best = std::numeric_limits<float>::max(); int best_axis = -1, best_bin = 0;
+    // ---- the binary tree: a split BVH (Stich, Friedrich, Dietrich: "Spatial Splits in Bounding Volume Hierarchies",
+    // HPG 2009), the algorithm of the reference's builder (src/driver/bvh.h:102-246) in this repository's own form.
+    // A node owns a list of REFERENCES (triangle id + the part of its bounds inside the node).  Candidates per node:
+    //   * object split: references sorted by centroid along each axis, full sweep of n * area(left) + n * area(right);
+    //   * spatial split, tried when the object split's children overlap by more than kAlpha of the root's area: the
+    //     node's extent cut into kSpatialBins slabs per axis, triangles clipped against the slab planes, sweep over the
+    //     planes; a reference straddling the chosen plane goes to both sides (clipped) unless keeping it whole on one
+    //     side is cheaper ("unsplitting");
+    // and the node becomes a leaf when the best split does not pay: cost(split) + area >= n * area
+    // (CostFn of converter.cpp:118-128: leaf_cost = count * area, traversal_cost = area), or at kLeafMin references.
+    // Leaves append their triangle ids to `order` (an id can then appear in several leaves).
+    struct Ref { int id; Box box; };
+    static constexpr int kSpatialBins = 64, kLeafMin = 2;
+    static constexpr float kAlpha = 1e-5f;
+    float root_area = 0.0f;
+    int spatial_splits = 0;
+
+    static float axis_of(const F3& v, int axis) { return (&v.x)[axis]; }
+    static float& axis_of(F3& v, int axis) { return (&v.x)[axis]; }
+    static Box intersect(const Box& a, const Box& b) { Box r; r.lo = fmax3(a.lo, b.lo); r.hi = fmin3(a.hi, b.hi); return r; }
+    static float ref_center(const Ref& r, int axis) { return 0.5f * (axis_of(r.box.lo, axis) + axis_of(r.box.hi, axis)); }
+
+    // Bounds of the two parts of triangle `id` on either side of the plane `axis = pos`.
+    void clip_triangle(int id, int axis, float pos, Box& left, Box& right) const {
+        const F3 v[3] = {v0[id], v1[id], v2[id]};
+        left = Box(); right = Box();
+        for (int k = 0; k < 3; k++) {
+            const F3 a = v[k], b = v[(k + 1) % 3];
+            const float pa = axis_of(a, axis), pb = axis_of(b, axis);
+            if (pa <= pos) left.grow(a);
+            if (pa >= pos) right.grow(a);
+            if ((pa < pos && pb > pos) || (pa > pos && pb < pos)) {
+                const float t = (pos - pa) / (pb - pa);
+                F3 x = a + (b - a) * t;
+                axis_of(x, axis) = pos;
+                left.grow(x); right.grow(x);
+            }
+        }
+    }
+
+    struct ObjectSplit { float cost = std::numeric_limits<float>::max(); int axis = -1, left_count = 0; Box left, right; };
+    struct SpatialSplit { float cost = std::numeric_limits<float>::max(); int axis = -1; float pos = 0; };
+
+    void find_object_split(std::vector<Ref>& refs, ObjectSplit& best, std::vector<Box>& scratch) {
+        const int n = int(refs.size());
+        scratch.resize(n);
         for (int axis = 0; axis < 3; axis++) {
-            const float lo = (&cb.lo.x)[axis], ext = (&cb.hi.x)[axis] - lo;
-            if (!(ext > 0)) continue;
-            Box bb[kBins]; int bc[kBins] = {};
-            for (int i = first; i < first + count; i++) {
-                const int b = std::min(kBins - 1, int(((&centers[order[i]].x)[axis] - lo) / ext * kBins));
-                bb[b].grow(boxes[order[i]]); bc[b]++;
-            }
-            float right_cost[kBins]; Box acc; int cnt = 0;
-            for (int b = kBins - 1; b > 0; b--) { acc.grow(bb[b]); cnt += bc[b]; right_cost[b] = cnt * acc.half_area(); }
-            acc = Box(); cnt = 0;
-            for (int b = 0; b < kBins - 1; b++) {
-                acc.grow(bb[b]); cnt += bc[b];
-                if (cnt == 0 || cnt == count) continue;
-                const float c = cnt * acc.half_area() + right_cost[b + 1];
-                if (c < best) { best = c; best_axis = axis; best_bin = b; }
+            std::sort(refs.begin(), refs.end(), [axis](const Ref& a, const Ref& b) {
+                const float ca = ref_center(a, axis), cb = ref_center(b, axis);
+                return ca < cb || (ca == cb && a.id < b.id);
+            });
+            Box acc;
+            for (int i = n - 1; i > 0; i--) { acc.grow(refs[i].box); scratch[i] = acc; }
+            acc = Box();
+            for (int i = 0; i < n - 1; i++) {
+                acc.grow(refs[i].box);
+                const float c = float(i + 1) * acc.half_area() + float(n - i - 1) * scratch[i + 1].half_area();
+                if (c < best.cost) { best.cost = c; best.axis = axis; best.left_count = i + 1; best.left = acc; best.right = scratch[i + 1]; }
             }
         }
-        int mid;
-        if (best_axis < 0) {
-            mid = first + count / 2;                   // all centroids coincide: split in the middle
-        } else {
-            const float lo = (&cb.lo.x)[best_axis], ext = (&cb.hi.x)[best_axis] - lo;
-            mid = int(std::partition(order.begin() + first, order.begin() + first + count, [&](int t) {
-                return std::min(kBins - 1, int(((&centers[t].x)[best_axis] - lo) / ext * kBins)) <= best_bin; }) - order.begin());
+    }
+
+    void find_spatial_split(const std::vector<Ref>& refs, const Box& box, SpatialSplit& best) {
+        const int n = int(refs.size());
+        for (int axis = 0; axis < 3; axis++) {
+            const float lo = axis_of(box.lo, axis), hi = axis_of(box.hi, axis);
+            if (!(hi > lo)) continue;
+            const float width = (hi - lo) / kSpatialBins, inv = 1.0f / width;
+            Box bins[kSpatialBins]; int enter[kSpatialBins] = {}, leave[kSpatialBins] = {};
+            auto bin_of = [&](float x) { return std::max(0, std::min(kSpatialBins - 1, int((x - lo) * inv))); };
+            for (const Ref& r : refs) {
+                const int first = bin_of(axis_of(r.box.lo, axis)), last = bin_of(axis_of(r.box.hi, axis));
+                Box rest = r.box;
+                for (int b = first; b < last; b++) {                  // chop the reference at every slab plane it crosses
+                    Box l, rr;
+                    clip_triangle(r.id, axis, lo + float(b + 1) * width, l, rr);
+                    bins[b].grow(intersect(l, rest));
+                    rest = intersect(rest, rr);
+                }
+                bins[last].grow(rest);
+                enter[first]++; leave[last]++;
+            }
+            Box right_acc[kSpatialBins]; Box acc;
+            for (int b = kSpatialBins - 1; b > 0; b--) { acc.grow(bins[b]); right_acc[b] = acc; }
+            acc = Box();
+            int nl = 0, nr = n;
+            for (int b = 0; b < kSpatialBins - 1; b++) {
+                acc.grow(bins[b]); nl += enter[b]; nr -= leave[b];
+                if (nl == 0 || nr == 0) continue;
+                const float c = float(nl) * acc.half_area() + float(nr) * right_acc[b + 1].half_area();
+                if (c < best.cost) { best.cost = c; best.axis = axis; best.pos = lo + float(b + 1) * width; }
+            }
         }
-        const int l = build2(first, mid - first), r = build2(mid, first + count - mid);
+    }
+
+    // Distributes the references over the two sides of the chosen plane; returns false when one side stays empty.
+    bool apply_spatial_split(std::vector<Ref>& refs, const SpatialSplit& sp, std::vector<Ref>& left, std::vector<Ref>& right, Box& lbox, Box& rbox) {
+        std::vector<Ref> straddling;
+        lbox = Box(); rbox = Box();
+        for (const Ref& r : refs) {
+            if (axis_of(r.box.hi, sp.axis) <= sp.pos) { left.push_back(r); lbox.grow(r.box); }
+            else if (axis_of(r.box.lo, sp.axis) >= sp.pos) { right.push_back(r); rbox.grow(r.box); }
+            else straddling.push_back(r);
+        }
+        for (const Ref& r : straddling) {
+            Box l, rr;
+            clip_triangle(r.id, sp.axis, sp.pos, l, rr);
+            l = intersect(l, r.box); rr = intersect(rr, r.box);
+            Box l_whole = lbox, r_whole = rbox, l_part = lbox, r_part = rbox;
+            l_whole.grow(r.box); r_whole.grow(r.box); l_part.grow(l); r_part.grow(rr);
+            const float nl = float(left.size()), nr = float(right.size());
+            const float to_left = (nl + 1) * l_whole.half_area() + nr * rbox.half_area();
+            const float to_right = nl * lbox.half_area() + (nr + 1) * r_whole.half_area();
+            const float both = (nl + 1) * l_part.half_area() + (nr + 1) * r_part.half_area();
+            if (to_left <= to_right && to_left <= both) { left.push_back(r); lbox = l_whole; }
+            else if (to_right <= both) { right.push_back(r); rbox = r_whole; }
+            else { left.push_back(Ref{r.id, l}); right.push_back(Ref{r.id, rr}); lbox = l_part; rbox = r_part; }
+        }
+        return !left.empty() && !right.empty() && left.size() < refs.size() && right.size() < refs.size();   // both sides must shrink
+    }
+
+    int make_leaf2(int id, const std::vector<Ref>& refs) {
+        n2[id].first = int(order.size());
+        n2[id].count = int(refs.size());
+        for (const Ref& r : refs) order.push_back(r.id);
+        return id;
+    }
+
+    int build2(std::vector<Ref>& refs, const Box& box, int depth) {
+        const int id = int(n2.size());
+        n2.emplace_back();
+        n2[id].box = box;
+        const int n = int(refs.size());
+        if (n <= kLeafMin || depth > 60) return make_leaf2(id, refs);
+        std::vector<Box> scratch;
+        ObjectSplit os;
+        find_object_split(refs, os, scratch);
+        SpatialSplit ss;
+        if (use_spatial_splits && os.axis >= 0 && intersect(os.left, os.right).half_area() > kAlpha * root_area) find_spatial_split(refs, box, ss);
+        const float best = std::min(os.cost, ss.cost);
+        // no split pays for itself: a leaf -- unless it would be a long one (more than kLeafMax references cost several
+        // Tri4 packets every time a ray enters it), which is split anyway
+        const bool split_pays = os.axis >= 0 && best + box.half_area() < float(n) * box.half_area();
+        if (!split_pays && n <= kLeafMax) return make_leaf2(id, refs);
+        std::vector<Ref> left, right; Box lbox, rbox;
+        bool done = false;
+        if (ss.cost < os.cost) {
+            done = apply_spatial_split(refs, ss, left, right, lbox, rbox);
+            if (done) spatial_splits++;
+            else { left.clear(); right.clear(); }
+        }
+        if (!done) {
+            if (os.axis < 0) {                      // identical centroids everywhere: halve the list
+                os.left_count = n / 2;
+                for (int i = 0; i < n; i++) (i < os.left_count ? os.left : os.right).grow(refs[i].box);
+            } else if (os.axis != 2) {              // the list is in z order after the sweeps
+                const int axis = os.axis;
+                std::sort(refs.begin(), refs.end(), [axis](const Ref& a, const Ref& b) {
+                    const float ca = ref_center(a, axis), cb = ref_center(b, axis);
+                    return ca < cb || (ca == cb && a.id < b.id);
+                });
+            }
+            left.assign(refs.begin(), refs.begin() + os.left_count);
+            right.assign(refs.begin() + os.left_count, refs.end());
+            lbox = os.left; rbox = os.right;
+        }
+        std::vector<Ref>().swap(refs);              // the parent's list is not needed below
+        const int l = build2(left, lbox, depth + 1);
+        const int r = build2(right, rbox, depth + 1);
         n2[id].left = l; n2[id].right = r;
         return id;
+    }
+    bool use_spatial_splits = true;
+    static constexpr int kLeafMax = 8;
+
+    int build_tree() {
+        const int n = int(v0.size());
+        std::vector<Ref> refs(n);
+        Box all;
+        for (int i = 0; i < n; i++) {
+            refs[i].id = i;
+            refs[i].box.grow(v0[i]); refs[i].box.grow(v1[i]); refs[i].box.grow(v2[i]);
+            all.grow(refs[i].box);
+        }
+        root_area = all.half_area();
+        order.clear();
+        if (const char* e = std::getenv("RODENT_B200_NO_SPATIAL_SPLITS")) use_spatial_splits = e[0] == '0' || e[0] == 0;
+        return build2(refs, all, 0);
     }
 
     // leaf writer of converter.cpp:207-259
@@ -402,14 +551,7 @@ struct Builder {
         return id;
     }
     void run2(std::vector<Node2>& out_nodes, std::vector<Tri1>& out_tris) {
-        const int n = int(v0.size());
-        boxes.resize(n); centers.resize(n); order.resize(n);
-        std::iota(order.begin(), order.end(), 0);
-        for (int i = 0; i < n; i++) {
-            boxes[i].grow(v0[i]); boxes[i].grow(v1[i]); boxes[i].grow(v2[i]);
-            centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
-        }
-        const int root = build2(0, n);
+        const int root = build_tree();
         if (n2[root].left < 0) {
             // a scene of one leaf: the root points at it twice (a triangle found twice is found at the same t)
             Node2 node{};
@@ -427,14 +569,7 @@ struct Builder {
     }
 
     void run() {
-        const int n = int(v0.size());
-        boxes.resize(n); centers.resize(n); order.resize(n);
-        std::iota(order.begin(), order.end(), 0);
-        for (int i = 0; i < n; i++) {
-            boxes[i].grow(v0[i]); boxes[i].grow(v1[i]); boxes[i].grow(v2[i]);
-            centers[i] = (boxes[i].lo + boxes[i].hi) * 0.5f;
-        }
-        const int root = build2(0, n);
+        const int root = build_tree();
         if (n2[root].left < 0) {
             // a single leaf: the root node (id 1) must still be an inner node
             nodes.emplace_back();
