@@ -342,6 +342,17 @@ void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* nu
 void    rodent_b200_scene_build_bvh2(RodentScene* scene);
 int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1);
 
+/* The converter's data/ directory (convert_obj, src/driver/converter.cpp:403-438, 682-745): the mesh as LZ4-framed buffers
+ * (vertices / normals / face_normals / texcoords .bin, 16-byte elements for the GPU targets, and indices.bin), the BVH of
+ * the target's layout in bvh.bin, and bvh.stamp ("<target> <obj file>").  rodent_b200_scene_load_data renders from such a
+ * directory: the arrays and whatever BVH it holds are adopted (a BVH8 as the scene's, a BVH2 / Tri1 as its second tree; what
+ * is missing is built), --fusion's simple_kd / ks / ns buffers become table entries again, and since the reference keeps
+ * materials and lights as generated code, those are read from the OBJ / MTL that `obj_file` -- or, if NULL, the stamp --
+ * names.  rodent_b200_scene_write_data writes the directory from a loaded scene (`bvh_arity` 2, 4 or 8; `padded` as for the
+ * GPU targets).  Both return NULL / 0 with a message on stderr when something does not fit. */
+RodentScene* rodent_b200_scene_load_data(const char* data_dir, const char* obj_file);
+int32_t rodent_b200_scene_write_data(RodentScene* scene, const char* data_dir, int32_t bvh_arity, int32_t padded, const char* obj_file);
+
 typedef struct RodentRenderer RodentRenderer;
 
 /* A wavefront path tracer bound to one scene and one device (the role of the generated

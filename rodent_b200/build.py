@@ -48,7 +48,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_tools(force: bool = False) -> None:
-    """ray_gen, fbuf2png, and -- linked against librodent_b200.so -- bench_traversal, bench_interface, bench_shading, bvh_extractor, rodent."""
+    """ray_gen, fbuf2png, and -- linked against librodent_b200.so -- bench_traversal, bench_interface, bench_shading, bvh_extractor, converter, rodent."""
     (TOOLS / "bin").mkdir(exist_ok=True)
     cxx = os.environ.get("CXX", "g++")
     common = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall"]
@@ -61,7 +61,7 @@ def build_tools(force: bool = False) -> None:
     if (TOOLS / "bvh_extractor.cpp").exists():
         jobs.append(("bvh_extractor", ["bvh_extractor.cpp"],
                      [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))
-    for name in ("bench_interface", "bench_shading"):
+    for name in ("bench_interface", "bench_shading", "converter"):
         if (TOOLS / f"{name}.cpp").exists():
             jobs.append((name, [f"{name}.cpp"],
                          [f"-L{PKG}", "-lrodent_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../../rodent_b200"]))

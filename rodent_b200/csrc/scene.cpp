@@ -616,17 +616,17 @@ void collect_lights(Scene& s, const std::vector<F3>& verts) {
 
 constexpr int kBvh2MinTriangles = 4096;
 
-Scene* load_obj_scene(const std::string& path) {
-    ObjFile obj;
-    if (!parse_obj(path, obj)) return nullptr;
+// OBJ + MTL -> the scene's material table and images (the first half of convert_obj, converter.cpp:565-602, 748-768, 870-913);
+// `obj` comes back with its faces' material ids rewritten to the cleaned-up table.
+static bool load_materials(const std::string& path, ObjFile& obj, Scene* scene) {
+    if (!parse_obj(path, obj)) return false;
     std::map<std::string, ObjMaterial> lib;
     const size_t slash = path.find_last_of('/');
     const std::string dir = slash == std::string::npos ? "." : path.substr(0, slash);
     for (auto& name : obj.mtl_libs)
-        if (!parse_mtl(dir + "/" + name, lib)) return nullptr;
+        if (!parse_mtl(dir + "/" + name, lib)) return false;
     cleanup_materials(obj, lib);
 
-    auto scene = new Scene();
     // Images, converter.cpp:595-602, 748-768: one per distinct file name, relative to the OBJ's directory, '\\' -> '/';
     // .png, .jpg / .jpeg and .tga are decoded, an unknown extension gives the reference's 1x1 black dummy image.  (The reference registers map_Ks
     // under map_Kd's name, :600, so a specular map silently samples image 0 there; here it samples its own file.)
@@ -672,7 +672,13 @@ Scene* load_obj_scene(const std::string& path) {
         scene->materials.push_back(r);
         scene->material_names.push_back(name);
     }
-    if (failed) { delete scene; return nullptr; }
+    return !failed;
+}
+
+Scene* load_obj_scene(const std::string& path) {
+    ObjFile obj;
+    auto scene = new Scene();
+    if (!load_materials(path, obj, scene)) { delete scene; return nullptr; }
 
     // compute_tri_mesh, obj.cpp:412-509: per object, vertices de-duplicated by (v, t, n) in order of first use
     std::vector<F3> verts, normals, face_normals;
@@ -832,6 +838,201 @@ Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int 
     return scene;
 }
 
+// ---- the converter's data/ directory (convert_obj, src/driver/converter.cpp:403-438, 682-745) ---------------------------
+// What the reference's converter leaves next to its generated main.impala: the mesh as LZ4-framed buffers
+// (data/vertices.bin, normals.bin, face_normals.bin, texcoords.bin -- elements padded to 16 bytes for the GPU targets --
+// and indices.bin, four ints per triangle, the fourth the geometry = material id), the BVH of the target's layout in
+// data/bvh.bin, and data/bvh.stamp naming the target and the OBJ file.  Materials and lights are NOT in there: the
+// converter prints them into main.impala as code.  Here they come from the OBJ / MTL the stamp names (the same
+// cleanup rules give the same ids); with --fusion the per-triangle simple_kd / ks / ns buffers are turned back into
+// table entries.
+extern "C" void* rodent_b200_load_buffer(const char* file, int64_t* size);
+extern "C" void rodent_b200_free_buffer(void* p);
+extern "C" int32_t rodent_b200_write_buffer(const char* file, const void* data, int64_t bytes);
+extern "C" int32_t rodent_b200_load_bvh_bin(const char* file, int32_t node_size, int32_t tri_size, void** nodes, int64_t* num_nodes, void** tris, int64_t* num_tris);
+extern "C" int32_t rodent_b200_append_bvh_bin(const char* file, int32_t node_size, int32_t tri_size, const void* nodes, int64_t num_nodes, const void* tris, int64_t num_tris);
+
+namespace {
+bool read_buffer_file(const std::string& file, std::vector<uint8_t>& out) {
+    int64_t n = 0;
+    void* p = rodent_b200_load_buffer(file.c_str(), &n);
+    if (!p) return false;
+    out.assign(static_cast<uint8_t*>(p), static_cast<uint8_t*>(p) + n);
+    rodent_b200_free_buffer(p);
+    return true;
+}
+// elements of `comps` floats, stored with a stride of `comps` or 4 floats -> float4 stride
+bool unpack_vectors(const std::vector<uint8_t>& raw, size_t count, int comps, std::vector<float>& out) {
+    if (count == 0 || raw.size() % (count * 4) != 0) return false;
+    const size_t stride = raw.size() / (count * 4);
+    if (stride != size_t(comps) && stride != 4) return false;
+    const float* src = reinterpret_cast<const float*>(raw.data());
+    out.assign(count * 4, 0.0f);
+    for (size_t i = 0; i < count; i++)
+        for (int c = 0; c < comps; c++) out[4 * i + c] = src[stride * i + c];
+    return true;
+}
+template <typename NodeT, typename TriT>
+bool load_bvh_block(const std::string& file, std::vector<NodeT>& nodes, std::vector<TriT>& tris) {
+    void* n = nullptr; void* t = nullptr; int64_t nn = 0, nt = 0;
+    std::FILE* probe = std::fopen(file.c_str(), "rb");
+    if (!probe) return false;
+    std::fclose(probe);
+    // (rodent_b200_load_bvh_bin reports a missing layout on stderr; probing three layouts, two of them are expected to miss)
+    std::fflush(stderr);
+    if (!rodent_b200_load_bvh_bin(file.c_str(), int32_t(sizeof(NodeT)), int32_t(sizeof(TriT)), &n, &nn, &t, &nt)) return false;
+    nodes.assign(static_cast<NodeT*>(n), static_cast<NodeT*>(n) + nn);
+    tris.assign(static_cast<TriT*>(t), static_cast<TriT*>(t) + nt);
+    rodent_b200_free_buffer(n); rodent_b200_free_buffer(t);
+    return true;
+}
+}  // namespace
+
+Scene* load_data_dir(const std::string& dir, const std::string& obj_path_arg) {
+    std::string obj_path = obj_path_arg;
+    if (obj_path.empty()) {                                   // data/bvh.stamp: "<target> <obj file>", converter.cpp:741-742
+        std::ifstream stamp(dir + "/bvh.stamp");
+        int target = 0;
+        if (!(stamp >> target) || !std::getline(stamp >> std::ws, obj_path) || obj_path.empty()) {
+            fail("'" + dir + "/bvh.stamp' does not name the OBJ file; pass it explicitly");
+            return nullptr;
+        }
+    }
+    auto scene = new Scene();
+    ObjFile obj;
+    if (!load_materials(obj_path, obj, scene)) { delete scene; return nullptr; }
+
+    std::vector<uint8_t> raw_idx, raw_v, raw_n, raw_fn, raw_t;
+    if (!read_buffer_file(dir + "/indices.bin", raw_idx) || !read_buffer_file(dir + "/vertices.bin", raw_v) ||
+        !read_buffer_file(dir + "/normals.bin", raw_n) || !read_buffer_file(dir + "/face_normals.bin", raw_fn) ||
+        !read_buffer_file(dir + "/texcoords.bin", raw_t)) { delete scene; return nullptr; }
+    if (raw_idx.empty() || raw_idx.size() % 16) { delete scene; fail("indices.bin is not a list of int4"); return nullptr; }
+    const int num_tris = int(raw_idx.size() / 16);
+    scene->indices.assign(reinterpret_cast<const int32_t*>(raw_idx.data()), reinterpret_cast<const int32_t*>(raw_idx.data()) + size_t(num_tris) * 4);
+    int num_verts = 0;
+    for (int i = 0; i < num_tris; i++)
+        for (int c = 0; c < 3; c++) {
+            if (scene->indices[4 * i + c] < 0) { delete scene; fail("negative vertex index in indices.bin"); return nullptr; }
+            num_verts = std::max(num_verts, scene->indices[4 * i + c] + 1);
+        }
+    // the arrays may hold vertices no triangle uses: their length follows from the file sizes.  Padded (GPU targets) or not:
+    // a vertex is 16 bytes in both vertices.bin and texcoords.bin when padded, 12 and 8 when not.
+    const bool padded = raw_v.size() == raw_t.size();
+    const size_t nv_guess = raw_v.size() / (padded ? 16 : 12);
+    const size_t nv = nv_guess >= size_t(num_verts) && raw_v.size() % (padded ? 16 : 12) == 0 ? nv_guess : 0;
+    if (nv == 0 || !unpack_vectors(raw_v, nv, 3, scene->vertices) || !unpack_vectors(raw_n, nv, 3, scene->normals) ||
+        !unpack_vectors(raw_fn, size_t(num_tris), 3, scene->face_normals) || !unpack_vectors(raw_t, nv, 2, scene->texcoords)) {
+        delete scene; fail("mesh buffers of '" + dir + "' do not agree in size"); return nullptr;
+    }
+
+    // --fusion: every simple material became geometry `num_complex`, its colours moved to per-triangle buffers
+    // (converter.cpp:682-709).  One table entry per distinct (kd, ks, ns) brings them back.
+    std::vector<uint8_t> raw_kd, raw_ks, raw_ns;
+    {
+        std::FILE* f = std::fopen((dir + "/simple_kd.bin").c_str(), "rb");
+        if (f) {
+            std::fclose(f);
+            std::vector<float> kd, ks;
+            if (!read_buffer_file(dir + "/simple_kd.bin", raw_kd) || !read_buffer_file(dir + "/simple_ks.bin", raw_ks) ||
+                !read_buffer_file(dir + "/simple_ns.bin", raw_ns) || !unpack_vectors(raw_kd, size_t(num_tris), 3, kd) ||
+                !unpack_vectors(raw_ks, size_t(num_tris), 3, ks) || raw_ns.size() != size_t(num_tris) * 4) {
+                delete scene; fail("simple_kd / simple_ks / simple_ns do not match the mesh"); return nullptr;
+            }
+            int fused = 0;                                     // the fused geometry is the last id in use (= num_complex)
+            for (int i = 0; i < num_tris; i++) fused = std::max(fused, scene->indices[4 * i + 3]);
+            if (fused > int(scene->materials.size())) { delete scene; fail("indices.bin names more geometries than the OBJ has materials"); return nullptr; }
+            const float* ns = reinterpret_cast<const float*>(raw_ns.data());
+            std::map<std::array<float, 7>, int> seen;
+            scene->materials.resize(size_t(fused));
+            scene->material_names.resize(size_t(fused));
+            for (int i = 0; i < num_tris; i++) {
+                if (scene->indices[4 * i + 3] != fused) continue;
+                const std::array<float, 7> key{kd[4 * i], kd[4 * i + 1], kd[4 * i + 2], ks[4 * i], ks[4 * i + 1], ks[4 * i + 2], ns[i]};
+                auto it = seen.find(key);
+                if (it == seen.end()) {
+                    ObjMaterial m;
+                    m.kd = {key[0], key[1], key[2]}; m.ks = {key[3], key[4], key[5]}; m.ns = key[6]; m.ni = 1.0f; m.illum = 2;
+                    it = seen.emplace(key, int(scene->materials.size())).first;
+                    scene->materials.push_back(make_material(m));
+                    scene->material_names.push_back("fused");
+                }
+                scene->indices[4 * i + 3] = it->second;
+            }
+        }
+    }
+    const int num_materials = int(scene->materials.size());
+    for (int i = 0; i < num_tris; i++)
+        if (scene->indices[4 * i + 3] < 0 || scene->indices[4 * i + 3] >= num_materials) {
+            delete scene; fail("indices.bin names geometry " + std::to_string(scene->indices[4 * i + 3]) + ", '" + obj_path + "' has " + std::to_string(num_materials) + " materials");
+            return nullptr;
+        }
+
+    std::vector<F3> verts(nv);
+    for (size_t i = 0; i < nv; i++) verts[i] = {scene->vertices[4 * i], scene->vertices[4 * i + 1], scene->vertices[4 * i + 2]};
+    collect_lights(*scene, verts);
+
+    // The BVH the converter wrote, whatever its layout; the geometry ids inside it are refreshed from indices.bin (fusion
+    // renumbered them).  A BVH8 is adopted as the scene's, a BVH2 / Tri1 as its second tree, and whatever is missing is
+    // built from the triangles.
+    const std::string bvh_file = dir + "/bvh.bin";
+    bool have8 = load_bvh_block(bvh_file, scene->nodes, scene->tris);
+    if (have8) {
+        for (Tri4& t : scene->tris)
+            for (int j = 0; j < 4; j++) {
+                if (t.prim_id[j] == -1) continue;
+                const int p = t.prim_id[j] & 0x7FFFFFFF;
+                if (p >= num_tris) { delete scene; fail("prim_id out of range in bvh.bin"); return nullptr; }
+                t.geom_id[j] = scene->indices[4 * p + 3];
+            }
+    }
+    std::vector<Node2> n2; std::vector<Tri1> t1;
+    const bool have2 = load_bvh_block(bvh_file, n2, t1);
+    load_bvh_block(bvh_file, scene->nodes4, scene->tris4);
+    if (!have8) {
+        std::vector<F3> a(num_tris), b(num_tris), c(num_tris); std::vector<int> geom(num_tris);
+        for (int i = 0; i < num_tris; i++) {
+            a[i] = verts[scene->indices[4 * i]]; b[i] = verts[scene->indices[4 * i + 1]]; c[i] = verts[scene->indices[4 * i + 2]];
+            geom[i] = scene->indices[4 * i + 3];
+        }
+        Builder<Node8> builder{a, b, c, geom, {}, {}, {}, {}, scene->nodes, scene->tris};
+        builder.run();
+    }
+    if (have2 && !set_bvh2(*scene, n2.data(), int(n2.size()), t1.data(), int(t1.size()))) { delete scene; return nullptr; }
+    if (!have2 && num_tris >= kBvh2MinTriangles) build_bvh2(*scene);
+    return scene;
+}
+
+// convert_obj's data/ directory from a loaded scene: `arity` 2, 4 or 8 picks the layout written to bvh.bin (the reference
+// writes the one of its target: 2 for the GPU targets, 4 for generic / sse42 / asimd, 8 for avx / avx2), `padded` the
+// 16-byte elements of the GPU targets (converter.cpp:630-633).
+bool write_data_dir(Scene& scene, const std::string& dir, int arity, bool padded, const std::string& obj_path) {
+    const size_t nv = scene.vertices.size() / 4, nt = scene.indices.size() / 4;
+    auto pack = [&](const std::vector<float>& src, size_t count, int comps) {
+        const int stride = padded ? 4 : comps;
+        std::vector<float> out(count * size_t(stride), 0.0f);
+        for (size_t i = 0; i < count; i++)
+            for (int c = 0; c < comps; c++) out[i * stride + c] = src[4 * i + c];
+        return out;
+    };
+    auto put = [&](const char* name, const std::vector<float>& v) {
+        return rodent_b200_write_buffer((dir + "/" + name).c_str(), v.data(), int64_t(v.size() * sizeof(float))) != 0;
+    };
+    if (!put("vertices.bin", pack(scene.vertices, nv, 3)) || !put("normals.bin", pack(scene.normals, nv, 3)) ||
+        !put("face_normals.bin", pack(scene.face_normals, nt, 3)) || !put("texcoords.bin", pack(scene.texcoords, nv, 2)) ||
+        !rodent_b200_write_buffer((dir + "/indices.bin").c_str(), scene.indices.data(), int64_t(scene.indices.size() * sizeof(int32_t))))
+        return fail("cannot write the mesh buffers into '" + dir + "'");
+    const std::string bvh_file = dir + "/bvh.bin";
+    std::remove(bvh_file.c_str());
+    bool ok = false;
+    if (arity == 8) ok = rodent_b200_append_bvh_bin(bvh_file.c_str(), sizeof(Node8), sizeof(Tri4), scene.nodes.data(), int64_t(scene.nodes.size()), scene.tris.data(), int64_t(scene.tris.size()));
+    else if (arity == 4) { build_bvh4(scene); ok = rodent_b200_append_bvh_bin(bvh_file.c_str(), sizeof(Node4), sizeof(Tri4), scene.nodes4.data(), int64_t(scene.nodes4.size()), scene.tris4.data(), int64_t(scene.tris4.size())); }
+    else if (arity == 2) { build_bvh2(scene); ok = rodent_b200_append_bvh_bin(bvh_file.c_str(), sizeof(Node2), sizeof(Tri1), scene.nodes2.data(), int64_t(scene.nodes2.size()), scene.tris1.data(), int64_t(scene.tris1.size())); }
+    if (!ok) return fail("cannot write '" + bvh_file + "'");
+    std::ofstream stamp(dir + "/bvh.stamp");
+    stamp << (arity == 2 ? 6 : arity == 4 ? 0 : 1) << " " << obj_path;          // Target enum of converter.cpp:24-36: generic 0, avx2 1, nvvm-streaming 6
+    return bool(stamp);
+}
+
 int Scene::add_texture(const uint32_t* rgba, int width, int height) {
     textures.push_back({width, height, int64_t(texture_pixels.size())});
     texture_pixels.insert(texture_pixels.end(), rgba, rgba + size_t(width) * height);
@@ -846,6 +1047,13 @@ extern "C" {
 
 RodentScene* rodent_b200_scene_load_obj(const char* obj_file) {
     return reinterpret_cast<RodentScene*>(rb200::load_obj_scene(obj_file));
+}
+RodentScene* rodent_b200_scene_load_data(const char* data_dir, const char* obj_file) {
+    return reinterpret_cast<RodentScene*>(rb200::load_data_dir(data_dir ? data_dir : "data", obj_file ? obj_file : ""));
+}
+int32_t rodent_b200_scene_write_data(RodentScene* scene, const char* data_dir, int32_t bvh_arity, int32_t padded, const char* obj_file) {
+    if (!scene || !data_dir || (bvh_arity != 2 && bvh_arity != 4 && bvh_arity != 8)) return 0;
+    return rb200::write_data_dir(*reinterpret_cast<Scene*>(scene), data_dir, bvh_arity, padded != 0, obj_file ? obj_file : "") ? 1 : 0;
 }
 RodentScene* rodent_b200_scene_from_bvh8(const Node8* nodes, int32_t num_nodes, const Tri4* tris, int32_t num_tri4,
                                          const RodentMaterial* materials, int32_t num_materials,

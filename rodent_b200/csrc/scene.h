@@ -36,6 +36,8 @@ bool load_jpg(const std::string& path, int& width, int& height, std::vector<uint
 bool load_tga(const std::string& path, int& width, int& height, std::vector<uint32_t>& pixels, std::string& why);
 
 Scene* load_obj_scene(const std::string& path);
+Scene* load_data_dir(const std::string& dir, const std::string& obj_path);
+bool write_data_dir(Scene& scene, const std::string& dir, int arity, bool padded, const std::string& obj_path);
 void build_bvh4(Scene& scene);
 void build_bvh2(Scene& scene);
 bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris, int num_tri1);

@@ -612,7 +612,9 @@ static std::mutex g_pool_serial;
 // ~10 GB/s on one core; the PCIe link takes five times that).  Jobs are byte ranges; parallel_copy returns when all are done.
 class CopyPool {
 public:
-    static CopyPool& get() { static CopyPool p; return p; }
+    // never destroyed: its threads wait on the condition variable for the life of the process, and destroying a
+    // condition variable that has waiters blocks (glibc) -- a static instance would hang every process at exit
+    static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }
     void parallel_copy(void* dst, const void* src, size_t bytes) {
         const size_t kMin = size_t(1) << 20;
         const int parts = int(std::min<size_t>(kThreads + 1, std::max<size_t>(1, bytes / kMin)));

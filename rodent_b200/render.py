@@ -41,6 +41,8 @@ class SceneView(ctypes.Structure):
 SIGNATURES = {
     "rodent_b200_scene_load_obj": (c_void_p, [ctypes.c_char_p]),
     "rodent_b200_scene_from_bvh8": (c_void_p, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32]),
+    "rodent_b200_scene_load_data": (c_void_p, [ctypes.c_char_p, ctypes.c_char_p]),
+    "rodent_b200_scene_write_data": (c_int32, [c_void_p, ctypes.c_char_p, c_int32, c_int32, ctypes.c_char_p]),
     "rodent_b200_scene_view": (None, [c_void_p, POINTER(SceneView)]),
     "rodent_b200_scene_free": (None, [c_void_p]),
     "rodent_b200_scene_add_texture": (c_int32, [c_void_p, c_void_p, c_int32, c_int32]),
@@ -110,6 +112,17 @@ class Scene:
     @classmethod
     def load_obj(cls, path) -> "Scene":
         return cls(_bind(lib.load()).rodent_b200_scene_load_obj(str(path).encode()))
+
+    @classmethod
+    def load_data(cls, data_dir, obj_file=None) -> "Scene":
+        """A scene from the reference converter's data/ directory (rodent_b200_scene_load_data); materials come from the
+        OBJ / MTL named by `obj_file` or by data/bvh.stamp."""
+        return cls(_bind(lib.load()).rodent_b200_scene_load_data(str(data_dir).encode(), str(obj_file).encode() if obj_file else None))
+
+    def write_data(self, data_dir, bvh_arity: int = 8, padded: bool = False, obj_file="") -> None:
+        """Writes the converter's data/ directory for this scene (rodent_b200_scene_write_data)."""
+        if not _bind(lib.load()).rodent_b200_scene_write_data(self.handle, str(data_dir).encode(), bvh_arity, int(padded), str(obj_file).encode()):
+            raise RuntimeError(f"cannot write {data_dir} (see stderr)")
 
     @classmethod
     def from_bvh8(cls, nodes: np.ndarray, tris: np.ndarray, materials: np.ndarray, material_of_prim: np.ndarray) -> "Scene":

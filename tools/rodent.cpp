@@ -39,6 +39,7 @@ void usage() {
               << "Available options:\n"
               << "   --help              Shows this message\n"
               << "   --scene  file.obj   Scene to render (the reference's SCENE_FILE)\n"
+              << "   --data   dir        Render from a converter-written data/ directory (materials from --scene, else from dir/bvh.stamp)\n"
               << "   --spp    n          Samples per pixel and iteration (the reference's SPP, default 4)\n"
               << "   --max-path-len n    Maximum path length (the reference's MAX_PATH_LEN, default 64)\n"
               << "   --dev    k          CUDA device index\n"
@@ -71,7 +72,7 @@ void save_image(const std::string& out_file, size_t width, size_t height, uint32
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string out_file, scene_file;
+    std::string out_file, scene_file, data_dir;
     size_t bench_iter = 0, width = 1080, height = 720;
     int spp = 4, max_path_len = 64, dev = 0, gpus = 1;
     float fov = 60.0f;
@@ -88,6 +89,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--bench")) { check_arg(argc, argv, i, 1); bench_iter = strtoul(argv[++i], nullptr, 10); }
         else if (!strcmp(argv[i], "-o")) { check_arg(argc, argv, i, 1); out_file = argv[++i]; }
         else if (!strcmp(argv[i], "--scene")) { check_arg(argc, argv, i, 1); scene_file = argv[++i]; }
+        else if (!strcmp(argv[i], "--data")) { check_arg(argc, argv, i, 1); data_dir = argv[++i]; }
         else if (!strcmp(argv[i], "--spp")) { check_arg(argc, argv, i, 1); spp = int(strtol(argv[++i], nullptr, 10)); }
         else if (!strcmp(argv[i], "--max-path-len")) { check_arg(argc, argv, i, 1); max_path_len = int(strtol(argv[++i], nullptr, 10)); }
         else if (!strcmp(argv[i], "--dev")) { check_arg(argc, argv, i, 1); dev = int(strtol(argv[++i], nullptr, 10)); }
@@ -95,7 +97,7 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--help")) { usage(); return 0; }
         else error(std::string("Unknown option '") + argv[i] + "'");
     }
-    if (scene_file.empty()) error("No scene: pass --scene file.obj");
+    if (scene_file.empty() && data_dir.empty()) error("No scene: pass --scene file.obj (or --data dir)");
     if (bench_iter == 0) error("No display in this build (the reference's DISABLE_GUI): pass --bench iterations");
     if (width == 0 || height == 0 || spp <= 0) error("Invalid image size or sample count");
 
@@ -104,7 +106,8 @@ int main(int argc, char** argv) {
     const F3 d = normalize(dir), right = normalize(cross(d, up)), u = normalize(cross(right, d));
     const float w = std::tan(fov * pi / 360.0f), h = w / (float(width) / float(height));
 
-    RodentScene* scene = rodent_b200_scene_load_obj(scene_file.c_str());
+    RodentScene* scene = data_dir.empty() ? rodent_b200_scene_load_obj(scene_file.c_str())
+                                          : rodent_b200_scene_load_data(data_dir.c_str(), scene_file.empty() ? nullptr : scene_file.c_str());
     if (!scene) return 1;
     if (gpus < 1 || dev < 0 || rodent_b200_device_count() < dev + gpus) error("No such CUDA device");
     if (gpus > 1) {
