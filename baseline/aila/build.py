@@ -29,6 +29,15 @@ def patch_kernel(text: str) -> str:
     text, n = re.subn(r"cudaBindTexture\(nullptr,\s*(t_\w+),\s*(\w+),[^;]*\)\);", r"cudaMemcpyToSymbol(\1, &\2, sizeof(\2)));", text)
     text, m = re.subn(r"^\s*CHECK_CUDA_CALL\(cudaUnbindTexture\(t_\w+\)\);\n", "", text, flags=re.M)
     assert n == 3 and m == 3, f"expected 3 binds and 3 unbinds, found {n} and {m}"
+    # The ray fetch broadcasts the warp's base index through a shared-memory word, written by one lane and read by the
+    # others with no barrier in between (:121-124) -- warp-synchronous code from before independent thread scheduling.
+    # On sm_70+ the lanes of a warp reach this point in groups, the groups race on the word, and ranges of rays are
+    # handed out and never traced (measured on B200: 21 % / 29 % of the two Sponza sets left unwritten).  The same
+    # broadcast as a shuffle among the lanes that fetch together:
+    text, k = re.subn(r"if \(idxTerminated == 0\)\s*\n\s*rayBase = atomicAdd\(&g_warpCounter, numTerminated\);\s*\n\s*rayidx = rayBase \+ idxTerminated;",
+                      "int fetchBase = 0;\n            if (idxTerminated == 0)\n                fetchBase = atomicAdd(&g_warpCounter, numTerminated);\n"
+                      "            fetchBase = __shfl_sync(maskTerminated, fetchBase, __ffs(maskTerminated) - 1);\n            rayidx = fetchBase + idxTerminated;", text)
+    assert k == 1, "ray fetch not found"
     return text
 
 

@@ -49,6 +49,7 @@ struct Tuning {
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
+    int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
     int host_chunks = 3;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 3..4)
 };
 static Tuning g_tuning;
@@ -706,11 +707,12 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     // follows the last byte of input is one piece's traversal -- including its stragglers -- and its copy out, so that
     // last piece is kept small.
     const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
-    const int64_t parts = int64_t(pieces) * (pieces + 1) / 2;
+    const bool ramp = g_tuning.host_ramp && pieces >= 3;      // weights 1, k-1, k-2, ..., 1: nothing runs before the first piece is in
+    const int64_t parts = ramp ? int64_t(pieces - 1) * pieces / 2 + 1 : int64_t(pieces) * (pieces + 1) / 2;
     int k = 0;
     int piece_first[17], piece_n[17];
     for (int first = 0; first < num_rays; k++) {
-        const int weight = std::max(1, pieces - k);
+        const int weight = ramp ? (k == 0 ? 1 : std::max(1, pieces - k)) : std::max(1, pieces - k);
         int n = int((int64_t(num_rays) * weight / parts + 3) & ~int64_t(3));
         n = std::max(n, 1 << 14);
         if (k >= pieces - 1 || n > num_rays - first) n = num_rays - first;
@@ -891,6 +893,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value != 0;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = clamp(value, 1, 16);
     else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
+    else if (!std::strcmp(key, "host_ramp")) g_tuning.host_ramp = value != 0;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = clamp(value, 8, 12);
     else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value != 0;
     else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = clamp(value, 12, 24);

@@ -27,7 +27,7 @@ def main(src, dst, passes=2):
 
     def val(l, m, scale=1.0):
         v, unit = l[m]
-        mult = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1}.get(unit, 1)
+        mult = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3, "nsecond": 1e-9, "ns": 1e-9, "second": 1, "s": 1}.get(unit, 1)
         return v * mult * scale
 
     out = {"source": f"{src}: ncu --metrics ... --clock-control none on scripts/one_pass.py, the last of {passes} launches per ray set (warm caches)",

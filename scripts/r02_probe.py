@@ -54,9 +54,67 @@ def render():
     lib.tune("render_fma", 1); lib.tune("render_lanes", 3)
 
 
+def e2e():
+    """Host-pointer entry points, both sets from two host threads (what bench.py's e2e does): piece count and schedule."""
+    from concurrent.futures import ThreadPoolExecutor
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8())
+    sets = {}
+    for name, (tmin, tmax) in testdata.RAY_SETS.items():
+        rays = formats.load_rays(testdata.rays(name), tmin, tmax)
+        pr = traversal.PinnedArray(formats.RAY1, len(rays)); pr.array[:] = rays
+        sets[name] = (pr, traversal.PinnedArray(formats.HIT1, len(rays)))
+    pool = ThreadPoolExecutor(2)
+
+    def step():
+        jobs = [pool.submit(traversal.intersect_host, nodes, tris, sets[n][0].array, sets[n][1].array) for n in ("random", "primary")]
+        for j in jobs:
+            j.result()
+
+    for ramp in (0, 1):
+        for chunks in (2, 3, 4, 5, 6, 8):
+            lib.tune("host_ramp", ramp); lib.tune("host_chunks", chunks)
+            for _ in range(3):
+                step()
+            ts = []
+            for _ in range(15):
+                t0 = time.perf_counter(); step(); ts.append((time.perf_counter() - t0) * 1e3)
+            print(f"ramp {ramp} chunks {chunks}: median {np.median(ts):.3f} ms, min {min(ts):.3f} ms -> {2 * (1 << 20) / np.median(ts) / 1e3:.0f} Mrays/s", flush=True)
+    lib.tune("host_ramp", 0); lib.tune("host_chunks", 3)
+
+
+def sbvh():
+    """Sponza render through the reference file's BVH2 block against a BVH2 from this repository's split-BVH builder."""
+    from rodent_b200 import render as R, workloads
+    cfg = workloads.RENDER_CONFIGS["sponza"]
+    W, H, depth, spp = cfg["width"], cfg["height"], cfg["max_path_len"], 32
+    cam = workloads.camera("sponza")
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8(), formats.BVH8_TRI4)
+    for which in ("reference BVH2 block", "own split BVH2"):
+        scene = R.Scene.from_bvh8(nodes, tris, workloads.sponza_materials(), workloads.sponza_material_of_prim(tris))
+        t0 = time.perf_counter()
+        if which.startswith("ref"):
+            scene.set_bvh2(*formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1))
+        else:
+            scene.build_bvh2()
+        build_s = time.perf_counter() - t0
+        r = R.Renderer(scene, 0, W, H, spp, depth)
+        r.render(cam, 0, present=False)
+        ms = [r.render(cam, it, present=False) for it in range(1, 3)]
+        film_mean = float(np.mean(r.film())) if False else 0.0
+        st = r.stats()
+        r.free()
+        print(f"sponza {W}x{H} {spp} spp, {which} ({scene.view.num_nodes2} Node2, {scene.view.num_tri1} Tri1, {build_s:.1f} s): "
+              f"{W * H * spp / np.mean(ms) / 1e3:8.1f} Msamples/s ({np.mean(ms):.2f} ms, {st['primary_rays']} + {st['shadow_rays']} rays)", flush=True)
+        scene.free()
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["trav", "render"]
     if "trav" in what:
         trav()
     if "render" in what:
         render()
+    if "e2e" in what:
+        e2e()
+    if "sbvh" in what:
+        sbvh()
