@@ -255,7 +255,8 @@ typedef struct RodentMaterial {
     float   kd[3], mix_k;
     float   ks[3]; int32_t map_kd;   /* 1 + index of the diffuse texture (MTL map_Kd), 0 = the constant kd  (converter.cpp:879-885) */
     float   tf[3]; int32_t map_ks;   /* 1 + index of the specular texture (MTL map_Ks), 0 = the constant ks (converter.cpp:887-893) */
-    float   ke[3], pad2;       /* emitted radiance of an emissive material (MTL Ke) */
+    float   ke[3]; int32_t map_ke;   /* emitted radiance of an emissive material (MTL Ke); 1 + index of the emission texture
+                                      * (MTL map_Ke, converter.cpp:794-801), 0 = the constant ke */
 } RodentMaterial;
 
 /* One image of the scene as load_png leaves it (src/driver/image.cpp:10-93): RGBA8 packed little-endian in a uint32_t
@@ -270,8 +271,8 @@ typedef struct RodentTexture {
  * data/light_{verts,norms,areas,colors}.bin of converter.cpp:807-818) */
 typedef struct RodentLight {
     float v0[3], inv_area;
-    float v1[3], pad0;
-    float v2[3], pad1;
+    float v1[3]; int32_t prim;       /* the triangle this light is (its texture coordinates are looked up through it) */
+    float v2[3]; int32_t map_ke;     /* the material's map_ke: with it, `color` is replaced by the texture at the sampled point */
     float n[3],  pad2;
     float color[3], pad3;
 } RodentLight;

@@ -306,7 +306,7 @@ static Col rgba32_texture(const uint32_t* pixels, int width, int height, float u
  * (surf.attr(0), geometry.impala:44-47), the mix weight recomputed from the sampled colours. */
 static RodentMaterial textured_material(const RodentSceneView* sc, int geom, int prim, float u, float v) {
     RodentMaterial m = sc->materials[geom];
-    if ((m.map_kd | m.map_ks) == 0) return m;
+    if ((m.map_kd | m.map_ks | m.map_ke) == 0) return m;
     const int i0 = sc->indices[prim * 4], i1 = sc->indices[prim * 4 + 1], i2 = sc->indices[prim * 4 + 2];
     const float* tc = sc->texcoords;
     const float tu = lerp2(tc[i0 * 4], tc[i1 * 4], tc[i2 * 4], u, v), tv = lerp2(tc[i0 * 4 + 1], tc[i1 * 4 + 1], tc[i2 * 4 + 1], u, v);
@@ -320,11 +320,26 @@ static RodentMaterial textured_material(const RodentSceneView* sc, int geom, int
         const Col c = rgba32_texture(sc->texture_pixels + t->offset, t->width, t->height, tu, tv);
         m.ks[0] = c.r; m.ks[1] = c.g; m.ks[2] = c.b;
     }
+    if (m.map_ke) {                                              /* the light's colour at this point, converter.cpp:794-801 */
+        const RodentTexture* t = &sc->textures[m.map_ke - 1];
+        const Col c = rgba32_texture(sc->texture_pixels + t->offset, t->width, t->height, tu, tv);
+        m.ke[0] = c.r; m.ke[1] = c.g; m.ke[2] = c.b;
+    }
     if (m.bsdf == RODENT_BSDF_MIX) {
         const float lum_ks = luminance(col(m.ks[0], m.ks[1], m.ks[2])), lum_kd = luminance(col(m.kd[0], m.kd[1], m.kd[2]));
         m.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
     }
     return m;
+}
+
+/* Radiance a light emits from the point with barycentrics (u, v): its constant colour, or its material's map_Ke there. */
+static Col light_color(const RodentSceneView* sc, const RodentLight* l, float u, float v) {
+    if (l->map_ke == 0) return col(l->color[0], l->color[1], l->color[2]);
+    const int i0 = sc->indices[l->prim * 4], i1 = sc->indices[l->prim * 4 + 1], i2 = sc->indices[l->prim * 4 + 2];
+    const float* tc = sc->texcoords;
+    const RodentTexture* t = &sc->textures[l->map_ke - 1];
+    return rgba32_texture(sc->texture_pixels + t->offset, t->width, t->height,
+                          lerp2(tc[i0 * 4], tc[i1 * 4], tc[i2 * 4], u, v), lerp2(tc[i0 * 4 + 1], tc[i1 * 4 + 1], tc[i2 * 4 + 1], u, v));
 }
 
 static void render_rows(RenderJob* job) {
@@ -368,7 +383,7 @@ static void render_rows(RenderJob* job) {
                         const RodentLight* l = &sc->lights[sc->light_ids[hit.tri_id]];
                         const float pdf_dir = cosine_hemisphere_pdf(vdot(v3(l->n[0], l->n[1], l->n[2]), out_dir));
                         Col intensity = kBlack; float pdf_area = 1.0f;                /* make_emission_value, light.impala:94-108 */
-                        if (pdf_dir > 0.0f) { intensity = col(l->color[0], l->color[1], l->color[2]); pdf_area = l->inv_area; }
+                        if (pdf_dir > 0.0f) { intensity = col(mat->ke[0], mat->ke[1], mat->ke[2]); pdf_area = l->inv_area; }   /* = the light's colour */
                         const float next_mis = mis * hit.t * hit.t / vdot(out_dir, surf.local.c2);
                         const float w = 1.0f / (1.0f + next_mis * pdf_lightpick * pdf_area);
                         const Col c = cmulf(cmul(contrib, intensity), w);
@@ -387,7 +402,7 @@ static void render_rows(RenderJob* job) {
                         const V3 ln = v3(l->n[0], l->n[1], l->n[2]);
                         const V3 from_dir = vsub(surf.point, pos);
                         float cos_l = vdot(from_dir, ln) / vlen(from_dir);
-                        Col intensity = col(l->color[0], l->color[1], l->color[2]);
+                        Col intensity = light_color(sc, l, u, v);
                         float pdf_area = l->inv_area;
                         if (!(pdf_area > 0.0f && cosine_hemisphere_pdf(cos_l) > 0.0f && cos_l > 0.0f)) {   /* make_direct_sample */
                             intensity = kBlack; pdf_area = 1.0f; cos_l = 0.0f;

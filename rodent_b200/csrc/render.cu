@@ -284,7 +284,7 @@ shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, S
             const RodentLight& l = sc.lights[sc.light_ids[prim]];
             const float pdf_dir = cosine_hemisphere_pdf(dot(v3(l.n[0], l.n[1], l.n[2]), out_dir));
             Col intensity = col(0, 0, 0); float pdf_area = 1.0f;                               // make_emission_value, light.impala:94-108
-            if (pdf_dir > 0.0f) { intensity = col(l.color[0], l.color[1], l.color[2]); pdf_area = l.inv_area; }
+            if (pdf_dir > 0.0f) { intensity = col(mat.ke[0], mat.ke[1], mat.ke[2]); pdf_area = l.inv_area; }   // (= the light's colour; map_Ke sampled at the hit by apply_textures)
             const float next_mis = mis * t * t / dot(out_dir, surf.local.c2);
             const float w = 1.0f / (1.0f + next_mis * pdf_lightpick * pdf_area);
             const Col c = (contrib * intensity) * w;
@@ -302,7 +302,7 @@ shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, S
             const V3 pos = v3(l.v0[0], l.v0[1], l.v0[2]) * (1.0f - v - u) + v3(l.v1[0], l.v1[1], l.v1[2]) * u + v3(l.v2[0], l.v2[1], l.v2[2]) * v;
             const V3 from_dir = surf.point - pos;
             float cos_l = dot(from_dir, v3(l.n[0], l.n[1], l.n[2])) / length(from_dir);
-            Col intensity = col(l.color[0], l.color[1], l.color[2]);
+            Col intensity = light_color(l, sc.texcoords, sc.indices, sc.textures, sc.texture_pixels, u, v);
             float pdf_area = l.inv_area;
             if (!(pdf_area > 0.0f && cosine_hemisphere_pdf(cos_l) > 0.0f && cos_l > 0.0f)) {   // make_direct_sample, light.impala:76-92
                 intensity = col(0, 0, 0); pdf_area = 1.0f; cos_l = 0.0f;
@@ -451,11 +451,12 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     if (width <= 0 || height <= 0 || spp <= 0 || num_parts <= 0 || part < 0 || part >= num_parts || band <= 0) return nullptr;
     bool textured = false;
     for (auto& m : sc.materials) {
-        if (m.map_kd < 0 || m.map_ks < 0 || size_t(m.map_kd) > sc.textures.size() || size_t(m.map_ks) > sc.textures.size()) {
+        if (m.map_kd < 0 || m.map_ks < 0 || m.map_ke < 0 || size_t(m.map_kd) > sc.textures.size() || size_t(m.map_ks) > sc.textures.size() ||
+            size_t(m.map_ke) > sc.textures.size()) {
             std::fprintf(stderr, "rodent_b200: a material names texture %d / %d, the scene has %zu\n", m.map_kd, m.map_ks, sc.textures.size());
             return nullptr;
         }
-        textured |= (m.map_kd | m.map_ks) != 0;
+        textured |= (m.map_kd | m.map_ks | m.map_ke) != 0;
     }
     // the stream kernels index per-material tables and shared-memory bins with the ids stored in the BVHs
     const int num_materials = int(sc.materials.size());

@@ -607,6 +607,7 @@ void collect_lights(Scene& s, const std::vector<F3>& verts) {
         l.v0[0] = a.x; l.v0[1] = a.y; l.v0[2] = a.z; l.v1[0] = b.x; l.v1[1] = b.y; l.v1[2] = b.z; l.v2[0] = c.x; l.v2[1] = c.y; l.v2[2] = c.z;
         l.n[0] = n.x; l.n[1] = n.y; l.n[2] = n.z;
         for (int k = 0; k < 3; k++) l.color[k] = s.materials[m].ke[k];
+        l.prim = i; l.map_ke = s.materials[m].map_ke;
         s.light_ids[i] = int(s.lights.size());
         s.lights.push_back(l);
     }
@@ -663,8 +664,8 @@ static bool load_materials(const std::string& path, ObjFile& obj, Scene* scene) 
     };
     for (auto& name : obj.materials) {
         const ObjMaterial& m = lib[name];
-        if (!m.map_ke.empty()) warn("material '" + name + "': map_Ke is not sampled, the constant Ke is emitted");
         RodentMaterial r = make_material(m);
+        r.map_ke = image_of(m.map_ke, name);            // converter.cpp:794-801: the light's colour is the texture
         if (r.bsdf == RODENT_BSDF_DIFFUSE || r.bsdf == RODENT_BSDF_PHONG || r.bsdf == RODENT_BSDF_MIX) {
             r.map_kd = image_of(m.map_kd, name);
             r.map_ks = image_of(m.map_ks, name);

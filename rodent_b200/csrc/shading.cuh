@@ -153,7 +153,7 @@ __device__ __forceinline__ Col rgba32_texture(const unsigned* __restrict__ pixel
 __device__ __forceinline__ void apply_textures(RodentMaterial& m, const float4* __restrict__ texcoords, const int4* __restrict__ indices,
                                                const RodentTexture* __restrict__ textures, const unsigned* __restrict__ texture_pixels,
                                                int prim, float u, float v) {
-    if ((m.map_kd | m.map_ks) == 0) return;
+    if ((m.map_kd | m.map_ks | m.map_ke) == 0) return;
     const int4 idx = __ldg(indices + prim);
     const float4 t0 = __ldg(texcoords + idx.x), t1 = __ldg(texcoords + idx.y), t2 = __ldg(texcoords + idx.z);
     const float tu = lerp2(t0.x, t1.x, t2.x, u, v), tv = lerp2(t0.y, t1.y, t2.y, u, v);
@@ -167,10 +167,25 @@ __device__ __forceinline__ void apply_textures(RodentMaterial& m, const float4* 
         const Col c = rgba32_texture(texture_pixels + t.offset, t.width, t.height, tu, tv);
         m.ks[0] = c.r; m.ks[1] = c.g; m.ks[2] = c.b;
     }
+    if (m.map_ke) {                                              // the light's colour at this point (converter.cpp:794-801)
+        const RodentTexture t = textures[m.map_ke - 1];
+        const Col c = rgba32_texture(texture_pixels + t.offset, t.width, t.height, tu, tv);
+        m.ke[0] = c.r; m.ke[1] = c.g; m.ke[2] = c.b;
+    }
     if (m.bsdf == RODENT_BSDF_MIX) {
         const float lum_ks = luminance(col(m.ks[0], m.ks[1], m.ks[2])), lum_kd = luminance(col(m.kd[0], m.kd[1], m.kd[2]));
         m.mix_k = (lum_ks + lum_kd == 0.0f) ? 0.0f : lum_ks / (lum_ks + lum_kd);
     }
+}
+
+// Radiance a light emits from the point with barycentrics (u, v): its constant colour, or its material's map_Ke there.
+__device__ __forceinline__ Col light_color(const RodentLight& l, const float4* __restrict__ texcoords, const int4* __restrict__ indices,
+                                           const RodentTexture* __restrict__ textures, const unsigned* __restrict__ texture_pixels, float u, float v) {
+    if (l.map_ke == 0) return col(l.color[0], l.color[1], l.color[2]);
+    const int4 idx = __ldg(indices + l.prim);
+    const float4 t0 = __ldg(texcoords + idx.x), t1 = __ldg(texcoords + idx.y), t2 = __ldg(texcoords + idx.z);
+    const RodentTexture t = textures[l.map_ke - 1];
+    return rgba32_texture(texture_pixels + t.offset, t.width, t.height, lerp2(t0.x, t1.x, t2.x, u, v), lerp2(t0.y, t1.y, t2.y, u, v));
 }
 
 // material.impala:54-192, interpreted from the RodentMaterial table

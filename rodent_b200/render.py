@@ -12,9 +12,9 @@ import numpy as np
 from . import lib
 
 MATERIAL = np.dtype([("bsdf", "<i4"), ("is_emissive", "<i4"), ("ns", "<f4"), ("ni", "<f4"), ("kd", "<f4", (3,)), ("mix_k", "<f4"),
-                     ("ks", "<f4", (3,)), ("map_kd", "<i4"), ("tf", "<f4", (3,)), ("map_ks", "<i4"), ("ke", "<f4", (3,)), ("pad2", "<f4")])
+                     ("ks", "<f4", (3,)), ("map_kd", "<i4"), ("tf", "<f4", (3,)), ("map_ks", "<i4"), ("ke", "<f4", (3,)), ("map_ke", "<i4")])
 TEXTURE = np.dtype([("width", "<i4"), ("height", "<i4"), ("offset", "<i8")])
-LIGHT = np.dtype([("v0", "<f4", (3,)), ("inv_area", "<f4"), ("v1", "<f4", (3,)), ("pad0", "<f4"), ("v2", "<f4", (3,)), ("pad1", "<f4"),
+LIGHT = np.dtype([("v0", "<f4", (3,)), ("inv_area", "<f4"), ("v1", "<f4", (3,)), ("prim", "<i4"), ("v2", "<f4", (3,)), ("map_ke", "<i4"),
                   ("n", "<f4", (3,)), ("pad2", "<f4"), ("color", "<f4", (3,)), ("pad3", "<f4")])
 assert MATERIAL.itemsize == 80 and LIGHT.itemsize == 80
 BSDF_BLACK, BSDF_DIFFUSE, BSDF_PHONG, BSDF_MIX, BSDF_MIRROR, BSDF_GLASS = range(6)

@@ -1,4 +1,4 @@
-"""Textured materials (MTL map_Kd / map_Ks): the PNG loader against src/driver/image.cpp's behaviour, the binding of
+"""Textured materials (MTL map_Kd / map_Ks / map_Ke): the PNG loader against src/driver/image.cpp's behaviour, the binding of
 images to materials (converter.cpp:595-602, 748-768, 876-903), the oracle's texturing, and CUDA against the oracle."""
 import numpy as np
 import pytest
@@ -349,6 +349,85 @@ def test_oracle_sees_the_checker(tmp_path):
     floor_row = film[H - 6].sum(axis=1)
     smooth = np.convolve(floor_row, np.ones(3) / 3, "valid")
     assert smooth.max() > 3.0 * smooth.min(), (smooth.max(), smooth.min())
+
+
+# ---- emission textures (MTL map_Ke, converter.cpp:794-801) -----------------------------------------------------
+LAMP_OBJ = OBJ.replace("f 7 8 9 10", "f 7/1 8/2 9/3 10/4")        # the lamp quad gets texture coordinates 0..3 as well
+
+
+def write_lamp_scene(tmp_path, ke_line, map_ke):
+    (tmp_path / "tex.obj").write_text(LAMP_OBJ)
+    mtl = MTL.format(floor="", wall="", wall_kd="0.4 0.3 0.2").replace("map_Kd \n", "").replace("map_Ks \n", "")
+    mtl = mtl.replace("Ke 12 12 10\n", ke_line + (f"map_Ke {map_ke}\n" if map_ke else ""))
+    (tmp_path / "tex.mtl").write_text(mtl)
+    return tmp_path / "tex.obj"
+
+
+def test_map_ke_binds_to_the_material_and_its_lights(tmp_path):
+    Image.fromarray(checker(8, 2, 4)).save(tmp_path / "glow.png")
+    scene = R.Scene.load_obj(write_lamp_scene(tmp_path, "Ke 0 0 0\n", "glow.png"))
+    mats, lights = scene.array("materials"), scene.array("lights")
+    assert scene.view.num_textures == 1 and scene.view.num_lights == 2      # an emitter through its texture alone
+    assert mats["is_emissive"].tolist() == [1, 0, 0] and mats["map_ke"].tolist() == [1, 0, 0]
+    idx = scene.array("indices")
+    for l in lights:
+        assert l["map_ke"] == 1 and idx[l["prim"], 3] == 0                   # the light knows its triangle
+        assert np.array_equal(scene.array("vertices")[idx[l["prim"], 0], :3], l["v0"])
+
+
+def test_oracle_constant_emission_texture_equals_constant_ke(tmp_path):
+    """A one-colour map_Ke is the constant Ke = lut[p] / 255: same film up to the rounding of the bilinear lerp."""
+    p = np.array([250, 180, 90], np.uint8)
+    const = np.zeros((4, 4, 4), np.uint8)
+    const[..., :3], const[..., 3] = p, 255
+    Image.fromarray(const).save(tmp_path / "glow.png")
+    k = gamma_lut()[p].astype(np.float32) * np.float32(1.0 / 255.0)
+    textured = R.Scene.load_obj(write_lamp_scene(tmp_path, "Ke 0 0 0\n", "glow.png"))
+    (tmp_path / "flat").mkdir()
+    flat = R.Scene.load_obj(write_lamp_scene(tmp_path / "flat", "Ke " + " ".join(repr(float(x)) for x in k) + "\n", None))
+    W, H = 48, 32
+    a, _ = oracle.render(textured.view, camera(W, H), W, H, 4, 6, 0)
+    b, _ = oracle.render(flat.view, camera(W, H), W, H, 4, 6, 0)
+    assert b.mean() > 0.005
+    rel = np.abs(a - b) / (np.abs(b) + 1e-3)
+    assert abs(a.mean() - b.mean()) / b.mean() < 1e-4 and (rel < 1e-5).mean() > 0.99, (a.mean(), b.mean(), (rel < 1e-5).mean())
+
+
+def test_oracle_emission_texture_shapes_the_light(tmp_path):
+    """Half of the emission image black: the scene receives about half the light of the all-bright image."""
+    bright = np.full((8, 8, 4), 255, np.uint8)
+    half = bright.copy()
+    half[:, :4, :3] = 0
+    films = {}
+    for name, img in (("bright", bright), ("half", half)):
+        d = tmp_path / name
+        d.mkdir()
+        Image.fromarray(img).save(d / "glow.png")
+        scene = R.Scene.load_obj(write_lamp_scene(d, "Ke 0 0 0\n", "glow.png"))
+        film = np.zeros((32, 48, 3), np.float32)
+        for it in range(4):
+            film, _ = oracle.render(scene.view, camera(48, 32), 48, 32, 8, 4, it, film)
+        films[name] = film
+    ratio = films["half"][20:].mean() / films["bright"][20:].mean()          # the floor rows: lit by next-event estimation
+    assert 0.35 < ratio < 0.65, ratio
+
+
+@pytest.mark.gpu
+def test_emission_texture_film_matches_oracle(tmp_path):
+    Image.fromarray(checker(8, 2, 4)).save(tmp_path / "glow.png")
+    scene = R.Scene.load_obj(write_lamp_scene(tmp_path, "Ke 0 0 0\n", "glow.png"))
+    W, H, spp, depth = 120, 90, 4, 6
+    cam = camera(W, H)
+    r = R.Renderer(scene, 0, W, H, spp, depth)
+    want = np.zeros((H, W, 3), np.float32)
+    for it in range(2):
+        r.render(cam, it)
+        want, _ = oracle.render(scene.view, cam, W, H, spp, depth, it, want)
+    got = r.film().copy()
+    r.free()
+    e = np.abs(got - want) / (np.abs(want) + 1e-3)
+    assert want.mean() > 0.002
+    assert np.median(e) < 1e-5 and (e < 1e-3).mean() > 0.995, (np.median(e), (e < 1e-3).mean())
 
 
 # ---- CUDA ------------------------------------------------------------------------------------------------------
