@@ -38,6 +38,13 @@ def patch_kernel(text: str) -> str:
                       "int fetchBase = 0;\n            if (idxTerminated == 0)\n                fetchBase = atomicAdd(&g_warpCounter, numTerminated);\n"
                       "            fetchBase = __shfl_sync(maskTerminated, fetchBase, __ffs(maskTerminated) - 1);\n            rayidx = fetchBase + idxTerminated;", text)
     assert k == 1, "ray fetch not found"
+    # Both warp votes name the full warp (`__ballot_sync(all_mask, ...)`, a blind translation of Kepler's `__ballot`): one at
+    # the head of the persistent loop, one inside the traversal loop where only the lanes still traversing arrive.  The
+    # hardware pairs the two sites, so the head's vote also sees the `true` of lanes that are in the traversal loop, counts
+    # them as terminated and hands out rays for them.  Kepler's `__ballot` voted among the ACTIVE lanes; so do these:
+    text, a = re.subn(r"__ballot_sync\(all_mask, terminated\)", "__ballot_sync(__activemask(), terminated)", text)
+    text, b = re.subn(r"__popc\(__ballot_sync\(all_mask, true\)\)", "__popc(__activemask())", text)
+    assert a == 1 and b == 1, f"expected the two warp votes, found {a} and {b}"
     return text
 
 

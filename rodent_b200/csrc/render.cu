@@ -232,22 +232,34 @@ __global__ void scan_bins(int* __restrict__ histogram, int* __restrict__ cursor,
 // ---- scatter: counting sort by material (gpu_sort_primary third pass, :210-220) ----
 // The reference moves the whole 80-byte ray to its sorted position (copy_primary_ray, :136-164).  Here only the
 // ray's INDEX is moved: order[d] = i, 8 bytes of traffic per ray instead of 164, and the shade kernel gathers its
-// inputs through `order` (rays of one material keep their stream order, so the gather stays sector-friendly).
-__global__ void __launch_bounds__(256)
+// inputs through `order`.  Slots are handed out in two levels: a CTA counts its rays per material in shared memory (one
+// shared-memory atomic per warp and material, peers found with __match_any_sync), takes ONE range per material from the
+// global cursor, and its rays fill that range -- with a handful of materials (the Cornell box has four) the global
+// cursors would otherwise serialise a hundred thousand atomics per wavefront on four addresses (33 us of a 1 Mi-ray
+// wavefront in round 1, a seventh of the Cornell render).
+constexpr int kScatterBlock = 512;
+__global__ void __launch_bounds__(kScatterBlock)
 scatter_by_material(PrimaryStream src, int* __restrict__ order, const LoopState* __restrict__ st, int num_geoms, int* __restrict__ cursor) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int bins[];                              // [num_geoms] counts, then [num_geoms] bases
     const int size = st->size;
-    if ((i & ~31) >= size) return;                             // whole warp beyond the stream
+    if (int(blockIdx.x) * kScatterBlock >= size) return;       // whole CTA beyond the stream
+    int* const count = bins;
+    int* const base = bins + num_geoms;
+    for (int b = threadIdx.x; b < num_geoms; b += kScatterBlock) count[b] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * kScatterBlock + threadIdx.x;
     const int g = i < size ? src.geom[i] : num_geoms;
-    const bool live = g < num_geoms;
-    // one atomicAdd per (warp, material): peers with the same material take consecutive slots
+    const bool live = g < num_geoms;                           // misses (the last bin) are dropped here
     const unsigned peers = __match_any_sync(0xffffffffu, live ? g : -1 - int(lane_id()));
     const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (live && int(lane_id()) == leader) base = atomicAdd(cursor + g, __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (!live) return;
-    order[base + __popc(peers & lanemask_lt())] = i;
+    int rank = 0;
+    if (live && int(lane_id()) == leader) rank = atomicAdd(count + g, __popc(peers));
+    rank = __shfl_sync(0xffffffffu, rank, leader) + __popc(peers & lanemask_lt());
+    __syncthreads();
+    for (int b = threadIdx.x; b < num_geoms; b += kScatterBlock)
+        base[b] = count[b] ? atomicAdd(cursor + b, count[b]) : 0;
+    __syncthreads();
+    if (live) order[base[g] + rank] = i;
 }
 
 // ---- shade (gpu_shade, mapping_gpu.impala:82-134, with the path tracer of renderer.impala:62-162) ----
@@ -613,7 +625,7 @@ static void enqueue_wavefront(Renderer& r, float* film, const CameraDev& cam, in
                                           r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, kRefillMin);
     }
     scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
-    scatter_by_material<<<(bound + 255) / 256, 256, 0, s>>>(P, r.order, r.state, num_geoms, r.cursor);
+    scatter_by_material<<<(bound + kScatterBlock - 1) / kScatterBlock, kScatterBlock, 2 * num_geoms * sizeof(int), s>>>(P, r.order, r.state, num_geoms, r.cursor);
     RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
     shade_rays<<<(bound + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
     RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));

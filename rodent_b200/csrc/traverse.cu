@@ -50,7 +50,7 @@ struct Tuning {
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
-    int host_chunks = 3;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (measured best: 3..4)
+    int host_chunks = 5;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (two calls in flight: 5..6 measured best, one: 3..4)
 };
 static Tuning g_tuning;
 

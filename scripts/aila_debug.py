@@ -10,7 +10,7 @@ nodes, tris = formats.load_bvh(testdata.sponza_bvh2(), formats.BVH2_TRI1)
 bvh = traversal.Bvh8(0, nodes, tris)
 for name, (tmin, tmax) in testdata.RAY_SETS.items():
     out = Path(tempfile.mkdtemp()) / "a.fbuf"
-    subprocess.run([str(exe), "-bvh", str(testdata.sponza_bvh2()), "-ray", str(testdata.rays(name)), "--tmin", str(tmin), "--tmax", str(tmax), "-o", str(out)], check=True, capture_output=True)
+    subprocess.run([str(exe), "-bvh", str(testdata.sponza_bvh2()), "-ray", str(testdata.rays(name)), "--tmin", str(tmin), "--tmax", str(tmax), "-o", str(out)], check=True, capture_output=True, timeout=60)
     ta = np.fromfile(out, "<f4")
     rays = formats.load_rays(testdata.rays(name), tmin, tmax)
     d_rays = traversal.DeviceArray.from_host(0, rays); d_hits = traversal.DeviceArray.from_host(0, np.zeros(len(rays), formats.HIT1))

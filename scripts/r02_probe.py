@@ -79,7 +79,7 @@ def e2e():
             for _ in range(15):
                 t0 = time.perf_counter(); step(); ts.append((time.perf_counter() - t0) * 1e3)
             print(f"ramp {ramp} chunks {chunks}: median {np.median(ts):.3f} ms, min {min(ts):.3f} ms -> {2 * (1 << 20) / np.median(ts) / 1e3:.0f} Mrays/s", flush=True)
-    lib.tune("host_ramp", 0); lib.tune("host_chunks", 3)
+    lib.tune("host_ramp", 0); lib.tune("host_chunks", 5)
 
 
 def sbvh():

@@ -186,7 +186,7 @@ def test_aila_comparator_agrees_with_the_bvh2_kernel(tmp_path):
     for name, (tmin, tmax) in testdata.RAY_SETS.items():
         out = tmp_path / f"{name}.fbuf"
         r = subprocess.run([str(exe), "-bvh", str(testdata.sponza_bvh2()), "-ray", str(testdata.rays(name)), "--tmin", str(tmin),
-                            "--tmax", str(tmax), "-o", str(out)], capture_output=True, text=True, timeout=300)
+                            "--tmax", str(tmax), "-o", str(out)], capture_output=True, text=True, timeout=60)
         assert r.returncode == 0, r.stderr
         t_aila = np.fromfile(out, "<f4")
         rays = formats.load_rays(testdata.rays(name), tmin, tmax)
