@@ -618,7 +618,7 @@ public:
     static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }
     void parallel_copy(void* dst, const void* src, size_t bytes) {
         const size_t kMin = size_t(1) << 20;
-        const int parts = int(std::min<size_t>(kThreads + 1, std::max<size_t>(1, bytes / kMin)));
+        const int parts = int(std::min<size_t>(kPartsPerCopy, std::max<size_t>(1, bytes / kMin)));
         if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
         const size_t each = ((bytes / parts) + 4095) & ~size_t(4095);
         std::atomic<int> pending{parts - 1};
@@ -635,8 +635,13 @@ public:
     }
 private:
     struct Job { char* dst; const char* src; size_t bytes; std::atomic<int>* pending; };
-    static constexpr int kThreads = 3;
-    CopyPool() { for (int i = 0; i < kThreads; i++) std::thread([this] { work(); }).detach(); }
+    // a copy is cut into at most kPartsPerCopy parts (the caller's thread takes one); the pool is large enough for the
+    // calls of several devices' threads at once (rodent_b200_set_devices) without oversubscribing a small host
+    static constexpr int kPartsPerCopy = 4;
+    CopyPool() {
+        const int threads = int(std::max(3u, std::min(16u, std::thread::hardware_concurrency() / 2)));
+        for (int i = 0; i < threads; i++) std::thread([this] { work(); }).detach();
+    }
     void work() {
         for (;;) {
             Job j;

@@ -32,3 +32,11 @@ r = R.Renderer(cornell, 0, 64, 64, 2, 6)
 r.render(workloads.camera("cornell", 64, 64), 0)
 print("cornell film", float(r.film().mean()))
 r.free()
+# several pipelines (device-driven wavefront loop, two-level scatter) and a stream smaller than the image: many wavefronts
+lib.tune("render_capacity", 4096)
+r = R.Renderer(cornell, 0, 96, 128, 3, 5)
+for it in range(2):
+    r.render(workloads.camera("cornell", 96, 128), it)
+print("cornell film, 3 pipelines, 4096-ray streams", float(r.film().mean()), r.stats())
+r.free()
+lib.tune("render_capacity", 1 << 20)

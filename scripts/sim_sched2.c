@@ -9,7 +9,7 @@
  * a separate sort phase, handing the last rays of a launch to a second kernel) before GPU time is spent on them.
  *
  * build: gcc -O2 -march=x86-64-v3 -ffp-contract=off -o /tmp/sim2 scripts/sim_sched2.c -lpthread -lm
- * usage: sim2 BVH8_FILE RAYS_FILE tmin tmax
+ * usage: sim2 BVH8_FILE RAYS_FILE tmin tmax [max_rays [mortonB]]   (mortonB: rays reordered by a 3B-bit Morton key of the origin)
  */
 #include <stdio.h>
 #include <stdint.h>
@@ -216,12 +216,42 @@ int main(int argc, char** argv) {
     int num_rays = (int)(rs / 24);
     if (argc > 5 && atoi(argv[5]) < num_rays) num_rays = atoi(argv[5]);
     pthread_once(&g_net_once, init_networks);
+    int* perm = malloc(sizeof(int) * (size_t)num_rays);
+    for (int i = 0; i < num_rays; i++) perm[i] = i;
+    if (argc > 6) {                                        /* "mortonB": B bits per axis of the ray origin; stable */
+        const int bits = atoi(argv[6] + 6);
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int i = 0; i < num_rays; i++) for (int c = 0; c < 3; c++) { const float v = rf[6 * i + c]; if (v < lo[c]) lo[c] = v; if (v > hi[c]) hi[c] = v; }
+        unsigned* key = malloc(sizeof(unsigned) * (size_t)num_rays);
+        for (int i = 0; i < num_rays; i++) {
+            unsigned k = 0;
+            unsigned q[3];
+            for (int c = 0; c < 3; c++) { float f = hi[c] > lo[c] ? (rf[6 * i + c] - lo[c]) / (hi[c] - lo[c]) : 0; q[c] = (unsigned)(f * ((1u << bits) - 1)); }
+            for (int b = bits - 1; b >= 0; b--) for (int c = 0; c < 3; c++) k = (k << 1) | ((q[c] >> b) & 1);
+            const unsigned oct = (rf[6 * i + 3] > 0) | ((rf[6 * i + 4] > 0) << 1) | ((rf[6 * i + 5] > 0) << 2);
+            if (strstr(argv[6], "+octlo")) k = (k << 3) | oct;            /* octant as the least significant bits */
+            if (strstr(argv[6], "+octhi")) k |= oct << (3 * bits);         /* ... or the most significant ones */
+            key[i] = k;
+        }
+        /* stable counting sort on the key, 11 bits at a time */
+        int* tmp = malloc(sizeof(int) * (size_t)num_rays);
+        for (int shift = 0; shift < 3 * bits + 3; shift += 11) {
+            static int cnt[2049];
+            memset(cnt, 0, sizeof cnt);
+            for (int i = 0; i < num_rays; i++) cnt[((key[perm[i]] >> shift) & 2047) + 1]++;
+            for (int b = 0; b < 2048; b++) cnt[b + 1] += cnt[b];
+            for (int i = 0; i < num_rays; i++) tmp[cnt[(key[perm[i]] >> shift) & 2047]++] = perm[i];
+            memcpy(perm, tmp, sizeof(int) * (size_t)num_rays);
+        }
+        fprintf(stderr, "rays reordered by a %d-bit Morton key of the origin\n", 3 * bits);
+    }
     size_t* start = malloc(((size_t)num_rays + 1) * sizeof(size_t));
     const float tmin = (float)atof(argv[3]), tmax = (float)atof(argv[4]);
-    for (int i = 0; i < num_rays; i++) {
+    for (int j = 0; j < num_rays; j++) {
+        const int i = perm[j];
         Ray1 r = {{rf[6 * i], rf[6 * i + 1], rf[6 * i + 2]}, tmin, {rf[6 * i + 3], rf[6 * i + 4], rf[6 * i + 5]}, tmax};
         Hit1 h;
-        start[i] = g_len; g_ray_first = g_len;
+        start[j] = g_len; g_ray_first = g_len;
         traverse_single(8, 0, nodes, tris, &r, &h, NULL, NULL);
     }
     start[num_rays] = g_len;
