@@ -206,6 +206,14 @@ void    rodent_b200_set_device(int32_t dev);          /* device used by the host
 /* ... or several: every host-pointer call is then cut into contiguous ray ranges, one per device, BVH replicated, each
  * range copied back into its slice of the caller's array (no collective on this path). */
 void    rodent_b200_set_devices(const int32_t* devs, int32_t num_devs);
+/* One process per GPU: a device allocation (from rodent_b200_alloc_device) exported as a 64-byte CUDA IPC handle, and
+ * such a handle opened in another process on its own device -- the pointer it returns is peer memory over NVLink /
+ * NVSwitch and can be passed as the `hits` array of the cuda_* entry points, so that a rank's kernel writes its records
+ * straight into the gathering rank's HBM (no collective afterwards; bench.py --gpus N).  export returns 0 and open NULL
+ * (with a message on stderr) where IPC or peer access is not available. */
+int32_t rodent_b200_ipc_export(int32_t dev, const void* device_ptr, void* handle_out_64_bytes);
+void*   rodent_b200_ipc_open(int32_t dev, const void* handle_64_bytes);
+void    rodent_b200_ipc_close(int32_t dev, void* ptr);
 void*   rodent_b200_alloc_device(int32_t dev, size_t bytes);
 void    rodent_b200_free_device(int32_t dev, void* ptr);
 void*   rodent_b200_alloc_host(size_t bytes);         /* page-locked */

@@ -873,6 +873,30 @@ void rodent_b200_copy_to_host(int32_t dev, void* dst, const void* src, size_t by
     device_state(dev);
     RB_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
 }
+// ---- peer memory (one process per GPU) -------------------------------------------------------------------------
+// A device allocation of another process mapped into this one (CUDA IPC; the devices are NVLink / NVSwitch peers): what
+// lets a rank's traversal kernel write its hit records straight into the gathering rank's HBM instead of into local memory
+// and through a collective afterwards.  Failures are reported, not fatal: the caller falls back to a gather.
+int32_t rodent_b200_ipc_export(int32_t dev, const void* device_ptr, void* handle_out) {
+    device_state(dev);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t h;
+    const cudaError_t err = cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr));
+    if (err != cudaSuccess) { std::fprintf(stderr, "rodent_b200: cudaIpcGetMemHandle: %s\n", cudaGetErrorString(err)); cudaGetLastError(); return 0; }
+    std::memcpy(handle_out, &h, sizeof h);
+    return 1;
+}
+void* rodent_b200_ipc_open(int32_t dev, const void* handle) {
+    device_state(dev);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    const cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) { std::fprintf(stderr, "rodent_b200: cudaIpcOpenMemHandle: %s\n", cudaGetErrorString(err)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void rodent_b200_ipc_close(int32_t dev, void* ptr) { device_state(dev); if (ptr) RB_CUDA_CHECK(cudaIpcCloseMemHandle(ptr)); }
+
 void rodent_b200_sync(int32_t dev) { device_state(dev); RB_CUDA_CHECK(cudaDeviceSynchronize()); }
 double rodent_b200_last_kernel_ms(int32_t dev) { return device_state(dev).last_ms; }
 int64_t rodent_b200_launch_count(void) { return g_launches.load(); }

@@ -42,6 +42,9 @@ SIGNATURES = {
     "rodent_b200_device_count": (c_int32, []),
     "rodent_b200_set_device": (None, [c_int32]),
     "rodent_b200_set_devices": (None, [ctypes.POINTER(c_int32), c_int32]),
+    "rodent_b200_ipc_export": (c_int32, [c_int32, c_void_p, c_void_p]),
+    "rodent_b200_ipc_open": (c_void_p, [c_int32, c_void_p]),
+    "rodent_b200_ipc_close": (None, [c_int32, c_void_p]),
     "rodent_b200_alloc_device": (c_void_p, [c_int32, c_size_t]),
     "rodent_b200_free_device": (None, [c_int32, c_void_p]),
     "rodent_b200_alloc_host": (c_void_p, [c_size_t]),

@@ -98,3 +98,41 @@ def gather_hits_device(local_hits, out_list, dst: int = 0, async_op: bool = Fals
     `out_list` on rank `dst` a list of world tensors of that shape (None elsewhere).  Every rank passes the same n."""
     import torch.distributed as dist
     return dist.gather(local_hits, out_list, dst=dst, async_op=async_op)
+
+
+class PeerBuffer:
+    """A device buffer on rank `dst` that every rank can write: allocated there, exported with CUDA IPC, opened on the
+    other ranks as NVLink peer memory (rodent_b200_ipc_*).  `ptr` is the address of the buffer in THIS process; None on
+    every rank when IPC / peer access is not available (the caller then gathers with a collective instead)."""
+
+    def __init__(self, local_device: int, rank: int, nbytes: int, dst: int = 0):
+        import ctypes
+        import torch.distributed as dist
+        from . import lib
+        L = lib.load()
+        self.L, self.dev, self.rank, self.dst, self.nbytes = L, local_device, rank, dst, nbytes
+        self.ptr, self.owner = None, rank == dst
+        handle = None
+        if self.owner:
+            self.ptr = L.rodent_b200_alloc_device(local_device, nbytes)
+            buf = ctypes.create_string_buffer(64)
+            handle = bytes(buf.raw) if L.rodent_b200_ipc_export(local_device, self.ptr, buf) else None
+        box = [handle]
+        dist.broadcast_object_list(box, src=dst)
+        ok = box[0] is not None
+        if ok and not self.owner:
+            self.ptr = L.rodent_b200_ipc_open(local_device, ctypes.create_string_buffer(box[0], 64))
+            ok = bool(self.ptr)
+        flags = [None] * dist.get_world_size()
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            self.close()
+            self.ptr = None
+
+    def close(self):
+        if self.ptr:
+            if self.owner:
+                self.L.rodent_b200_free_device(self.dev, self.ptr)
+            else:
+                self.L.rodent_b200_ipc_close(self.dev, self.ptr)
+            self.ptr = None
