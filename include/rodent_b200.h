@@ -226,6 +226,7 @@ void    rodent_b200_sync(int32_t dev);
  * measured with CUDA events around the launch (the role anydsl_get_kernel_time
  * plays at tools/bench_traversal/bench_traversal.cpp:125-133). */
 double  rodent_b200_last_kernel_ms(int32_t dev);
+const char* rodent_b200_last_kernel_name(int32_t dev);   /* the BVH8 kernel variant the last launch on `dev` picked */
 
 /* Number of kernels this library launched so far in this process. */
 int64_t rodent_b200_launch_count(void);

@@ -298,6 +298,7 @@ struct DeviceState {
     int* counter = nullptr;    // 64 ints: slot 0 for the synchronous entry points, 8/16/24 for the host-path streams
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
+    const char* last_kernel = "";   // the variant the last traversal launch on this device picked (rodent_b200_last_kernel_name)
     int occ[2] = {0, 0};       // resident CTAs per SM of the persistent kernels (closest, any)
     int occ_quad[2] = {0, 0};
     int occ_pool[2] = {0, 0};
@@ -394,6 +395,7 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
                 s.pool_overflow_warps = warps;
             }
         }
+        s.last_kernel = "traverse_bvh8_pool";
         traverse_bvh8_pool<ANY><<<std::min(grid, s.sm_count * 16), kPoolBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.pool_refill_min, s.pool_overflow, g_tuning.pool_prefetch);
     } else if (g_tuning.mapping == 2) {
         if (!counter) counter = s.counter;
@@ -405,6 +407,12 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
                         !wide ? traverse_bvh8_vote<ANY, 5> :
                         g_tuning.vote_smem_depth >= 24 ? traverse_bvh8_vote<ANY, 5, true> :
                         g_tuning.vote_smem_depth >= 16 ? traverse_bvh8_vote<ANY, 5, true, 16> : traverse_bvh8_vote<ANY, 5, true, 12>;
+        s.last_kernel = v == 4 ? (ANY ? "traverse_bvh8_vote<true, 4>" : "traverse_bvh8_vote<false, 4>") :
+                        v == 6 ? (ANY ? "traverse_bvh8_vote<true, 6>" : "traverse_bvh8_vote<false, 6>") :
+                        !wide ? (ANY ? "traverse_bvh8_vote<true, 5>" : "traverse_bvh8_vote<false, 5>") :
+                        g_tuning.vote_smem_depth >= 24 ? (ANY ? "traverse_bvh8_vote<true, 5, true, 24>" : "traverse_bvh8_vote<false, 5, true, 24>") :
+                        g_tuning.vote_smem_depth >= 16 ? (ANY ? "traverse_bvh8_vote<true, 5, true, 16>" : "traverse_bvh8_vote<false, 5, true, 16>") :
+                                                         (ANY ? "traverse_bvh8_vote<true, 5, true, 12>" : "traverse_bvh8_vote<false, 5, true, 12>");
         // the persistent grid is sized from the occupancy of the very instantiation that is launched
         const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(kernel), kBlock);
         const int needed = (num_rays + kBlock - 1) / kBlock;
@@ -417,6 +425,7 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
         const int rays_per_block = kQuadBlock / 4;
         const int needed = (num_rays + rays_per_block - 1) / rays_per_block;
         const int grid = std::min(needed, s.sm_count * per_sm);
+        s.last_kernel = "traverse_bvh8_quad";
         traverse_bvh8_quad<ANY><<<grid, kQuadBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.quad_refill_below);
     } else if (g_tuning.persistent) {
         if (!counter) counter = s.counter;
@@ -424,6 +433,7 @@ static void launch(DeviceState& s, const Node8* nodes, const Tri4* tris, const R
         const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : s.occ[ANY ? 1 : 0];
         const int needed = (num_rays + kBlock - 1) / kBlock;
         const int grid = std::min(needed, s.sm_count * per_sm);     // a multiple of the SM count when saturated
+        s.last_kernel = "traverse_bvh8_persistent";
         traverse_bvh8_persistent<ANY><<<grid, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays, counter, g_tuning.refill_below);
     } else {
         traverse_bvh8_grid<ANY><<<(num_rays + kBlock - 1) / kBlock, kBlock, 0, stream>>>(nodes, tris, rays, hits, num_rays);
@@ -899,6 +909,7 @@ void rodent_b200_ipc_close(int32_t dev, void* ptr) { device_state(dev); if (ptr)
 
 void rodent_b200_sync(int32_t dev) { device_state(dev); RB_CUDA_CHECK(cudaDeviceSynchronize()); }
 double rodent_b200_last_kernel_ms(int32_t dev) { return device_state(dev).last_ms; }
+const char* rodent_b200_last_kernel_name(int32_t dev) { return device_state(dev).last_kernel; }
 int64_t rodent_b200_launch_count(void) { return g_launches.load(); }
 void rodent_b200_count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // for the other translation units
 const char* rodent_b200_version(void) { return "rodent_b200 0.1 sm_100a"; }

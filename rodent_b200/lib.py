@@ -53,6 +53,7 @@ SIGNATURES = {
     "rodent_b200_copy_to_host": (None, [c_int32, c_void_p, c_void_p, c_size_t]),
     "rodent_b200_sync": (None, [c_int32]),
     "rodent_b200_last_kernel_ms": (c_double, [c_int32]),
+    "rodent_b200_last_kernel_name": (c_char_p, [c_int32]),
     "rodent_b200_launch_count": (c_int64, []),
     "rodent_b200_version": (c_char_p, []),
 }

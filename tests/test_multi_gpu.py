@@ -82,3 +82,54 @@ def test_tools_take_gpus(devices, tmp_path):
                         "-o", str(png)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "min/med/max Msamples/s" in r.stdout and png.stat().st_size > 1000
+
+
+def _peer_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle
+    from rodent_b200 import formats, lib, sharding, testdata, traversal
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nodes, tris = formats.load_bvh(testdata.sponza_bvh8(), formats.BVH8_TRI4)
+        rays = formats.load_rays(testdata.rays("random"), 0.0, 1.0)[:200_000]
+        n = len(rays)
+        bvh = traversal.Bvh8(rank, nodes, tris)
+        b, e = sharding.ray_range(rank, world, n)
+        d_rays = traversal.DeviceArray.from_host(rank, np.ascontiguousarray(rays[b:e]))
+        pb = sharding.PeerBuffer(rank, rank, n * 16)
+        assert pb.ptr, "CUDA IPC / peer access not available between the two devices"
+
+        class View:
+            def __init__(self, ptr, count):
+                self.ptr, self.count = ptr, count
+
+        traversal.intersect(bvh, d_rays, View(pb.ptr + b * 16, e - b))       # records land in rank 0's memory
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            got = np.empty(n, formats.HIT1)
+            lib.load().rodent_b200_copy_to_host(0, got.ctypes.data, pb.ptr, n * 16)
+            want = oracle.traverse(nodes, tris, rays, threads=4)
+            np.savez(Path(out_dir) / "peer.npz", got=got.view(np.int32), want=want.view(np.int32))
+        dist.barrier()
+        pb.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_buffer_between_processes(devices, tmp_path):
+    """One process per GPU: rank 1's traversal kernel writes its hit records straight into a buffer in rank 0's HBM
+    (sharding.PeerBuffer: CUDA IPC mapping over NVLink), rank 0 finds the whole job's records there -- bit-identical to
+    the oracle's."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    z = np.load(tmp_path / "peer.npz")
+    assert z["got"].tobytes() == z["want"].tobytes()
