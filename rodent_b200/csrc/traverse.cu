@@ -291,6 +291,7 @@ struct BvhCopy {
     void* d_nodes = nullptr; Tri4* d_tris = nullptr;
     size_t num_nodes = 0, num_tri4 = 0, node_size = 0;
     uint64_t fingerprint = 0, last_use = 0;
+    unsigned char root[sizeof(Node8)] = {};       // the root node as uploaded
 };
 struct DeviceState {
     std::atomic<bool> init{false};
@@ -559,7 +560,10 @@ static std::pair<NodeT*, Tri4*> cached_bvh(DeviceState& s, const NodeT* nodes, c
     auto it = s.bvh_cache.find(key);
     if (it != s.bvh_cache.end()) {
         BvhCopy& c = it->second;
-        if (c.node_size == sizeof(NodeT) && c.fingerprint == bvh_fingerprint(nodes, c.num_nodes * sizeof(NodeT), tris, c.num_tri4 * sizeof(Tri4))) {
+        // The root node first: it exists in every BVH, so reading it is safe whatever now lives at this address; only
+        // when it is the one that was uploaded are the sampled lines of the (then almost surely same-sized) arrays read.
+        if (c.node_size == sizeof(NodeT) && std::memcmp(nodes, c.root, sizeof(NodeT)) == 0 &&
+            c.fingerprint == bvh_fingerprint(nodes, c.num_nodes * sizeof(NodeT), tris, c.num_tri4 * sizeof(Tri4))) {
             c.last_use = ++s.bvh_clock;
             return std::make_pair(static_cast<NodeT*>(c.d_nodes), c.d_tris);
         }
@@ -584,6 +588,7 @@ static std::pair<NodeT*, Tri4*> cached_bvh(DeviceState& s, const NodeT* nodes, c
     RB_CUDA_CHECK(cudaMalloc(&dt, std::max<size_t>(c.num_tri4, 1) * sizeof(Tri4)));
     RB_CUDA_CHECK(cudaMemcpy(dn, nodes, c.num_nodes * sizeof(NodeT), cudaMemcpyHostToDevice));
     RB_CUDA_CHECK(cudaMemcpy(dt, tris, c.num_tri4 * sizeof(Tri4), cudaMemcpyHostToDevice));
+    std::memcpy(c.root, nodes, sizeof(NodeT));
     c.d_nodes = dn; c.d_tris = dt; c.last_use = ++s.bvh_clock;
     s.bvh_cache[key] = c;
     s.bvh_uploads++;
