@@ -350,6 +350,9 @@ void rodent_b200_scene_bvh4(RodentScene* scene, const Node4** nodes, int32_t* nu
  * ids; returns 0 if a prim_id is out of range).  Renderers created afterwards trace their rays through it with the
  * reference GPU path's traversal (Sponza: 1.7x the samples/s of the BVH8 walk). */
 void    rodent_b200_scene_build_bvh2(RodentScene* scene);
+/* Replaces the scene's BVH8 / Tri4 by one from this library's split-BVH builder over the scene's own triangles (a scene
+ * made with rodent_b200_scene_from_bvh8 carries the caller's tree until then). */
+void    rodent_b200_scene_rebuild_bvh8(RodentScene* scene);
 int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1);
 
 /* The converter's data/ directory (convert_obj, src/driver/converter.cpp:403-438, 682-745): the mesh as LZ4-framed buffers

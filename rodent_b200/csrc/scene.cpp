@@ -762,6 +762,21 @@ void build_bvh4(Scene& scene) {
     builder.run();
 }
 
+// Replaces the scene's BVH8 by one from this repository's builder over the scene's own triangles (a scene made with
+// scene_from_bvh8 carries the caller's tree until then).
+void rebuild_bvh8(Scene& scene) {
+    const int num_tris = int(scene.indices.size() / 4);
+    std::vector<F3> a(num_tris), b(num_tris), c(num_tris); std::vector<int> geom(num_tris);
+    for (int i = 0; i < num_tris; i++) {
+        const int* idx = &scene.indices[4 * i];
+        auto vert = [&](int k) { return F3{scene.vertices[4 * k], scene.vertices[4 * k + 1], scene.vertices[4 * k + 2]}; };
+        a[i] = vert(idx[0]); b[i] = vert(idx[1]); c[i] = vert(idx[2]); geom[i] = idx[3];
+    }
+    scene.nodes.clear(); scene.tris.clear();
+    Builder<Node8> builder{a, b, c, geom, {}, {}, {}, {}, scene.nodes, scene.tris};
+    builder.run();
+}
+
 void build_bvh2(Scene& scene) {
     if (!scene.nodes2.empty()) return;
     const int num_tris = int(scene.indices.size() / 4);
@@ -1075,6 +1090,7 @@ void rodent_b200_scene_view(const RodentScene* scene, RodentSceneView* out) {
     out->num_nodes2 = int32_t(s.nodes2.size()); out->num_tri1 = int32_t(s.tris1.size());
 }
 void rodent_b200_scene_build_bvh2(RodentScene* scene) { rb200::build_bvh2(*reinterpret_cast<Scene*>(scene)); }
+void rodent_b200_scene_rebuild_bvh8(RodentScene* scene) { rb200::rebuild_bvh8(*reinterpret_cast<Scene*>(scene)); }
 int32_t rodent_b200_scene_set_bvh2(RodentScene* scene, const Node2* nodes, int32_t num_nodes, const Tri1* tris, int32_t num_tri1) {
     return rb200::set_bvh2(*reinterpret_cast<Scene*>(scene), nodes, num_nodes, tris, num_tri1) ? 1 : 0;
 }

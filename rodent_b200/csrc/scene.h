@@ -40,6 +40,7 @@ Scene* load_data_dir(const std::string& dir, const std::string& obj_path);
 bool write_data_dir(Scene& scene, const std::string& dir, int arity, bool padded, const std::string& obj_path);
 void build_bvh4(Scene& scene);
 void build_bvh2(Scene& scene);
+void rebuild_bvh8(Scene& scene);
 bool set_bvh2(Scene& scene, const Node2* nodes, int num_nodes, const Tri1* tris, int num_tri1);
 Scene* scene_from_bvh8(const Node8* nodes, int num_nodes, const Tri4* tris, int num_tri4,
                        const RodentMaterial* materials, int num_materials, const int32_t* material_of_prim, int num_prims);

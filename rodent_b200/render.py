@@ -50,6 +50,7 @@ SIGNATURES = {
     "rodent_b200_scene_add_jpg": (c_int32, [c_void_p, ctypes.c_char_p]),
     "rodent_b200_scene_add_tga": (c_int32, [c_void_p, ctypes.c_char_p]),
     "rodent_b200_scene_build_bvh2": (None, [c_void_p]),
+    "rodent_b200_scene_rebuild_bvh8": (None, [c_void_p]),
     "rodent_b200_scene_set_bvh2": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32]),
     "rodent_b200_scene_bvh4": (None, [c_void_p, POINTER(c_void_p), POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32)]),
     "rodent_b200_renderer_create": (c_void_p, [c_void_p] + [c_int32] * 8),
@@ -136,6 +137,12 @@ class Scene:
         closest-hit rays through it (rodent_b200_scene_build_bvh2)."""
         L = _bind(lib.load())
         L.rodent_b200_scene_build_bvh2(self.handle)
+        L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
+
+    def rebuild_bvh8(self) -> None:
+        """Replaces the scene's BVH8 by one from this library's builder over its own triangles."""
+        L = _bind(lib.load())
+        L.rodent_b200_scene_rebuild_bvh8(self.handle)
         L.rodent_b200_scene_view(self.handle, ctypes.byref(self._view))
 
     def set_bvh2(self, nodes: np.ndarray, tris: np.ndarray) -> None:

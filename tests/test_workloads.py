@@ -62,3 +62,23 @@ def test_scene_from_bvh8_rejects_material_ids_outside_the_table(capfd):
         with pytest.raises(RuntimeError):
             render.Scene.from_bvh8(nodes, tris, mats, bad)
     assert "material_of_prim[12345]" in capfd.readouterr().err
+
+
+def test_rebuild_bvh8_gives_the_same_hits_with_fewer_visits():
+    """rodent_b200_scene_rebuild_bvh8: the split-BVH builder over the triangles of a scene that came with its own tree
+    (the reference's Sponza block) -- same hits, `t` to rounding (the edges are recomputed), fewer nodes and packets visited."""
+    from oracle import oracle
+    from rodent_b200 import formats, render, testdata, workloads
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8(), formats.BVH8_TRI4)
+    scene = render.Scene.from_bvh8(nodes, tris, workloads.sponza_materials(), workloads.sponza_material_of_prim(tris))
+    scene.rebuild_bvh8()
+    mine = (scene.array("nodes").copy(), scene.array("tris").copy())
+    assert len(mine[0]) != len(nodes)
+    rays = formats.load_rays(testdata.rays("random"), 0.0, 1.0)[::16].copy()
+    a, sa = oracle.traverse(*mine, rays, want_stats=True)
+    b, sb = oracle.traverse(nodes, tris, rays, want_stats=True)
+    assert ((a["tri_id"] >= 0) == (b["tri_id"] >= 0)).all()
+    hit = b["tri_id"] >= 0
+    assert np.abs(a["t"][hit] - b["t"][hit]).max() <= 1e-6 * np.abs(b["t"][hit]).max()
+    assert sa.nodes < 0.8 * sb.nodes and sa.tri4 < 0.7 * sb.tri4
+    scene.free()
