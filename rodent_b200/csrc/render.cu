@@ -263,7 +263,10 @@ scatter_by_material(PrimaryStream src, int* __restrict__ order, const LoopState*
 }
 
 // ---- shade (gpu_shade, mapping_gpu.impala:82-134, with the path tracer of renderer.impala:62-162) ----
-__global__ void __launch_bounds__(128)
+// MIN_BLOCKS: resident CTAs per SM asked of ptxas (6: 74 registers, 8: 64 with 16 bytes spilled, 10: 48 with 90): the kernel
+// waits on gathered loads (66 % long-scoreboard stalls at 22 warps per SM), so it trades registers for warps.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 shade_rays(PrimaryStream in, const int* __restrict__ order, PrimaryStream out, ShadowStream shadow, SceneDev sc,
            int* __restrict__ counters, float* __restrict__ film, float inv_spp, int max_path_len) {
     using namespace shade;
@@ -432,6 +435,7 @@ static int g_render_wide = 0;          // 256-bit record loads in the BVH8 strea
 static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b200_tune "render_shadow_bvh2"; 0: BVH8 any hit)
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
+static int g_render_shade_blocks = 8;   // shade_rays: resident CTAs per SM asked of ptxas (rodent_b200_tune "render_shade_blocks": 6, 8 or 10)
 static int g_render_fma = 1;       // contracted slab / triangle arithmetic in the stream kernels (rodent_b200_tune "render_fma")
 static int g_render_poly_trig = 0; // test switch: sin / cos from poly_trig.h (rodent_b200_tune "render_poly_trig")
 constexpr int kBvh2Stack = 16;     // BVH2 stream kernels: stack levels in shared memory (8 / 16 / 24 / 32 measured 518 / 518 / 518 / 513 Msamples/s)
@@ -627,7 +631,8 @@ static void enqueue_wavefront(Renderer& r, float* film, const CameraDev& cam, in
     scan_bins<<<1, 32, 0, s>>>(r.histogram, r.cursor, num_geoms, counters);
     scatter_by_material<<<(bound + kScatterBlock - 1) / kScatterBlock, kScatterBlock, 2 * num_geoms * sizeof(int), s>>>(P, r.order, r.state, num_geoms, r.cursor);
     RB_CUDA_CHECK(cudaStreamWaitEvent(s, r.ev_shadow_done, 0));      // the previous shadow pass has read the shadow stream
-    shade_rays<<<(bound + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
+    auto shade = g_render_shade_blocks >= 10 ? shade_rays<10> : g_render_shade_blocks >= 8 ? shade_rays<8> : shade_rays<6>;
+    shade<<<(bound + 127) / 128, 128, 0, s>>>(P, r.order, Q, r.shadow, r.scene, counters, film, inv_spp, r.max_path_len);
     RB_CUDA_CHECK(cudaEventRecord(r.ev_shaded, s));
     std::swap(r.prim[0], r.prim[1]);                        // the survivors (in Q) are the next wavefront's stream
     RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
@@ -840,6 +845,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = clamp(value, 1, 32);
     else if (!std::strcmp(key, "render_bvh2_stack")) {}        // fixed at 16 since round 2 (8 .. 32 measured the same)
     else if (!std::strcmp(key, "render_fma")) g_render_fma = value != 0;
+    else if (!std::strcmp(key, "render_shade_blocks")) g_render_shade_blocks = clamp(value, 6, 10);
     else if (!std::strcmp(key, "render_poly_trig")) g_render_poly_trig = value != 0;
     else if (!std::strcmp(key, "render_capacity")) g_capacity = clamp(value, 1024, 1 << 24);
     else if (!std::strcmp(key, "render_streak_min")) g_render_streak_min = clamp(value, 1, 33);
