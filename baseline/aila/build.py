@@ -1,6 +1,7 @@
 """Builds the same-box Aila-Laine comparator from the reference's own sources (see README.md).
     python baseline/aila/build.py           -> baseline/_ref/aila/bench_aila
-Nothing from /root/reference is copied into the tracked tree: the patched sources live under baseline/_ref/ (git-ignored)."""
+Nothing from /root/reference is copied into the repository: the rewritten sources exist in a temporary directory for the
+duration of the compile; what stays under baseline/_ref/ (git-ignored) is the binary."""
 from __future__ import annotations
 
 import os
@@ -55,13 +56,17 @@ def build(force: bool = False) -> Path | None:
     if not force and BINARY.exists() and all(s.stat().st_mtime <= BINARY.stat().st_mtime for s in srcs):
         return BINARY
     OUT.mkdir(parents=True, exist_ok=True)
-    (OUT / "CudaTracerKernels.hpp").write_text(patch_header((REF / "CudaTracerKernels.hpp").read_text()))
-    (OUT / "kepler_dynamic_fetch.cu").write_text(patch_kernel((REF / "kepler_dynamic_fetch.cu").read_text()))
-    cmd = [NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-w",
-           f"-I{OUT}", f"-I{HERE}", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tools'}",
-           "-o", str(BINARY), str(OUT / "kepler_dynamic_fetch.cu"), str(HERE / "bench_aila_main.cpp")]
-    print("+", " ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True)
+    import tempfile
+    # the rewritten sources exist only for the duration of the compile, outside the repository: what stays is the binary
+    with tempfile.TemporaryDirectory(prefix="aila_build_") as tmp:
+        tmp = Path(tmp)
+        (tmp / "CudaTracerKernels.hpp").write_text(patch_header((REF / "CudaTracerKernels.hpp").read_text()))
+        (tmp / "kepler_dynamic_fetch.cu").write_text(patch_kernel((REF / "kepler_dynamic_fetch.cu").read_text()))
+        cmd = [NVCC, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-w",
+               f"-I{tmp}", f"-I{HERE}", f"-I{ROOT / 'include'}", f"-I{ROOT / 'tools'}",
+               "-o", str(BINARY), str(tmp / "kepler_dynamic_fetch.cu"), str(HERE / "bench_aila_main.cpp")]
+        print("+", " ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True)
     return BINARY
 
 
