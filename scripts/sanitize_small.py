@@ -39,4 +39,4 @@ for it in range(2):
     r.render(workloads.camera("cornell", 96, 128), it)
 print("cornell film, 3 pipelines, 4096-ray streams", float(r.film().mean()), r.stats())
 r.free()
-lib.tune("render_capacity", 1 << 20)
+lib.tune("render_capacity", 1 << 21)
