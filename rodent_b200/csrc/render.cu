@@ -77,6 +77,7 @@ struct LoopState {
 struct SceneDev {
     const Node8* nodes; const Tri4* tris;
     const Node2* nodes2; const Tri1* tris1;          // null unless the scene carries a BVH2 (closest-hit rays then use it)
+    const Node2q* nodes2q; QuantGrid grid;           // the same tree in 32-byte nodes (render_quant), null when switched off
     const float4* normals; const float4* face_normals; const int4* indices; const int* light_ids;
     const RodentMaterial* materials; const RodentLight* lights;
     const float4* texcoords; const RodentTexture* textures; const unsigned* texture_pixels;   // null without textured materials
@@ -177,9 +178,9 @@ traverse_stream(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
 // STACK: levels of the id stack kept in shared memory (deeper ones go to a thread-local array).  The per-material counts
 // live in dynamic shared memory, (num_geoms + 1) ints for the closest-hit form: what a CTA does not take as shared memory
 // the SM keeps as L1, which serves two thirds of this kernel's record reads.
-template <bool SHADOW, int STACK, bool FMA = false>
+template <bool SHADOW, int STACK, bool FMA = false, bool QUANT = false>
 __global__ void __launch_bounds__(kRBlock, 8)
-traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris,
+traverse_stream_bvh2(const void* __restrict__ nodes, QuantGrid grid, const Tri1* __restrict__ tris,
                      const float4* __restrict__ ray_o, const float4* __restrict__ ray_d, const int* __restrict__ count_ptr, int count_max,
                      float4* __restrict__ hit_out, int* __restrict__ geom_out, int num_geoms, int* __restrict__ histogram,
                      const int* __restrict__ pixels, const float4* __restrict__ colors, float* __restrict__ film, float inv_spp,
@@ -192,7 +193,7 @@ traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ t
         __syncthreads();
     }
     int* const hist_bins = hist;
-    traverse_bvh2_scheduled<SHADOW, STACK, kRBlock, FMA>(
+    traverse_bvh2_scheduled<SHADOW, STACK, kRBlock, FMA, QUANT>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min, streak_min,
         [ray_o, ray_d](int i, float4& r0, float4& r1) { r0 = __ldg(ray_o + i); r1 = __ldg(ray_d + i); },
         [=](int i, const HitRecord& h) {
@@ -210,7 +211,7 @@ traverse_stream_bvh2(const Node2* __restrict__ nodes, const Tri1* __restrict__ t
                 geom_out[i] = g;
                 atomicAdd(hist_bins + g, 1);
             }
-        }, leaf_streak_min);
+        }, leaf_streak_min, grid);
     if (!SHADOW) {
         __syncthreads();
         for (int b = threadIdx.x; b <= num_geoms; b += kRBlock)
@@ -437,6 +438,7 @@ static int g_render_shadow_bvh2 = 1;   // ... and the shadow rays too (rodent_b2
 static int g_render_bvh2 = 1;      // closest-hit rays through the scene's BVH2 when it has one (rodent_b200_tune "render_bvh2")
 static int g_render_lanes = 3;     // pipelines per renderer (rodent_b200_tune "render_lanes")
 static int g_render_shade_blocks = 8;   // shade_rays: resident CTAs per SM asked of ptxas (rodent_b200_tune "render_shade_blocks": 6, 8 or 10)
+static int g_render_quant = 1;     // BVH2 stream kernels walk 32-byte quantised nodes (rodent_b200_tune "render_quant")
 static int g_render_fma = 1;       // contracted slab / triangle arithmetic in the stream kernels (rodent_b200_tune "render_fma")
 static int g_render_poly_trig = 0; // test switch: sin / cos from poly_trig.h (rodent_b200_tune "render_poly_trig")
 constexpr int kBvh2Stack = 16;     // BVH2 stream kernels: stack levels in shared memory (8 / 16 / 24 / 32 measured 518 / 518 / 518 / 513 Msamples/s)
@@ -461,6 +463,43 @@ static void alloc_pipeline(Renderer* r) {
     RB_CUDA_CHECK(cudaMemset(r->histogram, 0, kMaxBins * sizeof(int)));
     r->d_rows = const_cast<int*>(r->upload(r->rows.data(), r->rows.size()));
     RB_CUDA_CHECK(cudaMallocHost(&r->h_state, (kLookahead + 1) * sizeof(LoopState)));
+}
+
+// Node2 -> Node2q on a 16-bit grid over the union of all boxes.  Lower bounds are rounded down and upper bounds up, then
+// moved two more steps outwards (the kernel evaluates origin + code * step with its own rounding, see set_grid), so a
+// quantised box always contains the original.  Returns false (the renderer then walks the 64-byte nodes) when a coordinate is not finite.
+static bool quantise_bvh2(const std::vector<Node2>& nodes, std::vector<Node2q>& out, QuantGrid& grid) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (const Node2& n : nodes)
+        for (int k = 0; k < 2; k++)
+            for (int a = 0; a < 3; a++) {
+                const double l = n.bounds[6 * k + 2 * a], h = n.bounds[6 * k + 2 * a + 1];
+                if (!std::isfinite(l) || !std::isfinite(h)) return false;
+                lo[a] = std::min(lo[a], l); hi[a] = std::max(hi[a], h);
+            }
+    double step[3];
+    for (int a = 0; a < 3; a++) {
+        step[a] = std::max((hi[a] - lo[a]) / 65529.0, 1e-30);          // codes 3 .. 65532 span the extent
+        grid.origin[a] = float(lo[a] - 3.0 * step[a]);
+        grid.step[a] = float(step[a]);
+        if (!(grid.step[a] > 0.0f) || !std::isfinite(grid.origin[a])) return false;
+        // the margin of one step must cover the kernel's fp32 rounding of origin + code * step: not so for a small scene
+        // far from the coordinate origin
+        if (std::max(std::fabs(lo[a]), std::fabs(hi[a])) * 2.4e-7 > step[a]) return false;
+    }
+    out.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) {
+        for (int k = 0; k < 2; k++)
+            for (int a = 0; a < 3; a++) {
+                const double l = nodes[i].bounds[6 * k + 2 * a], h = nodes[i].bounds[6 * k + 2 * a + 1];
+                const double ql = std::floor((l - double(grid.origin[a])) / double(grid.step[a])) - 2.0;
+                const double qh = std::ceil((h - double(grid.origin[a])) / double(grid.step[a])) + 2.0;
+                out[i].b[6 * k + 2 * a] = uint16_t(std::min(std::max(ql, 0.0), 65535.0));
+                out[i].b[6 * k + 2 * a + 1] = uint16_t(std::min(std::max(qh, 0.0), 65535.0));
+            }
+        out[i].child[0] = nodes[i].child[0]; out[i].child[1] = nodes[i].child[1];
+    }
+    return true;
 }
 
 static Renderer* create_renderer(const Scene& sc, int dev, int width, int height, int spp, int max_path_len, int part, int num_parts, int band) {
@@ -520,10 +559,19 @@ static Renderer* create_renderer(const Scene& sc, int dev, int width, int height
     if (!sc.nodes2.empty() && g_render_bvh2) {
         d.nodes2 = r->upload(sc.nodes2.data(), sc.nodes2.size());
         d.tris1 = r->upload(sc.tris1.data(), sc.tris1.size());
+        if (g_render_quant) {
+            std::vector<Node2q> q;
+            if (quantise_bvh2(sc.nodes2, q, d.grid)) d.nodes2q = r->upload(q.data(), q.size());
+        }
     }
     // persistent grids are sized from the occupancy of the instantiations that are launched
     const size_t bins = (sc.materials.size() + 1) * sizeof(int);
-    if (g_render_fma) {
+    if (g_render_fma && d.nodes2q) {
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, kBvh2Stack, true, true>, kRBlock, bins));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, kBvh2Stack, true, true>, kRBlock, sizeof(int)));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false, false, true>, kRBlock, 0));
+        RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow, traverse_stream<true, false, true>, kRBlock, 0));
+    } else if (g_render_fma) {
         RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary2, traverse_stream_bvh2<false, kBvh2Stack, true>, kRBlock, bins));
         RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_shadow2, traverse_stream_bvh2<true, kBvh2Stack, true>, kRBlock, sizeof(int)));
         RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r->occ_primary, traverse_stream<false, false, true>, kRBlock, 0));
@@ -620,8 +668,10 @@ static void enqueue_wavefront(Renderer& r, float* film, const CameraDev& cam, in
         generate_rays<<<(cap + 255) / 256, 256, 0, s>>>(P, r.state, cam, r.width, r.height, r.spp, iter, r.d_rows);
     if (r.scene.nodes2) {
         const int grid_p = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary2);
-        traverse_stream_bvh2<false, kBvh2Stack, FMA><<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(
-            r.scene.nodes2, r.scene.tris1, P.ray_o, P.ray_d, &r.state->size, cap, P.hit, P.geom, num_geoms,
+        const bool quant = r.scene.nodes2q != nullptr;
+        auto kernel = quant ? traverse_stream_bvh2<false, kBvh2Stack, FMA, true> : traverse_stream_bvh2<false, kBvh2Stack, FMA, false>;
+        kernel<<<grid_p, kRBlock, (num_geoms + 1) * sizeof(int), s>>>(
+            quant ? static_cast<const void*>(r.scene.nodes2q) : static_cast<const void*>(r.scene.nodes2), r.scene.grid, r.scene.tris1, P.ray_o, P.ray_d, &r.state->size, cap, P.hit, P.geom, num_geoms,
             r.histogram, nullptr, nullptr, nullptr, 0.0f, counters + kWorkPrimary, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
     } else {
         const int grid_p = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_primary);
@@ -639,8 +689,10 @@ static void enqueue_wavefront(Renderer& r, float* film, const CameraDev& cam, in
     RB_CUDA_CHECK(cudaStreamWaitEvent(s2, r.ev_shaded, 0));
     if (r.scene.nodes2 && g_render_shadow_bvh2) {
         const int grid_s = std::min((bound + kRBlock - 1) / kRBlock, r.sm_count * r.occ_shadow2);
-        traverse_stream_bvh2<true, kBvh2Stack, FMA><<<grid_s, kRBlock, sizeof(int), s2>>>(
-            r.scene.nodes2, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, cap,
+        const bool quant = r.scene.nodes2q != nullptr;
+        auto kernel = quant ? traverse_stream_bvh2<true, kBvh2Stack, FMA, true> : traverse_stream_bvh2<true, kBvh2Stack, FMA, false>;
+        kernel<<<grid_s, kRBlock, sizeof(int), s2>>>(
+            quant ? static_cast<const void*>(r.scene.nodes2q) : static_cast<const void*>(r.scene.nodes2), r.scene.grid, r.scene.tris1, r.shadow.ray_o, r.shadow.ray_d, counters + kShadows, cap,
             nullptr, nullptr, num_geoms, nullptr, r.shadow.pixel, r.shadow.color, film, inv_spp,
             counters + kWorkShadow, g_render_refill_min, g_render_streak_min, g_render_leaf_streak_min);
     } else {
@@ -846,6 +898,7 @@ void rodent_b200_render_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "render_refill_min")) g_render_refill_min = clamp(value, 1, 32);
     else if (!std::strcmp(key, "render_bvh2_stack")) {}        // fixed at 16 since round 2 (8 .. 32 measured the same)
     else if (!std::strcmp(key, "render_fma")) g_render_fma = value != 0;
+    else if (!std::strcmp(key, "render_quant")) g_render_quant = value != 0;
     else if (!std::strcmp(key, "render_shade_blocks")) g_render_shade_blocks = clamp(value, 6, 10);
     else if (!std::strcmp(key, "render_poly_trig")) g_render_poly_trig = value != 0;
     else if (!std::strcmp(key, "render_capacity")) g_capacity = clamp(value, 1024, 1 << 24);

@@ -15,6 +15,15 @@
 
 namespace rb200 {
 
+// A Node2 in 32 bytes for the renderer's stream kernels: the twelve bounds as 16-bit steps of the scene's extent (lower
+// bounds rounded down, upper bounds up, one step of margin each way), the two child ids as they are.  One 256-bit load
+// per node instead of two, twice as many nodes per cache line -- the kernels wait on L2 hits for half of their stall
+// samples (profiles/r02_render_kernels_ncu.txt).  Boxes only grow, so a ray finds the same triangles; it may enter a few
+// more nodes.  The bench_traversal entry points keep the reference's 64-byte Node2 (their records are compared bit for bit).
+struct Node2q { uint16_t b[12]; int32_t child[2]; };
+static_assert(sizeof(Node2q) == 32, "Node2q is one 256-bit load");
+struct QuantGrid { float origin[3], step[3]; };       // value of code q on axis a: origin[a] + q * step[a]
+
 // Node ids only (the GPU path pushes undef keys): first SMEM_DEPTH levels in shared memory, [level][thread].
 template <int SMEM_DEPTH, int BLOCK>
 struct IdStack {
@@ -27,9 +36,11 @@ struct IdStack {
     }
 };
 
-template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false>
+// QUANT: the node array holds Node2q; `qa`, `qb` are the ray's slab coefficients on the quantisation grid.
+template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false, bool QUANT = false>
 struct Bvh2Walker {
     RaySetup ray;
+    float qax, qay, qaz, qbx, qby, qbz;          // t = qa * code + qb  (= inv_dir * (origin + code * step) + inv_org)
     float tmax;
     int top, ptr;
     int leaf;                       // next Tri1 of the leaf being tested, -1 when not inside a leaf
@@ -43,6 +54,28 @@ struct Bvh2Walker {
         tmax = r1.w;
         hit.prim = -1; hit.geom = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;   // empty_hit
         st.store(0, 0); ptr = 0; top = 1; leaf = -1;                       // stack.push(1, undef) on the empty stack, :103
+    }
+    // A 16-bit code is turned into a float without a conversion instruction: 0x4B000000 | q is the float 2^23 + q, and
+    // the 2^23 is folded into the ray's offset, qb = inv_dir * origin + inv_org - qa * 2^23 (its rounding is half a grid
+    // step at most, inside the two steps of margin the quantisation leaves).  One PRMT and one FMA per plane.
+    __device__ __forceinline__ void set_grid(const QuantGrid& g) {
+        qax = ray.idx * g.step[0]; qay = ray.idy * g.step[1]; qaz = ray.idz * g.step[2];
+        qbx = __fmaf_rn(-qax, 8388608.0f, __fmaf_rn(ray.idx, g.origin[0], ray.iox));
+        qby = __fmaf_rn(-qay, 8388608.0f, __fmaf_rn(ray.idy, g.origin[1], ray.ioy));
+        qbz = __fmaf_rn(-qaz, 8388608.0f, __fmaf_rn(ray.idz, g.origin[2], ray.ioz));
+    }
+    // the same test on a quantised box: lo / hi codes of the three axes packed two to a word
+    __device__ __forceinline__ bool hit_box_q(unsigned wx, unsigned wy, unsigned wz, float& tentry) const {
+        auto lo = [](unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)); };     // 2^23 + low half
+        auto hi = [](unsigned w) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)); };     // 2^23 + high half
+        const float t0x = __fmaf_rn(qax, lo(wx), qbx), t1x = __fmaf_rn(qax, hi(wx), qbx);
+        const float t0y = __fmaf_rn(qay, lo(wy), qby), t1y = __fmaf_rn(qay, hi(wy), qby);
+        const float t0z = __fmaf_rn(qaz, lo(wz), qbz), t1z = __fmaf_rn(qaz, hi(wz), qbz);
+        const int zmin = max(min(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(ray.tmin));
+        const int zmax = min(max(__float_as_int(t0z), __float_as_int(t1z)), __float_as_int(tmax));
+        tentry = __int_as_float(__vimax3_s32(__float_as_int(fminf(t0x, t1x)), __float_as_int(fminf(t0y, t1y)), zmin));
+        const float texit = __int_as_float(__vimin3_s32(__float_as_int(fmaxf(t0x, t1x)), __float_as_int(fmaxf(t0y, t1y)), zmax));
+        return tentry <= texit;
     }
     __device__ __forceinline__ bool finished() const { return leaf < 0 && top == 0; }
     __device__ __forceinline__ bool wants_node() const { return leaf < 0 && top > 0; }
@@ -61,14 +94,23 @@ struct Bvh2Walker {
     }
 
     // One iteration of the outer loop up to the leaf loop (:106-135).
-    __device__ __forceinline__ void node_step(const Node2* __restrict__ nodes) {
-        const float4* p = reinterpret_cast<const float4*>(nodes + (top - 1));
-        const F8 lo = ldg8(p), hi = ldg8(p + 2);                           // a Node2 is two 256-bit loads (32-byte aligned array)
-        const float4 b0 = lo.lo, b1 = lo.hi, b2 = hi.lo;
-        const int4 ch = make_int4(__float_as_int(hi.hi.x), __float_as_int(hi.hi.y), __float_as_int(hi.hi.z), __float_as_int(hi.hi.w));
+    __device__ __forceinline__ void node_step(const void* __restrict__ nodes_v) {
+        int2 ch;
         float t0, t1;
-        const bool h0 = hit_box(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, t0);   // box 0: lo/hi x, y, z (:33-36)
-        const bool h1 = hit_box(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, t1);   // box 1 (:37-40)
+        bool h0, h1;
+        if constexpr (QUANT) {
+            const F8 n = ldg8(reinterpret_cast<const float4*>(static_cast<const Node2q*>(nodes_v) + (top - 1)));   // the whole node
+            ch = make_int2(__float_as_int(n.hi.z), __float_as_int(n.hi.w));
+            h0 = hit_box_q(__float_as_uint(n.lo.x), __float_as_uint(n.lo.y), __float_as_uint(n.lo.z), t0);
+            h1 = hit_box_q(__float_as_uint(n.lo.w), __float_as_uint(n.hi.x), __float_as_uint(n.hi.y), t1);
+        } else {
+            const float4* p = reinterpret_cast<const float4*>(static_cast<const Node2*>(nodes_v) + (top - 1));
+            const F8 lo = ldg8(p), hi = ldg8(p + 2);                       // a Node2 is two 256-bit loads (32-byte aligned array)
+            const float4 b0 = lo.lo, b1 = lo.hi, b2 = hi.lo;
+            ch = make_int2(__float_as_int(hi.hi.x), __float_as_int(hi.hi.y));
+            h0 = hit_box(b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, t0);          // box 0: lo/hi x, y, z (:33-36)
+            h1 = hit_box(b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, t1);          // box 1 (:37-40)
+        }
         if (h0 && h1) {
             const bool first0 = t0 < t1;                                   // :127-131
             top = first0 ? ch.x : ch.y;
@@ -100,14 +142,14 @@ struct Bvh2Walker {
 };
 
 // The scheduler of traverse_vote_scheduled (traverse_sched.cuh) for this walker.
-template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false, typename Fetch, typename Sink>
-__device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict__ nodes, const Tri1* __restrict__ tris, int* smem_column,
+template <bool ANY, int SMEM_DEPTH, int BLOCK, bool FMA = false, bool QUANT = false, typename Fetch, typename Sink>
+__device__ __forceinline__ void traverse_bvh2_scheduled(const void* __restrict__ nodes, const Tri1* __restrict__ tris, int* smem_column,
                                                         int num_rays, int* __restrict__ work_counter, int refill_min, int node_streak_min,
-                                                        Fetch fetch, Sink sink, int leaf_streak_min = 0) {
+                                                        Fetch fetch, Sink sink, int leaf_streak_min = 0, QuantGrid grid = QuantGrid{}) {
     if (leaf_streak_min <= 0) leaf_streak_min = node_streak_min;
     const unsigned lane = lane_id();
     int overflow[kStackSize - SMEM_DEPTH];
-    Bvh2Walker<ANY, SMEM_DEPTH, BLOCK, FMA> w;
+    Bvh2Walker<ANY, SMEM_DEPTH, BLOCK, FMA, QUANT> w;
     w.st.smem = smem_column;
     w.st.overflow = overflow;
     w.leaf = -1; w.top = 0;
@@ -128,6 +170,7 @@ __device__ __forceinline__ void traverse_bvh2_scheduled(const Node2* __restrict_
                     float4 r0, r1;
                     fetch(i, r0, r1);
                     w.begin(r0, r1);
+                    if constexpr (QUANT) w.set_grid(grid);
                 }
             }
             if (base + __popc(idle) >= num_rays) drained = true;
