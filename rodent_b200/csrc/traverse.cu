@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <vector>
+#include <type_traits>
 
 #include "traverse.cuh"
 #include "traverse_quad.cuh"
@@ -49,6 +50,9 @@ struct Tuning {
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
+    int host_direct = 1;     // host-pointer entry points, pinned buffers, BVH8: one launch per call, rays read and records written over PCIe by the kernel itself (0: copy-engine pieces)
+    int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
+    int host_trace = 0;          // ... print the device time of every such call (developer probe)
     int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
     int host_chunks = 5;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (two calls in flight: 5..6 measured best, one: 3..4)
 };
@@ -144,6 +148,24 @@ traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
             r0 = ldg4(rp); r1 = ldg4(rp + 1);
         },
         [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min);
+}
+
+// The host-pointer entry points with pinned caller memory: the default kernel reads its rays straight from the caller's
+// array over PCIe as its warps refill, and sends the records home itself (PushHome, traverse_sched.cuh).  No copy engine,
+// no second buffer for the rays, one launch per call.
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 5)
+traverse_bvh8_direct(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
+                     const Ray1* __restrict__ caller_rays, Hit1* __restrict__ hits, int num_rays,
+                     int* __restrict__ work_counter, int refill_min, int node_streak_min, PushHome records) {
+    __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 8, true>(
+        nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
+        [caller_rays](int i, float4& r0, float4& r1) {
+            const float4* rp = reinterpret_cast<const float4*>(caller_rays + i);
+            r0 = ldg4(rp); r1 = ldg4(rp + 1);        // (ld.global.cv of 16 bytes per lane over PCIe is ten times slower)
+        },
+        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min, records);
 }
 
 // The same loop over a BVH4 (Node4: 6 rows of 4 floats, 4 children; leaves are Tri4 as well): the CPU single-ray
@@ -321,6 +343,7 @@ struct HostContext {
     // pinned staging for callers whose buffers are pageable (grown on demand, kept)
     Ray1* h_rays = nullptr; Hit1* h_hits = nullptr; size_t stage_capacity = 0;
     cudaEvent_t piece_done[16] = {};
+    unsigned* group_counts = nullptr; size_t group_capacity = 0;   // run_host_direct: finished records per group of 16 rays
 };
 static DeviceState g_dev[64];
 static std::mutex g_mutex;
@@ -615,6 +638,12 @@ static HostContext* acquire_host_context(DeviceState& s, size_t num_rays) {
         RB_CUDA_CHECK(cudaMalloc(&c->d_hits, num_rays * sizeof(Hit1)));
         c->ray_capacity = num_rays;
     }
+    const size_t groups = (num_rays >> kPushShift) + 1;
+    if (c->group_capacity < groups) {
+        if (c->group_counts) RB_CUDA_CHECK(cudaFree(c->group_counts));
+        RB_CUDA_CHECK(cudaMalloc(&c->group_counts, groups * sizeof(unsigned)));
+        c->group_capacity = groups;
+    }
     return c;
 }
 static void release_host_context(DeviceState& s, HostContext* c) {
@@ -672,10 +701,10 @@ private:
     std::mutex m_; std::condition_variable cv_; std::vector<Job> jobs_;
 };
 
-static bool is_pinned(const void* p) {
+static bool is_pinned(const void* p, bool host_only = false) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    return a.type == cudaMemoryTypeHost || (!host_only && a.type == cudaMemoryTypeManaged);
 }
 
 // Copy-in / trace / copy-out, pipelined in chunks over three streams so the PCIe
@@ -700,6 +729,43 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     for (auto& t : threads) t.join();
 }
 
+// Pinned caller buffers, BVH8, default kernel: one launch per call and no copy at all (traverse_bvh8_direct).  Against
+// the copy-engine pieces below: the traversal starts at once instead of after a fifth of the rays, pays the tail of a
+// launch once per call, keeps all its CTAs for the whole call, and the records need no pass of their own.
+template <bool ANY>
+static bool run_host_direct(DeviceState& s, HostContext* c, const Node8* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays) {
+    const Ray1* caller_rays = nullptr; Hit1* caller_hits = nullptr;
+    if (cudaHostGetDevicePointer(const_cast<void**>(reinterpret_cast<const void**>(&caller_rays)), const_cast<Ray1*>(rays), 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&caller_hits), hits, 0) != cudaSuccess) {
+        cudaGetLastError();                      // page-locked but not mapped for this device: the copy-engine path takes it
+        return false;
+    }
+    cudaStream_t run = c->streams[0];
+    const bool push = g_tuning.host_direct_push == 1, copy_after = g_tuning.host_direct_push == 2;
+    const PushHome records{push ? c->group_counts : nullptr, reinterpret_cast<const float4*>(c->d_hits), reinterpret_cast<float4*>(caller_hits)};
+    cudaEvent_t ev[2] = {};
+    if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
+    if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> kPushShift) + 1) * sizeof(unsigned), run));
+    RB_CUDA_CHECK(cudaMemsetAsync(c->counters, 0, sizeof(int), run));
+    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(traverse_bvh8_direct<ANY>), kBlock);
+    const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
+    s.last_kernel = ANY ? "traverse_bvh8_direct<true>" : "traverse_bvh8_direct<false>";
+    traverse_bvh8_direct<ANY><<<grid, kBlock, 0, run>>>(d_nodes, d_tris, caller_rays, push || copy_after ? c->d_hits : caller_hits, num_rays, c->counters,
+                                                         g_tuning.refill_min, g_tuning.node_streak_min, records);
+    RB_CUDA_CHECK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (ev[1]) RB_CUDA_CHECK(cudaEventRecord(ev[1], run));
+    if (copy_after) RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, run));
+    RB_CUDA_CHECK(cudaStreamSynchronize(run));
+    if (ev[1]) {
+        float ms = 0;
+        RB_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+        std::fprintf(stderr, "direct call, %d rays: %.3f ms on the device\n", num_rays, ms);
+        for (auto& e : ev) RB_CUDA_CHECK(cudaEventDestroy(e));
+    }
+    return true;
+}
+
 template <bool ANY, typename NodeT>
 static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int num_rays) {
     if (num_rays <= 0) return;
@@ -719,6 +785,16 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     }
     const Ray1* src = stage_in ? c->h_rays : rays;
     Hit1* dst = stage_out ? c->h_hits : hits;
+    if constexpr (std::is_same<NodeT, Node8>::value) {
+        // (closest hit only: an any-hit call changes tri_id alone, 4 bytes of every 16 -- stored over PCIe one by one that
+        // is slower than the pieces' round trip of the caller's records: 1.79 / 1.95 against 1.13 / 1.40 ms per Mi rays)
+        if (!ANY && g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && is_pinned(rays, true) && is_pinned(hits, true)) {
+            if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
+                release_host_context(s, c);
+                return;
+            }
+        }
+    }
     if (ANY) {  // occluded leaves t/u/v untouched: round-trip the caller's records
         RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, c->streams[0]));
         RB_CUDA_CHECK(cudaStreamSynchronize(c->streams[0]));
@@ -939,6 +1015,9 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = clamp(value, 1, 16);
     else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
     else if (!std::strcmp(key, "host_ramp")) g_tuning.host_ramp = value != 0;
+    else if (!std::strcmp(key, "host_direct")) g_tuning.host_direct = value != 0;
+    else if (!std::strcmp(key, "host_direct_push")) g_tuning.host_direct_push = clamp(value, 0, 2);
+    else if (!std::strcmp(key, "host_trace")) g_tuning.host_trace = value != 0;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = clamp(value, 8, 12);
     else if (!std::strcmp(key, "wide_loads")) g_tuning.wide_loads = value != 0;
     else if (!std::strcmp(key, "vote_smem_depth")) g_tuning.vote_smem_depth = clamp(value, 12, 24);

@@ -215,15 +215,32 @@ struct RayWalker {
     }
 };
 
+// What happens to a finished ray's record.
+//   StoreAtOnce  the sink is called when the ray finishes (records in device memory).
+//   PushHome     the host-pointer entry points with pinned caller memory (traverse.cu: run_host_direct): the records go
+//                to the caller's array over PCIe, written by the kernel itself -- but never one by one: a write of
+//                part of a cache line makes the host read the line first, and incoherent rays finish one at a time.
+//                A finished ray's record stays in its lane until the warp refills (or drains); the sink then stores it
+//                in device memory, the warp counts the records of every group of 16 rays (256 bytes), and the warp
+//                whose count completes a group copies it home as whole lines.  Small groups, because a group waits
+//                for its slowest ray.  (`counts` == nullptr: no groups, the sink writes wherever it likes.)
+struct StoreAtOnce { static constexpr bool kActive = false; };
+constexpr int kPushShift = 4;                      // records per group: 16; at most 16 (two groups per warp round)
+struct PushHome {
+    static constexpr bool kActive = true;
+    unsigned* counts;                              // finished records per group, zeroed by the launcher
+    const float4* staged; float4* home;            // the records in device memory; the caller's array
+};
+
 // The persistent loop shared by the bench_traversal kernels and the renderer's stream kernels.
 //   fetch(i, r0, r1)  loads ray i (origin+tmin, direction+tmax)
 //   sink(i, hit)      consumes the finished ray's record
 // `refill_min`: idle lanes are refilled once at least this many wait (or none is busy).
 // `node_streak_min`: see the node branch at the end of the loop (33: one step per vote).
-template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, bool FMA = false, typename Fetch, typename Sink>
+template <bool ANY, bool WANT_GEOM, int SMEM_DEPTH, int BLOCK, int ARITY = 8, bool WIDE = false, bool FMA = false, typename Fetch, typename Sink, typename Records = StoreAtOnce>
 __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
                                                         StackEntry* smem_column, int num_rays, int* __restrict__ work_counter,
-                                                        int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8) {
+                                                        int refill_min, Fetch fetch, Sink sink, int node_streak_min = 8, Records records = Records()) {
     const unsigned lane = lane_id();
     StackEntry overflow[kStackSize - SMEM_DEPTH];
     RayWalker<ANY, SMEM_DEPTH, BLOCK, ARITY, WIDE, FMA> w;
@@ -233,10 +250,44 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
     int ray_idx = -1;
     bool drained = false;
     for (;;) {
-        // a finished ray leaves its lane
-        if (ray_idx >= 0 && w.finished()) { sink(ray_idx, w.hit); ray_idx = -1; }
+        // a finished ray leaves its lane (PushHome: its record waits there, ray_idx = -2 - index, for the warp's next refill)
+        if (ray_idx >= 0 && w.finished()) {
+            if constexpr (Records::kActive) ray_idx = -2 - ray_idx;
+            else { sink(ray_idx, w.hit); ray_idx = -1; }
+        }
         // ---- refill idle lanes: one atomicAdd per warp, ranks from ballot/popc ----
         const unsigned idle = __ballot_sync(0xffffffffu, ray_idx < 0);
+        if constexpr (Records::kActive) {
+            const unsigned um = __ballot_sync(0xffffffffu, ray_idx < -1);
+            if (um != 0 && (drained || __popc(idle) >= refill_min || idle == 0xffffffffu)) {
+                const bool mine = ray_idx < -1;
+                const int done = -2 - ray_idx;
+                if (mine) { sink(done, w.hit); ray_idx = -1; }
+                if (records.counts != nullptr) {
+                    __threadfence();                                   // the records before their count
+                    unsigned complete = 0;                             // this lane's count filled a group
+                    const int group = done >> kPushShift;
+                    if (mine) {
+                        const unsigned same = __match_any_sync(um, group);
+                        if (int(lane) == __ffs(same) - 1) {
+                            const unsigned n = unsigned(__popc(same));
+                            const unsigned size = unsigned(min(1 << kPushShift, num_rays - (group << kPushShift)));
+                            complete = atomicAdd(records.counts + group, n) + n == size;
+                        }
+                    }
+                    // two complete groups per round, 16 lanes each: 256 contiguous bytes = four whole lines per group
+                    for (unsigned cm = __ballot_sync(0xffffffffu, complete != 0); cm != 0;) {
+                        const int a = __ffs(cm) - 1; cm &= cm - 1;
+                        const int b = cm != 0 ? __ffs(cm) - 1 : a; cm &= cm - 1;
+                        const int ga = __shfl_sync(0xffffffffu, group, a), gb = __shfl_sync(0xffffffffu, group, b);
+                        const bool second = lane >= (1u << kPushShift);
+                        const int j = ((second ? gb : ga) << kPushShift) + int(lane & ((1u << kPushShift) - 1));
+                        __threadfence();                               // the other warps' records after their counts
+                        if (j < num_rays && !(second && b == a)) records.home[j] = __ldcg(records.staged + j);
+                    }
+                }
+            }
+        }
         if (!drained && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
             const int leader = __ffs(idle) - 1;
             int base = 0;

@@ -82,6 +82,97 @@ def e2e():
     lib.tune("host_ramp", 0); lib.tune("host_chunks", 5)
 
 
+def e2e_direct():
+    """One launch per host-pointer call, rays and records over PCIe by the kernel itself (run_host_direct), against the copy-engine pieces."""
+    from concurrent.futures import ThreadPoolExecutor
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8())
+    bvh = traversal.Bvh8(0, nodes, tris)
+    sets, want = {}, {}
+    for name, (tmin, tmax) in testdata.RAY_SETS.items():
+        rays = formats.load_rays(testdata.rays(name), tmin, tmax)
+        pr = traversal.PinnedArray(formats.RAY1, len(rays)); pr.array[:] = rays
+        sets[name] = (pr, traversal.PinnedArray(formats.HIT1, len(rays)))
+        d_rays, d_hits = traversal.DeviceArray.from_host(0, rays), traversal.DeviceArray(0, formats.HIT1, len(rays))
+        traversal.intersect(bvh, d_rays, d_hits)
+        want[name] = d_hits.to_host().tobytes()
+    pool = ThreadPoolExecutor(2)
+
+    def step(names):
+        jobs = [pool.submit(traversal.intersect_host, nodes, tris, sets[n][0].array, sets[n][1].array) for n in names]
+        for j in jobs:
+            j.result()
+
+    def measure(label):
+        for names in (("random", "primary"), ("primary", "random"), ("primary",), ("random",)):
+            for n in names:
+                sets[n][1].array[:] = 0
+            for _ in range(3):
+                step(names)
+            ok = all(sets[n][1].array.tobytes() == want[n] for n in names)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter(); step(names); ts.append((time.perf_counter() - t0) * 1e3)
+            ok &= all(sets[n][1].array.tobytes() == want[n] for n in names)
+            print(f"{label:28s} {'+'.join(names):15s}: median {np.median(ts):.3f} ms, min {min(ts):.3f} ms -> "
+                  f"{len(names) * (1 << 20) / np.median(ts) / 1e3:.0f} Mrays/s, records equal to the device path: {ok}, "
+                  f"kernel {lib.load().rodent_b200_last_kernel_name(0).decode()}", flush=True)
+
+    lib.tune("host_direct", 0); measure("copy-engine pieces")
+    lib.tune("host_direct", 1)
+    for push in (1, 2, 0):
+        lib.tune("host_direct_push", push); measure(f"direct, push {push}")
+        lib.tune("host_trace", 1); step(("primary",)); step(("random",)); step(("random", "primary")); lib.tune("host_trace", 0)
+    lib.tune("host_direct_push", 1)
+    # any hit: the pieces round-trip the caller's records, the direct kernel stores tri_id alone
+    for direct in (0, 1):
+        lib.tune("host_direct", direct)
+        for n in ("primary", "random"):
+            for _ in range(3):
+                traversal.intersect_host(nodes, tris, sets[n][0].array, sets[n][1].array, any_hit=True)
+            ts = []
+            for _ in range(12):
+                t0 = time.perf_counter(); traversal.intersect_host(nodes, tris, sets[n][0].array, sets[n][1].array, any_hit=True); ts.append((time.perf_counter() - t0) * 1e3)
+            print(f"any hit, direct {direct}, {n}: median {np.median(ts):.3f} ms", flush=True)
+    lib.tune("host_direct", 1)
+    # ragged sizes and any-hit
+    rays = sets["random"][0].array
+    for n in (1 << 12, (1 << 12) + 1, 100_003, 777_777):
+        for any_hit in (False, True):
+            outs = []
+            for direct in (1, 0):
+                lib.tune("host_direct", direct)
+                h = traversal.PinnedArray(formats.HIT1, n); h.array[:] = 0
+                traversal.intersect_host(nodes, tris, rays[:n], h.array, any_hit=any_hit)
+                outs.append(h.array.tobytes())
+            print(f"n {n} any {any_hit}: direct == pieces: {outs[0] == outs[1]}", flush=True)
+    lib.tune("host_direct", 1)
+
+
+def zero_copy():
+    """The device-pointer entry point handed PINNED HOST pointers (UVA): the kernel reads its rays and writes its records
+    over PCIe itself, no copy engine.  ms per launch (CUDA events), records against the device-resident run."""
+    import types
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8())
+    bvh = traversal.Bvh8(0, nodes, tris)
+    for name, (tmin, tmax) in testdata.RAY_SETS.items():
+        rays = formats.load_rays(testdata.rays(name), tmin, tmax)
+        n = len(rays)
+        pr = traversal.PinnedArray(formats.RAY1, n); pr.array[:] = rays
+        ph = traversal.PinnedArray(formats.HIT1, n)
+        d_rays, d_hits = traversal.DeviceArray.from_host(0, rays), traversal.DeviceArray(0, formats.HIT1, n)
+        traversal.intersect(bvh, d_rays, d_hits)
+        want = d_hits.to_host().tobytes()
+        h_rays = types.SimpleNamespace(ptr=pr.ptr, count=n); h_hits = types.SimpleNamespace(ptr=ph.ptr, count=n)
+        for label, r, h in (("device rays, device records", d_rays, d_hits), ("host rays, device records", h_rays, d_hits),
+                            ("device rays, host records", d_rays, h_hits), ("host rays, host records", h_rays, h_hits)):
+            ph.array[:] = 0
+            for _ in range(3):
+                traversal.intersect(bvh, r, h)
+            ts = [traversal.intersect(bvh, r, h) for _ in range(12)]
+            got = ph.array.tobytes() if h is h_hits else d_hits.to_host().tobytes()
+            print(f"{name:8s} {label:30s}: {np.median(ts):.3f} ms -> {n / np.median(ts) / 1e3:.0f} Mrays/s, equal {got == want}", flush=True)
+
+
 def sbvh():
     """Sponza render through the reference file's BVH2 block against a BVH2 from this repository's split-BVH builder."""
     from rodent_b200 import render as R, workloads
@@ -116,5 +207,9 @@ if __name__ == "__main__":
         render()
     if "e2e" in what:
         e2e()
+    if "e2e_direct" in what:
+        e2e_direct()
+    if "zero_copy" in what:
+        zero_copy()
     if "sbvh" in what:
         sbvh()

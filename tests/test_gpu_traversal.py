@@ -208,6 +208,66 @@ def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
     pin_r.free(); pin_h.free()
 
 
+def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
+    """Pinned caller buffers, closest hit: one launch reads the rays from the caller's memory and sends the records home
+    itself (traverse_bvh8_direct).  Bit-exact against the oracle at ragged sizes (group of 16 records: full, ragged,
+    single), in all three record modes, from sub-ranges of one allocation, from several threads at once, and with the
+    path switched off (copy-engine pieces)."""
+    import threading
+    from rodent_b200 import lib, traversal
+    L = lib.load()
+    nodes, tris = sponza
+    full = len(ray_sets["random"])
+    pin_r, pin_h = traversal.PinnedArray(formats.RAY1, full), traversal.PinnedArray(formats.HIT1, full)
+    pin_r.array[:] = ray_sets["random"]
+    for n in (1, 15, 16, 17, 33, 4097, 300001, full):
+        pin_h.array[:n] = 0
+        got = traversal.intersect_host(nodes, tris, pin_r.array[:n], pin_h.array[:n])
+        assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_bvh8_direct<false>"
+        assert_records_equal(got.copy(), oracle_hits["random"][:n])
+    try:
+        for mode in (0, 2, 1):
+            lib.tune("host_direct_push", mode)
+            pin_h.array[:] = 0
+            assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:100003], pin_h.array[:100003]).copy(), oracle_hits["random"][:100003])
+    finally:
+        lib.tune("host_direct_push", 1)
+    # a range in the middle of the allocation (what rodent_b200_set_devices hands every device); its neighbours stay untouched
+    pin_h.array[:] = 0
+    traversal.intersect_host(nodes, tris, pin_r.array[1001:70001], pin_h.array[1001:70001])
+    assert_records_equal(pin_h.array[1001:70001].copy(), oracle_hits["random"][1001:70001])
+    assert not pin_h.array[:1001].view(np.uint8).any() and not pin_h.array[70001:].view(np.uint8).any()
+    # two sets from two threads, repeatedly
+    pin_r2, pin_h2 = traversal.PinnedArray(formats.RAY1, full), traversal.PinnedArray(formats.HIT1, full)
+    pin_r2.array[:] = ray_sets["primary"]
+
+    def work(r, h):
+        for _ in range(4):
+            h.array[:] = 0
+            traversal.intersect_host(nodes, tris, r.array, h.array)
+    threads = [threading.Thread(target=work, args=a) for a in ((pin_r, pin_h), (pin_r2, pin_h2))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert_records_equal(pin_h.array.copy(), oracle_hits["random"])
+    assert_records_equal(pin_h2.array.copy(), oracle_hits["primary"])
+    # any hit keeps the caller's t, u, v (copy-engine path), and the direct path can be switched off
+    pin_h.array[:] = 0
+    pin_h.array["t"] = 7.0
+    occl = traversal.intersect_host(nodes, tris, pin_r.array[:50000], pin_h.array[:50000], any_hit=True)
+    assert ((occl["tri_id"] >= 0) == (oracle_hits["random"][:50000]["tri_id"] >= 0)).all() and (occl["t"] == 7.0).all()
+    lib.tune("host_direct", 0)
+    try:
+        pin_h.array[:] = 0
+        assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:4097], pin_h.array[:4097]).copy(), oracle_hits["random"][:4097])
+        assert L.rodent_b200_last_kernel_name(0).decode().startswith("traverse_bvh8_vote")
+    finally:
+        lib.tune("host_direct", 1)
+    for a in (pin_r, pin_h, pin_r2, pin_h2):
+        a.free()
+
+
 def test_host_entry_points_are_reentrant(sponza, ray_sets, oracle_hits):
     """The cpu_* functions are pure; their drop-ins may be called from several host threads at once -- different sets,
     sizes and closest / any hit mixed, repeatedly (contexts are reused)."""
