@@ -51,6 +51,7 @@ struct Tuning {
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_direct = 1;     // host-pointer entry points, pinned buffers, BVH8: one launch per call, rays read and records written over PCIe by the kernel itself (0: copy-engine pieces)
+    int host_direct_rays = 1;    // ... 1 = a copy engine brings the rays in while the kernel runs (armed slots, traverse_sched.cuh), 0 = the warps read them from the caller's memory as they refill
     int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
     int host_trace = 0;          // ... print the device time of every such call (developer probe)
     int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
@@ -161,7 +162,8 @@ traverse_bvh8_direct(const Node8* __restrict__ nodes, const Tri4* __restrict__ t
     __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
     traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 8, true>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
-        [caller_rays](int i, float4& r0, float4& r1) {
+        [caller_rays, records](int i, float4& r0, float4& r1) {
+            if (records.arriving != nullptr) { records.take(i, r0, r1); return; }
             const float4* rp = reinterpret_cast<const float4*>(caller_rays + i);
             r0 = ldg4(rp); r1 = ldg4(rp + 1);        // (ld.global.cv of 16 bytes per lane over PCIe is ten times slower)
         },
@@ -333,6 +335,9 @@ struct DeviceState {
     std::map<std::pair<const void*, const void*>, struct BvhCopy> bvh_cache;
     uint64_t bvh_clock = 0; int64_t bvh_uploads = 0, bvh_reuploads = 0;
     std::map<const void*, int> occupancy;      // kernel -> resident CTAs per SM
+    // the ray copies of all direct host-pointer calls go through ONE stream, first come first served at the full rate of
+    // the link: the first call's kernel has its rays early, the second's arrive while the first is traced
+    cudaStream_t copy_in = nullptr; std::mutex copy_in_mutex;
 };
 // What one host-pointer call needs on the device.  The reference's cpu_* functions are reentrant, so their drop-ins are
 // too: every call takes a context of its own, and concurrent calls (from several host threads) overlap on the device.
@@ -344,6 +349,8 @@ struct HostContext {
     Ray1* h_rays = nullptr; Hit1* h_hits = nullptr; size_t stage_capacity = 0;
     cudaEvent_t piece_done[16] = {};
     unsigned* group_counts = nullptr; size_t group_capacity = 0;   // run_host_direct: finished records per group of 16 rays
+    bool rays_armed = false;               // every slot of d_rays carries the all-ones words (the kernel re-arms what it takes)
+    unsigned* copied = nullptr; unsigned* epochs = nullptr; unsigned epoch = 0;   // device word / pinned values: "this call's rays are all in"
 };
 static DeviceState g_dev[64];
 static std::mutex g_mutex;
@@ -631,12 +638,16 @@ static HostContext* acquire_host_context(DeviceState& s, size_t num_rays) {
         c = new HostContext();
         for (auto& st : c->streams) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         RB_CUDA_CHECK(cudaMalloc(&c->counters, 3 * 8 * sizeof(int)));
+        RB_CUDA_CHECK(cudaMalloc(&c->copied, sizeof(unsigned)));
+        RB_CUDA_CHECK(cudaMemset(c->copied, 0, sizeof(unsigned)));
+        RB_CUDA_CHECK(cudaMallocHost(&c->epochs, 8 * sizeof(unsigned)));
     }
     if (c->ray_capacity < num_rays) {
         if (c->d_rays) { RB_CUDA_CHECK(cudaFree(c->d_rays)); RB_CUDA_CHECK(cudaFree(c->d_hits)); }
         RB_CUDA_CHECK(cudaMalloc(&c->d_rays, num_rays * sizeof(Ray1)));
         RB_CUDA_CHECK(cudaMalloc(&c->d_hits, num_rays * sizeof(Hit1)));
         c->ray_capacity = num_rays;
+        c->rays_armed = false;
     }
     const size_t groups = (num_rays >> kPushShift) + 1;
     if (c->group_capacity < groups) {
@@ -742,7 +753,18 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const Node8* d_nodes
     }
     cudaStream_t run = c->streams[0];
     const bool push = g_tuning.host_direct_push == 1, copy_after = g_tuning.host_direct_push == 2;
-    const PushHome records{push ? c->group_counts : nullptr, reinterpret_cast<const float4*>(c->d_hits), reinterpret_cast<float4*>(caller_hits)};
+    PushHome records{push ? c->group_counts : nullptr, reinterpret_cast<const float4*>(c->d_hits), reinterpret_cast<float4*>(caller_hits), nullptr, c->copied, ++c->epoch};
+    if (g_tuning.host_direct_rays) {
+        // arm the slots if somebody else wrote to this context's ray array since (the kernel re-arms every slot it takes)
+        if (!c->rays_armed) { RB_CUDA_CHECK(cudaMemsetAsync(c->d_rays, 0xFF, c->ray_capacity * sizeof(Ray1), run)); RB_CUDA_CHECK(cudaStreamSynchronize(run)); c->rays_armed = true; }
+        unsigned* value = c->epochs + (records.epoch & 7);
+        *value = records.epoch;
+        std::lock_guard<std::mutex> lock(s.copy_in_mutex);
+        if (!s.copy_in) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, s.copy_in));
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->copied, value, sizeof(unsigned), cudaMemcpyHostToDevice, s.copy_in));
+        records.arriving = reinterpret_cast<float4*>(c->d_rays);
+    }
     cudaEvent_t ev[2] = {};
     if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
     if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> kPushShift) + 1) * sizeof(unsigned), run));
@@ -756,7 +778,7 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const Node8* d_nodes
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (ev[1]) RB_CUDA_CHECK(cudaEventRecord(ev[1], run));
     if (copy_after) RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, run));
-    RB_CUDA_CHECK(cudaStreamSynchronize(run));
+    RB_CUDA_CHECK(cudaStreamSynchronize(run));      // (the kernel has seen every ray arrive, or the word behind the copy)
     if (ev[1]) {
         float ms = 0;
         RB_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
@@ -802,6 +824,7 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     // Pieces of decreasing size (k, k-1, ..., 1 parts of k(k+1)/2): the copy engine is the critical resource, and what
     // follows the last byte of input is one piece's traversal -- including its stragglers -- and its copy out, so that
     // last piece is kept small.
+    c->rays_armed = false;                            // the copies below overwrite the slots run_host_direct keeps armed
     const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
     const bool ramp = g_tuning.host_ramp && pieces >= 3;      // weights 1, k-1, k-2, ..., 1: nothing runs before the first piece is in
     const int64_t parts = ramp ? int64_t(pieces - 1) * pieces / 2 + 1 : int64_t(pieces) * (pieces + 1) / 2;
@@ -845,6 +868,7 @@ static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* r
     HostContext* c = acquire_host_context(s, size_t(num_rays));
     cudaStream_t st = c->streams[0];
     int* counter = c->counters;
+    c->rays_armed = false;
     RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));     // a packet is W * 32 bytes
     if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st)); // t/u/v stay the caller's
     RB_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), st));
@@ -1016,6 +1040,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
     else if (!std::strcmp(key, "host_ramp")) g_tuning.host_ramp = value != 0;
     else if (!std::strcmp(key, "host_direct")) g_tuning.host_direct = value != 0;
+    else if (!std::strcmp(key, "host_direct_rays")) g_tuning.host_direct_rays = value != 0;
     else if (!std::strcmp(key, "host_direct_push")) g_tuning.host_direct_push = clamp(value, 0, 2);
     else if (!std::strcmp(key, "host_trace")) g_tuning.host_trace = value != 0;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = clamp(value, 8, 12);

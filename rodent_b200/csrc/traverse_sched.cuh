@@ -226,10 +226,39 @@ struct RayWalker {
 //                for its slowest ray.  (`counts` == nullptr: no groups, the sink writes wherever it likes.)
 struct StoreAtOnce { static constexpr bool kActive = false; };
 constexpr int kPushShift = 4;                      // records per group: 16; at most 16 (two groups per warp round)
+//                The rays may still be on their way when the kernel starts (`arriving` != nullptr): a copy engine is
+//                writing them into the device array, whose slots were armed with all-ones words where tmin and tmax go.
+//                A warp reserves rays only when the last one it would get has arrived (it goes on with the rays it
+//                has meanwhile), every lane then checks its own slot and re-arms it for the next call.  A ray whose
+//                tmin or tmax really is the all-ones NaN looks as if it had not arrived: `*copied` == epoch (written by
+//                the same stream behind the copy) ends every wait.
+constexpr unsigned kArmed = 0xFFFFFFFFu;
 struct PushHome {
     static constexpr bool kActive = true;
     unsigned* counts;                              // finished records per group, zeroed by the launcher
     const float4* staged; float4* home;            // the records in device memory; the caller's array
+    float4* arriving; const unsigned* copied; unsigned epoch;
+    static __device__ __forceinline__ unsigned peek(const void* p) {
+        unsigned v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ bool arrived(int i) const {
+        const unsigned* slot = reinterpret_cast<const unsigned*>(arriving + 2 * i);
+        return (peek(slot + 3) != kArmed && peek(slot + 7) != kArmed) || peek(copied) == epoch;
+    }
+    // the fetch functor of a kernel whose rays are arriving: wait for the slot, take the ray, re-arm the slot
+    __device__ __forceinline__ void take(int i, float4& r0, float4& r1) const {
+        float4* slot = arriving + 2 * i;
+        for (;;) {
+            r0 = __ldcv(slot); r1 = __ldcv(slot + 1);
+            if (__float_as_uint(r0.w) != kArmed && __float_as_uint(r1.w) != kArmed) break;
+            if (peek(copied) == epoch) { r0 = __ldcv(slot); r1 = __ldcv(slot + 1); break; }
+            __nanosleep(128);
+        }
+        reinterpret_cast<unsigned*>(slot)[3] = kArmed;
+        reinterpret_cast<unsigned*>(slot)[7] = kArmed;
+    }
 };
 
 // The persistent loop shared by the bench_traversal kernels and the renderer's stream kernels.
@@ -288,7 +317,20 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
                 }
             }
         }
-        if (!drained && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
+        bool refill = !drained && (__popc(idle) >= refill_min || idle == 0xffffffffu);
+        if constexpr (Records::kActive) {
+            if (refill && records.arriving != nullptr) {       // only rays that have arrived are reserved
+                const int leader = __ffs(idle) - 1;
+                int ok = 1;
+                if (int(lane) == leader) {
+                    const int next = *reinterpret_cast<volatile int*>(work_counter);
+                    ok = next >= num_rays || records.arrived(min(next + __popc(idle), num_rays) - 1);
+                }
+                refill = __shfl_sync(0xffffffffu, ok, leader) != 0;
+                if (!refill && idle == 0xffffffffu) __nanosleep(256);
+            }
+        }
+        if (refill) {
             const int leader = __ffs(idle) - 1;
             int base = 0;
             if (int(lane) == leader) base = atomicAdd(work_counter, __popc(idle));

@@ -209,10 +209,11 @@ def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
 
 
 def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
-    """Pinned caller buffers, closest hit: one launch reads the rays from the caller's memory and sends the records home
-    itself (traverse_bvh8_direct).  Bit-exact against the oracle at ragged sizes (group of 16 records: full, ragged,
-    single), in all three record modes, from sub-ranges of one allocation, from several threads at once, and with the
-    path switched off (copy-engine pieces)."""
+    """Pinned caller buffers, closest hit: one launch that starts while a copy engine is still bringing the rays in
+    (armed slots) and sends the records home itself (traverse_bvh8_direct).  Bit-exact against the oracle at ragged sizes
+    (group of 16 records: full, ragged, single), in every ray / record mode, from sub-ranges of one allocation, from
+    several threads at once, interleaved with calls that overwrite the same context's ray array, with rays whose
+    tmin / tmax look like an armed slot, and with the path switched off (copy-engine pieces)."""
     import threading
     from rodent_b200 import lib, traversal
     L = lib.load()
@@ -226,12 +227,33 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
         assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_bvh8_direct<false>"
         assert_records_equal(got.copy(), oracle_hits["random"][:n])
     try:
-        for mode in (0, 2, 1):
-            lib.tune("host_direct_push", mode)
-            pin_h.array[:] = 0
-            assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:100003], pin_h.array[:100003]).copy(), oracle_hits["random"][:100003])
+        for by_copy_engine in (0, 1):
+            for mode in (0, 2, 1):
+                lib.tune("host_direct_rays", by_copy_engine); lib.tune("host_direct_push", mode)
+                pin_h.array[:] = 0
+                assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:100003], pin_h.array[:100003]).copy(), oracle_hits["random"][:100003])
     finally:
-        lib.tune("host_direct_push", 1)
+        lib.tune("host_direct_push", 1); lib.tune("host_direct_rays", 1)
+    # the same context serves a pageable call (copy-engine pieces into the same device array) in between: no stale ray
+    # may be taken for an arrived one afterwards
+    pageable = np.ascontiguousarray(ray_sets["primary"][:100003])
+    for _ in range(2):
+        assert_records_equal(traversal.intersect_host(nodes, tris, pageable), oracle_hits["primary"][:100003])
+        pin_h.array[:] = 0
+        assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:100003], pin_h.array[:100003]).copy(), oracle_hits["random"][:100003])
+        assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[5:50005], pin_h.array[5:50005]).copy(), oracle_hits["random"][5:50005])
+    # rays whose tmin or tmax is the all-ones NaN look like slots that have not arrived: the call still ends, with the
+    # records the device-pointer entry point gives for the same rays
+    odd = traversal.PinnedArray(formats.RAY1, 40000)
+    odd.array[:] = ray_sets["random"][:40000]
+    odd.array["tmax"].view(np.uint32)[::7] = 0xFFFFFFFF
+    odd.array["tmin"].view(np.uint32)[3::11] = 0xFFFFFFFF
+    d_rays, d_hits = traversal.DeviceArray.from_host(0, odd.array), traversal.DeviceArray(0, formats.HIT1, 40000)
+    traversal.intersect(traversal.Bvh8(0, nodes, tris), d_rays, d_hits)
+    pin_h.array[:] = 0
+    got = traversal.intersect_host(nodes, tris, odd.array, pin_h.array[:40000]).copy()
+    assert got.tobytes() == d_hits.to_host().tobytes()
+    odd.free()
     # a range in the middle of the allocation (what rodent_b200_set_devices hands every device); its neighbours stay untouched
     pin_h.array[:] = 0
     traversal.intersect_host(nodes, tris, pin_r.array[1001:70001], pin_h.array[1001:70001])
