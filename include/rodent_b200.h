@@ -221,6 +221,11 @@ void*   rodent_b200_alloc_device(int32_t dev, size_t bytes);
 void    rodent_b200_free_device(int32_t dev, void* ptr);
 void*   rodent_b200_alloc_host(size_t bytes);         /* page-locked */
 void    rodent_b200_free_host(void* ptr);
+/* Page-lock an array the host allocated itself (malloc, std::vector, anydsl::Array host memory) in place, and release it
+ * before the host frees it: the b200_* calls then treat it like rodent_b200_alloc_host memory (one launch per call, no
+ * staging).  0 on success, -1 when the driver refuses (not page-lockable, already registered, unknown pointer). */
+int32_t rodent_b200_pin_host(void* ptr, size_t bytes);
+int32_t rodent_b200_unpin_host(void* ptr);
 void    rodent_b200_copy_to_device(int32_t dev, void* dst, const void* src, size_t bytes);
 void    rodent_b200_copy_to_host(int32_t dev, void* dst, const void* src, size_t bytes);
 void    rodent_b200_sync(int32_t dev);

@@ -980,6 +980,15 @@ void* rodent_b200_alloc_host(size_t bytes) {
     return p;
 }
 void rodent_b200_free_host(void* ptr) { RB_CUDA_CHECK(cudaFreeHost(ptr)); }
+int32_t rodent_b200_pin_host(void* ptr, size_t bytes) {
+    if (ptr == nullptr || bytes == 0) return -1;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+int32_t rodent_b200_unpin_host(void* ptr) {
+    if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
 void rodent_b200_copy_to_device(int32_t dev, void* dst, const void* src, size_t bytes) {
     device_state(dev);
     RB_CUDA_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));

@@ -49,6 +49,8 @@ SIGNATURES = {
     "rodent_b200_free_device": (None, [c_int32, c_void_p]),
     "rodent_b200_alloc_host": (c_void_p, [c_size_t]),
     "rodent_b200_free_host": (None, [c_void_p]),
+    "rodent_b200_pin_host": (c_int32, [c_void_p, c_size_t]),
+    "rodent_b200_unpin_host": (c_int32, [c_void_p]),
     "rodent_b200_copy_to_device": (None, [c_int32, c_void_p, c_void_p, c_size_t]),
     "rodent_b200_copy_to_host": (None, [c_int32, c_void_p, c_void_p, c_size_t]),
     "rodent_b200_sync": (None, [c_int32]),

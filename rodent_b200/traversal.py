@@ -98,6 +98,15 @@ def intersect_host(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, hits: 
     return hits
 
 
+def pin_host(arr: np.ndarray) -> bool:
+    """Page-lock a numpy array in place (rodent_b200_pin_host): host-pointer calls on it then take the direct path."""
+    return lib.load().rodent_b200_pin_host(arr.ctypes.data, arr.nbytes) == 0
+
+
+def unpin_host(arr: np.ndarray) -> bool:
+    return lib.load().rodent_b200_unpin_host(arr.ctypes.data) == 0
+
+
 class PinnedArray:
     """Page-locked host array viewed as numpy (for the end-to-end path)."""
 

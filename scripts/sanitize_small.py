@@ -17,6 +17,17 @@ for loader, typ in ((testdata.sponza_bvh8, F.BVH8_TRI4), (testdata.sponza_bvh4, 
     if typ == F.BVH8_TRI4:
         sub = np.ascontiguousarray(F.load_rays(testdata.rays("random"), 0.0, 1.0)[:40000])
         traversal.intersect_host(nodes, tris, sub)
+        # pinned buffers: the direct path (armed slots, records sent home by groups), twice through the same context,
+        # with the copy-engine pieces in between
+        pr, ph = traversal.PinnedArray(F.RAY1, len(sub)), traversal.PinnedArray(F.HIT1, len(sub))
+        pr.array[:] = sub
+        want = traversal.intersect_host(nodes, tris, sub)
+        for n in (len(sub), 1000, 17):
+            ph.array[:] = 0
+            traversal.intersect_host(nodes, tris, pr.array[:n], ph.array[:n])
+            assert ph.array[:n].tobytes() == want[:n].tobytes()
+            traversal.intersect_host(nodes, tris, sub[:n])
+        print("direct host-pointer path", lib.load().rodent_b200_last_kernel_name(0).decode(), flush=True)
         for mapping in (1, 3, 4):
             lib.tune("mapping", mapping)
             traversal.intersect(bvh, d_rays, d_hits)

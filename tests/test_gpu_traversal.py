@@ -242,6 +242,16 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
         pin_h.array[:] = 0
         assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[:100003], pin_h.array[:100003]).copy(), oracle_hits["random"][:100003])
         assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array[5:50005], pin_h.array[5:50005]).copy(), oracle_hits["random"][5:50005])
+    # arrays the host allocated itself, page-locked in place (rodent_b200_pin_host): the same path; a second registration
+    # of the same range is refused, and after the release the staged path serves them again
+    own_r, own_h = np.ascontiguousarray(ray_sets["primary"][:70001]), np.zeros(70001, formats.HIT1)
+    assert traversal.pin_host(own_r) and traversal.pin_host(own_h) and not traversal.pin_host(own_r)
+    assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
+    assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_bvh8_direct<false>"
+    assert traversal.unpin_host(own_r) and traversal.unpin_host(own_h) and not traversal.unpin_host(own_h)
+    own_h[:] = 0
+    assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
+    assert L.rodent_b200_last_kernel_name(0).decode().startswith("traverse_bvh8_vote")
     # rays whose tmin or tmax is the all-ones NaN look like slots that have not arrived: the call still ends, with the
     # records the device-pointer entry point gives for the same rays
     odd = traversal.PinnedArray(formats.RAY1, 40000)

@@ -31,7 +31,7 @@ struct Options {
     std::string bvh_file, ray_file, out_file, gpu;
     float tmin = 0.0f, tmax = 1e9f;
     int iters = 1, warmup = 0, dev = 0, bvh_width = 4, ray_width = 8, gpus = 1;
-    bool any_hit = false, single = false, packet = false, bvh_width_given = false;
+    bool any_hit = false, single = false, packet = false, bvh_width_given = false, pinned = false;
 };
 
 [[noreturn]] void fail(const std::string& msg) { std::cerr << msg << std::endl; std::exit(1); }
@@ -47,6 +47,7 @@ void usage() {
                  "        --gpus n     with -s: cut every call into n contiguous ray ranges over devices dev .. dev+n-1 (BVH replicated)\n"
                  "  -any               exit at the first intersection\n"
                  "  -s    --single     host-buffer single-ray entry point\n"
+                 "        --pinned     with -s: page-lock the ray and hit arrays in place (rodent_b200_pin_host)\n"
                  "        --bvh-width  4 or 8 (default 4; 2 with -gpu: the reference GPU path's BVH2 block) ; --ray-width 4 or 8 (default 8)\n"
                  "  -o    --output     write hit distances as .fbuf\n";
 }
@@ -70,6 +71,7 @@ Options parse(int argc, char** argv) {
         else if (a == "-dev" || a == "--gpu-device") o.dev = int(std::strtol(value(), nullptr, 10));
         else if (a == "--gpus") o.gpus = int(std::strtol(value(), nullptr, 10));
         else if (a == "-any") o.any_hit = true;
+        else if (a == "--pinned") o.pinned = true;
         else if (a == "-s" || a == "--single") o.single = true;
         else if (a == "-p" || a == "--packet") o.packet = true;
         else if (a == "--bvh-width") { o.bvh_width = int(std::strtol(value(), nullptr, 10)); o.bvh_width_given = true; }
@@ -129,6 +131,10 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
         } else {
             rodent_b200_set_device(o.dev);
         }
+        // the two lines a host adds to get one launch per call and no staging: its own arrays, page-locked in place
+        if (o.pinned && ray_count > 0 &&
+            (rodent_b200_pin_host(rays.data(), ray_count * sizeof(Ray1)) != 0 || rodent_b200_pin_host(hits.data(), ray_count * sizeof(Hit1)) != 0))
+            fail("Cannot page-lock the ray / hit arrays");
         bench = [&] {
             const auto t0 = std::chrono::steady_clock::now();
             (o.any_hit ? host_occluded : host_intersect)(nodes.data(), tris.data(), rays.data(), hits.data(), int32_t(ray_count));
@@ -141,6 +147,7 @@ int run(const Options& o, rb200::BlockType block, DevFn dev_intersect, DevFn dev
     for (int i = 0; i < o.iters; i++) timings.push_back(bench());
 
     if (use_gpu) rodent_b200_copy_to_host(o.dev, hits.data(), d_hits, hits.size() * sizeof(Hit1));
+    if (!use_gpu && o.pinned && ray_count > 0) { rodent_b200_unpin_host(rays.data()); rodent_b200_unpin_host(hits.data()); }
     size_t intr = 0;
     for (const Hit1& h : hits) intr += h.tri_id >= 0;
     if (!o.out_file.empty() && !rb200::write_fbuf(o.out_file, hits)) fail("Cannot write output file");
