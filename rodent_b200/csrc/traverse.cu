@@ -154,13 +154,13 @@ traverse_bvh8_vote(const Node8* __restrict__ nodes, const Tri4* __restrict__ tri
 // The host-pointer entry points with pinned caller memory: the default kernel reads its rays straight from the caller's
 // array over PCIe as its warps refill, and sends the records home itself (PushHome, traverse_sched.cuh).  No copy engine,
 // no second buffer for the rays, one launch per call.
-template <bool ANY>
-__global__ void __launch_bounds__(kBlock, 5)
-traverse_bvh8_direct(const Node8* __restrict__ nodes, const Tri4* __restrict__ tris,
-                     const Ray1* __restrict__ caller_rays, Hit1* __restrict__ hits, int num_rays,
-                     int* __restrict__ work_counter, int refill_min, int node_streak_min, PushHome records) {
+template <bool ANY, int ARITY>
+__global__ void __launch_bounds__(kBlock, ARITY == 8 ? 5 : 6)
+traverse_direct(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
+                const Ray1* __restrict__ caller_rays, Hit1* __restrict__ hits, int num_rays,
+                int* __restrict__ work_counter, int refill_min, int node_streak_min, PushHome records) {
     __shared__ StackEntry smem_stack[kVoteSmemDepth][kBlock];
-    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, 8, true>(
+    traverse_vote_scheduled<ANY, false, kVoteSmemDepth, kBlock, ARITY, ARITY == 8>(
         nodes, tris, &smem_stack[0][threadIdx.x], num_rays, work_counter, refill_min,
         [caller_rays, records](int i, float4& r0, float4& r1) {
             if (records.arriving != nullptr) { records.take(i, r0, r1); return; }
@@ -740,11 +740,12 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
     for (auto& t : threads) t.join();
 }
 
-// Pinned caller buffers, BVH8, default kernel: one launch per call and no copy at all (traverse_bvh8_direct).  Against
+// Pinned caller buffers, default kernel (BVH8 or BVH4): one launch per call and one copy (traverse_direct).  Against
 // the copy-engine pieces below: the traversal starts at once instead of after a fifth of the rays, pays the tail of a
 // launch once per call, keeps all its CTAs for the whole call, and the records need no pass of their own.
-template <bool ANY>
-static bool run_host_direct(DeviceState& s, HostContext* c, const Node8* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays) {
+template <bool ANY, typename NodeT>
+static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays) {
+    constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
     const Ray1* caller_rays = nullptr; Hit1* caller_hits = nullptr;
     if (cudaHostGetDevicePointer(const_cast<void**>(reinterpret_cast<const void**>(&caller_rays)), const_cast<Ray1*>(rays), 0) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&caller_hits), hits, 0) != cudaSuccess) {
@@ -769,10 +770,10 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const Node8* d_nodes
     if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
     if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> kPushShift) + 1) * sizeof(unsigned), run));
     RB_CUDA_CHECK(cudaMemsetAsync(c->counters, 0, sizeof(int), run));
-    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(traverse_bvh8_direct<ANY>), kBlock);
+    const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(traverse_direct<ANY, ARITY>), kBlock);
     const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
-    s.last_kernel = ANY ? "traverse_bvh8_direct<true>" : "traverse_bvh8_direct<false>";
-    traverse_bvh8_direct<ANY><<<grid, kBlock, 0, run>>>(d_nodes, d_tris, caller_rays, push || copy_after ? c->d_hits : caller_hits, num_rays, c->counters,
+    s.last_kernel = ARITY == 8 ? "traverse_direct<false, 8>" : "traverse_direct<false, 4>";
+    traverse_direct<ANY, ARITY><<<grid, kBlock, 0, run>>>(d_nodes, d_tris, caller_rays, push || copy_after ? c->d_hits : caller_hits, num_rays, c->counters,
                                                          g_tuning.refill_min, g_tuning.node_streak_min, records);
     RB_CUDA_CHECK(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -807,10 +808,11 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     }
     const Ray1* src = stage_in ? c->h_rays : rays;
     Hit1* dst = stage_out ? c->h_hits : hits;
-    if constexpr (std::is_same<NodeT, Node8>::value) {
-        // (closest hit only: an any-hit call changes tri_id alone, 4 bytes of every 16 -- stored over PCIe one by one that
-        // is slower than the pieces' round trip of the caller's records: 1.79 / 1.95 against 1.13 / 1.40 ms per Mi rays)
-        if (!ANY && g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && is_pinned(rays, true) && is_pinned(hits, true)) {
+    // (closest hit only: an any-hit call changes tri_id alone, 4 bytes of every 16 -- stored over PCIe one by one that
+    // is slower than the pieces' round trip of the caller's records: 1.79 / 1.95 against 1.13 / 1.40 ms per Mi rays)
+    if constexpr (!ANY) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
+        if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && is_pinned(rays, true) && is_pinned(hits, true)) {
             if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
                 release_host_context(s, c);
                 return;

@@ -59,13 +59,13 @@ def test_fbuf2png_matches_reference_quantisation(tools, tmp_path, oracle_hits):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [["-gpu", "cuda"], ["-s", "--bvh-width", "8"], ["-s"], ["-gpu", "cuda", "--bvh-width", "4"],
-                                  ["-gpu", "cuda", "--bvh-width", "2"], ["-s", "--pinned", "--bvh-width", "8"]])
+                                  ["-gpu", "cuda", "--bvh-width", "2"], ["-s", "--pinned", "--bvh-width", "8"], ["-s", "--pinned"]])
 @pytest.mark.parametrize("name,tmin,tmax,hits", [("primary", "0.01", "5000", None), ("random", "0", "1", 959359)])
 def test_ctest_procedure_on_gpu(tools, tmp_path, mode, name, tmin, tmax, hits):
     """single_bvh8 / single_bvh4 of tools/CMakeLists.txt:26-31 (`-s` alone is the reference's default width, 4); width 2 with
     -gpu is the block and the semantics of the reference's `-gpu nvvm`."""
     fbuf = tmp_path / "out.fbuf"
-    bvh = testdata.sponza_bvh4() if mode in (["-s"], ["-gpu", "cuda", "--bvh-width", "4"]) else \
+    bvh = testdata.sponza_bvh4() if mode in (["-s"], ["-s", "--pinned"], ["-gpu", "cuda", "--bvh-width", "4"]) else \
         testdata.sponza_bvh2() if mode[-1] == "2" else testdata.sponza_bvh8()      # (--pinned: the direct host-pointer path)
     r = run(tools / "bench_traversal", "-bvh", bvh, "-ray", testdata.rays(name), "--bench", "3", "--warmup", "1",
             "--tmin", tmin, "--tmax", tmax, "-o", fbuf, *mode)

@@ -210,7 +210,7 @@ def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
 
 def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
     """Pinned caller buffers, closest hit: one launch that starts while a copy engine is still bringing the rays in
-    (armed slots) and sends the records home itself (traverse_bvh8_direct).  Bit-exact against the oracle at ragged sizes
+    (armed slots) and sends the records home itself (traverse_direct).  Bit-exact against the oracle at ragged sizes
     (group of 16 records: full, ragged, single), in every ray / record mode, from sub-ranges of one allocation, from
     several threads at once, interleaved with calls that overwrite the same context's ray array, with rays whose
     tmin / tmax look like an armed slot, and with the path switched off (copy-engine pieces)."""
@@ -224,7 +224,7 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
     for n in (1, 15, 16, 17, 33, 4097, 300001, full):
         pin_h.array[:n] = 0
         got = traversal.intersect_host(nodes, tris, pin_r.array[:n], pin_h.array[:n])
-        assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_bvh8_direct<false>"
+        assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<false, 8>"
         assert_records_equal(got.copy(), oracle_hits["random"][:n])
     try:
         for by_copy_engine in (0, 1):
@@ -247,7 +247,7 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
     own_r, own_h = np.ascontiguousarray(ray_sets["primary"][:70001]), np.zeros(70001, formats.HIT1)
     assert traversal.pin_host(own_r) and traversal.pin_host(own_h) and not traversal.pin_host(own_r)
     assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
-    assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_bvh8_direct<false>"
+    assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<false, 8>"
     assert traversal.unpin_host(own_r) and traversal.unpin_host(own_h) and not traversal.unpin_host(own_h)
     own_h[:] = 0
     assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
@@ -414,7 +414,16 @@ def test_bvh4_degenerate_rays_and_host_entry_point(gpu4, sponza4, ray_sets):
     rays["tmax"][::17] = 0.1
     assert_records_equal(run_gpu(gpu4, rays), oracle.traverse(nodes4, tris4, rays))
     some = np.ascontiguousarray(ray_sets["random"][:20_001])
-    assert_records_equal(traversal.intersect_host(nodes4, tris4, some), oracle.traverse(nodes4, tris4, some))
+    want = oracle.traverse(nodes4, tris4, some)
+    assert_records_equal(traversal.intersect_host(nodes4, tris4, some), want)
+    # page-locked arrays: the direct path over the BVH4 (the reference's default --bvh-width), the degenerate rays too
+    from rodent_b200 import lib
+    for r, w in ((some, want), (rays, oracle.traverse(nodes4, tris4, rays))):
+        pr, ph = traversal.PinnedArray(formats.RAY1, len(r)), traversal.PinnedArray(formats.HIT1, len(r))
+        pr.array[:] = r
+        assert_records_equal(traversal.intersect_host(nodes4, tris4, pr.array, ph.array).copy(), w)
+        assert lib.load().rodent_b200_last_kernel_name(0).decode() == "traverse_direct<false, 4>"
+        pr.free(); ph.free()
 
 
 # ---- packet / hybrid entry points ------------------------------------------------------------------------
