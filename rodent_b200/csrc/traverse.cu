@@ -13,19 +13,25 @@
 // Measurements and what each experiment showed: profiles/r01_experiments.md.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <thread>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <vector>
 #include <type_traits>
+
+#include <emmintrin.h>
 
 #include "traverse.cuh"
 #include "traverse_quad.cuh"
 #include "traverse_sched.cuh"
 #include "traverse_pool.cuh"
 #include "traverse_bvh2.cuh"
+
+extern "C" char** environ;
 
 namespace rb200 {
 
@@ -52,8 +58,11 @@ struct Tuning {
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_direct = 1;     // host-pointer entry points, pinned buffers, BVH8: one launch per call, rays read and records written over PCIe by the kernel itself (0: copy-engine pieces)
     int host_direct_rays = 1;    // ... 1 = a copy engine brings the rays in while the kernel runs (armed slots, traverse_sched.cuh), 0 = the warps read them from the caller's memory as they refill
+    int host_staged_direct = 1;  // ... pageable buffers through the staging arrays with the same single launch: 1 = unless a profiling tool is injected, 2 = always, 0 = never (copy-engine pieces)
     int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
     int host_trace = 0;          // ... print the device time of every such call (developer probe)
+    int host_stream_stores = 1;  // ... staging copies with non-temporal stores
+    int host_copy_parts = 4; // host-pointer entry points, pageable buffers: threads that share one staging memcpy (the caller's included)
     int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
     int host_chunks = 5;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (two calls in flight: 5..6 measured best, one: 3..4)
 };
@@ -349,6 +358,7 @@ struct HostContext {
     Ray1* h_rays = nullptr; Hit1* h_hits = nullptr; size_t stage_capacity = 0;
     cudaEvent_t piece_done[16] = {};
     unsigned* group_counts = nullptr; size_t group_capacity = 0;   // run_host_direct: finished records per group of 16 rays
+    bool hits_armed = false;               // every record of h_hits carries kRecordArmed in tri_id (the copy-out re-arms what it takes)
     bool rays_armed = false;               // every slot of d_rays carries the all-ones words (the kernel re-arms what it takes)
     unsigned* copied = nullptr; unsigned* epochs = nullptr; unsigned epoch = 0;   // device word / pinned values: "this call's rays are all in"
 };
@@ -664,51 +674,111 @@ static void release_host_context(DeviceState& s, HostContext* c) {
 // The ray-pool variant (mapping 3) indexes one per-device overflow buffer by warp: its launches must not overlap.
 static std::mutex g_pool_serial;
 
-// A few helper threads that copy between the caller's pageable buffers and pinned staging memory (one memcpy runs at
-// ~10 GB/s on one core; the PCIe link takes five times that).  Jobs are byte ranges; parallel_copy returns when all are done.
+// A few helper threads for the host side of calls with pageable buffers: copies between the caller's memory and pinned
+// staging memory (one memcpy runs at ~10 GB/s on one core; the PCIe link takes five times that).  A task returns true when
+// it is finished and false to be run again later (a copy-out task whose records have not all arrived yet); run_all
+// returns when all its tasks are finished, the calling thread works along.
+// memcpy with non-temporal stores: the destination of a staging copy is not read by this core again (the copy engine or
+// the caller takes it from memory), so the lines need neither be fetched for ownership nor displace anything cached.
+static void stream_copy(void* dst, const void* src, size_t bytes) {
+    char* d = static_cast<char*>(dst); const char* s = static_cast<const char*>(src);
+    const size_t head = std::min(bytes, size_t(-reinterpret_cast<uintptr_t>(d)) & 15);
+    std::memcpy(d, s, head); d += head; s += head; bytes -= head;
+    size_t blocks = bytes / 64;
+    for (; blocks > 0; blocks--, d += 64, s += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+    }
+    _mm_sfence();
+    std::memcpy(d, s, bytes % 64);
+}
+
 class CopyPool {
 public:
+    using Task = std::function<bool()>;
     // never destroyed: its threads wait on the condition variable for the life of the process, and destroying a
     // condition variable that has waiters blocks (glibc) -- a static instance would hang every process at exit
     static CopyPool& get() { static CopyPool* p = new CopyPool; return *p; }
-    void parallel_copy(void* dst, const void* src, size_t bytes) {
-        const size_t kMin = size_t(1) << 20;
-        const int parts = int(std::min<size_t>(kPartsPerCopy, std::max<size_t>(1, bytes / kMin)));
-        if (parts <= 1) { std::memcpy(dst, src, bytes); return; }
-        const size_t each = ((bytes / parts) + 4095) & ~size_t(4095);
-        std::atomic<int> pending{parts - 1};
+    void run_all(std::vector<Task>& tasks) {
+        if (tasks.empty()) return;
+        std::atomic<int> pending{int(tasks.size())};
         {
             std::lock_guard<std::mutex> lock(m_);
-            for (int k = 1; k < parts; k++) {
-                const size_t b = std::min(bytes, each * k), e = std::min(bytes, each * (k + 1));
-                jobs_.push_back(Job{static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, e - b, &pending});
-            }
+            for (size_t k = tasks.size(); k-- > 0;) jobs_.push_back(Job{&tasks[k], &pending});     // popped from the back: in order
         }
         cv_.notify_all();
-        std::memcpy(dst, src, std::min(bytes, each));            // the caller's thread takes the first part
-        while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-    }
-private:
-    struct Job { char* dst; const char* src; size_t bytes; std::atomic<int>* pending; };
-    // a copy is cut into at most kPartsPerCopy parts (the caller's thread takes one); the pool is large enough for the
-    // calls of several devices' threads at once (rodent_b200_set_devices) without oversubscribing a small host
-    static constexpr int kPartsPerCopy = 4;
-    CopyPool() {
-        const int threads = int(std::max(3u, std::min(16u, std::thread::hardware_concurrency() / 2)));
-        for (int i = 0; i < threads; i++) std::thread([this] { work(); }).detach();
-    }
-    void work() {
-        for (;;) {
+        while (pending.load(std::memory_order_acquire) > 0) {
             Job j;
-            {
-                std::unique_lock<std::mutex> lock(m_);
-                cv_.wait(lock, [this] { return !jobs_.empty(); });
-                j = jobs_.back(); jobs_.pop_back();
-            }
-            std::memcpy(j.dst, j.src, j.bytes);
-            j.pending->fetch_sub(1, std::memory_order_release);
+            if (take(j, &pending)) run(j);
+            else for (int k = 0; k < 32; k++) __builtin_ia32_pause();
         }
     }
+    void parallel_copy(void* dst, const void* src, size_t bytes) {
+        const size_t kMin = size_t(1) << 20;
+        const int parts = int(std::min<size_t>(size_t(std::max(1, std::min(g_tuning.host_copy_parts, threads_ + 1))), std::max<size_t>(1, bytes / kMin)));
+        const bool stream = g_tuning.host_stream_stores != 0;
+        if (parts <= 1) { if (stream) stream_copy(dst, src, bytes); else std::memcpy(dst, src, bytes); return; }
+        const size_t each = ((bytes / parts) + 4095) & ~size_t(4095);
+        std::vector<Task> tasks;
+        for (int k = 0; k < parts; k++) {
+            const size_t b = std::min(bytes, each * k), e = std::min(bytes, each * (k + 1));
+            tasks.push_back([=] {
+                if (stream) stream_copy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, e - b);
+                else std::memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, e - b);
+                return true;
+            });
+        }
+        run_all(tasks);
+    }
+private:
+    struct Job { Task* task; std::atomic<int>* pending; };
+    // a copy is cut into at most g_tuning.host_copy_parts parts (the caller's thread takes one); the pool is large enough
+    // for the calls of several devices' threads at once (rodent_b200_set_devices) without oversubscribing a small host
+    int threads_ = 0;
+    CopyPool() {
+        threads_ = int(std::max(3u, std::min(16u, std::thread::hardware_concurrency() / 2)));
+        for (int i = 0; i < threads_; i++) std::thread([this] { work(); }).detach();
+    }
+    // a job of the caller's own batch if there is one (`mine`), else nothing: the caller never takes on another call's wait
+    bool take(Job& j, std::atomic<int>* mine) {
+        std::lock_guard<std::mutex> lock(m_);
+        for (size_t k = jobs_.size(); k-- > 0;)
+            if (jobs_[k].pending == mine) { j = jobs_[k]; jobs_.erase(jobs_.begin() + k); return true; }
+        return false;
+    }
+    void run(const Job& j) {
+        if ((*j.task)()) { j.pending->fetch_sub(1, std::memory_order_release); return; }
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            jobs_.insert(jobs_.begin(), j);                      // not finished: behind everything that is queued
+        }
+        for (int k = 0; k < 64; k++) __builtin_ia32_pause();
+    }
+    void work() {
+        // A call hands out its copies piece after piece, a few hundred microseconds apart: a helper that went to sleep on
+        // the condition variable after every job would need ~50 us to wake up for the next one.  So it keeps looking
+        // at the queue for a while after its last job and only then blocks.
+        auto last_job = std::chrono::steady_clock::now() - std::chrono::seconds(1);
+        for (;;) {
+            Job j;
+            bool have = false;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                if (jobs_.empty() && std::chrono::steady_clock::now() - last_job > std::chrono::microseconds(kLingerUs))
+                    cv_.wait(lock, [this] { return !jobs_.empty(); });
+                if (!jobs_.empty()) { j = jobs_.back(); jobs_.pop_back(); have = true; }
+            }
+            if (!have) {
+                for (int k = 0; k < 64; k++) __builtin_ia32_pause();
+                continue;
+            }
+            run(j);
+            last_job = std::chrono::steady_clock::now();
+        }
+    }
+    static constexpr int kLingerUs = 300;
     std::mutex m_; std::condition_variable cv_; std::vector<Job> jobs_;
 };
 
@@ -743,28 +813,64 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
 // Pinned caller buffers, default kernel (BVH8 or BVH4): one launch per call and one copy (traverse_direct).  Against
 // the copy-engine pieces below: the traversal starts at once instead of after a fifth of the rays, pays the tail of a
 // launch once per call, keeps all its CTAs for the whole call, and the records need no pass of their own.
+// Is a tool injected into this process that may run kernels one at a time, each to completion inside its launch call
+// (Nsight Compute's kernel replay)?  A kernel that waits for copies the host has not queued yet would never end there.
+static bool injected_tool() {
+    static const bool yes = [] {
+        for (char** e = ::environ; e && *e; e++)
+            if (!std::strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !std::strncmp(*e, "NV_NSIGHT", 9) || !std::strncmp(*e, "NV_COMPUTE_PROFILER", 19) ||
+                !std::strncmp(*e, "NV_TPS_LAUNCH", 13))
+                return true;
+        return false;
+    }();
+    return yes;
+}
+
+constexpr int32_t kRecordArmed = int32_t(0x80000000u);   // tri_id of a staging record that has not arrived (a real one is -1 or >= 0)
+
+// `stage_in` / `stage_out`: the caller's rays / hits are pageable and go through the context's pinned staging arrays --
+// still ONE launch.  The kernel is started first; the calling thread and the helper threads then copy the rays into the
+// staging array piece by piece, each piece followed by its copy to the device (the armed slots tell the kernel what is
+// in); the records arrive in the (armed) staging array by groups while the kernel runs, and the same threads move them
+// on to the caller's array chunk by chunk as they turn up, re-arming the staging array on the way.
 template <bool ANY, typename NodeT>
-static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays) {
+static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays,
+                            bool stage_in = false, bool stage_out = false) {
     constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
+    const Ray1* src = stage_in ? c->h_rays : rays;
+    Hit1* home = stage_out ? c->h_hits : hits;
     const Ray1* caller_rays = nullptr; Hit1* caller_hits = nullptr;
-    if (cudaHostGetDevicePointer(const_cast<void**>(reinterpret_cast<const void**>(&caller_rays)), const_cast<Ray1*>(rays), 0) != cudaSuccess ||
-        cudaHostGetDevicePointer(reinterpret_cast<void**>(&caller_hits), hits, 0) != cudaSuccess) {
+    if (cudaHostGetDevicePointer(const_cast<void**>(reinterpret_cast<const void**>(&caller_rays)), const_cast<Ray1*>(src), 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&caller_hits), home, 0) != cudaSuccess) {
         cudaGetLastError();                      // page-locked but not mapped for this device: the copy-engine path takes it
         return false;
     }
     cudaStream_t run = c->streams[0];
-    const bool push = g_tuning.host_direct_push == 1, copy_after = g_tuning.host_direct_push == 2;
+    const bool staged = stage_in || stage_out;
+    const bool push = staged || g_tuning.host_direct_push == 1, copy_after = !staged && g_tuning.host_direct_push == 2;
+    const bool by_copy_engine = staged || g_tuning.host_direct_rays;
     PushHome records{push ? c->group_counts : nullptr, reinterpret_cast<const float4*>(c->d_hits), reinterpret_cast<float4*>(caller_hits), nullptr, c->copied, ++c->epoch};
-    if (g_tuning.host_direct_rays) {
-        // arm the slots if somebody else wrote to this context's ray array since (the kernel re-arms every slot it takes)
-        if (!c->rays_armed) { RB_CUDA_CHECK(cudaMemsetAsync(c->d_rays, 0xFF, c->ray_capacity * sizeof(Ray1), run)); RB_CUDA_CHECK(cudaStreamSynchronize(run)); c->rays_armed = true; }
-        unsigned* value = c->epochs + (records.epoch & 7);
-        *value = records.epoch;
+    unsigned* epoch_value = c->epochs + (records.epoch & 7);
+    *epoch_value = records.epoch;
+    auto copy_in = [&](int first, int n, bool last) {
         std::lock_guard<std::mutex> lock(s.copy_in_mutex);
         if (!s.copy_in) RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
-        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, s.copy_in));
-        RB_CUDA_CHECK(cudaMemcpyAsync(c->copied, value, sizeof(unsigned), cudaMemcpyHostToDevice, s.copy_in));
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays + first, src + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, s.copy_in));
+        if (last) RB_CUDA_CHECK(cudaMemcpyAsync(c->copied, epoch_value, sizeof(unsigned), cudaMemcpyHostToDevice, s.copy_in));
+    };
+    if (by_copy_engine) {
+        // arm the slots if somebody else wrote to this context's ray array since (the kernel re-arms every slot it takes)
+        if (!c->rays_armed) { RB_CUDA_CHECK(cudaMemsetAsync(c->d_rays, 0xFF, c->ray_capacity * sizeof(Ray1), run)); RB_CUDA_CHECK(cudaStreamSynchronize(run)); c->rays_armed = true; }
+        if (!stage_in) copy_in(0, num_rays, true);           // everything the kernel waits for is queued before it
         records.arriving = reinterpret_cast<float4*>(c->d_rays);
+    }
+    if (stage_out && !c->hits_armed) {
+        std::vector<CopyPool::Task> arm;
+        const size_t step = size_t(1) << 16;
+        for (size_t b0 = 0; b0 < c->stage_capacity; b0 += step)
+            arm.push_back([=] { for (size_t i = b0; i < std::min(c->stage_capacity, b0 + step); i++) c->h_hits[i] = Hit1{kRecordArmed, 0.0f, 0.0f, 0.0f}; return true; });
+        CopyPool::get().run_all(arm);
+        c->hits_armed = true;
     }
     cudaEvent_t ev[2] = {};
     if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
@@ -779,6 +885,43 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (ev[1]) RB_CUDA_CHECK(cudaEventRecord(ev[1], run));
     if (copy_after) RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, run));
+    std::atomic<int> kernel_done{0};
+    if (stage_out) RB_CUDA_CHECK(cudaLaunchHostFunc(run, [](void* p) { static_cast<std::atomic<int>*>(p)->store(1, std::memory_order_release); }, &kernel_done));
+    if (stage_in) {                                          // pieces of ~4 MB: copy into the staging array, queue the copy to the device
+        const int piece = 1 << 17;
+        for (int first = 0; first < num_rays; first += piece) {
+            const int n = std::min(piece, num_rays - first);
+            CopyPool::get().parallel_copy(c->h_rays + first, rays + first, size_t(n) * sizeof(Ray1));
+            copy_in(first, n, first + n >= num_rays);
+        }
+    }
+    if (stage_out) {                                         // chunks of 512 KB of records, each taken home as far as it has arrived
+        const int chunk = 1 << 15;
+        const bool aligned_out = (reinterpret_cast<uintptr_t>(hits) & 15) == 0 && g_tuning.host_stream_stores != 0;
+        std::vector<int> pos;
+        for (int first = 0; first < num_rays; first += chunk) pos.push_back(first);
+        std::vector<CopyPool::Task> tasks;
+        for (size_t k = 0; k < pos.size(); k++)
+            tasks.push_back([&, k] {
+                const int end = std::min(num_rays, int(k + 1) * chunk);
+                std::atomic_thread_fence(std::memory_order_acquire);
+                for (int i = pos[k]; i < end; i++) {
+                    __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(c->h_hits + i));
+                    if (_mm_cvtsi128_si32(v) == kRecordArmed) {
+                        if (!kernel_done.load(std::memory_order_acquire)) { pos[k] = i; return false; }
+                        v = _mm_load_si128(reinterpret_cast<const __m128i*>(c->h_hits + i));      // the kernel is gone: everything it wrote is here
+                        if (_mm_cvtsi128_si32(v) == kRecordArmed) { std::fprintf(stderr, "rodent_b200: record %d never arrived in the staging array\n", i); std::abort(); }
+                    }
+                    if (aligned_out) _mm_stream_si128(reinterpret_cast<__m128i*>(hits + i), v);
+                    else _mm_storeu_si128(reinterpret_cast<__m128i*>(hits + i), v);
+                    c->h_hits[i].tri_id = kRecordArmed;
+                }
+                pos[k] = end;
+                _mm_sfence();
+                return true;
+            });
+        CopyPool::get().run_all(tasks);
+    }
     RB_CUDA_CHECK(cudaStreamSynchronize(run));      // (the kernel has seen every ray arrive, or the word behind the copy)
     if (ev[1]) {
         float ms = 0;
@@ -805,6 +948,7 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
         RB_CUDA_CHECK(cudaMallocHost(&c->h_rays, size_t(num_rays) * sizeof(Ray1)));
         RB_CUDA_CHECK(cudaMallocHost(&c->h_hits, size_t(num_rays) * sizeof(Hit1)));
         c->stage_capacity = size_t(num_rays);
+        c->hits_armed = false;
     }
     const Ray1* src = stage_in ? c->h_rays : rays;
     Hit1* dst = stage_out ? c->h_hits : hits;
@@ -812,8 +956,12 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     // is slower than the pieces' round trip of the caller's records: 1.79 / 1.95 against 1.13 / 1.40 ms per Mi rays)
     if constexpr (!ANY) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
-        if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && is_pinned(rays, true) && is_pinned(hits, true)) {
-            if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
+        // page-locked arrays as they are; pageable ones through the staging arrays, unless a tool is injected that may
+        // run a kernel to its end inside the launch call (the staged form queues copies after the launch)
+        const bool staged_ok = g_tuning.host_staged_direct == 2 || (g_tuning.host_staged_direct == 1 && !injected_tool());
+        const bool in_ok = stage_in ? staged_ok : is_pinned(rays, true), out_ok = stage_out ? staged_ok : is_pinned(hits, true);
+        if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && in_ok && out_ok) {
+            if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays, stage_in, stage_out)) {
                 release_host_context(s, c);
                 return;
             }
@@ -827,6 +975,7 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     // follows the last byte of input is one piece's traversal -- including its stragglers -- and its copy out, so that
     // last piece is kept small.
     c->rays_armed = false;                            // the copies below overwrite the slots run_host_direct keeps armed
+    if (stage_out) c->hits_armed = false;
     const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
     const bool ramp = g_tuning.host_ramp && pieces >= 3;      // weights 1, k-1, k-2, ..., 1: nothing runs before the first piece is in
     const int64_t parts = ramp ? int64_t(pieces - 1) * pieces / 2 + 1 : int64_t(pieces) * (pieces + 1) / 2;
@@ -1049,9 +1198,12 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value != 0;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = clamp(value, 1, 16);
     else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
+    else if (!std::strcmp(key, "host_stream_stores")) g_tuning.host_stream_stores = value != 0;
+    else if (!std::strcmp(key, "host_copy_parts")) g_tuning.host_copy_parts = clamp(value, 1, 17);
     else if (!std::strcmp(key, "host_ramp")) g_tuning.host_ramp = value != 0;
     else if (!std::strcmp(key, "host_direct")) g_tuning.host_direct = value != 0;
     else if (!std::strcmp(key, "host_direct_rays")) g_tuning.host_direct_rays = value != 0;
+    else if (!std::strcmp(key, "host_staged_direct")) g_tuning.host_staged_direct = clamp(value, 0, 2);
     else if (!std::strcmp(key, "host_direct_push")) g_tuning.host_direct_push = clamp(value, 0, 2);
     else if (!std::strcmp(key, "host_trace")) g_tuning.host_trace = value != 0;
     else if (!std::strcmp(key, "bvh2_min_blocks")) g_tuning.bvh2_min_blocks = clamp(value, 8, 12);

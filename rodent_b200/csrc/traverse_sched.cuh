@@ -233,6 +233,7 @@ constexpr int kPushShift = 4;                      // records per group: 16; at 
 //                tmin or tmax really is the all-ones NaN looks as if it had not arrived: `*copied` == epoch (written by
 //                the same stream behind the copy) ends every wait.
 constexpr unsigned kArmed = 0xFFFFFFFFu;
+constexpr int kArrivalPatience = 1 << 24;          // polls of >= 128 ns
 struct PushHome {
     static constexpr bool kActive = true;
     unsigned* counts;                              // finished records per group, zeroed by the launcher
@@ -250,10 +251,11 @@ struct PushHome {
     // the fetch functor of a kernel whose rays are arriving: wait for the slot, take the ray, re-arm the slot
     __device__ __forceinline__ void take(int i, float4& r0, float4& r1) const {
         float4* slot = arriving + 2 * i;
-        for (;;) {
+        for (int polls = 0;; polls++) {
             r0 = __ldcv(slot); r1 = __ldcv(slot + 1);
             if (__float_as_uint(r0.w) != kArmed && __float_as_uint(r1.w) != kArmed) break;
             if (peek(copied) == epoch) { r0 = __ldcv(slot); r1 = __ldcv(slot + 1); break; }
+            if (polls > kArrivalPatience) __trap();              // seconds: the copies have stopped coming; fail loudly rather than hang
             __nanosleep(128);
         }
         reinterpret_cast<unsigned*>(slot)[3] = kArmed;
@@ -278,6 +280,7 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
     w.leaf = -1; w.top_node = 0;
     int ray_idx = -1;
     bool drained = false;
+    [[maybe_unused]] int starved = 0;          // PushHome, arriving rays: polls in a row with nothing to trace and nothing to fetch
     for (;;) {
         // a finished ray leaves its lane (PushHome: its record waits there, ray_idx = -2 - index, for the warp's next refill)
         if (ray_idx >= 0 && w.finished()) {
@@ -327,7 +330,12 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
                     ok = next >= num_rays || records.arrived(min(next + __popc(idle), num_rays) - 1);
                 }
                 refill = __shfl_sync(0xffffffffu, ok, leader) != 0;
-                if (!refill && idle == 0xffffffffu) __nanosleep(256);
+                if (!refill && idle == 0xffffffffu) {
+                    __nanosleep(256);
+                    if (++starved > kArrivalPatience) __trap();
+                } else {
+                    starved = 0;
+                }
             }
         }
         if (refill) {

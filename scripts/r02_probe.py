@@ -173,6 +173,47 @@ def zero_copy():
             print(f"{name:8s} {label:30s}: {np.median(ts):.3f} ms -> {n / np.median(ts) / 1e3:.0f} Mrays/s, equal {got == want}", flush=True)
 
 
+def pageable():
+    """Host-pointer calls with pageable (numpy) buffers: threads per staging memcpy, pieces per call; one call at a time and two at once."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    nodes, tris = formats.load_bvh(testdata.sponza_bvh8())
+    sets = {}
+    for name, (tmin, tmax) in testdata.RAY_SETS.items():
+        rays = formats.load_rays(testdata.rays(name), tmin, tmax)
+        sets[name] = (rays, np.zeros(len(rays), formats.HIT1))
+    pool = ThreadPoolExecutor(2)
+    print("host cores:", os.cpu_count(), flush=True)
+
+    def step(names):
+        jobs = [pool.submit(traversal.intersect_host, nodes, tris, sets[n][0], sets[n][1]) for n in names]
+        for j in jobs:
+            j.result()
+
+    want = {}
+    for n in sets:
+        lib.tune("host_staged_direct", 0)
+        want[n] = traversal.intersect_host(nodes, tris, sets[n][0]).tobytes()
+    for staged, parts, nt in ((0, 4, 0), (0, 4, 1), (0, 8, 1), (1, 4, 0), (1, 4, 1), (1, 8, 1)):
+        if True:
+            lib.tune("host_staged_direct", staged); lib.tune("host_copy_parts", parts); lib.tune("host_stream_stores", nt)
+            row = []
+            for names in (("primary",), ("random",), ("random", "primary")):
+                for n in names:
+                    sets[n][1][:] = 0
+                for _ in range(3):
+                    step(names)
+                ok = all(sets[n][1].tobytes() == want[n] for n in names)
+                ts = []
+                for _ in range(12):
+                    t0 = time.perf_counter(); step(names); ts.append((time.perf_counter() - t0) * 1e3)
+                ok &= all(sets[n][1].tobytes() == want[n] for n in names)
+                row.append(f"{'+'.join(names)} {np.median(ts):.3f} ms ({'ok' if ok else 'WRONG'})")
+            print(f"staged direct {staged}, {parts} threads per copy, non-temporal stores {nt}: " + ", ".join(row) + f"  [{lib.load().rodent_b200_last_kernel_name(0).decode()}]", flush=True)
+    lib.tune("host_staged_direct", 1); lib.tune("host_stream_stores", 1)
+    lib.tune("host_copy_parts", 4); lib.tune("host_chunks", 5)
+
+
 def sbvh():
     """Sponza render through the reference file's BVH2 block against a BVH2 from this repository's split-BVH builder."""
     from rodent_b200 import render as R, workloads
@@ -211,5 +252,7 @@ if __name__ == "__main__":
         e2e_direct()
     if "zero_copy" in what:
         zero_copy()
+    if "pageable" in what:
+        pageable()
     if "sbvh" in what:
         sbvh()

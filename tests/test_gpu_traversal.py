@@ -183,14 +183,21 @@ def test_host_bvh_cache_follows_the_content(sponza, ray_sets, oracle_hits):
 
 
 def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
-    """Pinned caller buffers are copied by DMA as they are, pageable ones through the library's staging memory (or, with
-    the staging switched off, by the driver): same records every way, closest and any hit."""
+    """Pinned caller buffers are used as they are, pageable ones go through the library's staging memory (or, with the
+    staging switched off, to the driver): same records every way -- with and without non-temporal staging copies, one
+    buffer pinned and the other not --, closest and any hit."""
     from rodent_b200 import lib, traversal
     nodes, tris = sponza
     n = 300001
     rays = np.ascontiguousarray(ray_sets["random"][:n])
     want = oracle_hits["random"][:n]
     assert_records_equal(traversal.intersect_host(nodes, tris, rays), want)                      # pageable, staged
+    lib.tune("host_stream_stores", 0)
+    try:
+        assert_records_equal(traversal.intersect_host(nodes, tris, rays[1:]), want[1:])          # (and an odd address)
+    finally:
+        lib.tune("host_stream_stores", 1)
+    assert_records_equal(traversal.intersect_host(nodes, tris, rays[1:]), want[1:])
     lib.tune("host_staging", 0)
     try:
         assert_records_equal(traversal.intersect_host(nodes, tris, rays), want)                  # pageable, driver-staged
@@ -201,6 +208,8 @@ def test_host_buffers_pageable_and_pinned(sponza, ray_sets, oracle_hits):
     assert_records_equal(traversal.intersect_host(nodes, tris, pin_r.array, pin_h.array).copy(), want)     # pinned
     mixed = traversal.intersect_host(nodes, tris, pin_r.array)                                    # pinned in, pageable out
     assert_records_equal(mixed, want)
+    pin_h.array[:] = 0
+    assert_records_equal(traversal.intersect_host(nodes, tris, rays, pin_h.array).copy(), want)   # pageable in, pinned out
     pre = np.zeros(n, formats.HIT1)
     pre["t"] = 7.0
     occl = traversal.intersect_host(nodes, tris, rays, hits=pre, any_hit=True)
@@ -249,9 +258,18 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
     assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
     assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<false, 8>"
     assert traversal.unpin_host(own_r) and traversal.unpin_host(own_h) and not traversal.unpin_host(own_h)
-    own_h[:] = 0
-    assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
-    assert L.rodent_b200_last_kernel_name(0).decode().startswith("traverse_bvh8_vote")
+    # pageable again: the same single launch, fed through the library's staging arrays by helper threads -- or, switched
+    # off (as under an injected profiling tool), the copy-engine pieces
+    for staged, kernel in ((1, "traverse_direct<false, 8>"), (0, "traverse_bvh8_vote"), (2, "traverse_direct<false, 8>")):
+        lib.tune("host_staged_direct", staged)
+        try:
+            for n in (70001, 17, 40000):
+                own_h[:] = 0
+                assert_records_equal(traversal.intersect_host(nodes, tris, own_r[:n], own_h[:n]), oracle_hits["primary"][:n])
+                assert L.rodent_b200_last_kernel_name(0).decode().startswith(kernel)
+                assert not own_h[n:].view(np.uint8).any()
+        finally:
+            lib.tune("host_staged_direct", 1)
     # rays whose tmin or tmax is the all-ones NaN look like slots that have not arrived: the call still ends, with the
     # records the device-pointer entry point gives for the same rays
     odd = traversal.PinnedArray(formats.RAY1, 40000)
