@@ -49,13 +49,16 @@ typedef struct {
     double r_sm, r_warp;   /* issue rates, warp instructions per cycle */
     int warps_per_sm;
     double k_push, k_sort, k_refill, k_loop;   /* what-if scales of the push, sort, refill and loop-overhead costs (1: as measured) */
+    int postpone;          /* > 0: a lane that reaches a leaf keeps it pending and goes on with node steps until it reaches the
+                              next leaf (Aila-Laine's speculative traversal); a leaf step runs once this many lanes hold one.
+                              Optimistic: the same steps in another order, the extra node visits under the stale tmax not counted */
 } Policy;
 
 enum { SMS = 148 };
 enum { C_LOOP = 60, C_STREAK = 12, C_REFILL = 45, C_INIT = 130, C_NODE = 212, C_PUSH = 15, C_CHAIN_SLOT = 9, C_CHAIN_BASE = 16,
        C_SORT4 = 63, C_SORT8 = 153, C_CULL = 9, C_LEAF = 195, C_DUMP = 90, C_RESTORE = 110, C_VOTE_SORT = 8 };
 
-typedef struct { int ray; size_t pos, end; int need_sort; int age; } Lane;
+typedef struct { int ray; size_t pos, end; int need_sort; int age; size_t ppos, pend; } Lane;   /* [ppos, pend): the pending leaf run */
 typedef struct { Lane l[32]; int sm; int alive; int drained; double t; } Warp;
 
 typedef struct { double cat[8]; double time_us, drained_us, k1_us; double warp_inst, thread_inst; double node_exec, node_lanes, leaf_exec, leaf_lanes, sort_exec, sort_lanes; long orphans; } Result;
@@ -129,7 +132,7 @@ static Result simulate(const size_t* start, int num_rays, const Policy* P) {
         const int slots = quad ? 32 / P->orphan_quad : 32;
         /* finished rays leave */
         int idle = 0, live = 0;
-        for (int i = 0; i < slots; i++) { Lane* q = &w->l[i]; if (q->ray >= 0 && q->pos == q->end && !q->need_sort) q->ray = -1; if (q->ray < 0) idle++; else live++; }
+        for (int i = 0; i < slots; i++) { Lane* q = &w->l[i]; if (q->ray >= 0 && q->pos == q->end && !q->need_sort && q->ppos == q->pend) q->ray = -1; if (q->ray < 0) idle++; else live++; }
         /* hand old rays over */
         if (!phase2 && P->age_limit > 0) {
             int moved = 0;
@@ -145,7 +148,7 @@ static Result simulate(const size_t* start, int num_rays, const Policy* P) {
                     if (orph_taken < n_orph) { Orphan o = orph[orph_taken++]; q->ray = o.ray; q->pos = o.pos; q->end = o.end; q->age = o.age; q->need_sort = 0; took_orph++; live++; continue; }
                     if (phase2) continue;
                 }
-                if (next_ray < num_rays) { q->ray = next_ray; q->pos = start[next_ray]; q->end = start[next_ray + 1]; q->age = 0; q->need_sort = 0; next_ray++; took++; live++; }
+                if (next_ray < num_rays) { q->ray = next_ray; q->pos = start[next_ray]; q->end = start[next_ray + 1]; q->age = 0; q->need_sort = 0; q->ppos = q->pend = 0; next_ray++; took++; live++; }
             }
             if (took) cost += P->k_refill * C_INIT;
             if (took_orph) cost += C_RESTORE;
@@ -159,6 +162,47 @@ static Result simulate(const size_t* start, int num_rays, const Policy* P) {
         }
         /* vote */
         unsigned bn = 0, bl = 0, bs = 0;
+        if (P->postpone > 0) {
+            unsigned must = 0;                                     /* lanes that can only go on with a leaf step */
+            for (int i = 0; i < slots; i++) { Lane* q = &w->l[i]; if (q->ray < 0) continue;
+                if (q->ppos == q->pend && q->pos < q->end && g_steps[q->pos].kind == 'L') {      /* reached a leaf: keep it pending, look past it */
+                    q->ppos = q->pos; while (q->pos < q->end && g_steps[q->pos].kind == 'L') q->pos++; q->pend = q->pos;
+                }
+                const int can_node = q->pos < q->end && g_steps[q->pos].kind == 'N';
+                if (q->ppos < q->pend) { bl |= 1u << i; if (!can_node) must |= 1u << i; }
+                if (can_node) bn |= 1u << i;
+            }
+            /* leaf step when enough lanes hold one, or more lanes are stuck behind theirs than can take a node step */
+            const int cl = __builtin_popcount(bl), cn = __builtin_popcount(bn), cm = __builtin_popcount(must);
+            if (cl > 0 && (cl >= P->postpone || cn == 0 || cm > cn)) {
+                int maxcull = 0;
+                for (int i = 0; i < 32; i++) if (bl & (1u << i)) { Lane* q = &w->l[i]; if (g_steps[q->ppos].culls > maxcull) maxcull = g_steps[q->ppos].culls; q->ppos++; q->age++; }
+                cost += P->k_loop * C_LOOP + C_LEAF + C_CULL * maxcull;
+                R.leaf_exec++; R.leaf_lanes += cl; R.thread_inst += (double)C_LEAF * cl;
+                bn = bl = 0;
+            } else if (cn > 0) {
+                unsigned go = bn; int first = 1;
+                cost += P->k_loop * C_LOOP;
+                do {
+                    int any_sort;
+                    cost += node_cost(P, w, go, &R, &any_sort) + (first ? 0 : C_STREAK);
+                    first = 0; go = 0;
+                    for (int i = 0; i < slots; i++) { Lane* q = &w->l[i]; if (q->ray >= 0 && q->pos < q->end && g_steps[q->pos].kind == 'N') go |= 1u << i; }
+                } while (__builtin_popcount(go) >= P->streak_min);
+                bn = bl = 0;
+            } else if (live == 0 && w->drained) {
+                w->alive = 0; active[w->sm]--; t_end = w->t > t_end ? w->t : t_end;
+                R.warp_inst += cost;
+                continue;
+            } else {
+                cost += P->k_loop * C_LOOP;
+            }
+            R.warp_inst += cost;
+            double rate2 = P->r_sm / active[w->sm]; if (rate2 > P->r_warp) rate2 = P->r_warp;
+            w->t += cost / rate2;
+            heap_push(wi);
+            continue;
+        }
         for (int i = 0; i < slots; i++) { Lane* q = &w->l[i]; if (q->ray < 0) continue;
             if (q->need_sort) bs |= 1u << i; else if (q->pos < q->end) { if (g_steps[q->pos].kind == 'N') bn |= 1u << i; else bl |= 1u << i; } }
         cost += P->k_loop * C_LOOP + (P->sort_phase ? C_VOTE_SORT : 0);
@@ -256,7 +300,7 @@ int main(int argc, char** argv) {
     }
     start[num_rays] = g_len;
     fprintf(stderr, "rays %d steps %zu (%.2f per ray)\n", num_rays, g_len, (double)g_len / num_rays);
-    const Policy base = {24, 8, 0, 0, 0, 0, 1, 0, 1.95, 0.40, 20, 1, 1, 1, 1};
+    const Policy base = {24, 8, 0, 0, 0, 0, 1, 0, 1.95, 0.40, 20, 1, 1, 1, 1, 0};
     struct { const char* name; Policy p; } cfg[64]; int nc = 0;
     cfg[nc].name = "current (refill 24, streak 8)"; cfg[nc++].p = base;
     { Policy p = base; p.refill_min = 16; cfg[nc].name = "refill 16"; cfg[nc++].p = p; }
@@ -278,6 +322,7 @@ int main(int argc, char** argv) {
     { Policy p = base; p.refill_min = 16; p.streak_min = 4; cfg[nc].name = "refill 16 streak 4"; cfg[nc++].p = p; }
     { Policy p = base; p.refill_min = 16; p.streak_min = 12; cfg[nc].name = "refill 16 streak 12"; cfg[nc++].p = p; }
     { Policy p = base; p.warps_per_sm = 24; p.r_sm = 2.1; cfg[nc].name = "24 warps per SM (r_sm 2.1)"; cfg[nc++].p = p; }
+    for (int m = 8; m <= 32; m += 8) { Policy p = base; p.postpone = m; char* nm = malloc(64); sprintf(nm, "postponed leaves, leaf step at >= %d lanes", m); cfg[nc].name = nm; cfg[nc++].p = p; }
     for (int m = 4; m <= 12; m += 2) { Policy p = base; p.sort_phase = 1; p.sort_min = m; p.chain_push = 1; char* nm = malloc(64); sprintf(nm, "chain push + sort phase at >= %d lanes", m); cfg[nc].name = nm; cfg[nc++].p = p; }
     for (int c = 0; c < nc; c++) {
         Result r = simulate(start, num_rays, &cfg[c].p);
