@@ -233,7 +233,7 @@ constexpr int kPushShift = 4;                      // records per group: 16; at 
 //                tmin or tmax really is the all-ones NaN looks as if it had not arrived: `*copied` == epoch (written by
 //                the same stream behind the copy) ends every wait.
 constexpr unsigned kArmed = 0xFFFFFFFFu;
-constexpr int kArrivalPatience = 1 << 24;          // polls of >= 128 ns
+constexpr int kArrivalPatience = 1 << 26;          // polls of >= 128 ns: tens of seconds
 struct PushHome {
     static constexpr bool kActive = true;
     unsigned* counts;                              // finished records per group, zeroed by the launcher
