@@ -47,6 +47,21 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+SHIM = PKG / "librodent_b200_refnames.so"
+
+
+def build_shim(force: bool = False) -> Path:
+    """librodent_b200_refnames.so: the entry points under the reference's own exported names (cpu_*, nvvm_*), forwarding to librodent_b200.so."""
+    src = PKG / "shim" / "reference_names.cpp"
+    if not force and _newer(SHIM, [src, ROOT / "include" / "rodent_b200.h"]):
+        return SHIM
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-o", str(SHIM), str(src),
+           f"-L{PKG}", "-lrodent_b200", "-Wl,-rpath,$ORIGIN"]
+    print("+", " ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return SHIM
+
+
 def build_tools(force: bool = False) -> None:
     """ray_gen, fbuf2png, and -- linked against librodent_b200.so -- bench_traversal, bench_interface, bench_shading, bvh_extractor, converter, rodent."""
     (TOOLS / "bin").mkdir(exist_ok=True)
@@ -80,6 +95,7 @@ def build_tools(force: bool = False) -> None:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force, verbose)
+    build_shim(force)
     build_tools(force)
 
 

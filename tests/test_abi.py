@@ -43,3 +43,28 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         lib.load()
+
+
+def reference_names():
+    """What the reference's objects export for this path (`extern fn` of tools/bench_traversal/bench_traversal.impala:159-493,
+    tools/bench_shading/bench_shading.impala:22)."""
+    names = [f"cpu_{op}_{kind}_ray{w}_bvh{a}_tri4" for a in (4, 8) for kind in ("packet", "hybrid") for w in (4, 8) for op in ("intersect", "occluded")]
+    names += [f"cpu_{op}_single_ray1_bvh{a}_tri4" for a in (4, 8) for op in ("intersect", "occluded")]
+    names += ["nvvm_intersect_single_ray1_bvh2_tri1", "nvvm_occluded_single_ray1_bvh2_tri1", "cpu_bench_shading"]
+    return names
+
+
+def test_shim_exports_the_reference_names():
+    """librodent_b200_refnames.so: linked instead of the reference's generated traversal object, it gives the reference's
+    own programs their symbols; it forwards to librodent_b200.so (loaded through its rpath)."""
+    import subprocess
+    from rodent_b200 import build
+    build.build_cuda()
+    shim = build.build_shim()
+    S = ctypes.CDLL(str(shim))
+    names = reference_names()
+    assert len(names) == 23
+    for name in names:
+        assert hasattr(S, name), f"{name} missing from the shim"
+    exported = subprocess.run(["nm", "-D", "--defined-only", str(shim)], capture_output=True, text=True, check=True).stdout
+    assert sorted(line.split()[-1] for line in exported.splitlines() if " T " in line) == sorted(names)

@@ -318,6 +318,27 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
         a.free()
 
 
+def test_reference_names_shim(sponza, ray_sets, oracle_hits):
+    """cpu_intersect_single_ray1_bvh8_tri4 / cpu_occluded_... of librodent_b200_refnames.so: the reference's own symbol, host
+    pointers, the oracle's records."""
+    import ctypes
+    from rodent_b200 import build
+    S = ctypes.CDLL(str(build.build_shim()))
+    nodes, tris = sponza
+    n = 50001
+    rays = np.ascontiguousarray(ray_sets["random"][:n])
+    hits = np.zeros(n, formats.HIT1)
+    args = [ctypes.c_void_p(a.ctypes.data) for a in (nodes, tris, rays, hits)] + [ctypes.c_int32(n)]
+    S.cpu_intersect_single_ray1_bvh8_tri4.restype = None
+    S.cpu_intersect_single_ray1_bvh8_tri4(*args)
+    assert_records_equal(hits, oracle_hits["random"][:n])
+    hits[:] = 0
+    hits["t"] = 3.0
+    S.cpu_occluded_single_ray1_bvh8_tri4.restype = None
+    S.cpu_occluded_single_ray1_bvh8_tri4(*args)
+    assert ((hits["tri_id"] >= 0) == (oracle_hits["random"][:n]["tri_id"] >= 0)).all() and (hits["t"] == 3.0).all()
+
+
 def test_host_entry_points_are_reentrant(sponza, ray_sets, oracle_hits):
     """The cpu_* functions are pure; their drop-ins may be called from several host threads at once -- different sets,
     sizes and closest / any hit mixed, repeatedly (contexts are reused)."""
