@@ -49,6 +49,7 @@ typedef struct {
     double r_sm, r_warp;   /* issue rates, warp instructions per cycle */
     int warps_per_sm;
     double k_push, k_sort, k_refill, k_loop;   /* what-if scales of the push, sort, refill and loop-overhead costs (1: as measured) */
+    int coop_sort;         /* > 0: when at most this many lanes of a node step need a sort, the warp sorts them together (what if) */
     int postpone;          /* > 0: a lane that reaches a leaf keeps it pending and goes on with node steps until it reaches the
                               next leaf (Aila-Laine's speculative traversal); a leaf step runs once this many lanes hold one.
                               Optimistic: the same steps in another order, the extra node visits under the stale tmax not counted */
@@ -56,7 +57,7 @@ typedef struct {
 
 enum { SMS = 148 };
 enum { C_LOOP = 60, C_STREAK = 12, C_REFILL = 45, C_INIT = 130, C_NODE = 212, C_PUSH = 15, C_CHAIN_SLOT = 9, C_CHAIN_BASE = 16,
-       C_SORT4 = 63, C_SORT8 = 153, C_CULL = 9, C_LEAF = 195, C_DUMP = 90, C_RESTORE = 110, C_VOTE_SORT = 8 };
+       C_SORT4 = 63, C_SORT8 = 153, C_COOP_SORT = 95, C_CULL = 9, C_LEAF = 195, C_DUMP = 90, C_RESTORE = 110, C_VOTE_SORT = 8 };
 
 typedef struct { int ray; size_t pos, end; int need_sort; int age; size_t ppos, pend; } Lane;   /* [ppos, pend): the pending leaf run */
 typedef struct { Lane l[32]; int sm; int alive; int drained; double t; } Warp;
@@ -89,8 +90,13 @@ static double node_cost(const Policy* P, Warp* w, unsigned go, Result* R, int* a
     }
     if (P->chain_push) c += C_CHAIN_BASE + C_CHAIN_SLOT * __builtin_popcount(un);
     else c += P->k_push * C_PUSH * __builtin_popcount(blocks);
+    if (P->coop_sort > 0 && s4 + s8 > 0 && s4 + s8 <= P->coop_sort) {
+        /* the warp sorts up to eight lanes' entries together, four lanes per job, one comparator per lane and layer */
+        c += C_COOP_SORT * ((s4 + s8 + 7) / 8); R->sort_exec++; R->sort_lanes += 4 * (s4 + s8); R->thread_inst += C_COOP_SORT * 4 * (s4 + s8);
+    } else {
     if (s4) { c += P->k_sort * C_SORT4; R->sort_exec++; R->sort_lanes += s4; R->thread_inst += C_SORT4 * s4; }
     if (s8) { c += P->k_sort * C_SORT8; R->sort_exec++; R->sort_lanes += s8; R->thread_inst += C_SORT8 * s8; }
+    }
     c += C_CULL * maxcull;
     R->node_exec++; R->node_lanes += lanes; R->thread_inst += (double)C_NODE * lanes;
     *any_sort = s4 + s8;
@@ -300,7 +306,7 @@ int main(int argc, char** argv) {
     }
     start[num_rays] = g_len;
     fprintf(stderr, "rays %d steps %zu (%.2f per ray)\n", num_rays, g_len, (double)g_len / num_rays);
-    const Policy base = {24, 8, 0, 0, 0, 0, 1, 0, 1.95, 0.40, 20, 1, 1, 1, 1, 0};
+    const Policy base = {24, 8, 0, 0, 0, 0, 1, 0, 1.95, 0.40, 20, 1, 1, 1, 1, 0, 0};
     struct { const char* name; Policy p; } cfg[64]; int nc = 0;
     cfg[nc].name = "current (refill 24, streak 8)"; cfg[nc++].p = base;
     { Policy p = base; p.refill_min = 16; cfg[nc].name = "refill 16"; cfg[nc++].p = p; }
@@ -322,6 +328,9 @@ int main(int argc, char** argv) {
     { Policy p = base; p.refill_min = 16; p.streak_min = 4; cfg[nc].name = "refill 16 streak 4"; cfg[nc++].p = p; }
     { Policy p = base; p.refill_min = 16; p.streak_min = 12; cfg[nc].name = "refill 16 streak 12"; cfg[nc++].p = p; }
     { Policy p = base; p.warps_per_sm = 24; p.r_sm = 2.1; cfg[nc].name = "24 warps per SM (r_sm 2.1)"; cfg[nc++].p = p; }
+    { Policy p = base; p.coop_sort = 8; cfg[nc].name = "cooperative sort when <= 8 lanes need one"; cfg[nc++].p = p; }
+    { Policy p = base; p.coop_sort = 16; cfg[nc].name = "cooperative sort when <= 16 lanes need one"; cfg[nc++].p = p; }
+    { Policy p = base; p.coop_sort = 8; p.chain_push = 1; cfg[nc].name = "cooperative sort <= 8 + chain push"; cfg[nc++].p = p; }
     for (int m = 8; m <= 32; m += 8) { Policy p = base; p.postpone = m; char* nm = malloc(64); sprintf(nm, "postponed leaves, leaf step at >= %d lanes", m); cfg[nc].name = nm; cfg[nc++].p = p; }
     for (int m = 4; m <= 12; m += 2) { Policy p = base; p.sort_phase = 1; p.sort_min = m; p.chain_push = 1; char* nm = malloc(64); sprintf(nm, "chain push + sort phase at >= %d lanes", m); cfg[nc].name = nm; cfg[nc++].p = p; }
     for (int c = 0; c < nc; c++) {
