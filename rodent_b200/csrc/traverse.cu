@@ -56,7 +56,7 @@ struct Tuning {
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
-    int host_direct = 1;     // host-pointer entry points, pinned buffers, BVH8: one launch per call, rays read and records written over PCIe by the kernel itself (0: copy-engine pieces)
+    int host_direct = 1;     // host-pointer entry points, closest hit: one launch per call that follows its rays as they arrive and sends its records home itself (run_host_direct; 0: copy-engine pieces)
     int host_direct_rays = 1;    // ... 1 = a copy engine brings the rays in while the kernel runs (armed slots, traverse_sched.cuh), 0 = the warps read them from the caller's memory as they refill
     int host_staged_direct = 1;  // ... pageable buffers through the staging arrays with the same single launch: 1 = unless a profiling tool is injected, 2 = always, 0 = never (copy-engine pieces)
     int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
