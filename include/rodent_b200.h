@@ -226,6 +226,9 @@ void    rodent_b200_free_host(void* ptr);
  * staging).  0 on success, -1 when the driver refuses (not page-lockable, already registered, unknown pointer). */
 int32_t rodent_b200_pin_host(void* ptr, size_t bytes);
 int32_t rodent_b200_unpin_host(void* ptr);
+/* Checks the host side of the pageable-buffer path (helper-thread pool, staging copies) without touching a device:
+ * 0 when everything checks out.  tests/test_abi.py runs it where there is no GPU. */
+int32_t rodent_b200_selftest_host_copies(void);
 void    rodent_b200_copy_to_device(int32_t dev, void* dst, const void* src, size_t bytes);
 void    rodent_b200_copy_to_host(int32_t dev, void* dst, const void* src, size_t bytes);
 void    rodent_b200_sync(int32_t dev);

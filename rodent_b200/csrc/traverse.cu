@@ -1136,6 +1136,42 @@ int32_t rodent_b200_pin_host(void* ptr, size_t bytes) {
     if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); return -1; }
     return 0;
 }
+// The host side of the pageable-buffer path without a device: the helper-thread pool and the staging copies (plain and
+// non-temporal) over odd sizes and alignments, tasks that ask to be run again.  0 when everything checks out.
+int32_t rodent_b200_selftest_host_copies(void) {
+    const size_t n = (size_t(5) << 20) + 777;
+    std::vector<unsigned char> src(n + 64), dst(n + 64), want(n + 64);
+    for (size_t i = 0; i < src.size(); i++) src[i] = static_cast<unsigned char>(i * 2654435761u >> 24);
+    int bad = 0;
+    const int saved_parts = g_tuning.host_copy_parts, saved_stream = g_tuning.host_stream_stores;
+    for (int stream = 0; stream < 2; stream++)
+        for (int parts : {1, 3, 4, 9})
+            for (size_t off : {size_t(0), size_t(1), size_t(13), size_t(16)})
+                for (size_t bytes : {size_t(0), size_t(1), size_t(63), size_t(64), size_t(4097), n - 16}) {
+                    g_tuning.host_stream_stores = stream; g_tuning.host_copy_parts = parts;
+                    std::fill(dst.begin(), dst.end(), static_cast<unsigned char>(0xA5));
+                    want = dst;
+                    std::memcpy(want.data() + off, src.data() + 3, bytes);
+                    CopyPool::get().parallel_copy(dst.data() + off, src.data() + 3, bytes);
+                    bad += dst != want;
+                    std::fill(dst.begin(), dst.end(), static_cast<unsigned char>(0xA5));
+                    if (stream) stream_copy(dst.data() + off, src.data() + 3, bytes); else std::memcpy(dst.data() + off, src.data() + 3, bytes);
+                    bad += dst != want;
+                }
+    g_tuning.host_copy_parts = saved_parts; g_tuning.host_stream_stores = saved_stream;
+    // tasks that are not finished the first few times they run, from two callers at once
+    auto batch = [&bad] {
+        std::vector<int> runs(40, 0);
+        std::vector<CopyPool::Task> tasks;
+        for (size_t k = 0; k < runs.size(); k++) tasks.push_back([&runs, k] { return ++runs[k] > int(k % 4); });
+        CopyPool::get().run_all(tasks);
+        for (size_t k = 0; k < runs.size(); k++) if (runs[k] != int(k % 4) + 1) __atomic_fetch_add(&bad, 1, __ATOMIC_RELAXED);
+    };
+    std::thread other(batch);
+    batch();
+    other.join();
+    return bad;
+}
 int32_t rodent_b200_unpin_host(void* ptr) {
     if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return -1; }
     return 0;

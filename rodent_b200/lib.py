@@ -51,6 +51,7 @@ SIGNATURES = {
     "rodent_b200_free_host": (None, [c_void_p]),
     "rodent_b200_pin_host": (c_int32, [c_void_p, c_size_t]),
     "rodent_b200_unpin_host": (c_int32, [c_void_p]),
+    "rodent_b200_selftest_host_copies": (c_int32, []),
     "rodent_b200_copy_to_device": (None, [c_int32, c_void_p, c_void_p, c_size_t]),
     "rodent_b200_copy_to_host": (None, [c_int32, c_void_p, c_void_p, c_size_t]),
     "rodent_b200_sync": (None, [c_int32]),

@@ -68,3 +68,10 @@ def test_shim_exports_the_reference_names():
         assert hasattr(S, name), f"{name} missing from the shim"
     exported = subprocess.run(["nm", "-D", "--defined-only", str(shim)], capture_output=True, text=True, check=True).stdout
     assert sorted(line.split()[-1] for line in exported.splitlines() if " T " in line) == sorted(names)
+
+
+def test_host_side_of_the_pageable_path_without_a_device():
+    """The helper-thread pool and the staging copies (plain and non-temporal stores, odd sizes and alignments, tasks that
+    ask to be run again, two callers at once) need no GPU: the library checks them itself."""
+    from rodent_b200 import lib
+    assert lib.load().rodent_b200_selftest_host_copies() == 0
