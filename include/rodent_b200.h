@@ -145,8 +145,8 @@ void cuda_occluded_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, 
  * closest-hit call (BVH8 or BVH4) is ONE launch: a copy engine brings the rays in while the kernel already traces the first of
  * them, and the kernel writes its records into the caller's array itself (traverse.cu: run_host_direct).  Pageable
  * buffers (malloc, std::vector, anydsl::Array host memory) go through the library's own pinned staging buffers, filled
- * and drained by a few helper threads while that same launch runs; any-hit calls are cut into copy / launch / copy
- * pieces instead.
+ * and drained by a few helper threads while that same launch runs.  Any-hit calls bring home the triangle ids only;
+ * the helper threads write them into the caller's records, whose t, u, v are never touched.
  * Like the cpu_* functions they replace, the calls are reentrant: each takes its own device
  * staging buffers and streams, so calls from several host threads overlap on the device (one set's transfers under
  * another set's traversal). */

@@ -176,7 +176,10 @@ traverse_direct(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
             const float4* rp = reinterpret_cast<const float4*>(caller_rays + i);
             r0 = ldg4(rp); r1 = ldg4(rp + 1);        // (ld.global.cv of 16 bytes per lane over PCIe is ten times slower)
         },
-        [hits](int i, const HitRecord& h) { store_hit<ANY>(hits, i, h); }, node_streak_min, records);
+        [hits, records](int i, const HitRecord& h) {
+            if (ANY && records.counts != nullptr) reinterpret_cast<int32_t*>(hits)[i] = h.prim;      // the dense id array (see PushHome)
+            else store_hit<ANY>(hits, i, h);
+        }, node_streak_min, records);
 }
 
 // The same loop over a BVH4 (Node4: 6 rows of 4 floats, 4 children; leaves are Tri4 as well): the CPU single-ray
@@ -358,6 +361,7 @@ struct HostContext {
     Ray1* h_rays = nullptr; Hit1* h_hits = nullptr; size_t stage_capacity = 0;
     cudaEvent_t piece_done[16] = {};
     unsigned* group_counts = nullptr; size_t group_capacity = 0;   // run_host_direct: finished records per group of 16 rays
+    int32_t* h_ids = nullptr; size_t ids_capacity = 0;   // any-hit calls: the triangle ids as they come home (pinned, armed with kRecordArmed)
     bool hits_armed = false;               // every record of h_hits carries kRecordArmed in tri_id (the copy-out re-arms what it takes)
     bool rays_armed = false;               // every slot of d_rays carries the all-ones words (the kernel re-arms what it takes)
     unsigned* copied = nullptr; unsigned* epochs = nullptr; unsigned epoch = 0;   // device word / pinned values: "this call's rays are all in"
@@ -837,8 +841,19 @@ template <bool ANY, typename NodeT>
 static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays,
                             bool stage_in = false, bool stage_out = false) {
     constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
+    // Any hit: only tri_id changes.  The ids come home as a dense array (pinned, armed) and the helper threads write them
+    // into the caller's records as they arrive -- whatever memory those are in, so nothing is staged on the way out.
+    if (ANY) {
+        stage_out = false;
+        if (c->ids_capacity < size_t(num_rays) + 64) {
+            if (c->h_ids) RB_CUDA_CHECK(cudaFreeHost(c->h_ids));
+            c->ids_capacity = size_t(num_rays) + 64;
+            RB_CUDA_CHECK(cudaMallocHost(&c->h_ids, c->ids_capacity * sizeof(int32_t)));
+            std::fill(c->h_ids, c->h_ids + c->ids_capacity, kRecordArmed);
+        }
+    }
     const Ray1* src = stage_in ? c->h_rays : rays;
-    Hit1* home = stage_out ? c->h_hits : hits;
+    Hit1* home = ANY ? reinterpret_cast<Hit1*>(c->h_ids) : stage_out ? c->h_hits : hits;
     const Ray1* caller_rays = nullptr; Hit1* caller_hits = nullptr;
     if (cudaHostGetDevicePointer(const_cast<void**>(reinterpret_cast<const void**>(&caller_rays)), const_cast<Ray1*>(src), 0) != cudaSuccess ||
         cudaHostGetDevicePointer(reinterpret_cast<void**>(&caller_hits), home, 0) != cudaSuccess) {
@@ -847,7 +862,7 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
     }
     cudaStream_t run = c->streams[0];
     const bool staged = stage_in || stage_out;
-    const bool push = staged || g_tuning.host_direct_push == 1, copy_after = !staged && g_tuning.host_direct_push == 2;
+    const bool push = ANY || staged || g_tuning.host_direct_push == 1, copy_after = !push && g_tuning.host_direct_push == 2;
     const bool by_copy_engine = staged || g_tuning.host_direct_rays;
     PushHome records{push ? c->group_counts : nullptr, reinterpret_cast<const float4*>(c->d_hits), reinterpret_cast<float4*>(caller_hits), nullptr, c->copied, ++c->epoch};
     unsigned* epoch_value = c->epochs + (records.epoch & 7);
@@ -874,11 +889,11 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
     }
     cudaEvent_t ev[2] = {};
     if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
-    if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> kPushShift) + 1) * sizeof(unsigned), run));
+    if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> (ANY ? kPushShiftIds : kPushShift)) + 1) * sizeof(unsigned), run));
     RB_CUDA_CHECK(cudaMemsetAsync(c->counters, 0, sizeof(int), run));
     const int per_sm = g_tuning.blocks_per_sm > 0 ? g_tuning.blocks_per_sm : occupancy(s, reinterpret_cast<const void*>(traverse_direct<ANY, ARITY>), kBlock);
     const int grid = std::min((num_rays + kBlock - 1) / kBlock, s.sm_count * per_sm);
-    s.last_kernel = ARITY == 8 ? "traverse_direct<false, 8>" : "traverse_direct<false, 4>";
+    s.last_kernel = ANY ? (ARITY == 8 ? "traverse_direct<true, 8>" : "traverse_direct<true, 4>") : (ARITY == 8 ? "traverse_direct<false, 8>" : "traverse_direct<false, 4>");
     traverse_direct<ANY, ARITY><<<grid, kBlock, 0, run>>>(d_nodes, d_tris, caller_rays, push || copy_after ? c->d_hits : caller_hits, num_rays, c->counters,
                                                          g_tuning.refill_min, g_tuning.node_streak_min, records);
     RB_CUDA_CHECK(cudaGetLastError());
@@ -886,7 +901,7 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
     if (ev[1]) RB_CUDA_CHECK(cudaEventRecord(ev[1], run));
     if (copy_after) RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, run));
     std::atomic<int> kernel_done{0};
-    if (stage_out) RB_CUDA_CHECK(cudaLaunchHostFunc(run, [](void* p) { static_cast<std::atomic<int>*>(p)->store(1, std::memory_order_release); }, &kernel_done));
+    if (stage_out || ANY) RB_CUDA_CHECK(cudaLaunchHostFunc(run, [](void* p) { static_cast<std::atomic<int>*>(p)->store(1, std::memory_order_release); }, &kernel_done));
     if (stage_in) {                                          // pieces of ~4 MB: copy into the staging array, queue the copy to the device
         const int piece = 1 << 17;
         for (int first = 0; first < num_rays; first += piece) {
@@ -922,6 +937,31 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
             });
         CopyPool::get().run_all(tasks);
     }
+    if (ANY) {                                               // chunks of 128 KB of ids, each written into the records as far as it has arrived
+        const int chunk = 1 << 15;
+        std::vector<int> pos;
+        for (int first = 0; first < num_rays; first += chunk) pos.push_back(first);
+        std::vector<CopyPool::Task> tasks;
+        for (size_t k = 0; k < pos.size(); k++)
+            tasks.push_back([&, k] {
+                const int end = std::min(num_rays, int(k + 1) * chunk);
+                std::atomic_thread_fence(std::memory_order_acquire);
+                for (int i = pos[k]; i < end; i++) {
+                    int32_t v = *const_cast<volatile int32_t*>(c->h_ids + i);
+                    if (v == kRecordArmed) {
+                        if (!kernel_done.load(std::memory_order_acquire)) { pos[k] = i; return false; }
+                        v = *const_cast<volatile int32_t*>(c->h_ids + i);                          // the kernel is gone: everything it wrote is here
+                        if (v == kRecordArmed) { std::fprintf(stderr, "rodent_b200: the id of ray %d never arrived\n", i); std::abort(); }
+                    }
+                    hits[i].tri_id = v;
+                    c->h_ids[i] = kRecordArmed;
+                }
+                if (end == num_rays) for (int i = end; i < ((end + 3) & ~3); i++) c->h_ids[i] = kRecordArmed;   // the rest of the last float4
+                pos[k] = end;
+                return true;
+            });
+        CopyPool::get().run_all(tasks);
+    }
     RB_CUDA_CHECK(cudaStreamSynchronize(run));      // (the kernel has seen every ray arrive, or the word behind the copy)
     if (ev[1]) {
         float ms = 0;
@@ -952,14 +992,13 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     }
     const Ray1* src = stage_in ? c->h_rays : rays;
     Hit1* dst = stage_out ? c->h_hits : hits;
-    // (closest hit only: an any-hit call changes tri_id alone, 4 bytes of every 16 -- stored over PCIe one by one that
-    // is slower than the pieces' round trip of the caller's records: 1.79 / 1.95 against 1.13 / 1.40 ms per Mi rays)
-    if constexpr (!ANY) {
+    {
         const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
         // page-locked arrays as they are; pageable ones through the staging arrays, unless a tool is injected that may
-        // run a kernel to its end inside the launch call (the staged form queues copies after the launch)
+        // run a kernel to its end inside the launch call (the staged form queues copies after the launch).  An any-hit
+        // call touches the caller's records from the host only (tri_id, as the ids arrive): pageable or not is the same.
         const bool staged_ok = g_tuning.host_staged_direct == 2 || (g_tuning.host_staged_direct == 1 && !injected_tool());
-        const bool in_ok = stage_in ? staged_ok : is_pinned(rays, true), out_ok = stage_out ? staged_ok : is_pinned(hits, true);
+        const bool in_ok = stage_in ? staged_ok : is_pinned(rays, true), out_ok = ANY ? true : stage_out ? staged_ok : is_pinned(hits, true);
         if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && in_ok && out_ok) {
             if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays, stage_in, stage_out)) {
                 release_host_context(s, c);

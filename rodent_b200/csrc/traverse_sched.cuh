@@ -224,8 +224,11 @@ struct RayWalker {
 //                in device memory, the warp counts the records of every group of 16 rays (256 bytes), and the warp
 //                whose count completes a group copies it home as whole lines.  Small groups, because a group waits
 //                for its slowest ray.  (`counts` == nullptr: no groups, the sink writes wherever it likes.)
+//                Any hit: what goes home is the triangle id alone (the caller's t, u, v stay as they are), 4 bytes per
+//                ray in a dense array the host scatters into the records -- groups of 64 rays, 256 bytes again.
 struct StoreAtOnce { static constexpr bool kActive = false; };
-constexpr int kPushShift = 4;                      // records per group: 16; at most 16 (two groups per warp round)
+constexpr int kPushShift = 4;                      // records per group: 16 (closest hit)
+constexpr int kPushShiftIds = 6;                   // ids per group: 64 (any hit); a group is 16 float4 either way
 //                The rays may still be on their way when the kernel starts (`arriving` != nullptr): a copy engine is
 //                writing them into the device array, whose slots were armed with all-ones words where tmin and tmax go.
 //                A warp reserves rays only when the last one it would get has arrived (it goes on with the rays it
@@ -298,12 +301,14 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
                 if (records.counts != nullptr) {
                     __threadfence();                                   // the records before their count
                     unsigned complete = 0;                             // this lane's count filled a group
-                    const int group = done >> kPushShift;
+                    constexpr int kShift = ANY ? kPushShiftIds : kPushShift;
+                    const int units = ANY ? (num_rays + 3) >> 2 : num_rays;            // float4 to send home in all
+                    const int group = done >> kShift;
                     if (mine) {
                         const unsigned same = __match_any_sync(um, group);
                         if (int(lane) == __ffs(same) - 1) {
                             const unsigned n = unsigned(__popc(same));
-                            const unsigned size = unsigned(min(1 << kPushShift, num_rays - (group << kPushShift)));
+                            const unsigned size = unsigned(min(1 << kShift, num_rays - (group << kShift)));
                             complete = atomicAdd(records.counts + group, n) + n == size;
                         }
                     }
@@ -312,10 +317,10 @@ __device__ __forceinline__ void traverse_vote_scheduled(const void* __restrict__
                         const int a = __ffs(cm) - 1; cm &= cm - 1;
                         const int b = cm != 0 ? __ffs(cm) - 1 : a; cm &= cm - 1;
                         const int ga = __shfl_sync(0xffffffffu, group, a), gb = __shfl_sync(0xffffffffu, group, b);
-                        const bool second = lane >= (1u << kPushShift);
-                        const int j = ((second ? gb : ga) << kPushShift) + int(lane & ((1u << kPushShift) - 1));
+                        const bool second = lane >= 16u;
+                        const int j = ((second ? gb : ga) << 4) + int(lane & 15u);
                         __threadfence();                               // the other warps' records after their counts
-                        if (j < num_rays && !(second && b == a)) records.home[j] = __ldcg(records.staged + j);
+                        if (j < units && !(second && b == a)) records.home[j] = __ldcg(records.staged + j);
                     }
                 }
             }

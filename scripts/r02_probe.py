@@ -123,7 +123,7 @@ def e2e_direct():
         lib.tune("host_direct_rays", rays_by_ce); lib.tune("host_direct_push", push); measure(f"direct, rays by copy engine {rays_by_ce}, push {push}")
         lib.tune("host_trace", 1); step(("primary",)); step(("random",)); step(("random", "primary")); lib.tune("host_trace", 0)
     lib.tune("host_direct_push", 1); lib.tune("host_direct_rays", 1)
-    # any hit: the pieces round-trip the caller's records, the direct kernel stores tri_id alone
+    # any hit: the pieces round-trip the caller's records, the direct kernel sends a dense id array home
     for direct in (0, 1):
         lib.tune("host_direct", direct)
         for n in ("primary", "random"):

@@ -302,11 +302,25 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
         t.join()
     assert_records_equal(pin_h.array.copy(), oracle_hits["random"])
     assert_records_equal(pin_h2.array.copy(), oracle_hits["primary"])
-    # any hit keeps the caller's t, u, v (copy-engine path), and the direct path can be switched off
-    pin_h.array[:] = 0
-    pin_h.array["t"] = 7.0
-    occl = traversal.intersect_host(nodes, tris, pin_r.array[:50000], pin_h.array[:50000], any_hit=True)
-    assert ((occl["tri_id"] >= 0) == (oracle_hits["random"][:50000]["tri_id"] >= 0)).all() and (occl["t"] == 7.0).all()
+    # any hit: the same single launch; only tri_id comes home (a dense id array the helper threads scatter into the
+    # records), the caller's t, u, v stay -- page-locked or pageable records, ragged sizes on one context (the tail of the
+    # last group of ids must not leak into a later, longer call), ids equal to the device-pointer entry point's
+    bvh_dev = traversal.Bvh8(0, nodes, tris)
+    d_rays = traversal.DeviceArray.from_host(0, ray_sets["random"])
+    d_hits = traversal.DeviceArray(0, formats.HIT1, full)
+    traversal.intersect(bvh_dev, d_rays, d_hits, any_hit=True)
+    want_ids = d_hits.to_host()["tri_id"]
+    for n in (50001, 3, 64, 65, 200003, 50002):
+        pin_h.array[:] = 0
+        pin_h.array["t"] = 7.0
+        occl = traversal.intersect_host(nodes, tris, pin_r.array[:n], pin_h.array[:n], any_hit=True)
+        assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<true, 8>"
+        assert (occl["tri_id"] == want_ids[:n]).all() and (occl["t"] == 7.0).all() and (occl["u"] == 0.0).all()
+        assert (pin_h.array[n:]["tri_id"] == 0).all()
+        own = np.zeros(n, formats.HIT1)
+        own["v"] = 2.5
+        occl = traversal.intersect_host(nodes, tris, np.ascontiguousarray(ray_sets["random"][:n]), own, any_hit=True)      # pageable both
+        assert (occl["tri_id"] == want_ids[:n]).all() and (occl["v"] == 2.5).all()
     lib.tune("host_direct", 0)
     try:
         pin_h.array[:] = 0
