@@ -144,9 +144,10 @@ void cuda_occluded_single_ray1_bvh8_tri4_async(int32_t dev, const Node8* nodes, 
  * Rays come in and hits go out on every call.  With pinned (cudaMallocHost / rodent_b200_alloc_host) buffers a
  * closest-hit call (BVH8 or BVH4) is ONE launch: a copy engine brings the rays in while the kernel already traces the first of
  * them, and the kernel writes its records into the caller's array itself (traverse.cu: run_host_direct).  Pageable
- * buffers (malloc, std::vector, anydsl::Array host memory) go through the library's own pinned staging buffers, filled
- * and drained by a few helper threads while that same launch runs.  Any-hit calls bring home the triangle ids only;
- * the helper threads write them into the caller's records, whose t, u, v are never touched.
+ * rays (malloc, std::vector, anydsl::Array host memory) go through the library's own pinned staging buffers in copy /
+ * launch / copy pieces, filled and drained by a few helper threads; rodent_b200_pin_host page-locks such arrays in
+ * place.  Any-hit calls bring home the triangle ids only; the helper threads write them into the caller's records,
+ * whose t, u, v are never touched.
  * Like the cpu_* functions they replace, the calls are reentrant: each takes its own device
  * staging buffers and streams, so calls from several host threads overlap on the device (one set's transfers under
  * another set's traversal). */

@@ -31,8 +31,6 @@
 #include "traverse_pool.cuh"
 #include "traverse_bvh2.cuh"
 
-extern "C" char** environ;
-
 namespace rb200 {
 
 constexpr int kBlock = 128;          // 4 warps per CTA
@@ -58,7 +56,7 @@ struct Tuning {
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_direct = 1;     // host-pointer entry points, closest hit: one launch per call that follows its rays as they arrive and sends its records home itself (run_host_direct; 0: copy-engine pieces)
     int host_direct_rays = 1;    // ... 1 = a copy engine brings the rays in while the kernel runs (armed slots, traverse_sched.cuh), 0 = the warps read them from the caller's memory as they refill
-    int host_staged_direct = 1;  // ... pageable buffers through the staging arrays with the same single launch: 1 = unless a profiling tool is injected, 2 = always, 0 = never (copy-engine pieces)
+    int host_staged_direct = 1;  // ... 1 = pageable records and packets go through the staging arrays with the same single launch, 2 = pageable rays as well (staged before the launch), 0 = neither (copy-engine pieces)
     int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
     int host_trace = 0;          // ... print the device time of every such call (developer probe)
     int host_stream_stores = 1;  // ... staging copies with non-temporal stores
@@ -817,30 +815,34 @@ static void run_host(const NodeT* nodes, const Tri4* tris, const Ray1* rays, Hit
 // Pinned caller buffers, default kernel (BVH8 or BVH4): one launch per call and one copy (traverse_direct).  Against
 // the copy-engine pieces below: the traversal starts at once instead of after a fifth of the rays, pays the tail of a
 // launch once per call, keeps all its CTAs for the whole call, and the records need no pass of their own.
-// Is a tool injected into this process that may run kernels one at a time, each to completion inside its launch call
-// (Nsight Compute's kernel replay)?  A kernel that waits for copies the host has not queued yet would never end there.
-static bool injected_tool() {
-    static const bool yes = [] {
-        for (char** e = ::environ; e && *e; e++)
-            if (!std::strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !std::strncmp(*e, "NV_NSIGHT", 9) || !std::strncmp(*e, "NV_COMPUTE_PROFILER", 19) ||
-                !std::strncmp(*e, "NV_TPS_LAUNCH", 13))
-                return true;
-        return false;
-    }();
-    return yes;
+static void ensure_staging(HostContext* c, size_t num_rays) {
+    if (c->stage_capacity >= num_rays) return;
+    if (c->h_rays) { RB_CUDA_CHECK(cudaFreeHost(c->h_rays)); RB_CUDA_CHECK(cudaFreeHost(c->h_hits)); }
+    RB_CUDA_CHECK(cudaMallocHost(&c->h_rays, num_rays * sizeof(Ray1)));
+    RB_CUDA_CHECK(cudaMallocHost(&c->h_hits, num_rays * sizeof(Hit1)));
+    c->stage_capacity = num_rays;
+    c->hits_armed = false;
 }
 
 constexpr int32_t kRecordArmed = int32_t(0x80000000u);   // tri_id of a staging record that has not arrived (a real one is -1 or >= 0)
 
 // `stage_in` / `stage_out`: the caller's rays / hits are pageable and go through the context's pinned staging arrays --
-// still ONE launch.  The kernel is started first; the calling thread and the helper threads then copy the rays into the
-// staging array piece by piece, each piece followed by its copy to the device (the armed slots tell the kernel what is
-// in); the records arrive in the (armed) staging array by groups while the kernel runs, and the same threads move them
-// on to the caller's array chunk by chunk as they turn up, re-arming the staging array on the way.
-template <bool ANY, typename NodeT>
-static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const Ray1* rays, Hit1* hits, int num_rays,
+// still ONE launch.  The calling thread and the helper threads copy the rays into the staging array piece by piece, each
+// piece followed by its copy to the device; the kernel is launched when the last copy is queued and follows what is
+// still on its way (the armed slots tell it what is in); the records arrive in the (armed) staging array by groups
+// while the kernel runs, and the same threads move them on to the caller's array chunk by chunk as they turn up,
+// re-arming the staging array on the way.
+//
+// W = 4 or 8: the caller's arrays are the packet layouts of the packet / hybrid entry points (RayW: org[3][W] dir[3][W]
+// tmin[W] tmax[W]; HitW: tri_id[W] t[W] u[W] v[W]).  They always go through the staging arrays: the helper threads
+// transpose packets into Ray1 on the way in and records back into packets on the way out, the device sees rays.
+template <bool ANY, typename NodeT, int W = 1>
+static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes, const Tri4* d_tris, const void* rays_v, void* hits_v, int num_rays,
                             bool stage_in = false, bool stage_out = false) {
     constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
+    const Ray1* rays = static_cast<const Ray1*>(rays_v); Hit1* hits = static_cast<Hit1*>(hits_v);     // W == 1
+    const float* ray_packets = static_cast<const float*>(rays_v); float* hit_packets = static_cast<float*>(hits_v);   // W > 1
+    if (W > 1) { stage_in = true; stage_out = true; }
     // Any hit: only tri_id changes.  The ids come home as a dense array (pinned, armed) and the helper threads write them
     // into the caller's records as they arrive -- whatever memory those are in, so nothing is staged on the way out.
     if (ANY) {
@@ -887,6 +889,42 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
         CopyPool::get().run_all(arm);
         c->hits_armed = true;
     }
+    // Pieces of ~4 MB: into the staging array, then queued for the copy engine.  The kernel is launched only when every
+    // copy it will wait for is queued: a running kernel must never depend on a CUDA call this process has yet to make (a
+    // cudaFree in another thread waits for the device to go idle and may keep other threads' calls from going in
+    // meanwhile; a profiler may run a kernel to its end inside the launch call).  The copies overlap the staging of the
+    // later pieces, and the kernel finds most of its rays in place and follows the rest.
+    if (stage_in) {
+        const int piece = 1 << 17;
+        for (int first = 0; first < num_rays; first += piece) {
+            const int n = std::min(piece, num_rays - first);
+            if (W == 1) {
+                CopyPool::get().parallel_copy(c->h_rays + first, rays + first, size_t(n) * sizeof(Ray1));
+            } else {                                         // packets -> rays, a few threads per piece
+                std::vector<CopyPool::Task> tasks;
+                const int parts = std::max(1, std::min(g_tuning.host_copy_parts, 16)), each = ((n / parts + W * 4 - 1) / (W * 4)) * (W * 4);
+                for (int b0 = first; b0 < first + n; b0 += std::max(each, W * 4)) {
+                    const int e0 = std::min(first + n, b0 + std::max(each, W * 4));
+                    tasks.push_back([=] {
+                        for (int i = b0; i < e0; i += 4) {                       // four rays of one packet row group at a time
+                            const float* q = ray_packets + size_t(i / W) * (8 * W) + (i % W);
+                            __m128 ox = _mm_loadu_ps(q), oy = _mm_loadu_ps(q + W), oz = _mm_loadu_ps(q + 2 * W), t0 = _mm_loadu_ps(q + 6 * W);
+                            __m128 dx = _mm_loadu_ps(q + 3 * W), dy = _mm_loadu_ps(q + 4 * W), dz = _mm_loadu_ps(q + 5 * W), t1 = _mm_loadu_ps(q + 7 * W);
+                            _MM_TRANSPOSE4_PS(ox, oy, oz, t0);
+                            _MM_TRANSPOSE4_PS(dx, dy, dz, t1);
+                            float* r = reinterpret_cast<float*>(c->h_rays + i);
+                            _mm_stream_ps(r, ox); _mm_stream_ps(r + 4, dx); _mm_stream_ps(r + 8, oy); _mm_stream_ps(r + 12, dy);
+                            _mm_stream_ps(r + 16, oz); _mm_stream_ps(r + 20, dz); _mm_stream_ps(r + 24, t0); _mm_stream_ps(r + 28, t1);
+                        }
+                        _mm_sfence();
+                        return true;
+                    });
+                }
+                CopyPool::get().run_all(tasks);
+            }
+            copy_in(first, n, first + n >= num_rays);
+        }
+    }
     cudaEvent_t ev[2] = {};
     if (g_tuning.host_trace) { for (auto& e : ev) RB_CUDA_CHECK(cudaEventCreate(&e)); RB_CUDA_CHECK(cudaEventRecord(ev[0], run)); }
     if (push) RB_CUDA_CHECK(cudaMemsetAsync(c->group_counts, 0, (size_t((num_rays - 1) >> (ANY ? kPushShiftIds : kPushShift)) + 1) * sizeof(unsigned), run));
@@ -902,14 +940,6 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
     if (copy_after) RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, run));
     std::atomic<int> kernel_done{0};
     if (stage_out || ANY) RB_CUDA_CHECK(cudaLaunchHostFunc(run, [](void* p) { static_cast<std::atomic<int>*>(p)->store(1, std::memory_order_release); }, &kernel_done));
-    if (stage_in) {                                          // pieces of ~4 MB: copy into the staging array, queue the copy to the device
-        const int piece = 1 << 17;
-        for (int first = 0; first < num_rays; first += piece) {
-            const int n = std::min(piece, num_rays - first);
-            CopyPool::get().parallel_copy(c->h_rays + first, rays + first, size_t(n) * sizeof(Ray1));
-            copy_in(first, n, first + n >= num_rays);
-        }
-    }
     if (stage_out) {                                         // chunks of 512 KB of records, each taken home as far as it has arrived
         const int chunk = 1 << 15;
         const bool aligned_out = (reinterpret_cast<uintptr_t>(hits) & 15) == 0 && g_tuning.host_stream_stores != 0;
@@ -927,7 +957,12 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
                         v = _mm_load_si128(reinterpret_cast<const __m128i*>(c->h_hits + i));      // the kernel is gone: everything it wrote is here
                         if (_mm_cvtsi128_si32(v) == kRecordArmed) { std::fprintf(stderr, "rodent_b200: record %d never arrived in the staging array\n", i); std::abort(); }
                     }
-                    if (aligned_out) _mm_stream_si128(reinterpret_cast<__m128i*>(hits + i), v);
+                    if (W > 1) {                             // record -> its lane of the hit packet
+                        alignas(16) float rec[4];
+                        _mm_store_si128(reinterpret_cast<__m128i*>(rec), v);
+                        float* q = hit_packets + size_t(i / W) * (4 * W) + (i % W);
+                        q[0] = rec[0]; q[W] = rec[1]; q[2 * W] = rec[2]; q[3 * W] = rec[3];
+                    } else if (aligned_out) _mm_stream_si128(reinterpret_cast<__m128i*>(hits + i), v);
                     else _mm_storeu_si128(reinterpret_cast<__m128i*>(hits + i), v);
                     c->h_hits[i].tri_id = kRecordArmed;
                 }
@@ -953,7 +988,8 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
                         v = *const_cast<volatile int32_t*>(c->h_ids + i);                          // the kernel is gone: everything it wrote is here
                         if (v == kRecordArmed) { std::fprintf(stderr, "rodent_b200: the id of ray %d never arrived\n", i); std::abort(); }
                     }
-                    hits[i].tri_id = v;
+                    if (W > 1) std::memcpy(hit_packets + size_t(i / W) * (4 * W) + (i % W), &v, sizeof v);
+                    else hits[i].tri_id = v;
                     c->h_ids[i] = kRecordArmed;
                 }
                 if (end == num_rays) for (int i = end; i < ((end + 3) & ~3); i++) c->h_ids[i] = kRecordArmed;   // the rest of the last float4
@@ -983,22 +1019,19 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     // pageable buffers are staged through pinned memory of this context (cudaMemcpyAsync on pageable memory is
     // synchronous and slow); g_tuning.host_staging = 0 hands them to the driver as they are
     const bool stage_in = g_tuning.host_staging && !is_pinned(rays), stage_out = g_tuning.host_staging && !is_pinned(hits);
-    if ((stage_in || stage_out) && c->stage_capacity < size_t(num_rays)) {
-        if (c->h_rays) { RB_CUDA_CHECK(cudaFreeHost(c->h_rays)); RB_CUDA_CHECK(cudaFreeHost(c->h_hits)); }
-        RB_CUDA_CHECK(cudaMallocHost(&c->h_rays, size_t(num_rays) * sizeof(Ray1)));
-        RB_CUDA_CHECK(cudaMallocHost(&c->h_hits, size_t(num_rays) * sizeof(Hit1)));
-        c->stage_capacity = size_t(num_rays);
-        c->hits_armed = false;
-    }
+    if (stage_in || stage_out) ensure_staging(c, size_t(num_rays));
     const Ray1* src = stage_in ? c->h_rays : rays;
     Hit1* dst = stage_out ? c->h_hits : hits;
     {
         const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
-        // page-locked arrays as they are; pageable ones through the staging arrays, unless a tool is injected that may
-        // run a kernel to its end inside the launch call (the staged form queues copies after the launch).  An any-hit
-        // call touches the caller's records from the host only (tri_id, as the ids arrive): pageable or not is the same.
-        const bool staged_ok = g_tuning.host_staged_direct == 2 || (g_tuning.host_staged_direct == 1 && !injected_tool());
-        const bool in_ok = stage_in ? staged_ok : is_pinned(rays, true), out_ok = ANY ? true : stage_out ? staged_ok : is_pinned(hits, true);
+        // The single launch needs its rays where a copy engine can take them: page-locked.  Pageable rays would have
+        // to be staged before the launch (a running kernel must not wait for copies this process has yet to queue, see
+        // run_host_direct), which gives away the overlap the pieces below have: those keep the pageable rays
+        // (host_staged_direct = 2 forces the single launch for them as well).  Pageable RECORDS are no obstacle: they
+        // are taken home from the staging array while the kernel runs, and an any-hit call touches the caller's
+        // records from the host only (tri_id, as the ids arrive).
+        const bool in_ok = stage_in ? g_tuning.host_staged_direct == 2 : is_pinned(rays, true);
+        const bool out_ok = ANY ? true : stage_out ? g_tuning.host_staged_direct != 0 : is_pinned(hits, true);
         if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && in_ok && out_ok) {
             if (run_host_direct<ANY>(s, c, bvh.first, bvh.second, rays, hits, num_rays, stage_in, stage_out)) {
                 release_host_context(s, c);
@@ -1047,7 +1080,7 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     release_host_context(s, c);
 }
 
-// Packet entry points: copy in, one launch, copy out.
+// Packet entry points: the staged single launch (run_host_direct, W = 4 or 8); or copy in, one launch, copy out.
 template <bool ANY, typename NodeT, int W>
 static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* rays, void* hits, int num_packets) {
     if (num_packets <= 0) return;
@@ -1056,6 +1089,16 @@ static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* r
     auto bvh = cached_bvh(s, nodes, tris);
     const int num_rays = num_packets * W;
     HostContext* c = acquire_host_context(s, size_t(num_rays));
+    {   // the single launch of the single-ray calls, the packets transposed by the helper threads on the way in and out
+        const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
+        if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && g_tuning.host_staged_direct != 0) {
+            ensure_staging(c, size_t(num_rays));
+            if (run_host_direct<ANY, NodeT, W>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
+                release_host_context(s, c);
+                return;
+            }
+        }
+    }
     cudaStream_t st = c->streams[0];
     int* counter = c->counters;
     c->rays_armed = false;

@@ -258,9 +258,9 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
     assert_records_equal(traversal.intersect_host(nodes, tris, own_r, own_h), oracle_hits["primary"][:70001])
     assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<false, 8>"
     assert traversal.unpin_host(own_r) and traversal.unpin_host(own_h) and not traversal.unpin_host(own_h)
-    # pageable again: the same single launch, fed through the library's staging arrays by helper threads -- or, switched
-    # off (as under an injected profiling tool), the copy-engine pieces
-    for staged, kernel in ((1, "traverse_direct<false, 8>"), (0, "traverse_bvh8_vote"), (2, "traverse_direct<false, 8>")):
+    # pageable again: the copy-engine pieces (pageable rays would have to be staged before a single launch could start) --
+    # or, forced, the single launch fed through the library's staging arrays by helper threads
+    for staged, kernel in ((1, "traverse_bvh8_vote"), (0, "traverse_bvh8_vote"), (2, "traverse_direct<false, 8>")):
         lib.tune("host_staged_direct", staged)
         try:
             for n in (70001, 17, 40000):
@@ -319,7 +319,11 @@ def test_pinned_buffers_direct_path(sponza, ray_sets, oracle_hits):
         assert (pin_h.array[n:]["tri_id"] == 0).all()
         own = np.zeros(n, formats.HIT1)
         own["v"] = 2.5
-        occl = traversal.intersect_host(nodes, tris, np.ascontiguousarray(ray_sets["random"][:n]), own, any_hit=True)      # pageable both
+        occl = traversal.intersect_host(nodes, tris, np.ascontiguousarray(ray_sets["random"][:n]), own, any_hit=True)      # pageable both: pieces
+        assert (occl["tri_id"] == want_ids[:n]).all() and (occl["v"] == 2.5).all()
+        own["tri_id"] = 0
+        occl = traversal.intersect_host(nodes, tris, pin_r.array[:n], own, any_hit=True)       # page-locked rays, pageable records: the ids are scattered into them
+        assert L.rodent_b200_last_kernel_name(0).decode() == "traverse_direct<true, 8>"
         assert (occl["tri_id"] == want_ids[:n]).all() and (occl["v"] == 2.5).all()
     lib.tune("host_direct", 0)
     try:
@@ -498,3 +502,15 @@ def test_packet_entry_points(kind, width, arity, sponza, sponza4, ray_sets):
     occl = traversal.intersect_host_packets(nodes, tris, packets, kind, any_hit=True, hits=pre)
     assert np.array_equal(formats.unpack_hits(occl)["tri_id"], oracle.traverse(nodes, tris, np.ascontiguousarray(rays[:n]), any_hit=True)["tri_id"])
     assert (occl["t"] == 3.0).all()
+    # the staged single launch (packets transposed by the helper threads) and the plain copy / launch / copy form; one
+    # packet, a few, many
+    from rodent_b200 import lib
+    for staged, kernel in ((1, f"traverse_direct<false, {arity}>"), (0, "traverse_packets_vote")):
+        lib.tune("host_staged_direct", staged)
+        try:
+            for count in (1, 5, 4099):
+                got = formats.unpack_hits(traversal.intersect_host_packets(nodes, tris, packets[:count], kind))
+                assert_records_equal(got, want[:count * width])
+                assert lib.load().rodent_b200_last_kernel_name(0).decode().startswith(kernel) or staged == 0
+        finally:
+            lib.tune("host_staged_direct", 1)
