@@ -60,7 +60,7 @@ struct Tuning {
     int host_direct_push = 1;    // ... 1 = records staged in device memory and sent home group by group as whole lines, 0 = every record stored in the caller's memory by its lane, 2 = one copy after the kernel
     int host_trace = 0;          // ... print the device time of every such call (developer probe)
     int host_stream_stores = 1;  // ... staging copies with non-temporal stores
-    int host_copy_parts = 4; // host-pointer entry points, pageable buffers: threads that share one staging memcpy (the caller's included)
+    int host_copy_parts = 8; // host-pointer entry points, pageable buffers: threads that share one staging memcpy (the caller's included; 8 measured a little better than 4: profiles/r02_probe_pageable.txt)
     int host_ramp = 0;       // host-pointer entry points: 1 = a small first piece as well (1, k-1, k-2, ..., 1 parts): traversal starts sooner
     int host_chunks = 5;     // host-pointer entry points: pieces the ray array is cut into for copy/compute overlap (two calls in flight: 5..6 measured best, one: 3..4)
 };

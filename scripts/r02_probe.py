@@ -211,7 +211,7 @@ def pageable():
                 row.append(f"{'+'.join(names)} {np.median(ts):.3f} ms ({'ok' if ok else 'WRONG'})")
             print(f"staged direct {staged}, {parts} threads per copy, non-temporal stores {nt}: " + ", ".join(row) + f"  [{lib.load().rodent_b200_last_kernel_name(0).decode()}]", flush=True)
     lib.tune("host_staged_direct", 1); lib.tune("host_stream_stores", 1)
-    lib.tune("host_copy_parts", 4); lib.tune("host_chunks", 5)
+    lib.tune("host_copy_parts", 8); lib.tune("host_chunks", 5)
 
 
 def sbvh():
