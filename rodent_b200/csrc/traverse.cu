@@ -824,6 +824,52 @@ static void ensure_staging(HostContext* c, size_t num_rays) {
     c->hits_armed = false;
 }
 
+// Ray packets (org[3][W] dir[3][W] tmin[W] tmax[W]) -> rays [first, first + n) of the staging array, by the helper threads;
+// first and n are multiples of 4.  SSE 4 x 4 transposes, non-temporal stores.
+template <int W>
+static void stage_packets(HostContext* c, const float* ray_packets, int first, int n) {
+    std::vector<CopyPool::Task> tasks;
+    const int parts = std::max(1, std::min(g_tuning.host_copy_parts, 16)), each = std::max(((n / parts + W * 4 - 1) / (W * 4)) * (W * 4), W * 4);
+    for (int b0 = first; b0 < first + n; b0 += each) {
+        const int e0 = std::min(first + n, b0 + each);
+        tasks.push_back([=] {
+            for (int i = b0; i < e0; i += 4) {                       // four rays of one packet at a time
+                const float* q = ray_packets + size_t(i / W) * (8 * W) + (i % W);
+                __m128 ox = _mm_loadu_ps(q), oy = _mm_loadu_ps(q + W), oz = _mm_loadu_ps(q + 2 * W), t0 = _mm_loadu_ps(q + 6 * W);
+                __m128 dx = _mm_loadu_ps(q + 3 * W), dy = _mm_loadu_ps(q + 4 * W), dz = _mm_loadu_ps(q + 5 * W), t1 = _mm_loadu_ps(q + 7 * W);
+                _MM_TRANSPOSE4_PS(ox, oy, oz, t0);
+                _MM_TRANSPOSE4_PS(dx, dy, dz, t1);
+                float* r = reinterpret_cast<float*>(c->h_rays + i);
+                _mm_stream_ps(r, ox); _mm_stream_ps(r + 4, dx); _mm_stream_ps(r + 8, oy); _mm_stream_ps(r + 12, dy);
+                _mm_stream_ps(r + 16, oz); _mm_stream_ps(r + 20, dz); _mm_stream_ps(r + 24, t0); _mm_stream_ps(r + 28, t1);
+            }
+            _mm_sfence();
+            return true;
+        });
+    }
+    CopyPool::get().run_all(tasks);
+}
+// ... and records [first, first + n) of the staging array -> hit packets (tri_id[W] t[W] u[W] v[W]).
+template <int W>
+static void unstage_packets(HostContext* c, float* hit_packets, int first, int n) {
+    std::vector<CopyPool::Task> tasks;
+    const int parts = std::max(1, std::min(g_tuning.host_copy_parts, 16)), each = std::max(((n / parts + W * 4 - 1) / (W * 4)) * (W * 4), W * 4);
+    for (int b0 = first; b0 < first + n; b0 += each) {
+        const int e0 = std::min(first + n, b0 + each);
+        tasks.push_back([=] {
+            for (int i = b0; i < e0; i += 4) {
+                const float* r = reinterpret_cast<const float*>(c->h_hits + i);
+                __m128 a = _mm_load_ps(r), b = _mm_load_ps(r + 4), d = _mm_load_ps(r + 8), e = _mm_load_ps(r + 12);
+                _MM_TRANSPOSE4_PS(a, b, d, e);                       // rows: tri_id, t, u, v of the four rays
+                float* q = hit_packets + size_t(i / W) * (4 * W) + (i % W);
+                _mm_storeu_ps(q, a); _mm_storeu_ps(q + W, b); _mm_storeu_ps(q + 2 * W, d); _mm_storeu_ps(q + 3 * W, e);
+            }
+            return true;
+        });
+    }
+    CopyPool::get().run_all(tasks);
+}
+
 constexpr int32_t kRecordArmed = int32_t(0x80000000u);   // tri_id of a staging record that has not arrived (a real one is -1 or >= 0)
 
 // `stage_in` / `stage_out`: the caller's rays / hits are pageable and go through the context's pinned staging arrays --
@@ -900,27 +946,8 @@ static bool run_host_direct(DeviceState& s, HostContext* c, const NodeT* d_nodes
             const int n = std::min(piece, num_rays - first);
             if (W == 1) {
                 CopyPool::get().parallel_copy(c->h_rays + first, rays + first, size_t(n) * sizeof(Ray1));
-            } else {                                         // packets -> rays, a few threads per piece
-                std::vector<CopyPool::Task> tasks;
-                const int parts = std::max(1, std::min(g_tuning.host_copy_parts, 16)), each = ((n / parts + W * 4 - 1) / (W * 4)) * (W * 4);
-                for (int b0 = first; b0 < first + n; b0 += std::max(each, W * 4)) {
-                    const int e0 = std::min(first + n, b0 + std::max(each, W * 4));
-                    tasks.push_back([=] {
-                        for (int i = b0; i < e0; i += 4) {                       // four rays of one packet row group at a time
-                            const float* q = ray_packets + size_t(i / W) * (8 * W) + (i % W);
-                            __m128 ox = _mm_loadu_ps(q), oy = _mm_loadu_ps(q + W), oz = _mm_loadu_ps(q + 2 * W), t0 = _mm_loadu_ps(q + 6 * W);
-                            __m128 dx = _mm_loadu_ps(q + 3 * W), dy = _mm_loadu_ps(q + 4 * W), dz = _mm_loadu_ps(q + 5 * W), t1 = _mm_loadu_ps(q + 7 * W);
-                            _MM_TRANSPOSE4_PS(ox, oy, oz, t0);
-                            _MM_TRANSPOSE4_PS(dx, dy, dz, t1);
-                            float* r = reinterpret_cast<float*>(c->h_rays + i);
-                            _mm_stream_ps(r, ox); _mm_stream_ps(r + 4, dx); _mm_stream_ps(r + 8, oy); _mm_stream_ps(r + 12, dy);
-                            _mm_stream_ps(r + 16, oz); _mm_stream_ps(r + 20, dz); _mm_stream_ps(r + 24, t0); _mm_stream_ps(r + 28, t1);
-                        }
-                        _mm_sfence();
-                        return true;
-                    });
-                }
-                CopyPool::get().run_all(tasks);
+            } else {
+                stage_packets<W>(c, ray_packets, first, n);
             }
             copy_in(first, n, first + n >= num_rays);
         }
@@ -1080,7 +1107,8 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
     release_host_context(s, c);
 }
 
-// Packet entry points: the staged single launch (run_host_direct, W = 4 or 8); or copy in, one launch, copy out.
+// Packet entry points: closest hit in copy-engine pieces, any hit on the staged single launch (run_host_direct, W = 4 or 8);
+// with host_staged_direct = 0, copy in, one launch of the packet kernel, copy out.
 template <bool ANY, typename NodeT, int W>
 static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* rays, void* hits, int num_packets) {
     if (num_packets <= 0) return;
@@ -1089,14 +1117,45 @@ static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* r
     auto bvh = cached_bvh(s, nodes, tris);
     const int num_rays = num_packets * W;
     HostContext* c = acquire_host_context(s, size_t(num_rays));
-    {   // the single launch of the single-ray calls, the packets transposed by the helper threads on the way in and out
+    if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.host_staged_direct != 0) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
-        if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.wide_loads && aligned && g_tuning.host_staged_direct != 0) {
-            ensure_staging(c, size_t(num_rays));
-            if (run_host_direct<ANY, NodeT, W>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
+        ensure_staging(c, size_t(num_rays));
+        if constexpr (ANY) {
+            // the single launch of the single-ray calls behind the staging of the rays (transposed by the helper
+            // threads); the triangle ids come home as a dense array and are written into the hit packets
+            if (g_tuning.wide_loads && aligned && run_host_direct<ANY, NodeT, W>(s, c, bvh.first, bvh.second, rays, hits, num_rays)) {
                 release_host_context(s, c);
                 return;
             }
+        } else {
+            // The copy-engine pieces of the single-ray calls (run_host_on), with the helper threads transposing packets
+            // into rays on the way in and records into hit packets on the way out: the traversal of one piece runs
+            // under the staging of the next.
+            c->rays_armed = false; c->hits_armed = false;
+            const int pieces = std::max(1, std::min(g_tuning.host_chunks, 16));
+            const int64_t parts = int64_t(pieces) * (pieces + 1) / 2;
+            int k = 0, piece_first[17], piece_n[17];
+            for (int first = 0; first < num_rays; k++) {
+                int n = int((int64_t(num_rays) * std::max(1, pieces - k) / parts + 31) & ~int64_t(31));
+                n = std::max(n, 1 << 14);
+                if (k >= pieces - 1 || n > num_rays - first) n = num_rays - first;
+                cudaStream_t st = c->streams[k % 3];
+                stage_packets<W>(c, static_cast<const float*>(rays), first, n);
+                RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays + first, c->h_rays + first, size_t(n) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
+                launch<ANY>(s, bvh.first, bvh.second, c->d_rays + first, c->d_hits + first, n, st, c->counters + 8 * (k % 3));
+                RB_CUDA_CHECK(cudaMemcpyAsync(c->h_hits + first, c->d_hits + first, size_t(n) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+                if (!c->piece_done[k]) RB_CUDA_CHECK(cudaEventCreateWithFlags(&c->piece_done[k], cudaEventDisableTiming));
+                RB_CUDA_CHECK(cudaEventRecord(c->piece_done[k], st));
+                piece_first[k] = first; piece_n[k] = n;
+                first += n;
+            }
+            for (int j = 0; j < k; j++) {
+                RB_CUDA_CHECK(cudaEventSynchronize(c->piece_done[j]));
+                unstage_packets<W>(c, static_cast<float*>(hits), piece_first[j], piece_n[j]);
+            }
+            for (auto& st : c->streams) RB_CUDA_CHECK(cudaStreamSynchronize(st));
+            release_host_context(s, c);
+            return;
         }
     }
     cudaStream_t st = c->streams[0];

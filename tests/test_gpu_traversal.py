@@ -502,15 +502,20 @@ def test_packet_entry_points(kind, width, arity, sponza, sponza4, ray_sets):
     occl = traversal.intersect_host_packets(nodes, tris, packets, kind, any_hit=True, hits=pre)
     assert np.array_equal(formats.unpack_hits(occl)["tri_id"], oracle.traverse(nodes, tris, np.ascontiguousarray(rays[:n]), any_hit=True)["tri_id"])
     assert (occl["t"] == 3.0).all()
-    # the staged single launch (packets transposed by the helper threads) and the plain copy / launch / copy form; one
-    # packet, a few, many
+    # packets transposed by the helper threads on the way in and out (copy-engine pieces for closest hit, the single
+    # launch with its dense id array for any hit), and the plain copy / launch / copy of the packet kernel; one packet, a
+    # few, many
     from rodent_b200 import lib
-    for staged, kernel in ((1, f"traverse_direct<false, {arity}>"), (0, "traverse_packets_vote")):
+    want_any = oracle.traverse(nodes, tris, np.ascontiguousarray(rays[:n]), any_hit=True)["tri_id"]
+    for staged in (1, 0):
         lib.tune("host_staged_direct", staged)
         try:
-            for count in (1, 5, 4099):
+            for count in (1, 5, 4099, len(packets)):
                 got = formats.unpack_hits(traversal.intersect_host_packets(nodes, tris, packets[:count], kind))
                 assert_records_equal(got, want[:count * width])
-                assert lib.load().rodent_b200_last_kernel_name(0).decode().startswith(kernel) or staged == 0
+                pre = np.zeros(count, formats.packet_dtypes(width)[1])
+                pre["u"] = 0.25
+                occl = traversal.intersect_host_packets(nodes, tris, packets[:count], kind, any_hit=True, hits=pre)
+                assert np.array_equal(formats.unpack_hits(occl)["tri_id"], want_any[:count * width]) and (occl["u"] == 0.25).all()
         finally:
             lib.tune("host_staged_direct", 1)
