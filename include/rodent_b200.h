@@ -185,7 +185,10 @@ typedef struct Hit8 { int32_t tri_id[8]; float t[8]; float u[8]; float v[8]; } H
  * A GPU has no use for the CPU's packet traversal order, so every ray of a packet is traced by the single-ray kernel:
  * each ray gets the closest hit (or an any-hit flag) exactly as cpu_*_single_ray1_* defines it.  The reference's packet
  * kernels visit nodes in a per-packet order, which can pick another of several triangles hit at the same distance; `t`
- * agrees (the reference's own test accepts every variant against one golden image, tools/CMakeLists.txt:26-31). */
+ * agrees (the reference's own test accepts every variant against one golden image, tools/CMakeLists.txt:26-31).
+ * Measured against a restatement of that packet kernel (oracle/traversal_oracle.c: traverse_packet,
+ * tests/test_packet_oracle.py) on the two Sponza sets: the same rays hit, t within 1 ulp everywhere, another triangle of
+ * a tie on 6 .. 694 of 1 Mi primary rays and on 0.03 .. 2.1 % of the incoherent ones. */
 void b200_intersect_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
 void b200_occluded_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
 void b200_intersect_packet_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);

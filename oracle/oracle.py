@@ -65,6 +65,22 @@ def traverse(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit: boo
     return (hits, stats) if want_stats else hits
 
 
+def traverse_packets(nodes: np.ndarray, tris: np.ndarray, packets: np.ndarray, kind: str = "hybrid", any_hit: bool = False,
+                     threads: int | None = None) -> np.ndarray:
+    """The reference's packet / hybrid kernel (cpu_traverse_hybrid_helper, oracle/traversal_oracle.c: traverse_packet) on
+    Ray4 / Ray8 packets; returns Hit4 / Hit8 packets (any hit: only tri_id is written, the rest stays 0)."""
+    from rodent_b200.formats import packet_dtypes
+    width = packets.dtype["tmin"].shape[0]
+    arity = nodes.dtype["child"].shape[0]
+    hits = np.zeros(len(packets), packet_dtypes(width)[1])
+    fn = lib().oracle_traverse_packets
+    fn.restype = None
+    fn.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_int32, ctypes.c_int]
+    fn(arity, width, int(kind == "hybrid"), int(any_hit), _ptr(nodes), _ptr(tris), _ptr(packets), _ptr(hits), len(packets),
+       threads if threads is not None else (os.cpu_count() or 1))
+    return hits
+
+
 def traverse_bvh2(nodes: np.ndarray, tris: np.ndarray, rays: np.ndarray, any_hit: bool = False, threads: int | None = None,
                   want_counters: bool = False):
     """The reference's GPU traversal semantics on its BVH2 / Tri1 layout (oracle/traversal_bvh2_oracle.c)."""

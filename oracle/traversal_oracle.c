@@ -227,9 +227,9 @@ static inline int intersect_ray_tri4(const Tri4* tp, const float org[3], const f
  * child[N], pad[N]).  Stack discipline of src/traversal/stack.impala:52-123: the
  * top entry lives in (top_node, top_t); `st` is the memory part. */
 static inline __attribute__((always_inline))
-void traverse_single(const int N, const int any_hit,
-                     const void* nodes_v, const Tri4* tris, const Ray1* rp, Hit1* hp,
-                     OracleStats* stats, int32_t* geom_out) {
+void traverse_single_from(const int N, const int any_hit,
+                          const void* nodes_v, const Tri4* tris, const Ray1* rp, Hit1* hp,
+                          OracleStats* stats, int32_t* geom_out, const int32_t root) {
     const size_t node_stride = (size_t)N * 32;       /* 6N floats + N + N ints */
     const char* nodes = (const char*)nodes_v;
     const Network* nets = N == 8 ? g_batcher : g_bose_nelson;
@@ -256,7 +256,7 @@ void traverse_single(const int N, const int any_hit,
 #define PUSH(n_, t_)       do { ++ptr; st[ptr].node = top_node; st[ptr].tmin = top_t; top_node = (n_); top_t = (t_); } while (0)
 #define PUSH_AFTER(n_, t_) do { ++ptr; st[ptr].node = (n_); st[ptr].tmin = (t_); } while (0)
 #define POP()              do { top_node = st[ptr].node; top_t = st[ptr].tmin; --ptr; } while (0)
-    PUSH(1 /*root*/, tmin);                                              /* :153 */
+    PUSH(root, tmin);                                                    /* :153 (root = 1 but for the hybrid kernel's lanes) */
 
     uint64_t n_nodes = 0, n_tri4 = 0; int max_ptr = 0;
 
@@ -392,6 +392,167 @@ void traverse_single(const int N, const int any_hit,
         stats->nodes += n_nodes; stats->tri4 += n_tri4;
         if ((uint64_t)max_ptr > stats->max_stack) stats->max_stack = (uint64_t)max_ptr;
     }
+}
+
+static inline __attribute__((always_inline))
+void traverse_single(const int N, const int any_hit,
+                     const void* nodes_v, const Tri4* tris, const Ray1* rp, Hit1* hp,
+                     OracleStats* stats, int32_t* geom_out) {
+    traverse_single_from(N, any_hit, nodes_v, tris, rp, hp, stats, geom_out, 1 /*root*/);
+}
+
+/* ---- the packet / hybrid kernel, src/traversal/mapping_cpu.impala:259-384 ---------------------------------------------
+ * One packet of W rays (W = 4 or 8 lanes of the reference's vectorised region) with ONE stack of (node, tmin[W]):
+ * a node is visited when any lane enters it, the children are pushed in child order (no sort), the triangles of a leaf
+ * are tested one after the other (Tri4 lane i against every ray lane; `t <= tmax` accepts an equal distance, so of two
+ * triangles hit at the same t the LATER one stays -- the single-ray kernel keeps the FIRST of a Tri4).  `hybrid`: when
+ * at most `switch_threshold` lanes are still interested in the entry on top, those lanes walk its subtree with the
+ * single-ray kernel (:309-319).  Records therefore differ from the single-ray kernel's where hits tie; how often they do
+ * on the reference's ray sets is measured in tests/test_packet_oracle.py.
+ * rays: org[3][W] dir[3][W] tmin[W] tmax[W]; hits: tri_id[W] t[W] u[W] v[W] (make_cpu_ray4/8, make_cpu_hit4/8,
+ * tools/bench_traversal/bench_traversal.impala:96-157). */
+static void traverse_packet(const int N, const int W, const int hybrid, const int any_hit,
+                            const void* nodes_v, const Tri4* tris, const float* rp, float* hp) {
+    const size_t node_stride = (size_t)N * 32;
+    const char* nodes = (const char*)nodes_v;
+    const int switch_threshold = W == 4 ? 3 : W == 8 ? (N == 4 ? 4 : 6) : W / 2;           /* :268-273 */
+    float org[8][3], dir[8][3], inv_dir[8][3], inv_org[8][3], tmin[8], tmax[8];
+    int32_t hit_prim[8]; float hit_t[8], hit_u[8], hit_v[8]; int terminated[8];
+    for (int l = 0; l < W; l++) {                                        /* make_ray, intersection.impala:88-99 */
+        for (int a = 0; a < 3; a++) {
+            org[l][a] = rp[a * W + l]; dir[l][a] = rp[(3 + a) * W + l];
+            inv_dir[l][a] = safe_rcp(dir[l][a]);
+            inv_org[l][a] = -(org[l][a] * inv_dir[l][a]);
+        }
+        tmin[l] = rp[6 * W + l]; tmax[l] = rp[7 * W + l];
+        hit_prim[l] = -1; hit_t[l] = tmax[l]; hit_u[l] = 0.0f; hit_v[l] = 0.0f; terminated[l] = 0;      /* empty_hit */
+    }
+    int32_t st_node[STACK_SIZE + 8]; float st_t[STACK_SIZE + 8][8];
+    int ptr = -1; int32_t top_node = 0; float top_t[8];
+    for (int l = 0; l < W; l++) top_t[l] = FLT_MAX_;
+#define PPUSH(n_, t_)       do { ++ptr; st_node[ptr] = top_node; memcpy(st_t[ptr], top_t, sizeof top_t); top_node = (n_); memcpy(top_t, (t_), sizeof top_t); } while (0)
+#define PPUSH_AFTER(n_, t_) do { ++ptr; st_node[ptr] = (n_); memcpy(st_t[ptr], (t_), sizeof top_t); } while (0)
+#define PPOP()              do { top_node = st_node[ptr]; memcpy(top_t, st_t[ptr], sizeof top_t); --ptr; } while (0)
+    { float t0[8]; for (int l = 0; l < 8; l++) t0[l] = l < W ? tmin[l] : FLT_MAX_; PPUSH(1 /*root*/, t0); }    /* :278 */
+
+    for (;;) {
+        /* cull, and hand the last interested lanes to the single-ray kernel (:303-326) */
+        int done = 0;
+        for (;;) {
+            if (top_node == 0) { done = 1; break; }
+            unsigned mask = 0;
+            for (int l = 0; l < W; l++) if (top_t[l] <= tmax[l] && !terminated[l]) mask |= 1u << l;
+            if (mask != 0) {
+                if (hybrid && __builtin_popcount(mask) <= switch_threshold) {
+                    for (unsigned m = mask; m != 0; m &= m - 1) {
+                        const int l = __builtin_ctz(m);
+                        const Ray1 lane_ray = { { org[l][0], org[l][1], org[l][2] }, tmin[l], { dir[l][0], dir[l][1], dir[l][2] }, tmax[l] };
+                        Hit1 lane_hit = { -1, tmax[l], 0.0f, 0.0f };
+                        traverse_single_from(N, any_hit, nodes_v, tris, &lane_ray, &lane_hit, NULL, NULL, top_node);
+                        if (lane_hit.tri_id >= 0) {
+                            hit_prim[l] = lane_hit.tri_id;
+                            if (!any_hit) { hit_t[l] = lane_hit.t; hit_u[l] = lane_hit.u; hit_v[l] = lane_hit.v; tmax[l] = lane_hit.t; }
+                        }
+                    }
+                    if (any_hit) for (int l = 0; l < W; l++) terminated[l] = hit_prim[l] >= 0;
+                } else {
+                    break;
+                }
+            }
+            PPOP();
+        }
+        if (done) break;
+
+        /* inner nodes (:329-355) */
+        int culled = 0;
+        while (top_node > 0) {
+            const float* nb = (const float*)(nodes + (size_t)(top_node - 1) * node_stride);
+            const int32_t* child = (const int32_t*)(nb + 6 * N);
+            PPOP();
+            int pushed = 0;
+            for (int i = 0; i < N; i++) {
+                const int32_t child_id = child[i];
+                if (child_id == 0) break;
+                float thit[8]; int any = 0, nearer = 0;
+                for (int l = 0; l < W; l++) {                            /* intersect_ray_box, unordered, integer min / max */
+                    const float t0x = inv_dir[l][0] * nb[i] + inv_org[l][0],         t1x = inv_dir[l][0] * nb[N + i] + inv_org[l][0];
+                    const float t0y = inv_dir[l][1] * nb[2 * N + i] + inv_org[l][1], t1y = inv_dir[l][1] * nb[3 * N + i] + inv_org[l][1];
+                    const float t0z = inv_dir[l][2] * nb[4 * N + i] + inv_org[l][2], t1z = inv_dir[l][2] * nb[5 * N + i] + inv_org[l][2];
+                    const float tentry = imax(imax(imin(t0x, t1x), imin(t0y, t1y)), imax(imin(t0z, t1z), tmin[l]));
+                    const float texit  = imin(imin(imax(t0x, t1x), imax(t0y, t1y)), imin(imax(t0z, t1z), tmax[l]));
+                    const int miss = f2i(texit) < f2i(tentry);
+                    thit[l] = miss ? FLT_MAX_ : tentry;
+                    any |= !miss;
+                }
+                for (int l = W; l < 8; l++) thit[l] = FLT_MAX_;
+                if (any) {
+                    for (int l = 0; l < W; l++) nearer |= top_t[l] > thit[l];
+                    if (any_hit || nearer) PPUSH(child_id, thit);
+                    else                   PPUSH_AFTER(child_id, thit);
+                    pushed = 1;
+                }
+            }
+            if (!pushed) { culled = 1; break; }
+        }
+        if (culled) continue;
+
+        /* leaf (:357-381) */
+        if (top_node < 0) {
+            int active[8];
+            for (int l = 0; l < W; l++) active[l] = top_t[l] <= tmax[l] && !terminated[l];
+            int32_t prim_id = ~top_node;
+            PPOP();
+            int all_out = 0;
+            for (;;) {
+                const Tri4* tp = &tris[prim_id++];
+                for (int i = 0; i < 4; i++) {
+                    if (tp->prim_id[i] == -1) break;                     /* is_valid */
+                    for (int l = 0; l < W; l++) {
+                        if (!active[l]) continue;
+                        float t, u, v;
+                        if (intersect_ray_tri_lane(tp, i, org[l], dir[l], tmin[l], tmax[l], &t, &u, &v)) {
+                            hit_prim[l] = tp->prim_id[i] & 0x7FFFFFFF; hit_t[l] = t; hit_u[l] = u; hit_v[l] = v;
+                            tmax[l] = t;
+                            if (any_hit) { terminated[l] = 1; active[l] = 0; }
+                        }
+                    }
+                    if (any_hit) { int all = 1; for (int l = 0; l < W; l++) all &= terminated[l]; if (all) { all_out = 1; break; } }
+                }
+                if (all_out) break;
+                if (tp->prim_id[3] < 0) break;                           /* is_last */
+            }
+            if (all_out) break;
+        }
+    }
+#undef PPUSH
+#undef PPUSH_AFTER
+#undef PPOP
+    for (int l = 0; l < W; l++) {                                        /* make_cpu_hit4/8 */
+        memcpy(&hp[l], &hit_prim[l], 4);
+        if (!any_hit) { hp[W + l] = hit_t[l]; hp[2 * W + l] = hit_u[l]; hp[3 * W + l] = hit_v[l]; }
+    }
+}
+
+typedef struct { int arity, width, hybrid, any_hit; const void* nodes; const Tri4* tris; const float* rays; float* hits; int32_t begin, end; } PacketJob;
+static void* run_packets_thread(void* p) {
+    PacketJob* j = (PacketJob*)p;
+    for (int32_t i = j->begin; i < j->end; i++)
+        traverse_packet(j->arity, j->width, j->hybrid, j->any_hit, j->nodes, j->tris, j->rays + (size_t)i * 8 * j->width, j->hits + (size_t)i * 4 * j->width);
+    return NULL;
+}
+/* cpu_{intersect,occluded}_{packet,hybrid}_ray{4,8}_bvh{4,8}_tri4 of the reference, by name of their parameters */
+void oracle_traverse_packets(int arity, int width, int hybrid, int any_hit, const void* nodes, const Tri4* tris,
+                             const float* rays, float* hits, int32_t num_packets, int threads) {
+    pthread_once(&g_net_once, init_networks);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    PacketJob jobs[256]; pthread_t th[256];
+    for (int k = 0; k < threads; k++) {
+        jobs[k] = (PacketJob){ arity, width, hybrid, any_hit, nodes, tris, rays, hits,
+                               (int32_t)((int64_t)num_packets * k / threads), (int32_t)((int64_t)num_packets * (k + 1) / threads) };
+        pthread_create(&th[k], NULL, run_packets_thread, &jobs[k]);
+    }
+    for (int k = 0; k < threads; k++) pthread_join(th[k], NULL);
 }
 
 /* ---- cpu_traverse_single, src/traversal/mapping_cpu.impala:404-418 -------- */
