@@ -53,6 +53,7 @@ struct Tuning {
     int pool_prefetch = 0;   // (mapping 3) L1 prefetch of a ray's next node / leaf while it waits in the pool
     int pool_refill_min = 24; // (mapping 3) refill a pool once this many of its 64 slots are empty
     int blocks_per_sm = 0;   // 0: occupancy API
+    int packet_order = 0;    // packet / hybrid entry points: 1 = the reference's packet order to the bit (traverse_packets_ordered: one thread per packet), 0 = every ray gets the single-ray kernel's record
     int host_staging = 1;    // host-pointer entry points: pageable caller buffers go through pinned staging memory (0: straight to cudaMemcpyAsync)
     int host_direct = 1;     // host-pointer entry points, closest hit: one launch per call that follows its rays as they arrive and sends its records home itself (run_host_direct; 0: copy-engine pieces)
     int host_direct_rays = 1;    // ... 1 = a copy engine brings the rays in while the kernel runs (armed slots, traverse_sched.cuh), 0 = the warps read them from the caller's memory as they refill
@@ -240,6 +241,151 @@ traverse_packets_vote(const void* __restrict__ nodes, const Tri4* __restrict__ t
             p[0] = __int_as_float(h.prim);
             if (!ANY) { p[W] = h.t; p[2 * W] = h.u; p[3 * W] = h.v; }           // make_cpu_hit4/8, bench_traversal.impala:133-157
         }, node_streak_min);
+}
+
+// The reference's packet / hybrid kernel in ITS order (cpu_traverse_hybrid_helper, src/traversal/mapping_cpu.impala:259-384):
+// one stack of (node, tmin[W]) per packet, a node visited when any ray of the packet enters it, children pushed in child
+// order without a sort, the triangles of a leaf tested one after the other against every interested ray (`t <= tmax`: of
+// two hits at the same distance the later one stays), and -- hybrid -- the last few interested rays handed to the
+// single-ray walk of the subtree.  One THREAD per packet, its W rays in turn: this is the mode for callers that need the
+// packet kernels' records to the bit (rodent_b200_tune("packet_order", 1); tests/test_packet_oracle.py), not a fast one --
+// the default gives every ray of a packet the single-ray kernel's record, which differs only where hits tie.
+template <bool ANY, int ARITY, int W>
+__global__ void __launch_bounds__(64)
+traverse_packets_ordered(const void* __restrict__ nodes, const Tri4* __restrict__ tris,
+                         const float* __restrict__ rays, float* __restrict__ hits, int num_packets, int hybrid) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num_packets) return;
+    const float* rp = rays + size_t(p) * (8 * W);
+    constexpr int kSwitch = W == 4 ? 3 : (ARITY == 4 ? 4 : 6);                       // :268-273
+    RaySetup ray[W];
+    float tmax[W], hit_t[W], hit_u[W], hit_v[W];
+    int hit_prim[W];
+    bool terminated[W];
+    for (int l = 0; l < W; l++) {
+        ray[l].template init<ARITY / 4>(make_float4(rp[l], rp[W + l], rp[2 * W + l], rp[6 * W + l]),
+                                         make_float4(rp[3 * W + l], rp[4 * W + l], rp[5 * W + l], rp[7 * W + l]));
+        tmax[l] = rp[7 * W + l];
+        hit_prim[l] = -1; hit_t[l] = tmax[l]; hit_u[l] = 0.0f; hit_v[l] = 0.0f; terminated[l] = false;
+    }
+    int st_node[kStackSize + 8];
+    float st_t[kStackSize + 8][W];
+    int ptr = -1, top_node = 0;
+    float top_t[W];
+    for (int l = 0; l < W; l++) top_t[l] = kFltMax;
+    auto push = [&](int n, const float* t) { ++ptr; st_node[ptr] = top_node; for (int l = 0; l < W; l++) st_t[ptr][l] = top_t[l]; top_node = n; for (int l = 0; l < W; l++) top_t[l] = t[l]; };
+    auto push_after = [&](int n, const float* t) { ++ptr; st_node[ptr] = n; for (int l = 0; l < W; l++) st_t[ptr][l] = t[l]; };
+    auto pop = [&] { top_node = st_node[ptr]; for (int l = 0; l < W; l++) top_t[l] = st_t[ptr][l]; --ptr; };
+    { float t0[W]; for (int l = 0; l < W; l++) t0[l] = ray[l].tmin; push(1, t0); }   // :278
+
+    StackEntry walk_stack[kStackSize];                                               // of the single-ray walks of the hybrid form
+    for (;;) {
+        // cull; hand the last interested rays to the single-ray walk (:303-326)
+        bool done = false;
+        for (;;) {
+            if (top_node == 0) { done = true; break; }
+            unsigned mask = 0;
+            for (int l = 0; l < W; l++) if (top_t[l] <= tmax[l] && !terminated[l]) mask |= 1u << l;
+            if (mask != 0) {
+                if (hybrid && __popc(mask) <= kSwitch) {
+                    for (unsigned m = mask; m != 0; m &= m - 1) {
+                        const int l = __ffs(m) - 1;
+                        RayWalker<ANY, 0, 64, ARITY, false, false> w;
+                        w.st.smem = nullptr; w.st.overflow = walk_stack;
+                        w.begin(make_float4(ray[l].ox, ray[l].oy, ray[l].oz, ray[l].tmin), make_float4(ray[l].dx, ray[l].dy, ray[l].dz, tmax[l]), top_node);
+                        while (!w.finished()) {
+                            if (w.wants_node()) w.template node_step<true>(nodes);
+                            else if (w.template leaf_step<false>(tris)) break;
+                        }
+                        if (w.hit.prim >= 0) {
+                            hit_prim[l] = w.hit.prim;
+                            if (!ANY) { hit_t[l] = w.hit.t; hit_u[l] = w.hit.u; hit_v[l] = w.hit.v; tmax[l] = w.hit.t; }
+                        }
+                    }
+                    if (ANY) for (int l = 0; l < W; l++) terminated[l] = hit_prim[l] >= 0;
+                } else {
+                    break;
+                }
+            }
+            pop();
+        }
+        if (done) break;
+
+        // inner nodes (:329-355)
+        bool culled = false;
+        while (top_node > 0) {
+            const float* nb = reinterpret_cast<const float*>(nodes) + size_t(top_node - 1) * (8 * ARITY);
+            const int* child = reinterpret_cast<const int*>(nb + 6 * ARITY);
+            pop();
+            bool pushed = false;
+            for (int i = 0; i < ARITY; i++) {
+                const int child_id = __ldg(child + i);
+                if (child_id == 0) break;
+                const float bx0 = __ldg(nb + i), bx1 = __ldg(nb + ARITY + i), by0 = __ldg(nb + 2 * ARITY + i), by1 = __ldg(nb + 3 * ARITY + i);
+                const float bz0 = __ldg(nb + 4 * ARITY + i), bz1 = __ldg(nb + 5 * ARITY + i);
+                float thit[W];
+                bool any = false, nearer = false;
+                for (int l = 0; l < W; l++) {                                        // intersect_ray_box, unordered, integer min / max
+                    const float t0x = slab<true>(ray[l].idx, bx0, ray[l].iox), t1x = slab<true>(ray[l].idx, bx1, ray[l].iox);
+                    const float t0y = slab<true>(ray[l].idy, by0, ray[l].ioy), t1y = slab<true>(ray[l].idy, by1, ray[l].ioy);
+                    const float t0z = slab<true>(ray[l].idz, bz0, ray[l].ioz), t1z = slab<true>(ray[l].idz, bz1, ray[l].ioz);
+                    const float tentry = imax2(imax2(imin2(t0x, t1x), imin2(t0y, t1y)), imax2(imin2(t0z, t1z), ray[l].tmin));
+                    const float texit = imin2(imin2(imax2(t0x, t1x), imax2(t0y, t1y)), imin2(imax2(t0z, t1z), tmax[l]));
+                    const bool miss = __float_as_int(texit) < __float_as_int(tentry);
+                    thit[l] = miss ? kFltMax : tentry;
+                    any |= !miss;
+                }
+                if (any) {
+                    for (int l = 0; l < W; l++) nearer |= top_t[l] > thit[l];
+                    if (ANY || nearer) push(child_id, thit);
+                    else push_after(child_id, thit);
+                    pushed = true;
+                }
+            }
+            if (!pushed) { culled = true; break; }
+        }
+        if (culled) continue;
+
+        // leaf (:357-381)
+        if (top_node < 0) {
+            bool active[W];
+            for (int l = 0; l < W; l++) active[l] = top_t[l] <= tmax[l] && !terminated[l];
+            int prim_id = ~top_node;
+            pop();
+            bool all_out = false;
+            for (;;) {
+                const float* tp = reinterpret_cast<const float*>(tris + prim_id);
+                const int* ids = reinterpret_cast<const int*>(tp + 48);
+                prim_id++;
+                for (int i = 0; i < 4; i++) {
+                    const int id = __ldg(ids + i);
+                    if (id == -1) break;                                             // is_valid
+                    const float v0x = __ldg(tp + i), v0y = __ldg(tp + 4 + i), v0z = __ldg(tp + 8 + i);
+                    const float e1x = __ldg(tp + 12 + i), e1y = __ldg(tp + 16 + i), e1z = __ldg(tp + 20 + i);
+                    const float e2x = __ldg(tp + 24 + i), e2y = __ldg(tp + 28 + i), e2z = __ldg(tp + 32 + i);
+                    const float nx = __ldg(tp + 36 + i), ny = __ldg(tp + 40 + i), nz = __ldg(tp + 44 + i);
+                    for (int l = 0; l < W; l++) {
+                        if (!active[l]) continue;
+                        float t, u, v;
+                        if (intersect_tri_lane(ray[l], tmax[l], v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz, t, u, v)) {
+                            hit_prim[l] = id & 0x7FFFFFFF; hit_t[l] = t; hit_u[l] = u; hit_v[l] = v;
+                            tmax[l] = t;
+                            if (ANY) { terminated[l] = true; active[l] = false; }
+                        }
+                    }
+                    if (ANY) { bool all = true; for (int l = 0; l < W; l++) all &= terminated[l]; if (all) { all_out = true; break; } }
+                }
+                if (all_out) break;
+                if (__ldg(ids + 3) < 0) break;                                       // is_last
+            }
+            if (all_out) break;
+        }
+    }
+    float* hp = hits + size_t(p) * (4 * W);
+    for (int l = 0; l < W; l++) {                                                    // make_cpu_hit4/8
+        hp[l] = __int_as_float(hit_prim[l]);
+        if (!ANY) { hp[W + l] = hit_t[l]; hp[2 * W + l] = hit_u[l]; hp[3 * W + l] = hit_v[l]; }
+    }
 }
 
 // Ray-pool kernel (traverse_pool.cuh): 64 rays per warp in shared memory, compacted onto the lanes per step.
@@ -1110,13 +1256,28 @@ static void run_host_on(int dev, const NodeT* nodes, const Tri4* tris, const Ray
 // Packet entry points: closest hit in copy-engine pieces, any hit on the staged single launch (run_host_direct, W = 4 or 8);
 // with host_staged_direct = 0, copy in, one launch of the packet kernel, copy out.
 template <bool ANY, typename NodeT, int W>
-static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* rays, void* hits, int num_packets) {
+static void run_host_packets(const NodeT* nodes, const Tri4* tris, const void* rays, void* hits, int num_packets, bool hybrid) {
     if (num_packets <= 0) return;
     constexpr int ARITY = int(sizeof(NodeT::child) / sizeof(int32_t));
     DeviceState& s = device_state(g_host_dev);
     auto bvh = cached_bvh(s, nodes, tris);
     const int num_rays = num_packets * W;
     HostContext* c = acquire_host_context(s, size_t(num_rays));
+    if (g_tuning.packet_order) {                 // the reference's packet order to the bit: copy in, one launch, copy out
+        cudaStream_t st = c->streams[0];
+        c->rays_armed = false;
+        RB_CUDA_CHECK(cudaMemcpyAsync(c->d_rays, rays, size_t(num_rays) * sizeof(Ray1), cudaMemcpyHostToDevice, st));
+        if (ANY) RB_CUDA_CHECK(cudaMemcpyAsync(c->d_hits, hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyHostToDevice, st));   // t, u, v stay the caller's
+        traverse_packets_ordered<ANY, ARITY, W><<<(num_packets + 63) / 64, 64, 0, st>>>(bvh.first, bvh.second, reinterpret_cast<const float*>(c->d_rays),
+                                                                                        reinterpret_cast<float*>(c->d_hits), num_packets, hybrid ? 1 : 0);
+        RB_CUDA_CHECK(cudaGetLastError());
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        s.last_kernel = "traverse_packets_ordered";
+        RB_CUDA_CHECK(cudaMemcpyAsync(hits, c->d_hits, size_t(num_rays) * sizeof(Hit1), cudaMemcpyDeviceToHost, st));
+        RB_CUDA_CHECK(cudaStreamSynchronize(st));
+        release_host_context(s, c);
+        return;
+    }
     if (g_tuning.host_direct && g_tuning.mapping == 2 && g_tuning.host_staged_direct != 0) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(bvh.first) | reinterpret_cast<uintptr_t>(bvh.second)) & 31) == 0;
         ensure_staging(c, size_t(num_rays));
@@ -1221,15 +1382,15 @@ void b200_intersect_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, 
 void b200_occluded_single_ray1_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray1* rays, Hit1* hits, int32_t num_packets) {
     run_host<true>(nodes, tris, rays, hits, num_packets);
 }
-#define RB_PACKET_API(kind, W, B)                                                                                               \
+#define RB_PACKET_API(kind, W, B, HYBRID)                                                                                       \
     void b200_intersect_##kind##_ray##W##_bvh##B##_tri4(const Node##B* n, const Tri4* t, const Ray##W* r, Hit##W* h, int32_t k) { \
-        run_host_packets<false, Node##B, W>(n, t, r, h, k);                                                                     \
+        run_host_packets<false, Node##B, W>(n, t, r, h, k, HYBRID);                                                             \
     }                                                                                                                           \
     void b200_occluded_##kind##_ray##W##_bvh##B##_tri4(const Node##B* n, const Tri4* t, const Ray##W* r, Hit##W* h, int32_t k) {  \
-        run_host_packets<true, Node##B, W>(n, t, r, h, k);                                                                      \
+        run_host_packets<true, Node##B, W>(n, t, r, h, k, HYBRID);                                                              \
     }
-RB_PACKET_API(packet, 4, 4) RB_PACKET_API(packet, 8, 4) RB_PACKET_API(packet, 4, 8) RB_PACKET_API(packet, 8, 8)
-RB_PACKET_API(hybrid, 4, 4) RB_PACKET_API(hybrid, 8, 4) RB_PACKET_API(hybrid, 4, 8) RB_PACKET_API(hybrid, 8, 8)
+RB_PACKET_API(packet, 4, 4, false) RB_PACKET_API(packet, 8, 4, false) RB_PACKET_API(packet, 4, 8, false) RB_PACKET_API(packet, 8, 8, false)
+RB_PACKET_API(hybrid, 4, 4, true) RB_PACKET_API(hybrid, 8, 4, true) RB_PACKET_API(hybrid, 4, 8, true) RB_PACKET_API(hybrid, 8, 8, true)
 #undef RB_PACKET_API
 
 void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris) {
@@ -1374,6 +1535,7 @@ void rodent_b200_tune(const char* key, int32_t value) {
     else if (!std::strcmp(key, "pool_refill_min")) g_tuning.pool_refill_min = clamp(value, 1, 64);
     else if (!std::strcmp(key, "pool_prefetch")) g_tuning.pool_prefetch = value != 0;
     else if (!std::strcmp(key, "host_chunks")) g_tuning.host_chunks = clamp(value, 1, 16);
+    else if (!std::strcmp(key, "packet_order")) g_tuning.packet_order = value != 0;
     else if (!std::strcmp(key, "host_staging")) g_tuning.host_staging = value != 0;
     else if (!std::strcmp(key, "host_stream_stores")) g_tuning.host_stream_stores = value != 0;
     else if (!std::strcmp(key, "host_copy_parts")) g_tuning.host_copy_parts = clamp(value, 1, 17);

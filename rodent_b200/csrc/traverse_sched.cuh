@@ -63,12 +63,13 @@ struct RayWalker {
         }
     }
 
-    __device__ __forceinline__ void begin(float4 r0, float4 r1) {
+    // `root`: 1 but for the lanes the hybrid packet kernel hands over at an inner entry of its stack (:309-319)
+    __device__ __forceinline__ void begin(float4 r0, float4 r1, int root = 1) {
         ray.template init<ARITY / 4>(r0, r1);
         tmax = r1.w;
         hit.prim = -1; hit.geom = -1; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;   // empty_hit, intersection.impala:134-136
         ptr = -1; top_node = 0; top_t = kFltMax; leaf = -1;
-        push(1, ray.tmin);                                                          // :153
+        push(root, ray.tmin);                                                       // :153
         cull();
     }
 

@@ -73,3 +73,30 @@ def test_entry_points_against_the_packet_oracle(kind, width, arity, sponza, spon
         assert ((got["tri_id"] >= 0) == (want["tri_id"] >= 0)).all()
         assert int(ulps(got["t"], want["t"]).max()) <= 2
         assert float((got["tri_id"] != want["tri_id"]).mean()) <= limit
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,width,arity", [("hybrid", 8, 4), ("packet", 8, 4), ("hybrid", 4, 4), ("packet", 4, 8), ("hybrid", 8, 8), ("packet", 8, 8), ("hybrid", 4, 8)])
+def test_packet_order_mode_is_the_packet_oracle_to_the_bit(kind, width, arity, sponza, sponza4, ray_sets):
+    """rodent_b200_tune("packet_order", 1): traverse_packets_ordered walks in the reference's packet order -- every record
+    of both sets' first 300 000 rays identical to the restated packet kernel, closest and any hit, degenerate rays too."""
+    from rodent_b200 import lib, traversal
+    nodes, tris = sponza if arity == 8 else sponza4
+    lib.tune("packet_order", 1)
+    try:
+        for name in ("primary", "random"):
+            rays = np.ascontiguousarray(ray_sets[name][:300_000])
+            if name == "random":          # axis-parallel and clamped directions: the NaN paths of the slab test
+                rays["dir"][::97, 0] = 0.0; rays["dir"][::89, 1] = -0.0; rays["dir"][::83, 2] = 1e-12
+            packets = formats.pack_rays(rays, width)
+            want = oracle.traverse_packets(nodes, tris, packets, kind)
+            got = traversal.intersect_host_packets(nodes, tris, packets, kind)
+            assert lib.load().rodent_b200_last_kernel_name(0).decode() == "traverse_packets_ordered"
+            assert got.tobytes() == want.tobytes(), (name, int((formats.unpack_hits(got)["tri_id"] != formats.unpack_hits(want)["tri_id"]).sum()))
+            pre = np.zeros(len(packets), formats.packet_dtypes(width)[1])
+            pre["t"] = 5.0
+            occl = traversal.intersect_host_packets(nodes, tris, packets, kind, any_hit=True, hits=pre)
+            want_any = oracle.traverse_packets(nodes, tris, packets, kind, any_hit=True)
+            assert np.array_equal(occl["tri_id"], want_any["tri_id"]) and (occl["t"] == 5.0).all()
+    finally:
+        lib.tune("packet_order", 0)
