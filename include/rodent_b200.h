@@ -190,7 +190,8 @@ typedef struct Hit8 { int32_t tri_id[8]; float t[8]; float u[8]; float v[8]; } H
  * tests/test_packet_oracle.py) on the two Sponza sets: the same rays hit, t within 1 ulp everywhere, another triangle of
  * a tie on 6 .. 694 of 1 Mi primary rays and on 0.03 .. 2.1 % of the incoherent ones.  A caller that needs the packet
  * kernels' records to the bit switches these entry points to the packet walk itself with
- * rodent_b200_tune("packet_order", 1) (one thread per packet; several times slower). */
+ * rodent_b200_set_packet_order(1) (one thread per packet; several times slower; process-wide, default 0). */
+void rodent_b200_set_packet_order(int32_t on);
 void b200_intersect_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
 void b200_occluded_packet_ray4_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray4* rays, Hit4* hits, int32_t num_packets);
 void b200_intersect_packet_ray8_bvh4_tri4(const Node4* nodes, const Tri4* tris, const Ray8* rays, Hit8* hits, int32_t num_packets);

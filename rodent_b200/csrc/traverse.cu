@@ -1393,6 +1393,8 @@ RB_PACKET_API(packet, 4, 4, false) RB_PACKET_API(packet, 8, 4, false) RB_PACKET_
 RB_PACKET_API(hybrid, 4, 4, true) RB_PACKET_API(hybrid, 8, 4, true) RB_PACKET_API(hybrid, 4, 8, true) RB_PACKET_API(hybrid, 8, 8, true)
 #undef RB_PACKET_API
 
+void rodent_b200_set_packet_order(int32_t on) { g_tuning.packet_order = on != 0; }
+
 void rodent_b200_forget_bvh(const void* nodes, const Tri4* tris) {
     DeviceState& s = device_state(g_host_dev);
     std::lock_guard<std::mutex> lock(g_mutex);

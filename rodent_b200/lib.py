@@ -58,6 +58,7 @@ SIGNATURES = {
     "rodent_b200_last_kernel_ms": (c_double, [c_int32]),
     "rodent_b200_last_kernel_name": (c_char_p, [c_int32]),
     "rodent_b200_launch_count": (c_int64, []),
+    "rodent_b200_set_packet_order": (None, [c_int32]),
     "rodent_b200_version": (c_char_p, []),
 }
 for _kind in ("packet", "hybrid"):

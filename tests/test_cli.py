@@ -82,7 +82,8 @@ def test_ctest_procedure_on_gpu(tools, tmp_path, mode, name, tmin, tmax, hits):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [[], ["-p"], ["--ray-width", "4"], ["-p", "--ray-width", "4", "--bvh-width", "8"], ["--bvh-width", "8"]])
+@pytest.mark.parametrize("mode", [[], ["-p"], ["--ray-width", "4"], ["-p", "--ray-width", "4", "--bvh-width", "8"], ["--bvh-width", "8"],
+                                  ["--packet-order"], ["--packet-order", "-p"]])
 def test_packet_and_hybrid_variants_on_gpu(tools, tmp_path, mode):
     """hybrid_bvh4 (the reference's default command line), packet_bvh4, ..., of tools/CMakeLists.txt:26-31."""
     fbuf = tmp_path / "out.fbuf"

@@ -78,11 +78,11 @@ def test_entry_points_against_the_packet_oracle(kind, width, arity, sponza, spon
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,width,arity", [("hybrid", 8, 4), ("packet", 8, 4), ("hybrid", 4, 4), ("packet", 4, 8), ("hybrid", 8, 8), ("packet", 8, 8), ("hybrid", 4, 8)])
 def test_packet_order_mode_is_the_packet_oracle_to_the_bit(kind, width, arity, sponza, sponza4, ray_sets):
-    """rodent_b200_tune("packet_order", 1): traverse_packets_ordered walks in the reference's packet order -- every record
+    """rodent_b200_set_packet_order(1): traverse_packets_ordered walks in the reference's packet order -- every record
     of both sets' first 300 000 rays identical to the restated packet kernel, closest and any hit, degenerate rays too."""
     from rodent_b200 import lib, traversal
     nodes, tris = sponza if arity == 8 else sponza4
-    lib.tune("packet_order", 1)
+    lib.load().rodent_b200_set_packet_order(1)
     try:
         for name in ("primary", "random"):
             rays = np.ascontiguousarray(ray_sets[name][:300_000])
@@ -99,4 +99,4 @@ def test_packet_order_mode_is_the_packet_oracle_to_the_bit(kind, width, arity, s
             want_any = oracle.traverse_packets(nodes, tris, packets, kind, any_hit=True)
             assert np.array_equal(occl["tri_id"], want_any["tri_id"]) and (occl["t"] == 5.0).all()
     finally:
-        lib.tune("packet_order", 0)
+        lib.load().rodent_b200_set_packet_order(0)

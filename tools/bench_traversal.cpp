@@ -31,7 +31,7 @@ struct Options {
     std::string bvh_file, ray_file, out_file, gpu;
     float tmin = 0.0f, tmax = 1e9f;
     int iters = 1, warmup = 0, dev = 0, bvh_width = 4, ray_width = 8, gpus = 1;
-    bool any_hit = false, single = false, packet = false, bvh_width_given = false, pinned = false;
+    bool any_hit = false, single = false, packet = false, bvh_width_given = false, pinned = false, packet_order = false;
 };
 
 [[noreturn]] void fail(const std::string& msg) { std::cerr << msg << std::endl; std::exit(1); }
@@ -48,6 +48,7 @@ void usage() {
                  "  -any               exit at the first intersection\n"
                  "  -s    --single     host-buffer single-ray entry point\n"
                  "        --pinned     with -s: page-lock the ray and hit arrays in place (rodent_b200_pin_host)\n"
+                 "        --packet-order  without -s: walk in the reference's packet order (records of its packet / hybrid kernels to the bit; slower)\n"
                  "        --bvh-width  4 or 8 (default 4; 2 with -gpu: the reference GPU path's BVH2 block) ; --ray-width 4 or 8 (default 8)\n"
                  "  -o    --output     write hit distances as .fbuf\n";
 }
@@ -72,6 +73,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--gpus") o.gpus = int(std::strtol(value(), nullptr, 10));
         else if (a == "-any") o.any_hit = true;
         else if (a == "--pinned") o.pinned = true;
+        else if (a == "--packet-order") o.packet_order = true;
         else if (a == "-s" || a == "--single") o.single = true;
         else if (a == "-p" || a == "--packet") o.packet = true;
         else if (a == "--bvh-width") { o.bvh_width = int(std::strtol(value(), nullptr, 10)); o.bvh_width_given = true; }
@@ -180,6 +182,7 @@ int run_packets(const Options& o, rb200::BlockType block, Fn intersect, Fn occlu
             q[6 * W] = r.tmin; q[7 * W] = r.tmax;
         }
     rodent_b200_set_device(o.dev);
+    rodent_b200_set_packet_order(o.packet_order ? 1 : 0);
     using RayW = std::remove_pointer_t<std::tuple_element_t<2, typename FnArgs<Fn>::type>>;
     using HitW = std::remove_pointer_t<std::tuple_element_t<3, typename FnArgs<Fn>::type>>;
     auto bench = [&] {
