@@ -1,3 +1,4 @@
+"""Developer helper (run under ncu / compute-sanitizer): one host-pointer call with pageable arrays; prints the kernel it took."""
 import sys; sys.path.insert(0, '.')
 import numpy as np
 from rodent_b200 import formats, lib, testdata, traversal
