@@ -1,7 +1,9 @@
 // NCCL, bound at run time.  The library does not link libnccl: a process that also hosts PyTorch has PyTorch's own NCCL
 // loaded under the same soname, and a C++ host (tools/rodent --gpus N) has the system's.  The first multi-device call
 // dlopens "libnccl.so.2" -- which resolves to whatever the process already has, else to the system library -- and
-// aborts with a message when there is none.  Only the handful of calls the sharded paths use are bound: the film reduce
+// aborts with a message when there is none.  (The other order does not work: a process that loads the system library
+// here and imports PyTorch afterwards has the wrong NCCL under PyTorch's soname; rodent_b200/render.py imports PyTorch
+// first for that reason.)  Only the handful of calls the sharded paths use are bound: the film reduce
 // (ncclReduce) and the hit-record gather (ncclSend / ncclRecv in one group).
 #pragma once
 

@@ -220,6 +220,12 @@ class Renderer:
         self.L = _bind(lib.load())
         self.scene, self.width, self.height, self.spp = scene, width, height, spp
         if isinstance(dev, (list, tuple)):
+            # One libnccl.so.2 per process (csrc/nccl_dyn.h binds whichever is loaded, else the system's): a process that
+            # imports PyTorch AFTER the first multi-device call would find the system library under PyTorch's soname and
+            # fail to import.  So PyTorch, where installed, goes first.
+            import importlib.util
+            if importlib.util.find_spec("torch") is not None:
+                import torch  # noqa: F401
             devs = (c_int32 * len(dev))(*dev)
             self.handle = c_void_p(self.L.rodent_b200_renderer_create_multi(scene.handle, devs, len(dev), width, height, spp, max_path_len, band))
         else:
